@@ -1,0 +1,193 @@
+/*
+ * rover_b200.h -- C ABI of the B200-native rover hot path (librover_b200.so).
+ *
+ * The reference (abmoRobotics/isaac_rover_2.0) has no FFI: its boundary for this path is a set of
+ * Python call signatures.  Each entry point below replaces the arithmetic behind one of
+ * those calls and cites it (paths relative to omniisaacgymenvs/tasks/).  The Python mirror in
+ * isaac_rover_2.0_b200/ keeps the reference's names and signatures and binds these symbols with ctypes
+ * (INTEGRATION.md shows the stub).
+ *
+ * Conventions
+ *   - every pointer is a BORROWED DEVICE pointer into caller-owned memory unless the name ends in _host;
+ *     fp16 buffers are passed as uint16_t* (IEEE binary16 bits); outputs are pre-allocated by the caller;
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*; NULL = legacy default stream);
+ *     no hidden synchronisation except where stated;
+ *   - return value: 0 = ok, <0 = rvb_status; rvb_last_error() gives a thread-local message;
+ *   - nothing throws across this boundary; arguments are validated on the host before any launch;
+ *   - `sem` selects which torch backend's rounding is reproduced where torch-CPU and torch-CUDA differ
+ *     (division by a Python scalar is a reciprocal multiply on CUDA, and fp16-vs-scalar compares are done
+ *     in fp32 on CUDA but in fp16 on CPU).  The reference hard-wires 'cuda:0' (rover.py:90), so
+ *     RVB_SEM_TORCH_CUDA is the product default; RVB_SEM_TORCH_CPU exists so the CPU oracle / golden
+ *     vectors can be matched bit for bit.
+ */
+#ifndef ROVER_B200_H
+#define ROVER_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RVB_ABI_VERSION 1
+
+typedef enum rvb_status {
+    RVB_OK = 0,
+    RVB_ERR_INVALID = -1,   /* bad argument (null pointer, shape, range) */
+    RVB_ERR_CUDA = -2,      /* CUDA runtime error, see rvb_last_error() */
+    RVB_ERR_NOMEM = -3,
+    RVB_ERR_UNSUPPORTED = -4
+} rvb_status;
+
+typedef enum rvb_semantics { RVB_SEM_TORCH_CUDA = 0, RVB_SEM_TORCH_CPU = 1 } rvb_semantics;
+
+int rvb_abi_version(void);
+const char* rvb_last_error(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * Terrain layer handle: the grid-bucketed K-nearest-triangle index + mesh of ONE layer (terrain or
+ * big_rock_layer).  Replaces Camera._load_triangles_with_indices (utils/camera/camera.py:154-161) and
+ * Rock_Detection._load_triangles_with_indices (utils/rock_detection/rock_detect.py:151-158).
+ *
+ * map_indices is the [G0,G1,K] *view* the reference indexes (element strides given, so the permuted
+ * [K,G,G] tensor of camera.py:157-158 is accepted as is).  The handle owns a K-contiguous copy of the
+ * index and one pre-resolved 32-byte record per triangle (a = v2, b = v1-a, c = v0-a, b x c, all fp16
+ * with the reference's roundings, ray_casting.py:34-40).  Immutable after creation => usable from any
+ * stream concurrently.  Synchronises `stream` before returning.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct rvb_terrain rvb_terrain;
+
+int rvb_terrain_create(rvb_terrain** out,
+                       const int32_t* map_indices, int64_t G0, int64_t G1, int64_t K,
+                       int64_t stride_g0, int64_t stride_g1, int64_t stride_k,
+                       const int32_t* triangles, int64_t T,
+                       const uint16_t* vertices, int64_t V,
+                       float res, float shift_x, float shift_y,
+                       int sem, void* stream);
+int rvb_terrain_destroy(rvb_terrain* t);
+/* bytes of device memory owned by the handle */
+int64_t rvb_terrain_bytes(const rvb_terrain* t);
+
+/* ------------------------------------------------------------------------------------------------
+ * Camera.get_depths (utils/camera/camera.py:60-145) = _depth_transform (:165-212) + _height_lookup
+ * (:233-264) + the partitioned gather / ray_distance / min-over-K loop (:77-127).
+ *   pos, euler   f32 [N,3]           pattern f64 [P,3] (Heightmap.get_distribution())
+ *   trig         optional f32 [N,6] = sin,cos of -roll,-pitch,-yaw; NULL => computed with sinf/cosf
+ *   dist         f16 [N,P]  (required)         hit_slot i32 [N,P] (argmin position in the K list, optional)
+ *   hit_tri      i32 [N,P]  triangle id        pt, sources f16 [N,P,3] (optional)
+ *   obs/obs_ld/col_a/col_b: optional fused Heightmap.get_sparse_vector/get_dense_vector + rover.py:324-325:
+ *        obs[n*obs_ld + col_a[p]] = obs[n*obs_ld + col_b[p]] = f32(fp16(dist/2))  for columns >= 0.
+ * `variant`: 0 = production kernel, 1 = simple per-pair kernel kept for cross-checking.
+ * ---------------------------------------------------------------------------------------------- */
+int rvb_heightmap_raycast(const rvb_terrain* t, const float* pos, const float* euler, const float* trig,
+                          const double* pattern, int64_t P, int64_t N,
+                          uint16_t* dist, int32_t* hit_slot, int32_t* hit_tri, uint16_t* pt, uint16_t* sources,
+                          float* obs, int64_t obs_ld, const int32_t* col_a, const int32_t* col_b,
+                          int variant, void* stream);
+
+/* Cast pre-computed fp16 rays (sources/directions [R,3], directions NOT normalised, as handed to
+ * ray_distance by camera.py:110) against a layer: _height_lookup + gather + ray_distance + min over K. */
+int rvb_cast_rays(const rvb_terrain* t, const uint16_t* sources, const uint16_t* directions, int64_t R,
+                  uint16_t* dist, int32_t* hit_slot, int32_t* hit_tri, uint16_t* pt, int variant, void* stream);
+
+/* ray_distance(sources, directions, triangles) (utils/camera/ray_casting.py:3-66): n rays vs n triangles,
+ * fp16.  sources, directions [n,3]; triangles [n,3,3]; k [n]; pt [n,3] (optional). */
+int rvb_ray_distance(const uint16_t* sources, const uint16_t* directions, const uint16_t* triangles, int64_t n,
+                     uint16_t* k, uint16_t* pt, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Rock_Detection.get_collisions (utils/rock_detection/rock_detect.py:52-149: _get_wheel_rays :160-319,
+ * _get_body_rays :321-371, lookup + ray-cast against the big_rock_layer index) and
+ * RoverTask.check_collision (rover.py:663-668).
+ *   joints f32 [N,13] (DOF order rock_detect.py:174-188)    wheel_dist f16 [N,24]   body_dist f16 [N,2]
+ *   hit_tri i32 [N,26] optional    collision i64 [N] optional (|min wheel| < 0.8 or |min body| < 0.45)
+ *   rays_out f16 [N,26,6] optional (source xyz, direction xyz as fed to the ray-cast; for tests)
+ * ---------------------------------------------------------------------------------------------- */
+int rvb_rock_collision(const rvb_terrain* rocks, const float* pos, const float* euler, const float* trig,
+                       const float* joints, int64_t N,
+                       uint16_t* wheel_dist, uint16_t* body_dist, int32_t* hit_tri, int64_t* collision,
+                       uint16_t* rays_out, int variant, void* stream);
+/* check_collision alone (rover.py:663-668) on caller-provided distances. */
+int rvb_check_collision(const uint16_t* wheel_dist, const uint16_t* body_dist, int64_t N, int64_t* collision,
+                        int sem, void* stream);
+
+/* tensor_quat_to_eul (utils/math/tensor_quat_to_euler.py:6-31): wxyz f32 [N,4] -> (roll,pitch,yaw) f32 [N,3] */
+int rvb_quat_to_euler(const float* quat, int64_t N, float* euler, void* stream);
+
+/* Ackermann (utils/kinematics.py:14-67) + joint-target mapping (rover.py:396-409).
+ *   lin/ang: f32 with element strides (the reference passes column views of actions[N,2], rover.py:391)
+ *   steer, vel f32 [N,6] (FL,FR,ML,MR,RL,RR); pos_targets f32 [N,4] (FR,RR,FL,RL), vel_targets f32 [N,6]
+ *   (FR,CR,RR,FL,CL,RL), both optional. */
+int rvb_ackermann(const float* lin, int64_t lin_stride, const float* ang, int64_t ang_stride, int64_t N,
+                  float* steer, float* vel, float* pos_targets, float* vel_targets, int sem, void* stream);
+
+/* Memory.input_state (rover.py:76-77): hist f32 [N,H] shift right by one, newest at column 0. */
+int rvb_history_push(float* hist, int64_t N, int64_t H, const float* newest, int64_t newest_stride, void* stream);
+
+/* RoverTask.get_observations, proprioceptive part (rover.py:279-283, 320-323): heading f32 [N] and
+ * obs[:,0:4] = (|target-pos|/9, heading/pi, lin_now, ang_now).  obs row stride obs_ld (elements). */
+int rvb_obs_proprio(const float* pos, const float* euler, const float* target, const float* lin_now,
+                    const float* ang_now, int64_t N, float* obs, int64_t obs_ld, float* heading, int sem,
+                    void* stream);
+/* Heightmap.get_sparse_vector/get_dense_vector + rover.py:324-325 on an existing dist buffer:
+ * obs[n, col0 + i] = f32(fp16(dist[n, idx[i]] / 2)). */
+int rvb_obs_gather(const uint16_t* dist, int64_t P, int64_t N, const int64_t* idx, int64_t n_idx,
+                   float* obs, int64_t obs_ld, int64_t col0, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * RoverTask.calculate_metrics (rover.py:460-531) + RoverTask.is_done (:610-647), one pass.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct rvb_reward_params {
+    float pos_reward, heading_contraint_reward, motion_contraint_reward, goal_angle_reward,
+          boogie_contraint_reward;                 /* cfg/task/Rover.yaml:37-46 */
+    int32_t max_episode_length;                    /* rover.py:119 (3000) */
+    int32_t curriculum_level;                      /* rover.py:104,353 */
+    int64_t num_envs_total;                        /* collision_penalty = flag * num_envs (rover.py:517) */
+    int32_t sem;
+    int32_t reserved;
+} rvb_reward_params;
+
+#define RVB_N_STATS 16
+/* stats (f64 [16], optional, overwritten): 0 envs, 1 sum rew, 2 sum pos_reward, 3 collisions, 4 sum
+ * uprightness, 5 sum heading pen., 6 sum motion pen., 7 sum goal-angle pen., 8 resets, 9 timeouts,
+ * 10 tilt resets, 11 too-far resets, 12 goals reached, 13 collision resets, 14 sum target dist, 15 0.
+ * Deterministic (fixed-order two-stage reduction).  `stats_scratch` f64 [rvb_stats_scratch_len(N)]. */
+int64_t rvb_stats_scratch_len(int64_t N);
+int rvb_reward_reset(const rvb_reward_params* p,
+                     const float* pos, const float* target, const float* heading, const float* rover_rot,
+                     const float* lin, const float* lin_prev, const float* ang, const float* ang_prev,
+                     const float* joints, const int64_t* progress, const int64_t* rock_collision, int64_t N,
+                     float* rew, int64_t* reset,
+                     float* ex_pos_reward, int64_t* ex_collision, float* ex_uprightness, float* ex_heading,
+                     float* ex_motion, float* ex_goal_angle,
+                     double* stats, double* stats_scratch, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * stone_info validation (rover.py:533-542 check_goal_collision, :649-661 avoid_pos_rock_collision):
+ * nearest[m] = min_s(cdist(xy[m], stone[s].xy) - stone[s].radius), flag[m] = nearest <= thr.
+ *   xy f32 with row stride xy_ld; stones f32 [S,7]; nearest/flag/count optional; count i32 [1] += #flags.
+ * torch.cdist switches to its matmul formulation when M>25 or S>25; `force_mode` 0 = same rule,
+ * 1 = direct, 2 = matmul formulation.
+ * ---------------------------------------------------------------------------------------------- */
+int rvb_stone_validate(const float* xy, int64_t xy_ld, int64_t M, const float* stones, int64_t S, float thr,
+                       int force_mode, float* nearest, int64_t* flag, int32_t* count, void* stream);
+/* avoid_pos_rock_collision: the whole fixed-point loop on the device (x += 0.05 while nearest <= 1.4).
+ * pos f32 [N,3] updated in place; iterations i32 [1] optional (number of sweeps executed). */
+int rvb_spawn_validate(float* pos, int64_t N, const float* stones, int64_t S, int32_t max_iter,
+                       int32_t* iterations, void* stream);
+/* get_pos_height (rover.py:588-608): out[m] = heightmap[round(clamp((xy-shift)/hscale,0,H-1))] * vscale */
+int rvb_height_lookup(const float* heightmap, int64_t H0, int64_t H1, const float* xy, int64_t xy_ld, int64_t M,
+                      float hscale, float vscale, float shift_x, float shift_y, float* out, int sem, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Offline index builder (utils/rover_utils.py:52-118 _get_knn_triangles): per cell (i,j) at
+ * (i*res, j*res) the K triangles with the smallest fp16 centroid distance; ties ordered by triangle id
+ * (torch.topk leaves them unspecified).  out int32 [K,G0,G1] like map_indices.pt.
+ * ---------------------------------------------------------------------------------------------- */
+int rvb_build_knn_index(const int32_t* triangles, int64_t T, const uint16_t* vertices, int64_t V,
+                        int64_t G0, int64_t G1, float res, int64_t K, int32_t* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ROVER_B200_H */

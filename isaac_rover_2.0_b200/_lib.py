@@ -1,0 +1,103 @@
+"""ctypes binding of librover_b200.so (the C ABI declared in include/rover_b200.h).
+
+There is no fallback: if the shared library is missing or a call fails, a RuntimeError is raised.
+"""
+import ctypes as C
+import os
+
+import torch
+
+from . import _build
+
+_lib = None
+
+SEM_TORCH_CUDA = 0
+SEM_TORCH_CPU = 1
+N_STATS = 16
+
+p = C.c_void_p
+i64 = C.c_int64
+i32 = C.c_int32
+f32 = C.c_float
+
+
+class RewardParams(C.Structure):
+    _fields_ = [("pos_reward", f32), ("heading_contraint_reward", f32), ("motion_contraint_reward", f32),
+                ("goal_angle_reward", f32), ("boogie_contraint_reward", f32),
+                ("max_episode_length", i32), ("curriculum_level", i32), ("num_envs_total", i64),
+                ("sem", i32), ("reserved", i32)]
+
+
+_SIGNATURES = {
+    "rvb_abi_version": (C.c_int, []),
+    "rvb_last_error": (C.c_char_p, []),
+    "rvb_terrain_create": (C.c_int, [C.POINTER(p), p, i64, i64, i64, i64, i64, i64, p, i64, p, i64, f32, f32, f32, C.c_int, p]),
+    "rvb_terrain_destroy": (C.c_int, [p]),
+    "rvb_terrain_bytes": (i64, [p]),
+    "rvb_heightmap_raycast": (C.c_int, [p, p, p, p, p, i64, i64, p, p, p, p, p, p, i64, p, p, C.c_int, p]),
+    "rvb_cast_rays": (C.c_int, [p, p, p, i64, p, p, p, p, C.c_int, p]),
+    "rvb_ray_distance": (C.c_int, [p, p, p, i64, p, p, p]),
+    "rvb_rock_collision": (C.c_int, [p, p, p, p, p, i64, p, p, p, p, p, C.c_int, p]),
+    "rvb_check_collision": (C.c_int, [p, p, i64, p, C.c_int, p]),
+    "rvb_quat_to_euler": (C.c_int, [p, i64, p, p]),
+    "rvb_ackermann": (C.c_int, [p, i64, p, i64, i64, p, p, p, p, C.c_int, p]),
+    "rvb_history_push": (C.c_int, [p, i64, i64, p, i64, p]),
+    "rvb_obs_proprio": (C.c_int, [p, p, p, p, p, i64, p, i64, p, C.c_int, p]),
+    "rvb_obs_gather": (C.c_int, [p, i64, i64, p, i64, p, i64, i64, p]),
+    "rvb_stats_scratch_len": (i64, [i64]),
+    "rvb_reward_reset": (C.c_int, [C.POINTER(RewardParams)] + [p] * 11 + [i64] + [p] * 10 + [p]),
+    "rvb_stone_validate": (C.c_int, [p, i64, i64, p, i64, f32, C.c_int, p, p, p, p]),
+    "rvb_spawn_validate": (C.c_int, [p, i64, p, i64, i32, p, p]),
+    "rvb_height_lookup": (C.c_int, [p, i64, i64, p, i64, i64, f32, f32, f32, f32, p, C.c_int, p]),
+    "rvb_build_knn_index": (C.c_int, [p, i64, p, i64, i64, i64, f32, i64, p, p]),
+}
+
+EXPORTS = tuple(_SIGNATURES)
+
+
+def lib_path():
+    return _build.LIB
+
+
+def load():
+    """Load (building first if the sources are newer and nvcc is present).  Raises if impossible."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(_build.LIB) or (_build.needs_build() and os.environ.get("ROVER_B200_NO_REBUILD") != "1"):
+        try:
+            _build.build()
+        except Exception as e:                      # stale-but-present library is still usable
+            if not os.path.exists(_build.LIB):
+                raise RuntimeError("librover_b200.so is missing and could not be built: %s" % e)
+    lib = C.CDLL(_build.LIB)
+    for name, (res, args) in _SIGNATURES.items():
+        fn = getattr(lib, name)                     # AttributeError here = ABI mismatch, fail loudly
+        fn.restype = res
+        fn.argtypes = args
+    if lib.rvb_abi_version() != 1:
+        raise RuntimeError("librover_b200.so ABI version mismatch")
+    _lib = lib
+    return lib
+
+
+def check(rc):
+    if rc != 0:
+        raise RuntimeError("%s [status %d]" % (load().rvb_last_error().decode(), rc))
+
+
+def ptr(t):
+    """Device pointer of a tensor (None -> NULL)."""
+    if t is None:
+        return None
+    return C.c_void_p(t.data_ptr())
+
+
+def stream_of(t):
+    return C.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
+
+
+def require_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("rover_b200: expected a CUDA tensor (there is no CPU path)")

@@ -1,0 +1,168 @@
+// Shared device/host helpers for librover_b200 (sm_100a only).
+#pragma once
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/rover_b200.h"
+
+// ---------------------------------------------------------------- errors (thread-local, never thrown)
+int rvb_set_error(int code, const char* what, const char* detail);
+
+#define RVB_CUDA(expr)                                                                   \
+    do {                                                                                 \
+        cudaError_t e_ = (expr);                                                         \
+        if (e_ != cudaSuccess) return rvb_set_error(RVB_ERR_CUDA, #expr, cudaGetErrorString(e_)); \
+    } while (0)
+#define RVB_REQUIRE(cond, msg)                                                           \
+    do {                                                                                 \
+        if (!(cond)) return rvb_set_error(RVB_ERR_INVALID, msg, #cond);                  \
+    } while (0)
+#define RVB_LAUNCH_CHECK() RVB_CUDA(cudaGetLastError())
+
+// ---------------------------------------------------------------- terrain handle
+// One pre-resolved record per triangle, 32 B = one L2 sector, two 16-byte loads.
+// halves: a.xyz | b.xyz | c.xyz | n.xyz (n = b x c) | 4 x pad      (ray_casting.py:34-40)
+struct __align__(16) TriRec {
+    __half a[3], b[3], c[3], n[3], pad[4];
+};
+static_assert(sizeof(TriRec) == 32, "TriRec must be one 32-byte sector");
+
+struct rvb_terrain {
+    int32_t* index;    // [G0,G1,K] contiguous, device
+    TriRec* recs;      // [T], device
+    int64_t G0, G1, K, T, V;
+    float res, shift_x, shift_y;
+    int sem;
+    int device;
+};
+
+// ---------------------------------------------------------------- fp16 arithmetic with torch's roundings
+// ATen computes every Half element-wise op as fp32 op + one rounding; for + - * that equals the
+// correctly rounded fp16 op, so the *_rn intrinsics are used (they also forbid mul+add contraction).
+// Division goes through IEEE fp32 division and one rounding (innocuous double rounding).
+__device__ __forceinline__ __half h_add(__half a, __half b) { return __hadd_rn(a, b); }
+__device__ __forceinline__ __half h_sub(__half a, __half b) { return __hsub_rn(a, b); }
+__device__ __forceinline__ __half h_mul(__half a, __half b) { return __hmul_rn(a, b); }
+__device__ __forceinline__ __half h_div(__half a, __half b) {
+    return __float2half_rn(__fdiv_rn(__half2float(a), __half2float(b)));
+}
+__device__ __forceinline__ __half h_from_bits(unsigned short b) { return __ushort_as_half(b); }
+__device__ __forceinline__ unsigned short h_bits(__half h) { return __half_as_ushort(h); }
+
+#define RVB_H_LO 0xAE66u    // fp16(0 - 0.1)  = -0.0999755859375   (ray_casting.py:26)
+#define RVB_H_HI 0x3C66u    // fp16(1 + 0.1)  =  1.099609375       (ray_casting.py:27)
+#define RVB_H_MISS 0x4980u  // fp16(1.1 * 10) = 11.0               (ray_casting.py:28)
+
+struct H3 {
+    __half x, y, z;
+};
+
+__device__ __forceinline__ H3 h3_sub(H3 u, H3 v) { return {h_sub(u.x, v.x), h_sub(u.y, v.y), h_sub(u.z, v.z)}; }
+// Tensor.cross on Half: (u1*v2 - u2*v1, u2*v0 - u0*v2, u0*v1 - u1*v0), each op rounded.
+__device__ __forceinline__ H3 h3_cross(H3 u, H3 v) {
+    return {h_sub(h_mul(u.y, v.z), h_mul(u.z, v.y)), h_sub(h_mul(u.z, v.x), h_mul(u.x, v.z)),
+            h_sub(h_mul(u.x, v.y), h_mul(u.y, v.x))};
+}
+// left-to-right dot product (ray_casting.py:41)
+__device__ __forceinline__ __half h3_dot(H3 u, H3 v) {
+    return h_add(h_add(h_mul(u.x, v.x), h_mul(u.y, v.y)), h_mul(u.z, v.z));
+}
+
+// One (ray, triangle) test given pre-resolved a, b, c, n = b x c and d = -normalize(dir).
+// Returns k_after_check (ray_casting.py:40-59).
+__device__ __forceinline__ __half pair_test(H3 s, H3 d, H3 a, H3 b, H3 c, H3 n) {
+    const __half lo = h_from_bits(RVB_H_LO), hi = h_from_bits(RVB_H_HI), miss = h_from_bits(RVB_H_MISS);
+    H3 g = h3_sub(s, a);
+    __half det = h3_dot(n, d);
+    __half nn = h_div(h3_dot(h3_cross(g, c), d), det);
+    if (__heq(det, lo)) nn = miss;
+    __half mm = h_div(h3_dot(h3_cross(b, g), d), det);
+    if (__heq(det, hi)) mm = miss;
+    __half kk = h_div(h3_dot(n, g), det);
+    if (__heq(det, hi)) kk = miss;
+    bool ok = __hge(nn, lo) && __hge(mm, lo) && __hle(h_add(nn, mm), hi);
+    return ok ? kk : miss;
+}
+
+// -normalize(dir) (ray_casting.py:31): L2 norm accumulated in fp32, rounded to fp16, clamp_min(eps -> 0 in
+// fp16), fp16 division, negation.
+__device__ __forceinline__ H3 neg_normalize(H3 v) {
+    float x = __half2float(v.x), y = __half2float(v.y), z = __half2float(v.z);
+    float ss = __fadd_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y)), __fmul_rn(z, z));
+    __half nrm = __float2half_rn(__fsqrt_rn(ss));
+    __half den = __hmax_nan(nrm, __float2half_rn(1e-12f));
+    return {__hneg(h_div(v.x, den)), __hneg(h_div(v.y, den)), __hneg(h_div(v.z, den))};
+}
+
+// torch.min ordering on fp16: NaN first (propagates), -0 == +0, ties -> lower slot.
+__device__ __forceinline__ uint32_t min_key(__half k, uint32_t slot) {
+    unsigned short b = h_bits(k);
+    uint32_t key;
+    if ((b & 0x7fffu) > 0x7c00u) key = 0u;
+    else {
+        if ((b & 0x7fffu) == 0u) b = 0u;
+        key = (b & 0x8000u) ? (uint32_t)(unsigned short)~b : (uint32_t)(b | 0x8000u);
+    }
+    return (key << 16) | slot;
+}
+
+// f64 -> fp16 the way torch casts (double -> float -> half, two roundings) (camera.py:212)
+__device__ __forceinline__ __half h_from_double(double v) { return __float2half_rn(__double2float_rn(v)); }
+
+// (xy - shift)/res -> clamp -> round-half-even -> cell (camera.py:241-253).  torch-CUDA divides by a Python
+// scalar as a multiplication by fp32(1/res); torch-CPU performs a true division.
+__device__ __forceinline__ int cell_coord(__half v16, float shift, float res, float inv_res, int gmax, int sem) {
+    float v = __fsub_rn(__half2float(v16), shift);
+    v = (sem == RVB_SEM_TORCH_CPU) ? __fdiv_rn(v, res) : __fmul_rn(v, inv_res);
+    v = fminf(fmaxf(v, 0.0f), (float)gmax);     // NaN -> 0 (the reference would fault on NaN input)
+    return (int)rintf(v);
+}
+
+// Body transform shared by camera.py:197-199 and rock_detect.py:305-307,356-358 (no FMA contraction).
+template <typename T>
+struct Ops;
+template <>
+struct Ops<double> {
+    static __device__ __forceinline__ double mul(double a, double b) { return __dmul_rn(a, b); }
+    static __device__ __forceinline__ double add(double a, double b) { return __dadd_rn(a, b); }
+    static __device__ __forceinline__ double sub(double a, double b) { return __dsub_rn(a, b); }
+};
+template <>
+struct Ops<float> {
+    static __device__ __forceinline__ float mul(float a, float b) { return __fmul_rn(a, b); }
+    static __device__ __forceinline__ float add(float a, float b) { return __fadd_rn(a, b); }
+    static __device__ __forceinline__ float sub(float a, float b) { return __fsub_rn(a, b); }
+};
+
+struct Trig {
+    float sx, cx, sy, cy, sz, cz;   // sin/cos of -roll, -pitch, -yaw (camera.py:184-189)
+};
+
+__device__ __forceinline__ Trig make_trig(const float* euler, const float* trig, int64_t n) {
+    Trig t;
+    if (trig) {
+        const float* p = trig + n * 6;
+        t = {p[0], p[1], p[2], p[3], p[4], p[5]};
+    } else {
+        float r = -euler[n * 3 + 0], p = -euler[n * 3 + 1], y = -euler[n * 3 + 2];
+        t = {sinf(r), cosf(r), sinf(p), cosf(p), sinf(y), cosf(y)};
+    }
+    return t;
+}
+
+template <typename T>
+__device__ __forceinline__ void body_transform(T x, T y, T z, const Trig& t, T tx, T ty, T tz, T& xo, T& yo, T& zo) {
+    using O = Ops<T>;
+    T sx = (T)t.sx, cx = (T)t.cx, sy = (T)t.sy, cy = (T)t.cy, sz = (T)t.sz, cz = (T)t.cz;
+    T A = O::add(O::mul(y, cx), O::mul(z, sx));
+    T C = O::sub(O::mul(z, cx), O::mul(y, sx));
+    T B = O::sub(O::mul(x, cy), O::mul(sy, C));
+    xo = O::add(O::add(tx, O::mul(sz, A)), O::mul(cz, B));
+    yo = O::sub(O::add(ty, O::mul(cz, A)), O::mul(sz, B));
+    zo = O::add(O::add(tz, O::mul(x, sy)), O::mul(cy, C));
+}
+
+static inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }

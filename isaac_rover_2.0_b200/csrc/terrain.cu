@@ -1,0 +1,117 @@
+// Terrain-layer handle: K-contiguous index copy + pre-resolved triangle records.
+#include <new>
+#include <string.h>
+
+#include "common.cuh"
+
+static thread_local char g_err[512] = "";
+
+int rvb_set_error(int code, const char* what, const char* detail) {
+    snprintf(g_err, sizeof(g_err), "rover_b200: %s (%s)", what ? what : "error", detail ? detail : "");
+    return code;
+}
+
+extern "C" const char* rvb_last_error(void) { return g_err; }
+extern "C" int rvb_abi_version(void) { return RVB_ABI_VERSION; }
+
+// [G0,G1,K] strided view -> contiguous.  One thread per output element; consecutive threads walk K, so
+// the store is coalesced; the load is coalesced along whichever source stride is 1 only for K-major
+// inputs -- this runs once per terrain, bandwidth is irrelevant.
+__global__ void repack_index_kernel(const int32_t* __restrict__ src, int64_t G0, int64_t G1, int64_t K, int64_t s0,
+                                    int64_t s1, int64_t sk, int32_t T, int32_t* __restrict__ dst, int* bad) {
+    int64_t total = G0 * G1 * K;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        int64_t k = i % K, c = i / K;
+        int64_t g1 = c % G1, g0 = c / G1;
+        int32_t v = src[g0 * s0 + g1 * s1 + k * sk];
+        if (v < 0 || v >= T) {
+            atomicExch(bad, 1);
+            v = 0;
+        }
+        dst[i] = v;
+    }
+}
+
+// a = v[t2], b = v[t1]-a, c = v[t0]-a, n = b x c with fp16 roundings (ray_casting.py:34-40).
+__global__ void build_records_kernel(const int32_t* __restrict__ tri, int64_t T, const __half* __restrict__ vert,
+                                     int64_t V, TriRec* __restrict__ recs, int* bad) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= T) return;
+    int32_t i0 = tri[i * 3 + 0], i1 = tri[i * 3 + 1], i2 = tri[i * 3 + 2];
+    if (i0 < 0 || i0 >= V || i1 < 0 || i1 >= V || i2 < 0 || i2 >= V) {
+        atomicExch(bad, 2);
+        i0 = i1 = i2 = 0;
+    }
+    H3 v0 = {vert[i0 * 3], vert[i0 * 3 + 1], vert[i0 * 3 + 2]};
+    H3 v1 = {vert[i1 * 3], vert[i1 * 3 + 1], vert[i1 * 3 + 2]};
+    H3 a = {vert[i2 * 3], vert[i2 * 3 + 1], vert[i2 * 3 + 2]};
+    H3 b = h3_sub(v1, a), c = h3_sub(v0, a);
+    H3 n = h3_cross(b, c);
+    TriRec r;
+    r.a[0] = a.x; r.a[1] = a.y; r.a[2] = a.z;
+    r.b[0] = b.x; r.b[1] = b.y; r.b[2] = b.z;
+    r.c[0] = c.x; r.c[1] = c.y; r.c[2] = c.z;
+    r.n[0] = n.x; r.n[1] = n.y; r.n[2] = n.z;
+    r.pad[0] = r.pad[1] = r.pad[2] = r.pad[3] = __ushort_as_half(0);
+    recs[i] = r;
+}
+
+extern "C" int rvb_terrain_create(rvb_terrain** out, const int32_t* map_indices, int64_t G0, int64_t G1, int64_t K,
+                                  int64_t stride_g0, int64_t stride_g1, int64_t stride_k, const int32_t* triangles,
+                                  int64_t T, const uint16_t* vertices, int64_t V, float res, float shift_x,
+                                  float shift_y, int sem, void* stream) {
+    RVB_REQUIRE(out != nullptr, "rvb_terrain_create: out is null");
+    *out = nullptr;
+    RVB_REQUIRE(map_indices && triangles && vertices, "rvb_terrain_create: null device pointer");
+    RVB_REQUIRE(G0 > 0 && G1 > 0 && K > 0 && K <= 4096, "rvb_terrain_create: need G0,G1 > 0 and 0 < K <= 4096");
+    RVB_REQUIRE(T > 0 && T < (int64_t)1 << 31 && V > 0 && V < (int64_t)1 << 31, "rvb_terrain_create: bad T or V");
+    RVB_REQUIRE(res > 0.0f, "rvb_terrain_create: res must be > 0");
+    RVB_REQUIRE(sem == RVB_SEM_TORCH_CUDA || sem == RVB_SEM_TORCH_CPU, "rvb_terrain_create: bad sem");
+    cudaStream_t st = as_stream(stream);
+    rvb_terrain* t = new (std::nothrow) rvb_terrain();
+    if (!t) return rvb_set_error(RVB_ERR_NOMEM, "rvb_terrain_create", "host allocation failed");
+    memset(t, 0, sizeof(*t));
+    t->G0 = G0; t->G1 = G1; t->K = K; t->T = T; t->V = V;
+    t->res = res; t->shift_x = shift_x; t->shift_y = shift_y; t->sem = sem;
+    int* bad = nullptr;
+    int hbad = 0;
+    cudaError_t e = cudaGetDevice(&t->device);
+    if (e == cudaSuccess) e = cudaMalloc(&t->index, sizeof(int32_t) * G0 * G1 * K);
+    if (e == cudaSuccess) e = cudaMalloc(&t->recs, sizeof(TriRec) * T);
+    if (e == cudaSuccess) e = cudaMalloc(&bad, sizeof(int));
+    if (e == cudaSuccess) e = cudaMemsetAsync(bad, 0, sizeof(int), st);
+    if (e == cudaSuccess) {
+        repack_index_kernel<<<148 * 8, 256, 0, st>>>(map_indices, G0, G1, K, stride_g0, stride_g1, stride_k, (int32_t)T,
+                                                     t->index, bad);
+        build_records_kernel<<<(unsigned)ceil_div(T, 256), 256, 0, st>>>(triangles, T, (const __half*)vertices, V,
+                                                                         t->recs, bad);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(&hbad, bad, sizeof(int), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (bad) cudaFree(bad);
+    if (e != cudaSuccess || hbad) {
+        cudaFree(t->index);
+        cudaFree(t->recs);
+        delete t;
+        if (e != cudaSuccess) return rvb_set_error(RVB_ERR_CUDA, "rvb_terrain_create", cudaGetErrorString(e));
+        return rvb_set_error(RVB_ERR_INVALID, "rvb_terrain_create",
+                             hbad == 1 ? "map_indices holds a triangle id outside [0,T)"
+                                       : "triangles holds a vertex id outside [0,V)");
+    }
+    *out = t;
+    return RVB_OK;
+}
+
+extern "C" int rvb_terrain_destroy(rvb_terrain* t) {
+    if (!t) return RVB_OK;
+    cudaFree(t->index);
+    cudaFree(t->recs);
+    delete t;
+    return RVB_OK;
+}
+
+extern "C" int64_t rvb_terrain_bytes(const rvb_terrain* t) {
+    if (!t) return 0;
+    return (int64_t)sizeof(int32_t) * t->G0 * t->G1 * t->K + (int64_t)sizeof(TriRec) * t->T;
+}

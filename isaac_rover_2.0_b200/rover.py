@@ -1,0 +1,320 @@
+"""`RoverTask` hot path -- mirror of tasks/rover.py (RoverTask :80-676, Memory :60-77) and of the buffer
+contract of tasks/base/rl_task.py (:98-107 buffers, :239-259 post_physics_step ordering).
+
+Only the per-step data-parallel path is here; Isaac Sim scene set-up, PhysX stepping, reset poses, skrl
+and the teacher/student policies stay where they are.  The simulator is whatever object is
+passed as `rover_view`: it must offer the four ArticulationView calls the reference makes on this path
+  get_world_poses() -> (pos f32 [N,3], quat_wxyz f32 [N,4]),  get_joint_positions() -> f32 [N,13],
+  set_joint_position_targets(pos [N,4], indices=None, joint_indices=...),
+  set_joint_velocity_targets(vel [N,6], indices=None, joint_indices=...)           (rover.py:274-275,291,412-414)
+State lives in the same attribute names as the reference (obs_buf, rew_buf, reset_buf, progress_buf, extras,
+target_positions, initial_pos, stone_info, linear_velocity, angular_velocity, rover_positions, rover_rotation,
+rover_rot, heading_diff, rock_collison, curriculum_level, rew_scales, max_episode_length).
+"""
+import ctypes as C
+import math
+
+import torch
+
+from . import _lib
+from .camera import Camera
+from .kinematics import Ackermann
+from .rock_detect import Rock_Detection
+from .tensor_quat_to_euler import tensor_quat_to_eul
+
+DEFAULT_REWARDS = dict(pos_reward=1.0, terminalReward=0, collision_reward=0.3, heading_contraint_reward=0.05,
+                       motion_contraint_reward=-0.01, goal_angle_reward=0.3, boogie_contraint_reward=0.5)   # Rover.yaml:37-46
+
+STAT_NAMES = ("envs", "reward_sum", "pos_reward_sum", "collisions", "uprightness_sum", "heading_penalty_sum",
+              "motion_penalty_sum", "goal_angle_penalty_sum", "resets", "timeouts", "tilt_resets", "too_far_resets",
+              "goals_reached", "collision_resets", "target_dist_sum", "reserved")
+
+
+class Memory():
+    """[num_envs, num_states, horizon] shift register, newest at index 0 (rover.py:60-77).  The shift is done
+    in place by rvb_history_push instead of cat + slice re-allocation."""
+
+    def __init__(self, num_envs, num_states, horizon, device) -> None:
+        self.tracker = torch.zeros((num_envs, num_states, horizon), device=device)
+        self.device = device
+        self.num_envs = num_envs
+        self.num_states = num_states
+        self.horizon = horizon
+
+    def get_state(self, timestep):
+        data = self.tracker[:, :, timestep]
+        if data.shape[1] == 1:
+            return data.squeeze(1)
+        return data
+
+    def input_state(self, state):
+        _lib.require_cuda(self.tracker, state)
+        lib = _lib.load()
+        st = state.to(torch.float32)
+        if st.dim() != 1:
+            st = st.reshape(-1)
+        if st.shape[0] != self.num_envs * self.num_states:
+            raise ValueError("Memory.input_state: expected %d values" % (self.num_envs * self.num_states))
+        stride = st.stride(0) if st.shape[0] > 1 else 1
+        with torch.cuda.device(self.tracker.device):
+            _lib.check(lib.rvb_history_push(_lib.ptr(self.tracker), self.num_envs * self.num_states, self.horizon,
+                                            _lib.ptr(st), stride, _lib.stream_of(self.tracker)))
+
+
+class RoverTask():
+    def __init__(self, rover_view, num_envs, terrain_assets, rock_assets, stone_info, heightmap,
+                 device='cuda:0', shift=None, rewards=None, horizontal_scale=0.025, vertical_scale=1,
+                 sem=_lib.SEM_TORCH_CUDA, num_envs_total=None, rover_name="rover_view"):
+        """terrain_assets / rock_assets: (map_indices [K,G,G], triangles, vertices) of knn_terrain / knn_rocks
+        (None -> loaded from the reference's relative paths); stone_info f32 [S,7] (read_stone_info);
+        heightmap f32 [H,H] (heightmap_tensor.pt, rover.py:210)."""
+        self._lib = _lib.load()
+        self._device = device
+        self._rover = rover_view
+        self._rover_name = getattr(rover_view, "name", rover_name)
+        self._num_envs = self.num_envs = num_envs
+        self.num_envs_total = num_envs if num_envs_total is None else num_envs_total
+        self.sem = sem
+        self.shift = torch.tensor([0, 0, 0.0], device=device) if shift is None else shift.to(device)
+        self.Camera = Camera(device, self.shift, debug=False, assets=terrain_assets, sem=sem)
+        self.num_exteroceptive = self.Camera.get_num_exteroceptive()
+        self.Rock_detector = Rock_Detection(device, self.shift, debug=False, assets=rock_assets, sem=sem)
+        self.global_step = 0
+        self._num_proprioceptive = 4
+        self._num_observations = self.num_observations = (
+            self._num_proprioceptive + self.Camera.heightmap.get_num_sparse_vector()
+            + self.Camera.heightmap.get_num_dense_vector())
+        self._num_actions = self.num_actions = 2
+        self.curriculum_level = 1                                   # rover.py:104 (raised to 2 at :353)
+        self.max_episode_length = 3000                              # rover.py:119
+        self.is_evaluation = False
+        self.save_teacher_data = False
+        self.target_positions = torch.zeros((num_envs, 3), device=device, dtype=torch.float32)
+        self.initial_pos = torch.zeros((num_envs, 3), device=device, dtype=torch.float32)
+        self.stone_info = stone_info.to(device).float().contiguous()
+        self.heightmap = heightmap.to(device).float().contiguous() if heightmap is not None else None
+        self.horizontal_scale = horizontal_scale                    # rover.py:212
+        self.vertical_scale = vertical_scale
+        self.linear_velocity = Memory(num_envs, 1, 3, device)       # rover.py:154-155
+        self.angular_velocity = Memory(num_envs, 1, 3, device)
+        self.rew_scales = dict(DEFAULT_REWARDS if rewards is None else rewards)
+        # RLTask.cleanup buffers (rl_task.py:98-107)
+        self.obs_buf = torch.zeros((num_envs, self._num_observations), device=device, dtype=torch.float)
+        self.rew_buf = torch.zeros(num_envs, device=device, dtype=torch.float)
+        self.reset_buf = torch.ones(num_envs, device=device, dtype=torch.long)
+        self.progress_buf = torch.zeros(num_envs, device=device, dtype=torch.long)
+        self.extras = {}
+        self.rover_positions = None
+        self.rover_rotation = None
+        self.rover_rot = None
+        self.heading_diff = torch.zeros(num_envs, device=device)
+        self.rock_collison = torch.zeros(num_envs, device=device, dtype=torch.long)
+        self.rock_wheel_dist = None
+        self.rock_body_dist = None
+        # episode statistics (per-rank sums; all-reduced by dist.reduce_stats)
+        self.stats = torch.zeros(_lib.N_STATS, device=device, dtype=torch.float64)
+        self._stats_scratch = torch.zeros(int(self._lib.rvb_stats_scratch_len(num_envs)), device=device,
+                                          dtype=torch.float64)
+        self._ex = dict(pos_reward=torch.zeros(num_envs, device=device),
+                        collision_penalty=torch.zeros(num_envs, device=device, dtype=torch.long),
+                        uprightness_penalty=torch.zeros(num_envs, device=device),
+                        heading_contraint_penalty=torch.zeros(num_envs, device=device),
+                        motion_contraint_penalty=torch.zeros(num_envs, device=device),
+                        goal_angle_penalty=torch.zeros(num_envs, device=device))
+        self._count = torch.zeros(1, device=device, dtype=torch.int32)
+        self._reset_next = None
+        self.joint_position_targets = None
+        self.joint_velocity_targets = None
+
+    # ------------------------------------------------------------------ helpers
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(torch.device(self._device)).cuda_stream)
+
+    # ------------------------------------------------------------------ RLTask.post_physics_step (rl_task.py:239-259)
+    def post_physics_step(self):
+        self.progress_buf[:] += 1
+        self.get_observations()
+        self.calculate_metrics()
+        self.is_done()
+        return self.obs_buf, self.rew_buf, self.reset_buf, self.extras
+
+    # ------------------------------------------------------------------ get_observations (rover.py:272-336)
+    def get_observations(self) -> dict:
+        lib = self._lib
+        pos, quat = self._rover.get_world_poses()
+        self.rover_positions = pos.to(torch.float32).contiguous()
+        self.rover_rotation = tensor_quat_to_eul(quat)
+        lin_now = self.linear_velocity.tracker[:, 0, 0].contiguous()
+        ang_now = self.angular_velocity.tracker[:, 0, 0].contiguous()
+        with torch.cuda.device(torch.device(self._device)):
+            _lib.check(lib.rvb_obs_proprio(_lib.ptr(self.rover_positions), _lib.ptr(self.rover_rotation),
+                                           _lib.ptr(self.target_positions), _lib.ptr(lin_now), _lib.ptr(ang_now),
+                                           self.num_envs, _lib.ptr(self.obs_buf), self.obs_buf.stride(0),
+                                           _lib.ptr(self.heading_diff), self.sem, self._stream()))
+        # heightmap: ray-cast with the sparse/dense gather + /2 fused into obs_buf[:, 4:] (rover.py:286-288,324-325)
+        self.Camera.get_depths(self.rover_positions, self.rover_rotation, obs=self.obs_buf, want_pt=False)
+        # rock collision (rover.py:291-293)
+        want = self.curriculum_level >= 2
+        self.rock_wheel_dist, self.rock_body_dist = self.Rock_detector.get_collisions(
+            self.rover_positions, self.rover_rotation, self._rover.get_joint_positions(), want_collision=want)
+        if want:
+            self.rock_collison = self.Rock_detector.last_collision
+        return {self._rover_name: {"obs_buf": self.obs_buf}}
+
+    def check_collision(self, wheel_dists, body_dists):
+        """rover.py:663-668."""
+        _lib.require_cuda(wheel_dists, body_dists)
+        w = wheel_dists.to(torch.float16).contiguous()
+        b = body_dists.to(torch.float16).contiguous()
+        out = torch.empty(w.shape[0], dtype=torch.long, device=w.device)
+        with torch.cuda.device(w.device):
+            _lib.check(self._lib.rvb_check_collision(_lib.ptr(w), _lib.ptr(b), w.shape[0], _lib.ptr(out), self.sem,
+                                                     self._stream()))
+        self.rock_collison = out
+        return out
+
+    # ------------------------------------------------------------------ pre_physics_step, action part (rover.py:338-414)
+    def pre_physics_step(self, actions) -> None:
+        self.global_step += 1
+        self.rover_loc, quat = self._rover.get_world_poses()
+        self.rover_rot = tensor_quat_to_eul(quat)                   # used one step later by is_done (rover.py:343,615)
+        reset_env_ids = self.reset_buf.nonzero(as_tuple=False).squeeze(-1)
+        if len(reset_env_ids) > 0:
+            self.reset_idx(reset_env_ids)
+            self.set_targets(reset_env_ids)
+        self.apply_actions(actions)
+
+    def apply_actions(self, actions):
+        """History push + Ackermann + joint-target mapping (rover.py:366-414)."""
+        _actions = actions.to(self._device)
+        self.linear_velocity.input_state(_actions[:, 0])
+        self.angular_velocity.input_state(_actions[:, 1])
+        _, _, positions, velocities = Ackermann(_actions[:, 0], _actions[:, 1], self._device, sem=self.sem,
+                                                want_targets=True)
+        self.joint_position_targets, self.joint_velocity_targets = positions, velocities
+        if hasattr(self._rover, "set_joint_position_targets"):
+            self._rover.set_joint_position_targets(positions, indices=None,
+                                                   joint_indices=getattr(self._rover, "actuated_pos_indices", None))
+            self._rover.set_joint_velocity_targets(velocities, indices=None,
+                                                   joint_indices=getattr(self._rover, "actuated_vel_indices", None))
+
+    def reset_idx(self, env_ids):
+        """Book-keeping half of rover.py:416-453 (pose resets belong to the simulator)."""
+        if hasattr(self._rover, "reset_idx"):
+            self._rover.reset_idx(env_ids, self.initial_pos)
+        self.reset_buf[env_ids] = 0
+        self.progress_buf[env_ids] = 0
+
+    # ------------------------------------------------------------------ calculate_metrics + is_done (rover.py:460-531,610-647)
+    def _params(self):
+        r = self.rew_scales
+        return _lib.RewardParams(r["pos_reward"], r["heading_contraint_reward"], r["motion_contraint_reward"],
+                                 r["goal_angle_reward"], r["boogie_contraint_reward"], self.max_episode_length,
+                                 self.curriculum_level, self.num_envs_total, self.sem, 0)
+
+    def _reward_reset(self):
+        joints = self._rover.get_joint_positions().to(torch.float32).contiguous()
+        lin, ang = self.linear_velocity.tracker, self.angular_velocity.tracker
+        lin0, lin1 = lin[:, 0, 0].contiguous(), lin[:, 0, 1].contiguous()
+        ang0, ang1 = ang[:, 0, 0].contiguous(), ang[:, 0, 1].contiguous()
+        rot = self.rover_rot if self.rover_rot is not None else self.rover_rotation
+        self._reset_next = torch.empty_like(self.reset_buf)
+        p = self._params()
+        e = self._ex
+        with torch.cuda.device(torch.device(self._device)):
+            _lib.check(self._lib.rvb_reward_reset(
+                C.byref(p), _lib.ptr(self.rover_positions), _lib.ptr(self.target_positions), _lib.ptr(self.heading_diff),
+                _lib.ptr(rot), _lib.ptr(lin0), _lib.ptr(lin1), _lib.ptr(ang0), _lib.ptr(ang1), _lib.ptr(joints),
+                _lib.ptr(self.progress_buf), _lib.ptr(self.rock_collison if self.curriculum_level >= 2 else None),
+                self.num_envs, _lib.ptr(self.rew_buf), _lib.ptr(self._reset_next), _lib.ptr(e["pos_reward"]),
+                _lib.ptr(e["collision_penalty"]), _lib.ptr(e["uprightness_penalty"]),
+                _lib.ptr(e["heading_contraint_penalty"]), _lib.ptr(e["motion_contraint_penalty"]),
+                _lib.ptr(e["goal_angle_penalty"]), _lib.ptr(self.stats), _lib.ptr(self._stats_scratch), self._stream()))
+        self._lin0, self._ang0 = lin0, ang0
+
+    def calculate_metrics(self) -> None:
+        """One fused launch computes the reward terms AND the next reset mask; is_done() publishes the mask."""
+        self._reward_reset()
+        self.extras.update(self._ex)
+        self.extras["torque_penalty_driving"] = self._lin0          # rover.py:530-531
+        self.extras["torque_penalty_steering"] = self._ang0
+
+    def is_done(self) -> None:
+        if self._reset_next is None:
+            self._reward_reset()
+        self.reset_buf[:] = self._reset_next
+        self._reset_next = None
+
+    # ------------------------------------------------------------------ goals / spawn validation (rover.py:533-584,649-661)
+    def nearest_stone_edge(self, xy, thr):
+        """-> (nearest f32 [M], flag i64 [M], count i32 [1] tensor); xy: [M,>=2] f32 with unit inner stride."""
+        xy = xy if (xy.dim() == 2 and xy.stride(-1) == 1 and xy.dtype == torch.float32) else xy.float().contiguous()
+        M = xy.shape[0]
+        near = torch.empty(M, device=xy.device)
+        flag = torch.empty(M, device=xy.device, dtype=torch.long)
+        self._count.zero_()
+        with torch.cuda.device(xy.device):
+            _lib.check(self._lib.rvb_stone_validate(_lib.ptr(xy), xy.stride(0) if M > 1 else xy.shape[1], M,
+                                                    _lib.ptr(self.stone_info), self.stone_info.shape[0], float(thr), 0,
+                                                    _lib.ptr(near), _lib.ptr(flag), _lib.ptr(self._count), self._stream()))
+        return near, flag, self._count
+
+    def check_goal_collision(self, env_ids):
+        _, flag, count = self.nearest_stone_edge(self.target_positions[env_ids][:, 0:2], 1.0)
+        env_ids = flag * env_ids                                    # rover.py:540 (valid entries collapse to env 0)
+        return env_ids, int(count.item())
+
+    def generate_goals(self, env_ids, radius):
+        reset_buf_len = 1
+        while reset_buf_len > 0:
+            self.random_goals(env_ids, radius=radius)
+            env_ids, reset_buf_len = self.check_goal_collision(env_ids)
+
+    def random_goals(self, env_ids, radius):
+        num_sets = len(env_ids)
+        alpha = 2 * math.pi * torch.rand(num_sets, device=self._device)
+        self.target_positions[env_ids, 0] = radius * torch.cos(alpha) + 0 + self.initial_pos[env_ids, 0]
+        self.target_positions[env_ids, 1] = radius * torch.sin(alpha) + 0 + self.initial_pos[env_ids, 1]
+
+    def set_targets(self, env_ids):
+        self.generate_goals(env_ids, radius=8)
+        global_pos = self.target_positions[env_ids, 0:2]
+        height = self.get_pos_height(self.heightmap, global_pos[:, 0:2], self.horizontal_scale, self.vertical_scale,
+                                     self.shift[0:2])
+        self.target_positions[env_ids, 2] = height
+
+    def get_pos_height(self, heightmap, depth_points, horizontal_scale, vertical_scale, shift):
+        _lib.require_cuda(heightmap, depth_points)
+        hm = heightmap.to(torch.float32).contiguous()
+        xy = depth_points
+        xy = xy if (xy.dim() == 2 and xy.stride(-1) == 1 and xy.dtype == torch.float32) else xy.float().contiguous()
+        M = xy.shape[0]
+        sh = torch.as_tensor(shift).flatten().cpu()
+        out = torch.empty(M, device=xy.device)
+        with torch.cuda.device(xy.device):
+            _lib.check(self._lib.rvb_height_lookup(_lib.ptr(hm), hm.shape[0], hm.shape[1], _lib.ptr(xy),
+                                                   xy.stride(0) if M > 1 else xy.shape[1], M, float(horizontal_scale),
+                                                   float(vertical_scale), float(sh[0]), float(sh[1]), _lib.ptr(out),
+                                                   self.sem, self._stream()))
+        return out
+
+    def avoid_pos_rock_collision(self, curr_pos, max_iter=100000):
+        """Whole fixed-point loop in one launch (no host sync per sweep).  Updates and returns curr_pos."""
+        _lib.require_cuda(curr_pos)
+        pos = curr_pos if (curr_pos.is_contiguous() and curr_pos.dtype == torch.float32) else curr_pos.float().contiguous()
+        with torch.cuda.device(pos.device):
+            _lib.check(self._lib.rvb_spawn_validate(_lib.ptr(pos), pos.shape[0], _lib.ptr(self.stone_info),
+                                                    self.stone_info.shape[0], max_iter, _lib.ptr(self._count),
+                                                    self._stream()))
+        if pos is not curr_pos:
+            curr_pos.copy_(pos)
+        return curr_pos
+
+    def set_initial_positions(self, positions):
+        """set_up_scene's spawn validation (rover.py:214-219): stones, then terrain height + 0.5."""
+        positions = self.avoid_pos_rock_collision(positions.clone().float().contiguous())
+        h = self.get_pos_height(self.heightmap, positions[:, 0:2], self.horizontal_scale, self.vertical_scale,
+                                self.shift[0:2])
+        positions[:, 2] = h + 0.5
+        self.initial_pos = positions
+        return positions

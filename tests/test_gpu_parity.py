@@ -1,0 +1,363 @@
+"""GPU parity tests (run on the B200 box): CUDA kernels behind the C ABI vs (a) the golden vectors the
+reference itself produced, (b) the oracle restatement on the CPU and on the GPU.
+
+Tolerances (BASELINE.json north_star): bit-exact for fp16 distances given identical trig inputs, hit
+slots / triangle ids, collision flags, reset masks, validity flags; <= 1e-5 relative for fp32 heights,
+kinematics and rewards (libm atan2/asin/sin/cos differ by an ulp between torch-CPU, torch-CUDA and here).
+"""
+import math
+import os
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+RTOL = 1e-5
+ATOL = 1e-6
+
+
+def _skip_without_gpu():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+
+
+@pytest.fixture(scope="module")
+def R():
+    _skip_without_gpu()
+    import isaac_rover_b200
+    return isaac_rover_b200
+
+
+@pytest.fixture(scope="module")
+def O():
+    import rover_oracle
+    return rover_oracle
+
+
+@pytest.fixture(scope="module")
+def golden():
+    return torch.load(os.path.join(HERE, "golden", "rover_golden.pt"))
+
+
+@pytest.fixture(scope="module")
+def gcam(R, golden):
+    w = golden["world"]
+    return R.Camera("cuda:0", torch.tensor([0, 0, 0.0]), assets=(w["map_indices"].to(torch.int32), w["triangles"], w["vertices"]),
+                    sem=R.SEM_TORCH_CPU)
+
+
+@pytest.fixture(scope="module")
+def grock(R, golden):
+    w = golden["world"]
+    return R.Rock_Detection("cuda:0", torch.tensor([0, 0, 0.0]),
+                            assets=(w["rock_indices"].to(torch.int32), w["rock_triangles"], w["rock_vertices"]), sem=R.SEM_TORCH_CPU)
+
+
+def bits(t):
+    return t.view(torch.int16) if t.dtype == torch.float16 else t
+
+
+def assert_bits_equal(a, b, what):
+    a, b = a.cpu(), b.cpu()
+    assert a.shape == b.shape, "%s: shape %s vs %s" % (what, tuple(a.shape), tuple(b.shape))
+    neq = bits(a) != bits(b)
+    if a.dtype.is_floating_point:                      # -0 == +0 and NaN == NaN are still bit comparisons here
+        pass
+    assert not neq.any(), "%s: %d of %d elements differ, first at %s: %s vs %s" % (
+        what, int(neq.sum()), neq.numel(), neq.nonzero()[0].tolist(), a[neq][0].item(), b[neq][0].item())
+
+
+def close(a, b, what, rtol=RTOL, atol=ATOL):
+    a, b = a.cpu().double(), b.cpu().double()
+    err = (a - b).abs()
+    tol = atol + rtol * b.abs()
+    bad = err > tol
+    bad &= ~(a.isnan() & b.isnan())
+    bad &= ~((a == b))                                 # equal infinities
+    assert not bad.any(), "%s: %d of %d beyond tolerance, worst abs err %g" % (what, int(bad.sum()), bad.numel(), err[bad].max())
+
+
+# --------------------------------------------------------------------------- golden vectors (reference outputs)
+def test_golden_pattern(R, golden):
+    hm = R.Heightmap("cuda:0")
+    assert torch.equal(hm.get_distribution().cpu(), golden["ref_pattern"])
+    assert torch.equal(hm.coarse_idx.cpu(), golden["ref_coarse_idx"])
+    assert torch.equal(hm.fine_idx.cpu(), golden["ref_fine_idx"])
+    assert (hm.get_num_sparse_vector(), hm.get_num_dense_vector()) == (634, 1112)      # teacher_loader.py:47-48
+
+
+@pytest.mark.parametrize("variant", [0, 1])
+def test_golden_get_depths(R, golden, gcam, variant):
+    gcam.variant = variant
+    dist, pt, src = gcam.get_depths(golden["in_pos"].cuda(), golden["ref_euler"].cuda(), trig=golden["trig"].cuda(), want_hits=True)
+    assert_bits_equal(src, golden["ref_sources"], "sources")
+    assert_bits_equal(dist, golden["ref_dist"], "distances")
+    assert_bits_equal(pt, golden["ref_pt"], "intersection points")
+    assert_bits_equal(gcam.last_hit_slot, golden["oracle_slot"], "hit slot")
+    assert_bits_equal(gcam.last_hit_tri, golden["oracle_tri"], "hit triangle")
+    gcam.variant = 0
+
+
+def test_golden_rock_detection(R, golden, grock):
+    wheel, body = grock.get_collisions(golden["in_pos"].cuda(), golden["ref_euler"].cuda(), golden["in_joints"].cuda(),
+                                       trig=golden["trig"].cuda(), want_collision=True, want_rays=True)
+    rays = grock.last_rays.cpu()
+    # wheel-chain sin/cos of joint angles are libm calls on the device: sources/dirs within 1 fp16 ulp, mostly equal
+    ref_s, ref_d = golden["ref_rock_sources"], golden["ref_rock_dirs"]
+    ds = (rays[:, :, 0:3].float() - ref_s.float()).abs().max().item()
+    dd = (rays[:, :, 3:6].float() - ref_d.float()).abs().max().item()
+    assert ds <= 2e-3 and dd <= 1e-3, (ds, dd)
+    same = (bits(rays[:, :, 0:3]) == bits(ref_s)).all(2) & (bits(rays[:, :, 3:6]) == bits(ref_d)).all(2)
+    allw = torch.cat((wheel, body), 1).cpu()
+    refw = torch.cat((golden["ref_wheel"], golden["ref_body"]), 1)
+    # rays that came out bit-identical must give bit-identical distances
+    assert (bits(allw)[same] == bits(refw)[same]).all()
+    assert same.float().mean() > 0.95
+    if same.all():
+        assert torch.equal(grock.last_collision.cpu(), golden["ref_rock_collision"])
+
+
+def test_golden_rock_cast_given_reference_rays(R, golden, grock):
+    s, d = golden["ref_rock_sources"].cuda(), golden["ref_rock_dirs"].cuda()
+    dist, pt = R.cast_rays(grock.layer, s, d)
+    refw = torch.cat((golden["ref_wheel"], golden["ref_body"]), 1)
+    assert_bits_equal(dist.reshape(refw.shape), refw, "rock distances from reference rays")
+    task_col = torch.empty(refw.shape[0], dtype=torch.long, device="cuda")
+    lib = R._lib.load()
+    w, b = dist.reshape(refw.shape)[:, :24].contiguous(), dist.reshape(refw.shape)[:, 24:].contiguous()
+    R._lib.check(lib.rvb_check_collision(R._lib.ptr(w), R._lib.ptr(b), w.shape[0], R._lib.ptr(task_col), R.SEM_TORCH_CPU, None))
+    torch.cuda.synchronize()
+    assert torch.equal(task_col.cpu(), golden["ref_rock_collision"])
+
+
+def test_golden_ray_distance(R, golden):
+    k, pt = R.ray_distance(golden["in_rd_src"].cuda(), golden["in_rd_dir"].cuda(), golden["in_rd_tri"].cuda())
+    assert_bits_equal(k, golden["ref_rd_k"], "known-answer k")
+    assert_bits_equal(pt, golden["ref_rd_pt"], "known-answer pt")
+    assert k[0].item() == 1.0 and k[1].item() == -1.0 and k[2].item() == 11.0 and k[3].item() == 11.0 and k[4].item() == 11.0
+    k, pt = R.ray_distance(golden["in_rr_src"].cuda(), golden["in_rr_dir"].cuda(), golden["in_rr_tri"].cuda())
+    assert_bits_equal(k, golden["ref_rr_k"], "random-pair k")
+    assert_bits_equal(pt, golden["ref_rr_pt"], "random-pair pt")
+
+
+def test_golden_quat_to_euler(R, golden):
+    close(R.tensor_quat_to_eul(golden["in_quat"].cuda()), golden["ref_euler"], "euler")
+
+
+def test_golden_ackermann(R, golden):
+    for lin, ang, rs, rv in ((golden["in_ka_lin"], golden["in_ka_ang"], golden["ref_ka_steer"], golden["ref_ka_vel"]),
+                             (golden["in_actions"][:, 0], golden["in_actions"][:, 1], golden["ref_steer"], golden["ref_vel"])):
+        steer, vel = R.Ackermann(lin.cuda(), ang.cuda(), "cuda:0", sem=R.SEM_TORCH_CPU)
+        close(steer, rs, "steering angles")
+        close(vel, rv, "motor velocities")
+    steer, vel = R.Ackermann(torch.tensor([0.5], device="cuda"), torch.tensor([0.2], device="cuda"))
+    close(steer, torch.tensor([[0.20421, 0.15067, 0, 0, -0.19193, -0.14151]]), "SURVEY known answer steer", rtol=1e-4, atol=1e-5)
+    close(vel, torch.tensor([[2.1599, 2.9181, 2.0530, 2.9470, 2.1546, 2.9141]]), "SURVEY known answer vel", rtol=1e-4)
+    # strided column views of actions[N,2] (rover.py:391)
+    a = golden["in_actions"].cuda()
+    s2, v2, pt, vt = R.Ackermann(a[:, 0], a[:, 1], "cuda:0", sem=R.SEM_TORCH_CPU, want_targets=True)
+    close(s2, golden["ref_steer"], "strided steer")
+    assert torch.equal(pt, s2[:, [1, 5, 0, 4]]) and torch.equal(vt, v2[:, [1, 3, 5, 0, 2, 4]])
+
+
+def _golden_task(R, golden, level):
+    w = golden["world"]
+    world = R.synth.World(length=w["length"], res=w["res"], G=w["G"], K=w["K"], vertices=w["vertices"], triangles=w["triangles"],
+                          rock_vertices=w["rock_vertices"], rock_triangles=w["rock_triangles"], stone_info=w["stone_info6"],
+                          heightmap=w["heightmap"], hm_res=w["hm_res"], map_indices=w["map_indices"].to(torch.int32),
+                          rock_indices=w["rock_indices"].to(torch.int32))
+    st = {k[3:]: v for k, v in golden.items() if k.startswith("in_") and k[3:] in
+          ("pos", "quat", "joints", "actions", "prev_actions", "target", "progress")}
+    task = R.synth.make_task(world, st, level=level, sem=R.SEM_TORCH_CPU)
+    task.apply_actions(st["actions"].cuda())
+    task.rover_rot = R.tensor_quat_to_eul(st["quat"].cuda())
+    return task
+
+
+def test_golden_task_step(R, golden):
+    task = _golden_task(R, golden, 2)
+    obs = task.get_observations()["rover_view"]["obs_buf"]
+    ref = golden["ref_obs"]
+    close(obs[:, 0:4], ref[:, 0:4], "proprioceptive obs")
+    close(task.heading_diff, golden["ref_heading"], "heading")
+    hm_same = (obs[:, 4:].cpu() == ref[:, 4:]).float().mean().item()
+    assert hm_same >= 0.995, "heightmap obs columns equal fraction %g" % hm_same          # device libm trig, no override
+    task.calculate_metrics()
+    task.is_done()
+    if torch.equal(task.rock_collison.cpu(), golden["ref_rock_collision"]):
+        close(task.rew_buf, golden["ref_rew"], "rew_buf")
+        assert torch.equal(task.reset_buf.cpu(), golden["ref_reset"])
+        for k, v in golden["ref_extras"].items():
+            if v.dtype == torch.long:
+                assert torch.equal(task.extras[k].cpu(), v), k
+            else:
+                close(task.extras[k], v, "extras." + k)
+    st = task.stats.cpu()
+    assert st[0].item() == 8 and st[8].item() == task.reset_buf.sum().item()
+    assert abs(st[1].item() - task.rew_buf.double().sum().item()) < 1e-9
+    task1 = _golden_task(R, golden, 1)
+    task1.get_observations()
+    task1.calculate_metrics()
+    task1.is_done()
+    close(task1.rew_buf, golden["ref_rew_level1"], "rew_buf level 1")
+    assert torch.equal(task1.reset_buf.cpu(), golden["ref_reset_level1"])
+
+
+def test_golden_stones_and_heights(R, golden):
+    task = _golden_task(R, golden, 2)
+    assert torch.equal(task.stone_info.cpu(), golden["ref_stone7"])
+    near, flag, cnt = task.nearest_stone_edge(task.target_positions[:, 0:2], 1.0)
+    close(near, golden["ref_goal_nearest"], "goal nearest stone edge", rtol=1e-5, atol=1e-5)
+    ref_flag = (golden["ref_goal_nearest"] <= 1.0).long()
+    unstable = (golden["ref_goal_nearest"] - 1.0).abs() < 1e-4
+    assert torch.equal(flag.cpu()[~unstable], ref_flag[~unstable])
+    near, _, _ = task.nearest_stone_edge(golden["in_spawn_pos"].cuda()[:, 0:2], 1.4)
+    close(near, golden["ref_many_nearest"], "nearest stone edge (matmul formulation)", rtol=1e-5, atol=2e-5)
+    moved = task.avoid_pos_rock_collision(golden["in_spawn_pos"].cuda().clone())
+    ref = golden["ref_spawn_pos"]
+    same = (moved.cpu() == ref).all(1)
+    assert same.float().mean() >= 0.9, "spawn validation rows equal: %g" % same.float().mean()
+    h = task.get_pos_height(task.heightmap, ref[:, 0:2].cuda(), golden["world"]["hm_res"], 1, torch.tensor([0.0, 0.0]))
+    assert_bits_equal(h, golden["ref_spawn_height"], "get_pos_height")
+
+
+# --------------------------------------------------------------------------- oracle on CPU and on CUDA, larger world
+@pytest.fixture(scope="module")
+def world20(R):
+    return R.synth.make_world(length=20.0, nv=72, K=200, n_stones=12, seed=1)
+
+
+def _trig(euler):
+    return torch.stack([f(-euler[:, a]) for a in range(3) for f in (torch.sin, torch.cos)], 1)
+
+
+@pytest.mark.parametrize("N", [1, 6, 64])
+def test_oracle_cpu_semantics_bit_exact(R, O, world20, N):
+    w = world20
+    st = R.synth.make_env_state(w, N, seed=100 + N)
+    eul = O.quat_to_euler(st["quat"])
+    pat, _, _ = O.heightmap_pattern()
+    ref = O.get_depths(st["pos"], eul, pat, w.map_indices, w.triangles, w.vertices, torch.tensor([0, 0, 0.0]))
+    cam = R.Camera("cuda:0", torch.tensor([0, 0, 0.0]), assets=(w.map_indices, w.triangles, w.vertices), sem=R.SEM_TORCH_CPU)
+    for variant in (0, 1):
+        cam.variant = variant
+        dist, pt, src = cam.get_depths(st["pos"].cuda(), eul.cuda(), trig=_trig(eul).cuda(), want_hits=True)
+        assert_bits_equal(src, ref["sources"], "sources v%d" % variant)
+        assert_bits_equal(dist, ref["dist"], "dist v%d" % variant)
+        assert_bits_equal(pt, ref["pt"], "pt v%d" % variant)
+        assert_bits_equal(cam.last_hit_slot, ref["slot"].to(torch.int32), "slot v%d" % variant)
+        assert_bits_equal(cam.last_hit_tri, ref["tri"].to(torch.int32), "tri v%d" % variant)
+
+
+def test_oracle_cuda_semantics_end_to_end(R, O, world20):
+    """Oracle run with device='cuda' == the reference's real deployment (it hard-wires cuda:0): everything
+    bit-exact, trig included (same libdevice)."""
+    w = world20
+    N = 64
+    st = {k: v.cuda() for k, v in R.synth.make_env_state(w, N, seed=9).items()}
+    eul = O.quat_to_euler(st["quat"])
+    close(R.tensor_quat_to_eul(st["quat"]), eul, "euler", rtol=1e-6, atol=1e-7)
+    pat, ci, fi = O.heightmap_pattern()
+    shift = torch.tensor([0, 0, 0.0], device="cuda")
+    ref = O.get_depths(st["pos"], eul, pat, w.map_indices.cuda(), w.triangles.cuda(), w.vertices.cuda(), shift)
+    cam = R.Camera("cuda:0", shift, assets=(w.map_indices, w.triangles, w.vertices), sem=R.SEM_TORCH_CUDA)
+    dist, pt, src = cam.get_depths(st["pos"], eul, want_hits=True)
+    src_same = (bits(src.cpu()) == bits(ref["sources"].cpu())).all(2)
+    assert src_same.float().mean() > 0.9999, "sources equal fraction %g" % src_same.float().mean()
+    d_same = bits(dist.cpu()) == bits(ref["dist"].cpu())
+    assert d_same[src_same].all(), "rays with identical sources must have identical distances"
+    assert (cam.last_hit_tri.cpu().long() == ref["tri"].cpu())[src_same].all()
+    rc = O.get_collisions(st["pos"], eul, st["joints"], w.rock_indices.cuda(), w.rock_triangles.cuda(), w.rock_vertices.cuda(), shift)
+    rock = R.Rock_Detection("cuda:0", shift, assets=(w.rock_indices, w.rock_triangles, w.rock_vertices), sem=R.SEM_TORCH_CUDA)
+    wheel, body = rock.get_collisions(st["pos"], eul, st["joints"], want_collision=True, want_rays=True)
+    rays = rock.last_rays
+    same = (bits(rays[:, :, 0:3]) == bits(rc["sources"])).all(2) & (bits(rays[:, :, 3:6]) == bits(rc["dirs"])).all(2)
+    assert same.float().mean() > 0.99
+    got = torch.cat((wheel, body), 1)
+    want = torch.cat((rc["wheel"], rc["body"]), 1)
+    assert (bits(got)[same] == bits(want)[same]).all()
+    if same.all():
+        assert torch.equal(rock.last_collision, O.check_collision(rc["wheel"], rc["body"]))
+
+
+def test_oracle_task_terms(R, O, world20):
+    """calculate_metrics / is_done / Ackermann / obs against the oracle on the same device (CUDA semantics)."""
+    w = world20
+    N = 512
+    st = {k: v.cuda() for k, v in R.synth.make_env_state(w, N, seed=21).items()}
+    task = R.synth.make_task(w, st, level=2, sem=R.SEM_TORCH_CUDA)
+    task.apply_actions(st["actions"])
+    task.rover_rot = R.tensor_quat_to_eul(st["quat"])
+    task.get_observations()
+    task.calculate_metrics()
+    task.is_done()
+    eul = O.quat_to_euler(st["quat"])
+    heading, _ = O.heading_and_dist(st["pos"], eul, st["target"])
+    close(task.heading_diff, heading, "heading")
+    lin, ang, lp, ap = st["actions"][:, 0], st["actions"][:, 1], st["prev_actions"][:, 0], st["prev_actions"][:, 1]
+    rew, ex = O.metrics(st["pos"], st["target"], task.heading_diff, lin, lp, ang, ap, st["joints"], st["progress"],
+                        task.rock_collison, 2, num_envs=N)
+    close(task.rew_buf, rew, "rew_buf", rtol=1e-6, atol=1e-9)
+    for k in ("pos_reward", "uprightness_penalty", "heading_contraint_penalty", "motion_contraint_penalty", "goal_angle_penalty"):
+        close(task.extras[k], ex[k], k, rtol=1e-6, atol=1e-9)
+    assert torch.equal(task.extras["collision_penalty"], ex["collision_penalty"])
+    reset = O.is_done(st["pos"], st["target"], task.rover_rot, st["progress"], task.rock_collison, 2)
+    assert torch.equal(task.reset_buf, reset)
+    assert reset.sum() > 0 and reset.sum() < N
+    steer, vel = O.ackermann(lin, ang)
+    s2, v2 = R.Ackermann(lin, ang)
+    close(s2, steer, "steer")
+    close(v2, vel, "vel")
+    ps, vs = O.joint_targets(steer, vel)
+    close(task.joint_position_targets, ps, "position targets")
+    close(task.joint_velocity_targets, vs, "velocity targets")
+    stats = task.stats.cpu()
+    assert stats[0] == N and stats[8] == reset.sum().item() and stats[3] == task.rock_collison.sum().item()
+
+
+def test_edge_cases(R, O, world20):
+    w = world20
+    cam = R.Camera("cuda:0", torch.tensor([0, 0, 0.0]), assets=(w.map_indices, w.triangles, w.vertices), sem=R.SEM_TORCH_CPU)
+    # empty batch
+    d, pt, s = cam.get_depths(torch.zeros((0, 3), device="cuda"), torch.zeros((0, 3), device="cuda"))
+    assert d.shape == (0, 1634) and pt.shape == (0, 1634, 3)
+    # poses outside the map (cells clamp, camera.py:243), far above (all miss -> 11.0, slot 0) and upside down
+    pos = torch.tensor([[-5.0, -5.0, 1.0], [30.0, 3.0, 1.0], [10.0, 10.0, 40.0], [10.0, 10.0, 0.8], [0.0, 19.99, 0.5]])
+    eul = torch.tensor([[0.0, 0.0, 0.0], [0.1, -0.1, 2.0], [0.0, 0.0, 1.0], [3.1, 0.0, 0.0], [1.2, -1.2, -3.0]])
+    pat, _, _ = O.heightmap_pattern()
+    ref = O.get_depths(pos, eul, pat, w.map_indices, w.triangles, w.vertices, torch.tensor([0, 0, 0.0]))
+    for variant in (0, 1):
+        cam.variant = variant
+        d, pt, s = cam.get_depths(pos.cuda(), eul.cuda(), trig=_trig(eul).cuda(), want_hits=True)
+        assert_bits_equal(d, ref["dist"], "edge dist v%d" % variant)
+        assert_bits_equal(cam.last_hit_slot, ref["slot"].to(torch.int32), "edge slot v%d" % variant)
+        assert_bits_equal(pt, ref["pt"], "edge pt v%d" % variant)
+    assert (ref["dist"][2] == 11).all() and (ref["slot"][2] == 0).all()
+    # errors are Python exceptions, never a silent CPU path
+    with pytest.raises(RuntimeError):
+        cam.get_depths(pos, eul)
+    with pytest.raises(RuntimeError):
+        R.Ackermann(torch.zeros(4), torch.zeros(4))
+
+
+def test_full_size_properties(R, world20):
+    """4096 envs: variant 0 == variant 1 bit for bit, determinism, translation of the same env set."""
+    w = world20
+    N = 4096
+    st = {k: v.cuda() for k, v in R.synth.make_env_state(w, N, seed=77).items()}
+    eul = R.tensor_quat_to_eul(st["quat"])
+    cam = R.Camera("cuda:0", torch.tensor([0, 0, 0.0]), assets=(w.map_indices, w.triangles, w.vertices))
+    d0, pt0, s0 = cam.get_depths(st["pos"], eul, want_hits=True)
+    t0 = cam.last_hit_tri.clone()
+    cam.variant = 1
+    d1, pt1, s1 = cam.get_depths(st["pos"], eul, want_hits=True)
+    assert torch.equal(bits(d0), bits(d1)) and torch.equal(bits(pt0), bits(pt1)) and torch.equal(t0, cam.last_hit_tri)
+    cam.variant = 0
+    d2, _, _ = cam.get_depths(st["pos"], eul)
+    assert torch.equal(bits(d0), bits(d2))
+    perm = torch.randperm(N, device="cuda")
+    d3, _, _ = cam.get_depths(st["pos"][perm], eul[perm])
+    assert torch.equal(bits(d3), bits(d0[perm]))        # envs are independent
+    assert (d0 != 11).float().mean() > 0.5
