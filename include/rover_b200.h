@@ -180,12 +180,14 @@ int rvb_height_lookup(const float* heightmap, int64_t H0, int64_t H1, const floa
                       float hscale, float vscale, float shift_x, float shift_y, float* out, int sem, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
- * Offline index builder (utils/rover_utils.py:52-118 _get_knn_triangles): per cell (i,j) at
- * (i*res, j*res) the K triangles with the smallest fp16 centroid distance; ties ordered by triangle id
- * (torch.topk leaves them unspecified).  out int32 [K,G0,G1] like map_indices.pt.
+ * Offline index builder (utils/rover_utils.py:52-118 _get_knn_triangles): for cell (i,j) at fp16
+ * coordinates (cell_x[i], cell_y[j]) -- torch.arange(0, G*res, res, dtype=float16), rover_utils.py:77-78 --
+ * the K triangles with the smallest fp16 centroid distance; ties ordered by triangle id (torch.topk leaves
+ * them unspecified).  out int32 [K,G0,G1] like map_indices.pt.  Synchronises `stream` once (bounding box).
  * ---------------------------------------------------------------------------------------------- */
 int rvb_build_knn_index(const int32_t* triangles, int64_t T, const uint16_t* vertices, int64_t V,
-                        int64_t G0, int64_t G1, float res, int64_t K, int32_t* out, void* stream);
+                        const uint16_t* cell_x, const uint16_t* cell_y, int64_t G0, int64_t G1, int64_t K,
+                        int32_t* out, void* stream);
 
 #ifdef __cplusplus
 }

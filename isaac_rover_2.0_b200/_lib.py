@@ -49,7 +49,7 @@ _SIGNATURES = {
     "rvb_stone_validate": (C.c_int, [p, i64, i64, p, i64, f32, C.c_int, p, p, p, p]),
     "rvb_spawn_validate": (C.c_int, [p, i64, p, i64, i32, p, p]),
     "rvb_height_lookup": (C.c_int, [p, i64, i64, p, i64, i64, f32, f32, f32, f32, p, C.c_int, p]),
-    "rvb_build_knn_index": (C.c_int, [p, i64, p, i64, i64, i64, f32, i64, p, p]),
+    "rvb_build_knn_index": (C.c_int, [p, i64, p, i64, p, p, i64, i64, i64, p, p]),
 }
 
 EXPORTS = tuple(_SIGNATURES)

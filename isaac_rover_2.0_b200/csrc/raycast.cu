@@ -137,8 +137,9 @@ extern "C" int rvb_heightmap_raycast(const rvb_terrain* t, const float* pos, con
                                      const double* pattern, int64_t P, int64_t N, uint16_t* dist, int32_t* hit_slot,
                                      int32_t* hit_tri, uint16_t* pt, uint16_t* sources, float* obs, int64_t obs_ld,
                                      const int32_t* col_a, const int32_t* col_b, int variant, void* stream) {
-    RVB_REQUIRE(t && pos && euler && pattern && dist, "rvb_heightmap_raycast: null pointer");
     RVB_REQUIRE(N >= 0 && P > 0 && P <= 65535, "rvb_heightmap_raycast: need N >= 0, 0 < P <= 65535");
+    if (N == 0) return RVB_OK;
+    RVB_REQUIRE(t && pos && euler && pattern && dist, "rvb_heightmap_raycast: null pointer");
     RVB_REQUIRE(!obs || (col_a && col_b && obs_ld > 0), "rvb_heightmap_raycast: obs needs col_a, col_b, obs_ld");
     RVB_REQUIRE(variant == 0 || variant == 1, "rvb_heightmap_raycast: variant must be 0 or 1");
     if (N == 0) return RVB_OK;
@@ -166,8 +167,9 @@ extern "C" int rvb_heightmap_raycast(const rvb_terrain* t, const float* pos, con
 extern "C" int rvb_cast_rays(const rvb_terrain* t, const uint16_t* sources, const uint16_t* directions, int64_t R,
                              uint16_t* dist, int32_t* hit_slot, int32_t* hit_tri, uint16_t* pt, int variant,
                              void* stream) {
-    RVB_REQUIRE(t && sources && directions && dist, "rvb_cast_rays: null pointer");
     RVB_REQUIRE(R >= 0, "rvb_cast_rays: R < 0");
+    if (R == 0) return RVB_OK;
+    RVB_REQUIRE(t && sources && directions && dist, "rvb_cast_rays: null pointer");
     (void)variant;
     if (R == 0) return RVB_OK;
     cudaStream_t st = as_stream(stream);
@@ -205,8 +207,9 @@ __global__ void ray_distance_kernel(const __half* __restrict__ src, const __half
 
 extern "C" int rvb_ray_distance(const uint16_t* sources, const uint16_t* directions, const uint16_t* triangles,
                                 int64_t n, uint16_t* k, uint16_t* pt, void* stream) {
-    RVB_REQUIRE(sources && directions && triangles && k, "rvb_ray_distance: null pointer");
     RVB_REQUIRE(n >= 0, "rvb_ray_distance: n < 0");
+    if (n == 0) return RVB_OK;
+    RVB_REQUIRE(sources && directions && triangles && k, "rvb_ray_distance: null pointer");
     if (n == 0) return RVB_OK;
     ray_distance_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, as_stream(stream)>>>(
         (const __half*)sources, (const __half*)directions, (const __half*)triangles, n, (__half*)k, (__half*)pt);

@@ -59,10 +59,10 @@ __global__ void stone_validate_kernel(const float* __restrict__ xy, int64_t ld, 
 
 extern "C" int rvb_stone_validate(const float* xy, int64_t xy_ld, int64_t M, const float* stones, int64_t S, float thr,
                                   int force_mode, float* nearest, int64_t* flag, int32_t* count, void* stream) {
+    if (M <= 0) return RVB_OK;
     RVB_REQUIRE(xy && stones, "rvb_stone_validate: null pointer");
     RVB_REQUIRE(xy_ld >= 2 && S > 0 && S < (1 << 30), "rvb_stone_validate: bad xy_ld or S");
     RVB_REQUIRE(force_mode >= 0 && force_mode <= 2, "rvb_stone_validate: force_mode must be 0, 1 or 2");
-    if (M <= 0) return RVB_OK;
     const bool mm = force_mode == 2 || (force_mode == 0 && (M > 25 || S > 25));
     stone_validate_kernel<<<(unsigned)ceil_div(M * 32, 256), 256, 0, as_stream(stream)>>>(xy, xy_ld, M, stones, (int)S, thr,
                                                                                         mm, nearest, flag, count);
@@ -93,9 +93,9 @@ __global__ void spawn_validate_kernel(float* __restrict__ pos, int64_t N, const 
 
 extern "C" int rvb_spawn_validate(float* pos, int64_t N, const float* stones, int64_t S, int32_t max_iter,
                                   int32_t* iterations, void* stream) {
+    if (N <= 0) return RVB_OK;
     RVB_REQUIRE(pos && stones, "rvb_spawn_validate: null pointer");
     RVB_REQUIRE(S > 0 && S < (1 << 30) && max_iter > 0, "rvb_spawn_validate: bad S or max_iter");
-    if (N <= 0) return RVB_OK;
     cudaStream_t st = as_stream(stream);
     if (iterations) RVB_CUDA(cudaMemsetAsync(iterations, 0, sizeof(int32_t), st));
     const bool mm = (N > 25 || S > 25);
@@ -121,10 +121,10 @@ __global__ void height_lookup_kernel(const float* __restrict__ hm, int H0, int H
 extern "C" int rvb_height_lookup(const float* heightmap, int64_t H0, int64_t H1, const float* xy, int64_t xy_ld, int64_t M,
                                  float hscale, float vscale, float shift_x, float shift_y, float* out, int sem,
                                  void* stream) {
+    if (M <= 0) return RVB_OK;
     RVB_REQUIRE(heightmap && xy && out, "rvb_height_lookup: null pointer");
     RVB_REQUIRE(H0 > 0 && H1 > 0 && H0 < (1 << 30) && H1 < (1 << 30) && xy_ld >= 2 && hscale > 0.f,
                 "rvb_height_lookup: bad shape or scale");
-    if (M <= 0) return RVB_OK;
     height_lookup_kernel<<<(unsigned)ceil_div(M, 256), 256, 0, as_stream(stream)>>>(
         heightmap, (int)H0, (int)H1, xy, xy_ld, M, hscale, 1.0f / hscale, vscale, shift_x, shift_y, out, sem);
     RVB_LAUNCH_CHECK();

@@ -41,9 +41,9 @@ __global__ void quat_to_euler_kernel(const float4* __restrict__ quat, int64_t N,
 }
 
 extern "C" int rvb_quat_to_euler(const float* quat, int64_t N, float* euler, void* stream) {
+    if (N <= 0) return RVB_OK;
     RVB_REQUIRE(quat && euler, "rvb_quat_to_euler: null pointer");
     RVB_REQUIRE(((uintptr_t)quat & 15) == 0, "rvb_quat_to_euler: quat must be 16-byte aligned");
-    if (N <= 0) return RVB_OK;
     quat_to_euler_kernel<<<(unsigned)ceil_div(N, 256), 256, 0, as_stream(stream)>>>((const float4*)quat, N, euler);
     RVB_LAUNCH_CHECK();
     return RVB_OK;
@@ -95,9 +95,9 @@ __global__ void ackermann_kernel(const float* __restrict__ lin_p, int64_t lin_st
 
 extern "C" int rvb_ackermann(const float* lin, int64_t lin_stride, const float* ang, int64_t ang_stride, int64_t N,
                              float* steer, float* vel, float* pos_targets, float* vel_targets, int sem, void* stream) {
+    if (N <= 0) return RVB_OK;
     RVB_REQUIRE(lin && ang && steer && vel, "rvb_ackermann: null pointer");
     RVB_REQUIRE(lin_stride >= 0 && ang_stride >= 0, "rvb_ackermann: negative stride");
-    if (N <= 0) return RVB_OK;
     ackermann_kernel<<<(unsigned)ceil_div(N, 256), 256, 0, as_stream(stream)>>>(lin, lin_stride, ang, ang_stride, N, steer,
                                                                               vel, pos_targets, vel_targets, sem);
     RVB_LAUNCH_CHECK();
@@ -116,9 +116,9 @@ __global__ void history_push_kernel(float* __restrict__ hist, int64_t N, int H, 
 
 extern "C" int rvb_history_push(float* hist, int64_t N, int64_t H, const float* newest, int64_t newest_stride,
                                 void* stream) {
+    if (N <= 0) return RVB_OK;
     RVB_REQUIRE(hist && newest, "rvb_history_push: null pointer");
     RVB_REQUIRE(H >= 1 && H <= 64, "rvb_history_push: horizon out of range");
-    if (N <= 0) return RVB_OK;
     history_push_kernel<<<(unsigned)ceil_div(N, 256), 256, 0, as_stream(stream)>>>(hist, N, (int)H, newest, newest_stride);
     RVB_LAUNCH_CHECK();
     return RVB_OK;
@@ -146,9 +146,9 @@ __global__ void obs_proprio_kernel(const float* __restrict__ pos, const float* _
 extern "C" int rvb_obs_proprio(const float* pos, const float* euler, const float* target, const float* lin_now,
                                const float* ang_now, int64_t N, float* obs, int64_t obs_ld, float* heading, int sem,
                                void* stream) {
+    if (N <= 0) return RVB_OK;
     RVB_REQUIRE(pos && euler && target && lin_now && ang_now && obs, "rvb_obs_proprio: null pointer");
     RVB_REQUIRE(obs_ld >= 4, "rvb_obs_proprio: obs_ld < 4");
-    if (N <= 0) return RVB_OK;
     obs_proprio_kernel<<<(unsigned)ceil_div(N, 256), 256, 0, as_stream(stream)>>>(pos, euler, target, lin_now, ang_now, N,
                                                                                 obs, obs_ld, heading, sem);
     RVB_LAUNCH_CHECK();
@@ -166,9 +166,9 @@ __global__ void obs_gather_kernel(const __half* __restrict__ dist, int64_t P, in
 
 extern "C" int rvb_obs_gather(const uint16_t* dist, int64_t P, int64_t N, const int64_t* idx, int64_t n_idx, float* obs,
                               int64_t obs_ld, int64_t col0, void* stream) {
+    if (N <= 0 || n_idx <= 0) return RVB_OK;
     RVB_REQUIRE(dist && idx && obs, "rvb_obs_gather: null pointer");
     RVB_REQUIRE(N <= 65535, "rvb_obs_gather: at most 65535 envs per call");
-    if (N <= 0 || n_idx <= 0) return RVB_OK;
     dim3 grid((unsigned)ceil_div(n_idx, 256), (unsigned)N);
     obs_gather_kernel<<<grid, 256, 0, as_stream(stream)>>>((const __half*)dist, P, N, idx, (int)n_idx, obs, obs_ld, col0);
     RVB_LAUNCH_CHECK();

@@ -65,8 +65,11 @@ def build_knn_index(triangles, vertices, G, res, K, device='cuda:0'):
     dev = torch.device(device)
     tri = triangles.to(dev, torch.int32).contiguous()
     ver = vertices.to(dev, torch.float16).contiguous()
+    coord = torch.arange(0, G * res, res, dtype=torch.float16)[:G].to(dev).contiguous()      # rover_utils.py:77-78
+    if coord.shape[0] != G:
+        raise ValueError("arange(0, G*res, res) produced fewer than G cell coordinates")
     out = torch.empty((K, G, G), dtype=torch.int32, device=dev)
     with torch.cuda.device(dev):
-        _lib.check(lib.rvb_build_knn_index(_lib.ptr(tri), tri.shape[0], _lib.ptr(ver), ver.shape[0], G, G, float(res), K,
-                                           _lib.ptr(out), _lib.stream_of(out)))
+        _lib.check(lib.rvb_build_knn_index(_lib.ptr(tri), tri.shape[0], _lib.ptr(ver), ver.shape[0], _lib.ptr(coord),
+                                           _lib.ptr(coord), G, G, K, _lib.ptr(out), _lib.stream_of(out)))
     return out

@@ -361,3 +361,22 @@ def test_full_size_properties(R, world20):
     d3, _, _ = cam.get_depths(st["pos"][perm], eul[perm])
     assert torch.equal(bits(d3), bits(d0[perm]))        # envs are independent
     assert (d0 != 11).float().mean() > 0.5
+
+
+def test_knn_index_builder_matches_bruteforce(R, world20):
+    """Device index builder == brute-force restatement of rover_utils.py:52-118 (ties by triangle id)."""
+    w = world20
+    got = R.build_knn_index(w.triangles, w.vertices, w.G, w.res, w.K)
+    assert torch.equal(got.cpu(), w.map_indices)
+    gr = R.build_knn_index(w.rock_triangles, w.rock_vertices, w.G, w.res, min(w.K, w.rock_triangles.shape[0]))
+    assert torch.equal(gr.cpu(), w.rock_indices[:gr.shape[0]])
+    # sparse layer: 3 far-apart clusters, K larger than any cluster -> windows must grow
+    g = torch.Generator().manual_seed(3)
+    centers = torch.tensor([[2.0, 2.0], [17.0, 5.0], [9.0, 18.0]])
+    v = (centers[:, None, :] + torch.rand(3, 90, 2, generator=g) * 0.8).reshape(-1, 2)
+    v = torch.cat((v, torch.rand(v.shape[0], 1, generator=g)), 1).to(torch.float16)
+    t = torch.arange(0, 270 - 2, dtype=torch.int32)
+    t = torch.stack((t, t + 1, t + 2), 1)
+    ref = R.synth.knn_index_bruteforce(v, t, 200, 0.1, 128)
+    got = R.build_knn_index(t, v, 200, 0.1, 128)
+    assert torch.equal(got.cpu(), ref)
