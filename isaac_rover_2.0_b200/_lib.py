@@ -59,6 +59,31 @@ def lib_path():
     return _build.LIB
 
 
+# kernels launched per entry point (for bench.py's `gpu_launches` claim)
+KERNELS_PER_CALL = {"rvb_terrain_create": 2, "rvb_heightmap_raycast": 2, "rvb_cast_rays": 2, "rvb_ray_distance": 1,
+                    "rvb_rock_collision": 1, "rvb_check_collision": 1, "rvb_quat_to_euler": 1, "rvb_ackermann": 1,
+                    "rvb_history_push": 1, "rvb_obs_proprio": 1, "rvb_obs_gather": 1, "rvb_reward_reset": 2,
+                    "rvb_stone_validate": 1, "rvb_spawn_validate": 1, "rvb_height_lookup": 1, "rvb_build_knn_index": 6}
+launch_count = 0
+
+
+class _Counted:
+    """Thin callable around a ctypes function that counts the kernels it launches."""
+    __slots__ = ("fn", "n")
+
+    def __init__(self, fn, n):
+        self.fn, self.n = fn, n
+
+    def __call__(self, *args):
+        global launch_count
+        launch_count += self.n
+        return self.fn(*args)
+
+
+class _Lib:
+    pass
+
+
 def load():
     """Load (building first if the sources are newer and nvcc is present).  Raises if impossible."""
     global _lib
@@ -70,11 +95,13 @@ def load():
         except Exception as e:                      # stale-but-present library is still usable
             if not os.path.exists(_build.LIB):
                 raise RuntimeError("librover_b200.so is missing and could not be built: %s" % e)
-    lib = C.CDLL(_build.LIB)
+    raw = C.CDLL(_build.LIB)
+    lib = _Lib()
     for name, (res, args) in _SIGNATURES.items():
-        fn = getattr(lib, name)                     # AttributeError here = ABI mismatch, fail loudly
+        fn = getattr(raw, name)                     # AttributeError here = ABI mismatch, fail loudly
         fn.restype = res
         fn.argtypes = args
+        setattr(lib, name, _Counted(fn, KERNELS_PER_CALL[name]) if name in KERNELS_PER_CALL else fn)
     if lib.rvb_abi_version() != 1:
         raise RuntimeError("librover_b200.so ABI version mismatch")
     _lib = lib

@@ -34,6 +34,7 @@ class Camera():
         self.variant = variant
         self._col_a, self._col_b = self.heightmap.obs_columns(4)
         self.last_hit_slot = None
+        self.timing = None          # set to a list to collect (start, end) CUDA events of every ray-cast launch
         self.last_hit_tri = None
 
     def get_num_exteroceptive(self):
@@ -55,12 +56,19 @@ class Camera():
         tri = torch.empty((N, P), dtype=torch.int32, device=dev) if want_hits else None
         if trig is not None:
             trig = trig.to(torch.float32).contiguous()
+        ev = None
+        if self.timing is not None:
+            ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+            ev[0].record(torch.cuda.current_stream(dev))
         with torch.cuda.device(dev):
             _lib.check(lib.rvb_heightmap_raycast(
                 self.layer.handle, _lib.ptr(pos), _lib.ptr(rot), _lib.ptr(trig), _lib.ptr(self.heightmap_distribution), P, N,
                 _lib.ptr(dist), _lib.ptr(slot), _lib.ptr(tri), _lib.ptr(pt), _lib.ptr(src),
                 _lib.ptr(obs), 0 if obs is None else obs.stride(0), _lib.ptr(self._col_a if obs is not None else None),
                 _lib.ptr(self._col_b if obs is not None else None), self.variant, _lib.stream_of(pos)))
+        if ev is not None:
+            ev[1].record(torch.cuda.current_stream(dev))
+            self.timing.append(ev)
         self.last_hit_slot, self.last_hit_tri = slot, tri
         return dist, pt, src
 

@@ -138,6 +138,15 @@ class RoverTask():
         self.is_done()
         return self.obs_buf, self.rew_buf, self.reset_buf, self.extras
 
+    def hot_step(self, actions):
+        """One env-step of the hot path with PhysX excluded: the action half of pre_physics_step (history,
+        Ackermann, joint targets; rover.py:343,366-414) followed by post_physics_step (rl_task.py:239-259).
+        Reset poses / goal re-sampling (rover.py:356-361) are the caller's (simulator-side) business."""
+        _, quat = self._rover.get_world_poses()
+        self.rover_rot = tensor_quat_to_eul(quat)
+        self.apply_actions(actions)
+        return self.post_physics_step()
+
     # ------------------------------------------------------------------ get_observations (rover.py:272-336)
     def get_observations(self) -> dict:
         lib = self._lib

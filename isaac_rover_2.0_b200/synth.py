@@ -89,17 +89,35 @@ def heightfield_to_mesh(hf, length):
     return v, t
 
 
-def rock_layer(vertices, triangles, stones, min_size=1.5):
-    """Sub-mesh made of the triangles under the big stones (the reference's big_stones.ply role)."""
-    cen = vertices[triangles.astype(np.int64)].mean(1)[:, :2]
+def rock_layer(vertices, triangles, stones, min_size=1.5, nv=None):
+    """Sub-mesh made of the triangles under the big stones (the reference's big_stones.ply role).
+    With `nv` (heightfield mesh of nv x nv vertices) only the quads around each stone are examined."""
     keep = np.zeros(len(triangles), dtype=bool)
-    for s in stones:
-        if max(s[3], s[4]) < min_size:
-            continue
-        d = ((cen[:, 0] - s[0]) / (0.6 * s[3])) ** 2 + ((cen[:, 1] - s[1]) / (0.6 * s[4])) ** 2
-        keep |= d <= 1.0
+    if nv is not None:
+        sp = float(vertices[1, 1] - vertices[0, 1])
+        for s in stones:
+            if max(s[3], s[4]) < min_size:
+                continue
+            ri, rj = 0.6 * s[3] / sp + 2, 0.6 * s[4] / sp + 2
+            ia, ib = int(max(s[0] / sp - ri, 0)), int(min(s[0] / sp + ri + 1, nv - 1))
+            ja, jb = int(max(s[1] / sp - rj, 0)), int(min(s[1] / sp + rj + 1, nv - 1))
+            if ia >= ib or ja >= jb:
+                continue
+            ii, jj = np.meshgrid(np.arange(ia, ib), np.arange(ja, jb), indexing="ij")
+            tid = (2 * (ii * (nv - 1) + jj)).reshape(-1)
+            tid = np.concatenate((tid, tid + 1))
+            cen = vertices[triangles[tid].astype(np.int64)].mean(1)[:, :2]
+            d = ((cen[:, 0] - s[0]) / (0.6 * s[3])) ** 2 + ((cen[:, 1] - s[1]) / (0.6 * s[4])) ** 2
+            keep[tid[d <= 1.0]] = True
+    else:
+        cen = vertices[triangles.astype(np.int64)].mean(1)[:, :2]
+        for s in stones:
+            if max(s[3], s[4]) < min_size:
+                continue
+            d = ((cen[:, 0] - s[0]) / (0.6 * s[3])) ** 2 + ((cen[:, 1] - s[1]) / (0.6 * s[4])) ** 2
+            keep |= d <= 1.0
     tri = triangles[keep]
-    if len(tri) == 0:                       # keep the layer non-empty so every cell has K candidates
+    if len(tri) < 2:                        # keep the layer non-empty so every cell has candidates
         tri = triangles[:2]
     used, inv = np.unique(tri.reshape(-1), return_inverse=True)
     return vertices[used].copy(), inv.reshape(-1, 3).astype(np.int32)
@@ -148,7 +166,7 @@ def make_world(length=20.0, nv=72, K=200, res=0.1, n_stones=40, hm_res=0.025, se
     (caller builds the index on the GPU with `terrain.build_knn_index`)."""
     hf, stones = make_heightfield(length, nv, n_stones, seed)
     v, t = heightfield_to_mesh(hf, length)
-    rv, rt = rock_layer(v, t, stones)
+    rv, rt = rock_layer(v, t, stones, nv=nv)
     G = int(round(length / res))
     w = World(length=length, res=res, G=G, K=K,
               vertices=torch.from_numpy(v).to(torch.float16), triangles=torch.from_numpy(t),

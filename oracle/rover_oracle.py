@@ -495,3 +495,30 @@ def pos_height(heightmap, xy, hscale, vscale, shift_xy):
     """rover.py:588-608."""
     s = torch.round(torch.clamp((xy - shift_xy) / hscale, min=0, max=heightmap.size()[0] - 1))
     return heightmap[s[:, 0].long(), s[:, 1].long()] * vscale
+
+
+# --------------------------------------------------------------------------------------
+# whole env-step (used as the CPU baseline / reference arm by bench.py and by smoke())
+# --------------------------------------------------------------------------------------
+def full_step(assets, st, level=2, env_chunk=16):
+    """One env-step of the hot path with PhysX excluded, on whatever device the tensors live on:
+    pre_physics_step's action half (rover.py:343,366-409) then post_physics_step (rl_task.py:239-259).
+    assets: dict(pattern, coarse_idx, fine_idx, map_indices, triangles, vertices, rock_indices, rock_triangles,
+    rock_vertices, shift); st: dict(pos, quat, joints, actions, prev_actions, target, progress)."""
+    a = assets
+    rover_rot = quat_to_euler(st["quat"])                                   # rover.py:343
+    lin, ang = st["actions"][:, 0], st["actions"][:, 1]
+    steer, vel = ackermann(lin, ang)
+    pos_t, vel_t = joint_targets(steer, vel)
+    progress = st["progress"] + 1                                           # rl_task.py:250
+    euler = quat_to_euler(st["quat"])
+    dep = get_depths(st["pos"], euler, a["pattern"], a["map_indices"], a["triangles"], a["vertices"], a["shift"],
+                     env_chunk=env_chunk)
+    obs, _, heading = observations(st["pos"], st["quat"], st["target"], lin, ang, dep["dist"], a["coarse_idx"], a["fine_idx"])
+    col = get_collisions(st["pos"], euler, st["joints"], a["rock_indices"], a["rock_triangles"], a["rock_vertices"], a["shift"])
+    rock = check_collision(col["wheel"], col["body"]) if level >= 2 else None
+    rew, extras = metrics(st["pos"], st["target"], heading, lin, st["prev_actions"][:, 0], ang, st["prev_actions"][:, 1],
+                          st["joints"], progress, rock, level)
+    reset = is_done(st["pos"], st["target"], rover_rot, progress, rock, level)
+    return dict(obs=obs, rew=rew, reset=reset, extras=extras, rock_collision=rock, dist=dep["dist"], tri=dep["tri"],
+                wheel=col["wheel"], body=col["body"], pos_targets=pos_t, vel_targets=vel_t, heading=heading, euler=euler)

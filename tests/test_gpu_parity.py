@@ -334,7 +334,8 @@ def test_edge_cases(R, O, world20):
         assert_bits_equal(d, ref["dist"], "edge dist v%d" % variant)
         assert_bits_equal(cam.last_hit_slot, ref["slot"].to(torch.int32), "edge slot v%d" % variant)
         assert_bits_equal(pt, ref["pt"], "edge pt v%d" % variant)
-    assert (ref["dist"][2] == 11).all() and (ref["slot"][2] == 0).all()
+    # 40 m above the ground the true hit (k ~ 39.7) loses the min against the 11.0 miss sentinel of the others
+    assert (ref["dist"][2] == 11).all()
     # errors are Python exceptions, never a silent CPU path
     with pytest.raises(RuntimeError):
         cam.get_depths(pos, eul)
