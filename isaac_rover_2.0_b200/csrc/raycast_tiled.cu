@@ -1,19 +1,480 @@
-// Production heightmap ray-cast kernel (placeholder: routes to the simple kernel in env chunks).
+// Production heightmap ray-cast kernel: Camera.get_depths (camera.py:60-145) in ONE launch.
+//
+// One CTA per (env, ray tile).  Phases, all inside the CTA:
+//   1. every thread transforms its rays (fp64 body transform -> fp16 sources, camera.py:165-212) and looks up
+//      their grid cell (camera.py:233-264);
+//   2. the tile's rays are grouped by cell with a counting sort over the tile's cell bounding box (shared-memory
+//      histogram + scan) -- the dense part of the pattern puts ~4 rays in a cell, so a cell's K-candidate list and
+//      its K triangle records are fetched once per cell instead of once per ray;
+//   3. warps pull (cell, ray-range) items from a shared counter.  A lane owns TWO candidates of the cell's list:
+//      it gathers their pre-resolved 32-byte records (L2-resident table), packs them into half2 registers and
+//      then loops over the rays of the item.  All fp16 arithmetic of ray_casting.py:34-56 runs as packed
+//      HADD2/HMUL2 (.rn, never contracted) on the two candidates at once;
+//   4. the three divisions of ray_casting.py:44-56 are NOT executed for candidates that miss: the barycentric
+//      test `n >= -eps, m >= -eps, n + m <= 1 + eps` on the rounded quotients is decided exactly from the
+//      un-divided numerators (see pair2_keys); only candidates that pass (about 1 in 140) pay for the one
+//      IEEE division that produces k.  A candidate whose n+m lies within 2^-9 of the threshold is re-evaluated
+//      with the literal op sequence (pair_test), so the result is bit-identical by construction;
+//   5. per ray: warp REDUX.MIN over a 32-bit key (order-preserving fp16 bits << 16 | slot) reproduces torch.min
+//      (NaN first, ties -> lowest slot), merged across candidate chunks with a shared-memory atomicMin;
+//   6. epilogue in ray order: coalesced stores of dist / hit slot / hit triangle / pt / sources and the fused
+//      sparse+dense observation columns (heightmap_distribution.py:126-133, rover.py:324-325).
 #include "common.cuh"
+
+namespace {
+
+constexpr int TT = 256;            // threads per CTA
+constexpr int NW = TT / 32;
+constexpr int RT_MAX = 2048;       // rays per tile (<= 8 per thread)
+constexpr int RPT = RT_MAX / TT;
+constexpr int BIN_CAP = 8192;      // cells in the tile's bounding box that can be histogrammed (u16 counters)
+constexpr int MAX_ITEM_RAYS = 16;  // rays per work item (heavy cells are split)
+
+constexpr uint32_t KEY_NONE = 0xffffffffu;
+constexpr uint32_t ORD_MISS = 0xC980u;        // order key of fp16 11.0 (0x4980 | 0x8000)
+
+struct TiledParams {
+    const int32_t* index;
+    const TriRec* recs;
+    int G0, G1, K;
+    float res, inv_res, shift_x, shift_y;
+    int sem;
+    const float* pos;
+    const float* euler;
+    const float* trig;
+    const double* pattern;
+    int P, tiles, tile_size;
+    __half* dist;
+    int32_t* hit_slot;
+    int32_t* hit_tri;
+    __half* pt;
+    __half* sources;
+    float* obs;
+    int64_t obs_ld;
+    const int32_t* col_a;
+    const int32_t* col_b;
+};
+
+// two candidates of one cell, component-wise packed: .x = candidate j, .y = candidate j+1
+struct Tri2 {
+    __half2 ax, ay, az, bx, by, bz, cx, cy, cz, nx, ny, nz;
+};
+
+__device__ __forceinline__ __half2 u2h(uint32_t u) { return *reinterpret_cast<__half2*>(&u); }
+__device__ __forceinline__ uint32_t h2u(__half2 h) { return *reinterpret_cast<uint32_t*>(&h); }
+__device__ __forceinline__ __half2 add2(__half2 a, __half2 b) { return __hadd2_rn(a, b); }
+__device__ __forceinline__ __half2 sub2(__half2 a, __half2 b) { return __hsub2_rn(a, b); }
+__device__ __forceinline__ __half2 mul2(__half2 a, __half2 b) { return __hmul2_rn(a, b); }
+
+__device__ __forceinline__ Tri2 pack_tri2(const uint4& p0, const uint2& p1, const uint4& q0, const uint2& q1) {
+    // record halves: q0 = [a.x a.y | a.z b.x | b.y b.z | c.x c.y], q1 = [c.z n.x | n.y n.z]
+    Tri2 t;
+    t.ax = u2h(__byte_perm(p0.x, q0.x, 0x5410)); t.ay = u2h(__byte_perm(p0.x, q0.x, 0x7632));
+    t.az = u2h(__byte_perm(p0.y, q0.y, 0x5410)); t.bx = u2h(__byte_perm(p0.y, q0.y, 0x7632));
+    t.by = u2h(__byte_perm(p0.z, q0.z, 0x5410)); t.bz = u2h(__byte_perm(p0.z, q0.z, 0x7632));
+    t.cx = u2h(__byte_perm(p0.w, q0.w, 0x5410)); t.cy = u2h(__byte_perm(p0.w, q0.w, 0x7632));
+    t.cz = u2h(__byte_perm(p1.x, q1.x, 0x5410)); t.nx = u2h(__byte_perm(p1.x, q1.x, 0x7632));
+    t.ny = u2h(__byte_perm(p1.y, q1.y, 0x5410)); t.nz = u2h(__byte_perm(p1.y, q1.y, 0x7632));
+    return t;
+}
+
+// key of torch.min's total order: NaN < everything, -0 == +0, ties -> lower slot; bit 0 remembers a negative zero.
+__device__ __forceinline__ uint32_t make_key(unsigned short b, uint32_t slot) {
+    uint32_t ord, nz = 0;
+    if ((b & 0x7fffu) > 0x7c00u) ord = 0u;
+    else if ((b & 0x7fffu) == 0u) { ord = 0x8000u; nz = b >> 15; }
+    else ord = (b & 0x8000u) ? (uint32_t)(unsigned short)~b : (uint32_t)(b | 0x8000u);
+    return (ord << 16) | (slot << 1) | nz;
+}
+__device__ __forceinline__ unsigned short key_bits(uint32_t key) {
+    const uint32_t ord = key >> 16;
+    if (ord == 0u) return 0x7fffu;
+    if (ord == 0x8000u) return (key & 1u) ? 0x8000u : 0u;
+    return (ord & 0x8000u) ? (unsigned short)(ord & 0x7fffu) : (unsigned short)~ord;
+}
+
+// Exact thresholds.  With q = N/det (exact rational of two fp16 values) and n = fp16(fp32(q)):
+//   n >= fp16(-0.1) = -0x1.998p-4   <=>   q >= -3277/32768   (the rounding boundary below it; the tie goes to the
+//   even mantissa 0x266, i.e. to -0.1 itself, and a quotient of two 11-bit significands cannot fall strictly
+//   between the boundary and its fp32 neighbour, so the intermediate fp32 rounding is harmless).
+// 3277/32768 * |det| is exact in fp32 (12 x 11 bits), so sign(fma(|det|, 3277/32768, N')) decides it exactly.
+//   fp16(n + m) <= fp16(1.1) = 0x3C66   <=>   n + m <= 2253/2048  (boundary above it, tie -> even 0x066).
+// n and m differ from the exact quotients by at most 2^-11 relative each (|n|,|m| <= 1.31 here), i.e. by less than
+// 2^-9 together, so outside a 2^-9 band around 2253/2048 the third test is decided by (N'+M') vs c*|det|.
+#define C_LO 0.100006103515625f          /* 3277 / 32768 */
+#define C_PASS 1.09814453125f            /* 2253/2048 - 2^-9 */
+#define C_FAIL 1.10205078125f            /* 2253/2048 + 2^-9 */
+
+// Per candidate pair, invariant over the rays of an env (the direction is per env): det = (b x c) . d and the
+// exact thresholds derived from it.
+struct Cand2 {
+    uint32_t sgn;          // sign bits of det in both halves
+    __half2 det;           // (b x c) . d                                   (ray_casting.py:41)
+    float da0, da1;        // |det| as fp32
+    float lo0, lo1;        // 3277/32768 * |det| (exact); NaN when the candidate is out of range or det is 0 / NaN
+    float hi0, hi1;        // C_FAIL * |det|
+    uint32_t miss0, miss1; // key of a miss at this slot (KEY_NONE when out of range)
+};
+
+__device__ __forceinline__ Cand2 make_cand2(const Tri2& t, __half2 dx, __half2 dy, __half2 dz, int j0, int K) {
+    Cand2 c;
+    c.det = add2(add2(mul2(t.nx, dx), mul2(t.ny, dy)), mul2(t.nz, dz));
+    c.sgn = h2u(c.det) & 0x80008000u;
+    const __half2 da = u2h(h2u(c.det) ^ c.sgn);
+    c.da0 = __low2float(da);
+    c.da1 = __high2float(da);
+    const bool v0 = j0 < K, v1 = j0 + 1 < K;
+    const float nan = __int_as_float(0x7fc00000);
+    c.lo0 = (v0 && c.da0 > 0.f) ? __fmul_rn(c.da0, C_LO) : nan;     // det == 0 never passes (n, m = +-inf / NaN)
+    c.lo1 = (v1 && c.da1 > 0.f) ? __fmul_rn(c.da1, C_LO) : nan;
+    c.hi0 = __fmul_rn(c.da0, C_FAIL);
+    c.hi1 = __fmul_rn(c.da1, C_FAIL);
+    c.miss0 = v0 ? ((ORD_MISS << 16) | ((uint32_t)j0 << 1)) : KEY_NONE;
+    c.miss1 = v1 ? ((ORD_MISS << 16) | ((uint32_t)(j0 + 1) << 1)) : KEY_NONE;
+    return c;
+}
+
+// "may pass" from the oriented numerators N' = N*sgn(det), M' = M*sgn(det):  N' + lo >= 0 and M' + lo >= 0 decide
+// n >= -eps and m >= -eps exactly (lo is exact and an fp32 sum never rounds across zero); (N' + M') - hi < 0 rules
+// out everything that certainly fails n + m <= 1 + eps.  NaNs (lo of a dead candidate, overflowed numerators) make
+// the first two false or the last one true, i.e. dead candidates drop out and odd ones are re-checked.
+__device__ __forceinline__ bool may_pass(float Nf, float Mf, float lo, float hi) {
+    const float rn = __fadd_rn(Nf, lo), rm = __fadd_rn(Mf, lo);
+    const float rf = __fsub_rn(__fadd_rn(Nf, Mf), hi);
+    return (rn >= 0.f) && (rm >= 0.f) && !(rf >= 0.f);
+}
+
+// k for a candidate that may pass: certain hits take one IEEE division, the 2^-9 band around the n + m threshold
+// (and anything non-finite) replays the literal op sequence of ray_casting.py.
+__device__ __forceinline__ uint32_t resolve(float Nf, float Mf, float da, __half det, __half Kn, H3 s, H3 d, H3 a, H3 b,
+                                           H3 c, H3 n, uint32_t slot) {
+    const float rp = __fmaf_rn(da, -C_PASS, __fadd_rn(Nf, Mf));
+    __half k;
+    if (rp <= 0.f) {
+        const unsigned short db = h_bits(det);
+        k = (db == RVB_H_LO || db == RVB_H_HI) ? h_from_bits(RVB_H_MISS) : h_div(Kn, det);     // :46,51,54-56
+    } else {
+        k = pair_test(s, d, a, b, c, n);
+    }
+    return make_key(h_bits(k), slot);
+}
+
+// Both candidates of a lane against one ray.  s* hold the ray's source duplicated in both halves, d* the env's
+// -normalized direction likewise.  Returns the smaller of the two candidates' keys.
+__device__ __forceinline__ uint32_t pair2_keys(__half2 sx, __half2 sy, __half2 sz, __half2 dx, __half2 dy, __half2 dz,
+                                               const Tri2& t, const Cand2& c, uint32_t slot0) {
+    const __half2 gx = sub2(sx, t.ax), gy = sub2(sy, t.ay), gz = sub2(sz, t.az);                 // ray_casting.py:37
+    const __half2 ux = sub2(mul2(gy, t.cz), mul2(gz, t.cy));                                     // g x c  (:44)
+    const __half2 uy = sub2(mul2(gz, t.cx), mul2(gx, t.cz));
+    const __half2 uz = sub2(mul2(gx, t.cy), mul2(gy, t.cx));
+    const __half2 Nn = add2(add2(mul2(ux, dx), mul2(uy, dy)), mul2(uz, dz));                     // :45 numerator
+    const __half2 vx = sub2(mul2(t.by, gz), mul2(t.bz, gy));                                     // b x g  (:49)
+    const __half2 vy = sub2(mul2(t.bz, gx), mul2(t.bx, gz));
+    const __half2 vz = sub2(mul2(t.bx, gy), mul2(t.by, gx));
+    const __half2 Mn = add2(add2(mul2(vx, dx), mul2(vy, dy)), mul2(vz, dz));                     // :50 numerator
+    const __half2 Ns = u2h(h2u(Nn) ^ c.sgn), Ms = u2h(h2u(Mn) ^ c.sgn);                          // q = (N*sgn)/|det|
+    const float N0 = __low2float(Ns), M0 = __low2float(Ms), N1 = __high2float(Ns), M1 = __high2float(Ms);
+    const bool p0 = may_pass(N0, M0, c.lo0, c.hi0);
+    const bool p1 = may_pass(N1, M1, c.lo1, c.hi1);
+    uint32_t k0 = c.miss0, k1 = c.miss1;
+    if (p0 | p1) {
+        // about 1 candidate in 140 gets here: k = ((b x c) . g) / det          (:54-56)
+        const __half2 Kn = add2(add2(mul2(t.nx, gx), mul2(t.ny, gy)), mul2(t.nz, gz));
+        const H3 s = {__low2half(sx), __low2half(sy), __low2half(sz)}, d = {__low2half(dx), __low2half(dy), __low2half(dz)};
+        if (p0)
+            k0 = resolve(N0, M0, c.da0, __low2half(c.det), __low2half(Kn), s, d,
+                         {__low2half(t.ax), __low2half(t.ay), __low2half(t.az)}, {__low2half(t.bx), __low2half(t.by), __low2half(t.bz)},
+                         {__low2half(t.cx), __low2half(t.cy), __low2half(t.cz)}, {__low2half(t.nx), __low2half(t.ny), __low2half(t.nz)},
+                         slot0);
+        if (p1)
+            k1 = resolve(N1, M1, c.da1, __high2half(c.det), __high2half(Kn), s, d,
+                         {__high2half(t.ax), __high2half(t.ay), __high2half(t.az)}, {__high2half(t.bx), __high2half(t.by), __high2half(t.bz)},
+                         {__high2half(t.cx), __high2half(t.cy), __high2half(t.cz)}, {__high2half(t.nx), __high2half(t.ny), __high2half(t.nz)},
+                         slot0 + 1);
+    }
+    return min(k0, k1);
+}
+
+struct Smem {
+    uint4* ray_s;        // [RT]  sorted by cell: (sx2, sy2, sz2 duplicated halves, local ray id)
+    uint32_t* res;       // [RT]  best key per local ray id
+    uint2* items;        // [RT]  (cell, start | count << 16)
+    uint32_t* bins;      // [BIN_CAP / 2]  u16 counters, then exclusive offsets
+};
+
+__global__ void __launch_bounds__(TT, 3) hm_tiled_kernel(const TiledParams q) {
+    extern __shared__ uint4 smem_raw[];
+    __shared__ int s_box[4];          // min cx, min cy, max cx, max cy
+    __shared__ uint32_t s_warp[NW];
+    __shared__ int s_nitems, s_next;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t n = blockIdx.x / q.tiles;
+    const int tile = blockIdx.x % q.tiles;
+    const int p0 = tile * q.tile_size;
+    const int np = min(q.tile_size, q.P - p0);
+    const int RT = q.tile_size;
+
+    Smem sm;
+    sm.ray_s = smem_raw;
+    sm.res = reinterpret_cast<uint32_t*>(sm.ray_s + RT);
+    sm.items = reinterpret_cast<uint2*>(sm.res + ((RT + 3) & ~3));
+    sm.bins = reinterpret_cast<uint32_t*>(sm.items + ((RT + 1) & ~1));
+
+    // ---- phase 0: clear histogram, per-env constants
+    for (int i = tid; i < BIN_CAP / 8; i += TT) reinterpret_cast<uint4*>(sm.bins)[i] = make_uint4(0, 0, 0, 0);
+    if (tid == 0) {
+        s_box[0] = s_box[1] = 0x7fffffff;
+        s_box[2] = s_box[3] = -1;
+        s_next = NW;
+    }
+    const Trig tr = make_trig(q.euler, q.trig, n);
+    const double tx = (double)q.pos[n * 3 + 0], ty = (double)q.pos[n * 3 + 1], tz = (double)q.pos[n * 3 + 2];
+    __half2 dx2, dy2, dz2;
+    {
+        // the appended point (0,0,-1) minus the translation, normalised and negated (camera.py:179-181,202-207; ray_casting.py:31)
+        double xo, yo, zo;
+        body_transform<double>(0.0, 0.0, -1.0, tr, tx, ty, tz, xo, yo, zo);
+        const H3 d = neg_normalize({h_from_double(__dsub_rn(xo, tx)), h_from_double(__dsub_rn(yo, ty)), h_from_double(__dsub_rn(zo, tz))});
+        dx2 = __half2half2(d.x); dy2 = __half2half2(d.y); dz2 = __half2half2(d.z);
+    }
+    __syncthreads();
+
+    // ---- phase 1: sources + cells of this thread's rays (kept in registers across the sort)
+    uint32_t r_sxy[RPT], r_sz[RPT];
+    int r_cell[RPT];                // cx << 16 | cy   (G <= 65535 checked on the host)
+    int mnx = 0x7fffffff, mny = 0x7fffffff, mxx = -1, mxy = -1;
+#pragma unroll
+    for (int i = 0; i < RPT; ++i) {
+        const int p = tid + i * TT;
+        r_cell[i] = -1;
+        if (p < np) {
+            const double* pp = q.pattern + (int64_t)(p0 + p) * 3;
+            double xo, yo, zo;
+            body_transform<double>(pp[0], pp[1], pp[2], tr, tx, ty, tz, xo, yo, zo);
+            const __half hx = h_from_double(xo), hy = h_from_double(yo), hz = h_from_double(zo);
+            r_sxy[i] = (uint32_t)h_bits(hx) | ((uint32_t)h_bits(hy) << 16);
+            r_sz[i] = h_bits(hz);
+            const int cx = cell_coord(hx, q.shift_x, q.res, q.inv_res, q.G0 - 1, q.sem);
+            const int cy = min(cell_coord(hy, q.shift_y, q.res, q.inv_res, q.G0 - 1, q.sem), q.G1 - 1);   // camera.py:243
+            r_cell[i] = (cx << 16) | cy;
+            mnx = min(mnx, cx); mxx = max(mxx, cx); mny = min(mny, cy); mxy = max(mxy, cy);
+        }
+    }
+    mnx = __reduce_min_sync(0xffffffffu, mnx); mny = __reduce_min_sync(0xffffffffu, mny);
+    mxx = __reduce_max_sync(0xffffffffu, mxx); mxy = __reduce_max_sync(0xffffffffu, mxy);
+    if (lane == 0) {
+        atomicMin(&s_box[0], mnx); atomicMin(&s_box[1], mny);
+        atomicMax(&s_box[2], mxx); atomicMax(&s_box[3], mxy);
+    }
+    __syncthreads();
+    const int bx0 = s_box[0], by0 = s_box[1];
+    const int BW = s_box[2] - bx0 + 1, BH = s_box[3] - by0 + 1;
+    const bool grouped = (int64_t)BW * BH <= BIN_CAP;
+
+    int nitems;
+    if (grouped) {
+        // ---- phase 2: counting sort by cell
+        uint32_t r_rank[RPT];
+#pragma unroll
+        for (int i = 0; i < RPT; ++i) {
+            if (r_cell[i] >= 0) {
+                const int bin = ((r_cell[i] >> 16) - bx0) * BH + ((r_cell[i] & 0xffff) - by0);
+                const uint32_t old = atomicAdd(&sm.bins[bin >> 1], 1u << ((bin & 1) * 16));
+                r_rank[i] = (old >> ((bin & 1) * 16)) & 0xffffu;
+            }
+        }
+        __syncthreads();
+        // exclusive scan over bins; thread t owns words t, t + TT, ...  (order of cells is irrelevant);
+        // packed accumulator: rays in the low 16 bits, items in the high 16 bits
+        const int nwords = (BW * BH + 1) >> 1;
+        uint32_t tot = 0;
+        for (int w = tid; w < nwords; w += TT) {
+            const uint32_t v = sm.bins[w];
+            const uint32_t a = v & 0xffffu, b = v >> 16;
+            tot += (a + b) + (((a + MAX_ITEM_RAYS - 1) / MAX_ITEM_RAYS + (b + MAX_ITEM_RAYS - 1) / MAX_ITEM_RAYS) << 16);
+        }
+        uint32_t inc = tot;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t v = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += v;
+        }
+        if (lane == 31) s_warp[warp] = inc;
+        __syncthreads();
+        uint32_t base = 0, total = 0;
+#pragma unroll
+        for (int w = 0; w < NW; ++w) {
+            const uint32_t v = s_warp[w];
+            if (w < warp) base += v;
+            total += v;
+        }
+        uint32_t run = base + inc - tot;
+        for (int w = tid; w < nwords; w += TT) {
+            const uint32_t v = sm.bins[w];
+            uint32_t off[2];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const uint32_t cnt = h ? (v >> 16) : (v & 0xffffu);
+                off[h] = run & 0xffffu;
+                if (cnt) {
+                    const int bin = 2 * w + h;
+                    const int cx = bx0 + bin / BH, cy = by0 + bin % BH;
+                    const uint32_t cell = (uint32_t)cx * (uint32_t)q.G1 + (uint32_t)cy;
+                    uint32_t it = run >> 16, start = run & 0xffffu;
+                    for (uint32_t done = 0; done < cnt; done += MAX_ITEM_RAYS, ++it)
+                        sm.items[it] = make_uint2(cell, (start + done) | (min(cnt - done, (uint32_t)MAX_ITEM_RAYS) << 16));
+                    run += cnt + (((cnt + MAX_ITEM_RAYS - 1) / MAX_ITEM_RAYS) << 16);
+                }
+            }
+            sm.bins[w] = off[0] | (off[1] << 16);
+        }
+        nitems = (int)(total >> 16);
+        __syncthreads();
+        // scatter into cell order
+#pragma unroll
+        for (int i = 0; i < RPT; ++i) {
+            if (r_cell[i] >= 0) {
+                const int p = tid + i * TT;
+                const int bin = ((r_cell[i] >> 16) - bx0) * BH + ((r_cell[i] & 0xffff) - by0);
+                const uint32_t posn = ((sm.bins[bin >> 1] >> ((bin & 1) * 16)) & 0xffffu) + r_rank[i];
+                sm.ray_s[posn] = make_uint4(__byte_perm(r_sxy[i], 0, 0x1010), __byte_perm(r_sxy[i], 0, 0x3232),
+                                            __byte_perm(r_sz[i], 0, 0x1010), (uint32_t)p);
+                sm.res[p] = KEY_NONE;
+            }
+        }
+    } else {
+        // bounding box too large to histogram (rays spread over more than BIN_CAP cells): every ray is its own item
+#pragma unroll
+        for (int i = 0; i < RPT; ++i) {
+            if (r_cell[i] >= 0) {
+                const int p = tid + i * TT;
+                const uint32_t cell = (uint32_t)(r_cell[i] >> 16) * (uint32_t)q.G1 + (uint32_t)(r_cell[i] & 0xffff);
+                sm.items[p] = make_uint2(cell, (uint32_t)p | (1u << 16));
+                sm.ray_s[p] = make_uint4(__byte_perm(r_sxy[i], 0, 0x1010), __byte_perm(r_sxy[i], 0, 0x3232),
+                                         __byte_perm(r_sz[i], 0, 0x1010), (uint32_t)p);
+                sm.res[p] = KEY_NONE;
+            }
+        }
+        nitems = np;
+    }
+    __syncthreads();
+
+    // ---- phase 3: warps pull items; lanes own candidate pairs
+    const int K = q.K;
+    const bool k_even = (K & 1) == 0;
+    int item = warp;
+    while (item < nitems) {
+        int next = 0;
+        if (lane == 0) next = atomicAdd(&s_next, 1);
+        next = __shfl_sync(0xffffffffu, next, 0);
+        const uint2 it = sm.items[item];
+        const int32_t* row = q.index + (int64_t)it.x * K;
+        if (next < nitems && lane * 32 < K) {
+            // pull the next item's candidate list towards L2 while this one is being processed
+            const int32_t* nrow = q.index + (int64_t)sm.items[next].x * K + lane * 32;
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(nrow));
+        }
+        const int start = it.y & 0xffff, cnt = it.y >> 16;
+        for (int c0 = 0; c0 < K; c0 += 64) {
+            const int j0 = c0 + 2 * lane;
+            int id0 = 0, id1 = 0;
+            if (k_even) {
+                if (j0 < K) {
+                    const int2 v = __ldg(reinterpret_cast<const int2*>(row + j0));
+                    id0 = v.x; id1 = v.y;
+                }
+            } else {
+                if (j0 < K) id0 = __ldg(row + j0);
+                if (j0 + 1 < K) id1 = __ldg(row + j0 + 1);
+            }
+            const uint4* r0 = reinterpret_cast<const uint4*>(q.recs + id0);
+            const uint4* r1 = reinterpret_cast<const uint4*>(q.recs + id1);
+            const uint4 a0 = __ldg(r0), b0 = __ldg(r1);
+            const uint2 a1 = __ldg(reinterpret_cast<const uint2*>(r0 + 1)), b1 = __ldg(reinterpret_cast<const uint2*>(r1 + 1));
+            const Tri2 t = pack_tri2(a0, a1, b0, b1);
+            const Cand2 cd = make_cand2(t, dx2, dy2, dz2, j0, K);
+            for (int r = 0; r < cnt; ++r) {
+                const uint4 rs = sm.ray_s[start + r];
+                uint32_t key = pair2_keys(u2h(rs.x), u2h(rs.y), u2h(rs.z), dx2, dy2, dz2, t, cd, (uint32_t)j0);
+                key = __reduce_min_sync(0xffffffffu, key);
+                if (lane == 0) atomicMin(&sm.res[rs.w], key);
+            }
+        }
+        item = next;
+    }
+    __syncthreads();
+
+    // ---- phase 4: epilogue in ray order
+    const bool want_geo = q.hit_tri || q.pt || q.sources;
+    for (int p = tid; p < np; p += TT) {
+        const uint32_t key = sm.res[p];
+        const unsigned short kb = key_bits(key);
+        const int slot = (int)((key >> 1) & 0x7fffu);
+        const int64_t o = n * q.P + p0 + p;
+        q.dist[o] = h_from_bits(kb);
+        if (q.hit_slot) q.hit_slot[o] = slot;
+        if (want_geo) {
+            const double* pp = q.pattern + (int64_t)(p0 + p) * 3;
+            double xo, yo, zo;
+            body_transform<double>(pp[0], pp[1], pp[2], tr, tx, ty, tz, xo, yo, zo);
+            const __half hx = h_from_double(xo), hy = h_from_double(yo), hz = h_from_double(zo);
+            if (q.sources) { q.sources[o * 3 + 0] = hx; q.sources[o * 3 + 1] = hy; q.sources[o * 3 + 2] = hz; }
+            if (q.hit_tri) {
+                const int cx = cell_coord(hx, q.shift_x, q.res, q.inv_res, q.G0 - 1, q.sem);
+                const int cy = min(cell_coord(hy, q.shift_y, q.res, q.inv_res, q.G0 - 1, q.sem), q.G1 - 1);
+                q.hit_tri[o] = __ldg(q.index + ((int64_t)cx * q.G1 + cy) * K + slot);
+            }
+            if (q.pt) {
+                const __half k = h_from_bits(kb);
+                q.pt[o * 3 + 0] = h_sub(hx, h_mul(__low2half(dx2), k));     // ray_casting.py:63
+                q.pt[o * 3 + 1] = h_sub(hy, h_mul(__low2half(dy2), k));
+                q.pt[o * 3 + 2] = h_sub(hz, h_mul(__low2half(dz2), k));
+            }
+        }
+        if (q.obs) {
+            const float v = __half2float(h_mul(h_from_bits(kb), __float2half_rn(0.5f)));     // fp16(dist / 2) -> f32
+            const int ca = q.col_a[p0 + p], cb = q.col_b[p0 + p];
+            if (ca >= 0) q.obs[n * q.obs_ld + ca] = v;
+            if (cb >= 0) q.obs[n * q.obs_ld + cb] = v;
+        }
+    }
+}
+
+size_t tiled_smem_bytes(int RT) {
+    return (size_t)RT * 16 + (size_t)((RT + 3) & ~3) * 4 + (size_t)((RT + 1) & ~1) * 8 + (size_t)BIN_CAP * 2;
+}
+
+}  // namespace
 
 int launch_heightmap_tiled(const rvb_terrain* t, const float* pos, const float* euler, const float* trig,
                            const double* pattern, int64_t P, int64_t N, uint16_t* dist, int32_t* hit_slot,
                            int32_t* hit_tri, uint16_t* pt, uint16_t* sources, float* obs, int64_t obs_ld,
                            const int32_t* col_a, const int32_t* col_b, cudaStream_t st) {
-    const int64_t chunk = 32768;
-    for (int64_t n0 = 0; n0 < N; n0 += chunk) {
-        const int64_t n = (N - n0 < chunk) ? N - n0 : chunk;
-        int rc = rvb_heightmap_raycast(t, pos + n0 * 3, euler + n0 * 3, trig ? trig + n0 * 6 : nullptr, pattern, P, n,
-                                       dist + n0 * P, hit_slot ? hit_slot + n0 * P : nullptr,
-                                       hit_tri ? hit_tri + n0 * P : nullptr, pt ? pt + n0 * P * 3 : nullptr,
-                                       sources ? sources + n0 * P * 3 : nullptr, obs ? obs + n0 * obs_ld : nullptr, obs_ld,
-                                       col_a, col_b, 1, (void*)st);
-        if (rc != RVB_OK) return rc;
+    RVB_REQUIRE(t->G0 <= 32767 && t->G1 <= 65535, "heightmap ray-cast: grid larger than 32767 x 65535 cells");
+    RVB_REQUIRE(t->K <= 16383, "heightmap ray-cast: K > 16383");
+    RVB_REQUIRE(t->G0 * t->G1 < ((int64_t)1 << 32), "heightmap ray-cast: more than 2^32 cells");
+    TiledParams q;
+    q.index = t->index; q.recs = t->recs;
+    q.G0 = (int)t->G0; q.G1 = (int)t->G1; q.K = (int)t->K;
+    q.res = t->res; q.inv_res = 1.0f / t->res; q.shift_x = t->shift_x; q.shift_y = t->shift_y; q.sem = t->sem;
+    q.pos = pos; q.euler = euler; q.trig = trig; q.pattern = pattern;
+    q.P = (int)P;
+    q.tiles = (int)ceil_div(P, RT_MAX);
+    q.tile_size = (int)ceil_div(P, q.tiles);
+    q.dist = (__half*)dist; q.hit_slot = hit_slot; q.hit_tri = hit_tri; q.pt = (__half*)pt; q.sources = (__half*)sources;
+    q.obs = obs; q.obs_ld = obs_ld; q.col_a = col_a; q.col_b = col_b;
+    const int64_t blocks = N * q.tiles;
+    RVB_REQUIRE(blocks < ((int64_t)1 << 31), "heightmap ray-cast: too many (env, tile) blocks for one launch");
+    const size_t smem = tiled_smem_bytes(q.tile_size);
+    static thread_local int configured_device = -1;
+    int dev = 0;
+    RVB_CUDA(cudaGetDevice(&dev));
+    if (configured_device != dev) {
+        RVB_CUDA(cudaFuncSetAttribute(hm_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tiled_smem_bytes(RT_MAX)));
+        configured_device = dev;
     }
+    hm_tiled_kernel<<<(unsigned)blocks, TT, smem, st>>>(q);
+    RVB_LAUNCH_CHECK();
     return RVB_OK;
 }
