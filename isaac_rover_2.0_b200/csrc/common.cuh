@@ -30,9 +30,9 @@ struct __align__(16) TriRec {
 static_assert(sizeof(TriRec) == 32, "TriRec must be one 32-byte sector");
 
 struct rvb_terrain {
-    int32_t* index;    // [G0,G1,K] contiguous, device
+    int32_t* index;    // [G0,G1,Ks] device; row stride Ks = K rounded up to even (8-byte aligned id pairs), pad ids = 0
     TriRec* recs;      // [T], device
-    int64_t G0, G1, K, T, V;
+    int64_t G0, G1, K, Ks, T, V;
     float res, shift_x, shift_y;
     int sem;
     int device;

@@ -63,7 +63,7 @@ __global__ void normalize_dirs_kernel(const __half* __restrict__ dirs, int64_t R
 // simple cast: warp per ray
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-cast_simple_kernel(const int32_t* __restrict__ index, const TriRec* __restrict__ recs, int G0, int G1, int K,
+cast_simple_kernel(const int32_t* __restrict__ index, const TriRec* __restrict__ recs, int G0, int G1, int K, int Ks,
                    float res, float inv_res, float shift_x, float shift_y, int sem,
                    const __half* __restrict__ src16, const __half* __restrict__ dneg16, int64_t R,
                    int64_t rays_per_dir, __half* __restrict__ dist, int32_t* __restrict__ hit_slot,
@@ -78,7 +78,7 @@ cast_simple_kernel(const int32_t* __restrict__ index, const TriRec* __restrict__
     int cx = cell_coord(s.x, shift_x, res, inv_res, G0 - 1, sem);
     int cy = cell_coord(s.y, shift_y, res, inv_res, G0 - 1, sem);     // both axes clamp to size(0)-1 (camera.py:243)
     cy = min(cy, G1 - 1);
-    const int32_t* row = index + ((int64_t)cx * G1 + cy) * K;
+    const int32_t* row = index + ((int64_t)cx * G1 + cy) * Ks;
     uint32_t best = 0xffffffffu;
     unsigned short best_bits = RVB_H_MISS;
     for (int j = lane; j < K; j += 32) {
@@ -125,7 +125,7 @@ static int launch_cast_simple(const rvb_terrain* t, const __half* src16, const _
                               float* obs, int64_t obs_ld, const int32_t* col_a, const int32_t* col_b, cudaStream_t st) {
     const int64_t blocks = ceil_div(R * 32, 256);
     RVB_REQUIRE(blocks < ((int64_t)1 << 31), "cast: too many rays for one launch");
-    cast_simple_kernel<<<(unsigned)blocks, 256, 0, st>>>(t->index, t->recs, (int)t->G0, (int)t->G1, (int)t->K, t->res,
+    cast_simple_kernel<<<(unsigned)blocks, 256, 0, st>>>(t->index, t->recs, (int)t->G0, (int)t->G1, (int)t->K, (int)t->Ks, t->res,
                                                          1.0f / t->res, t->shift_x, t->shift_y, t->sem, src16, dneg16, R,
                                                          rays_per_dir, (__half*)dist, hit_slot, hit_tri, (__half*)pt, obs,
                                                          obs_ld, col_a, col_b);

@@ -29,14 +29,15 @@ constexpr int RT_MAX = 2048;       // rays per tile (<= 8 per thread)
 constexpr int RPT = RT_MAX / TT;
 constexpr int BIN_CAP = 8192;      // cells in the tile's bounding box that can be histogrammed (u16 counters)
 constexpr int MAX_ITEM_RAYS = 16;  // rays per work item (heavy cells are split)
+constexpr int WQ_CAP = 128;        // per-warp survivor ring (<= 31 pending + 64 new per ray)
 
-constexpr uint32_t KEY_NONE = 0xffffffffu;
+constexpr uint32_t KEY_INIT = 0xC9800000u;     // (11.0, slot 0): the result when every candidate misses
 constexpr uint32_t ORD_MISS = 0xC980u;        // order key of fp16 11.0 (0x4980 | 0x8000)
 
 struct TiledParams {
     const int32_t* index;
     const TriRec* recs;
-    int G0, G1, K;
+    int G0, G1, K, Ks;
     float res, inv_res, shift_x, shift_y;
     int sem;
     const float* pos;
@@ -93,76 +94,47 @@ __device__ __forceinline__ unsigned short key_bits(uint32_t key) {
     return (ord & 0x8000u) ? (unsigned short)(ord & 0x7fffu) : (unsigned short)~ord;
 }
 
-// Exact thresholds.  With q = N/det (exact rational of two fp16 values) and n = fp16(fp32(q)):
-//   n >= fp16(-0.1) = -0x1.998p-4   <=>   q >= -3277/32768   (the rounding boundary below it; the tie goes to the
-//   even mantissa 0x266, i.e. to -0.1 itself, and a quotient of two 11-bit significands cannot fall strictly
-//   between the boundary and its fp32 neighbour, so the intermediate fp32 rounding is harmless).
-// 3277/32768 * |det| is exact in fp32 (12 x 11 bits), so sign(fma(|det|, 3277/32768, N')) decides it exactly.
-//   fp16(n + m) <= fp16(1.1) = 0x3C66   <=>   n + m <= 2253/2048  (boundary above it, tie -> even 0x066).
-// n and m differ from the exact quotients by at most 2^-11 relative each (|n|,|m| <= 1.31 here), i.e. by less than
-// 2^-9 together, so outside a 2^-9 band around 2253/2048 the third test is decided by (N'+M') vs c*|det|.
-#define C_LO 0.100006103515625f          /* 3277 / 32768 */
-#define C_PASS 1.09814453125f            /* 2253/2048 - 2^-9 */
-#define C_FAIL 1.10205078125f            /* 2253/2048 + 2^-9 */
+// ------------------------------------------------------------------------------------------------------------
+// Conservative fp16 pre-filter.  With q_n = N/det, q_m = M/det (exact rationals of fp16 values), n = fp16(q_n),
+// m = fp16(q_m), a candidate passes ray_casting.py:59 only if
+//     n >= fp16(-0.1)        <=>  q_n >= -3277/32768   (rounding boundary below -0x1.998p-4, tie -> even = -0.1)
+//     m >= fp16(-0.1)        <=>  q_m >= -3277/32768
+//     fp16(n + m) <= fp16(1.1) =>  q_n + q_m < 2253/2048 + 2^-9   (n, m are within 2^-11 relative of q_n, q_m, both
+//                                                                   in [-0.11, 1.31] there, so n + m moves by < 2^-9)
+// Multiplying by |det| (N' = N*sgn(det), M' likewise):  N' >= -C_LO*|det|,  M' >= -C_LO*|det|,  N'+M' < C_FAIL*|det|.
+// The filter evaluates these in packed fp16 against thresholds rounded OUTWARDS:
+//     tlo = -RN(|det| * 0x2E68 + 2^-23)   <= -C_LO*|det|      (0x2E68 = 0.10009766 >= C_LO / (1 - 2^-11))
+//     thi =  RN(|det| * 0x3C6B + 2^-23)   >= RN16(x) for every x < C_FAIL*|det|   (0x3C6B = 1.10449 >= C_FAIL*(1+2^-11)^2)
+// (the 2^-23 term covers the absolute rounding error 2^-25 of subnormal results).  NaN thresholds or numerators
+// compare false -- exactly the cases the reference rejects (det = 0/NaN gives n, m = +-inf/NaN; a NaN numerator
+// gives a NaN quotient).  Every candidate the filter lets through is re-evaluated with the literal op sequence
+// (pair_test, divisions included), so the filter only has to be conservative, never exact.
+// ------------------------------------------------------------------------------------------------------------
+#define H_C1 0x2E68u
+#define H_C2 0x3C6Bu
+#define H_TINY 0x0002u
 
-// Per candidate pair, invariant over the rays of an env (the direction is per env): det = (b x c) . d and the
-// exact thresholds derived from it.
 struct Cand2 {
-    uint32_t sgn;          // sign bits of det in both halves
-    __half2 det;           // (b x c) . d                                   (ray_casting.py:41)
-    float da0, da1;        // |det| as fp32
-    float lo0, lo1;        // 3277/32768 * |det| (exact); NaN when the candidate is out of range or det is 0 / NaN
-    float hi0, hi1;        // C_FAIL * |det|
-    uint32_t miss0, miss1; // key of a miss at this slot (KEY_NONE when out of range)
+    uint32_t sgn;      // sign bits of det = (b x c) . d in both halves   (ray_casting.py:41; d is per env)
+    __half2 tlo, thi;  // outward-rounded thresholds; NaN for a slot beyond K
 };
 
-__device__ __forceinline__ Cand2 make_cand2(const Tri2& t, __half2 dx, __half2 dy, __half2 dz, int j0, int K) {
+__device__ __forceinline__ Cand2 make_cand2(const Tri2& t, __half2 dx, __half2 dy, __half2 dz, bool v0, bool v1) {
     Cand2 c;
-    c.det = add2(add2(mul2(t.nx, dx), mul2(t.ny, dy)), mul2(t.nz, dz));
-    c.sgn = h2u(c.det) & 0x80008000u;
-    const __half2 da = u2h(h2u(c.det) ^ c.sgn);
-    c.da0 = __low2float(da);
-    c.da1 = __high2float(da);
-    const bool v0 = j0 < K, v1 = j0 + 1 < K;
-    const float nan = __int_as_float(0x7fc00000);
-    c.lo0 = (v0 && c.da0 > 0.f) ? __fmul_rn(c.da0, C_LO) : nan;     // det == 0 never passes (n, m = +-inf / NaN)
-    c.lo1 = (v1 && c.da1 > 0.f) ? __fmul_rn(c.da1, C_LO) : nan;
-    c.hi0 = __fmul_rn(c.da0, C_FAIL);
-    c.hi1 = __fmul_rn(c.da1, C_FAIL);
-    c.miss0 = v0 ? ((ORD_MISS << 16) | ((uint32_t)j0 << 1)) : KEY_NONE;
-    c.miss1 = v1 ? ((ORD_MISS << 16) | ((uint32_t)(j0 + 1) << 1)) : KEY_NONE;
+    const __half2 det = add2(add2(mul2(t.nx, dx), mul2(t.ny, dy)), mul2(t.nz, dz));
+    c.sgn = h2u(det) & 0x80008000u;
+    const __half2 da = u2h(h2u(det) & 0x7fff7fffu);
+    const __half2 tiny = u2h(H_TINY | (H_TINY << 16));
+    c.tlo = __hneg2(__hfma2(da, u2h(H_C1 | (H_C1 << 16)), tiny));
+    c.thi = __hfma2(da, u2h(H_C2 | (H_C2 << 16)), tiny);
+    if (!v0) c.tlo = u2h((h2u(c.tlo) & 0xffff0000u) | 0x7fffu);
+    if (!v1) c.tlo = u2h((h2u(c.tlo) & 0x0000ffffu) | 0x7fff0000u);
     return c;
 }
 
-// "may pass" from the oriented numerators N' = N*sgn(det), M' = M*sgn(det):  N' + lo >= 0 and M' + lo >= 0 decide
-// n >= -eps and m >= -eps exactly (lo is exact and an fp32 sum never rounds across zero); (N' + M') - hi < 0 rules
-// out everything that certainly fails n + m <= 1 + eps.  NaNs (lo of a dead candidate, overflowed numerators) make
-// the first two false or the last one true, i.e. dead candidates drop out and odd ones are re-checked.
-__device__ __forceinline__ bool may_pass(float Nf, float Mf, float lo, float hi) {
-    const float rn = __fadd_rn(Nf, lo), rm = __fadd_rn(Mf, lo);
-    const float rf = __fsub_rn(__fadd_rn(Nf, Mf), hi);
-    return (rn >= 0.f) && (rm >= 0.f) && !(rf >= 0.f);
-}
-
-// k for a candidate that may pass: certain hits take one IEEE division, the 2^-9 band around the n + m threshold
-// (and anything non-finite) replays the literal op sequence of ray_casting.py.
-__device__ __forceinline__ uint32_t resolve(float Nf, float Mf, float da, __half det, __half Kn, H3 s, H3 d, H3 a, H3 b,
-                                           H3 c, H3 n, uint32_t slot) {
-    const float rp = __fmaf_rn(da, -C_PASS, __fadd_rn(Nf, Mf));
-    __half k;
-    if (rp <= 0.f) {
-        const unsigned short db = h_bits(det);
-        k = (db == RVB_H_LO || db == RVB_H_HI) ? h_from_bits(RVB_H_MISS) : h_div(Kn, det);     // :46,51,54-56
-    } else {
-        k = pair_test(s, d, a, b, c, n);
-    }
-    return make_key(h_bits(k), slot);
-}
-
-// Both candidates of a lane against one ray.  s* hold the ray's source duplicated in both halves, d* the env's
-// -normalized direction likewise.  Returns the smaller of the two candidates' keys.
-__device__ __forceinline__ uint32_t pair2_keys(__half2 sx, __half2 sy, __half2 sz, __half2 dx, __half2 dy, __half2 dz,
-                                               const Tri2& t, const Cand2& c, uint32_t slot0) {
+// 0xffff in the half of every candidate that may pass
+__device__ __forceinline__ uint32_t prefilter2(__half2 sx, __half2 sy, __half2 sz, __half2 dx, __half2 dy, __half2 dz,
+                                               const Tri2& t, const Cand2& c) {
     const __half2 gx = sub2(sx, t.ax), gy = sub2(sy, t.ay), gz = sub2(sz, t.az);                 // ray_casting.py:37
     const __half2 ux = sub2(mul2(gy, t.cz), mul2(gz, t.cy));                                     // g x c  (:44)
     const __half2 uy = sub2(mul2(gz, t.cx), mul2(gx, t.cz));
@@ -172,27 +144,17 @@ __device__ __forceinline__ uint32_t pair2_keys(__half2 sx, __half2 sy, __half2 s
     const __half2 vy = sub2(mul2(t.bz, gx), mul2(t.bx, gz));
     const __half2 vz = sub2(mul2(t.bx, gy), mul2(t.by, gx));
     const __half2 Mn = add2(add2(mul2(vx, dx), mul2(vy, dy)), mul2(vz, dz));                     // :50 numerator
-    const __half2 Ns = u2h(h2u(Nn) ^ c.sgn), Ms = u2h(h2u(Mn) ^ c.sgn);                          // q = (N*sgn)/|det|
-    const float N0 = __low2float(Ns), M0 = __low2float(Ms), N1 = __high2float(Ns), M1 = __high2float(Ms);
-    const bool p0 = may_pass(N0, M0, c.lo0, c.hi0);
-    const bool p1 = may_pass(N1, M1, c.lo1, c.hi1);
-    uint32_t k0 = c.miss0, k1 = c.miss1;
-    if (p0 | p1) {
-        // about 1 candidate in 140 gets here: k = ((b x c) . g) / det          (:54-56)
-        const __half2 Kn = add2(add2(mul2(t.nx, gx), mul2(t.ny, gy)), mul2(t.nz, gz));
-        const H3 s = {__low2half(sx), __low2half(sy), __low2half(sz)}, d = {__low2half(dx), __low2half(dy), __low2half(dz)};
-        if (p0)
-            k0 = resolve(N0, M0, c.da0, __low2half(c.det), __low2half(Kn), s, d,
-                         {__low2half(t.ax), __low2half(t.ay), __low2half(t.az)}, {__low2half(t.bx), __low2half(t.by), __low2half(t.bz)},
-                         {__low2half(t.cx), __low2half(t.cy), __low2half(t.cz)}, {__low2half(t.nx), __low2half(t.ny), __low2half(t.nz)},
-                         slot0);
-        if (p1)
-            k1 = resolve(N1, M1, c.da1, __high2half(c.det), __high2half(Kn), s, d,
-                         {__high2half(t.ax), __high2half(t.ay), __high2half(t.az)}, {__high2half(t.bx), __high2half(t.by), __high2half(t.bz)},
-                         {__high2half(t.cx), __high2half(t.cy), __high2half(t.cz)}, {__high2half(t.nx), __high2half(t.ny), __high2half(t.nz)},
-                         slot0 + 1);
-    }
-    return min(k0, k1);
+    const __half2 Ns = u2h(h2u(Nn) ^ c.sgn), Ms = u2h(h2u(Mn) ^ c.sgn);
+    return __hge2_mask(Ns, c.tlo) & __hge2_mask(Ms, c.tlo) & __hle2_mask(add2(Ns, Ms), c.thi);
+}
+
+__device__ __forceinline__ void unpack_rec(const TriRec* rec, H3& a, H3& b, H3& c, H3& n) {
+    const uint4 q0 = __ldg(reinterpret_cast<const uint4*>(rec));
+    const uint2 q1 = __ldg(reinterpret_cast<const uint2*>(rec) + 2);
+    a = {h_from_bits(q0.x & 0xffff), h_from_bits(q0.x >> 16), h_from_bits(q0.y & 0xffff)};
+    b = {h_from_bits(q0.y >> 16), h_from_bits(q0.z & 0xffff), h_from_bits(q0.z >> 16)};
+    c = {h_from_bits(q0.w & 0xffff), h_from_bits(q0.w >> 16), h_from_bits(q1.x & 0xffff)};
+    n = {h_from_bits(q1.x >> 16), h_from_bits(q1.y & 0xffff), h_from_bits(q1.y >> 16)};
 }
 
 struct Smem {
@@ -200,7 +162,38 @@ struct Smem {
     uint32_t* res;       // [RT]  best key per local ray id
     uint2* items;        // [RT]  (cell, start | count << 16)
     uint32_t* bins;      // [BIN_CAP / 2]  u16 counters, then exclusive offsets
+    uint2* wq;           // [NW][WQ_CAP]  per-warp ring of candidates that survived the pre-filter: (pos << 16 | slot, triangle)
+    uint32_t* far;       // [RT / 32]  rays holding a hit beyond the 11.0 miss sentinel (resolved literally in the epilogue)
 };
+
+// Literal evaluation of up to 32 queued (ray, candidate) pairs, one per lane (ray_casting.py:34-59).
+__device__ __forceinline__ void drain32(const Smem& sm, const uint2* wq, uint32_t head, uint32_t n, int lane, const TriRec* recs,
+                                        H3 d) {
+    if ((uint32_t)lane < n) {
+        const uint2 e = wq[(head + lane) & (WQ_CAP - 1)];
+        const uint4 rs = sm.ray_s[e.x >> 16];
+        H3 a, b, c, nn;
+        unpack_rec(recs + e.y, a, b, c, nn);
+        const H3 s = {h_from_bits(rs.x & 0xffff), h_from_bits(rs.y & 0xffff), h_from_bits(rs.z & 0xffff)};
+        const __half k = pair_test(s, d, a, b, c, nn);
+        const uint32_t key = make_key(h_bits(k), e.x & 0xffffu);
+        if ((key >> 16) > ORD_MISS) atomicOr(&sm.far[rs.w >> 5], 1u << (rs.w & 31));      // k > 11: see epilogue
+        else atomicMin(&sm.res[rs.w], key);
+    }
+}
+
+// A ray that holds a hit with k > 11.0 and no nearer one: the first slot whose value is <= 11.0 (a miss, or a hit at
+// exactly 11.0) wins torch.min, and that slot is not necessarily 0.  Vanishingly rare (the rover would have to hover
+// 11 m above the mesh), so one thread simply walks the K candidates with the literal op sequence.
+__device__ __noinline__ uint32_t literal_ray(const int32_t* row, int K, const TriRec* recs, H3 s, H3 d) {
+    uint32_t best = 0xffffffffu;
+    for (int j = 0; j < K; ++j) {
+        H3 a, b, c, nn;
+        unpack_rec(recs + __ldg(row + j), a, b, c, nn);
+        best = min(best, make_key(h_bits(pair_test(s, d, a, b, c, nn)), (uint32_t)j));
+    }
+    return best;
+}
 
 __global__ void __launch_bounds__(TT, 3) hm_tiled_kernel(const TiledParams q) {
     extern __shared__ uint4 smem_raw[];
@@ -220,9 +213,12 @@ __global__ void __launch_bounds__(TT, 3) hm_tiled_kernel(const TiledParams q) {
     sm.res = reinterpret_cast<uint32_t*>(sm.ray_s + RT);
     sm.items = reinterpret_cast<uint2*>(sm.res + ((RT + 3) & ~3));
     sm.bins = reinterpret_cast<uint32_t*>(sm.items + ((RT + 1) & ~1));
+    sm.wq = reinterpret_cast<uint2*>(sm.bins + BIN_CAP / 2);
+    sm.far = reinterpret_cast<uint32_t*>(sm.wq + NW * WQ_CAP);
 
     // ---- phase 0: clear histogram, per-env constants
     for (int i = tid; i < BIN_CAP / 8; i += TT) reinterpret_cast<uint4*>(sm.bins)[i] = make_uint4(0, 0, 0, 0);
+    for (int i = tid; i < (RT + 31) / 32; i += TT) sm.far[i] = 0u;
     if (tid == 0) {
         s_box[0] = s_box[1] = 0x7fffffff;
         s_box[2] = s_box[3] = -1;
@@ -340,7 +336,7 @@ __global__ void __launch_bounds__(TT, 3) hm_tiled_kernel(const TiledParams q) {
                 const uint32_t posn = ((sm.bins[bin >> 1] >> ((bin & 1) * 16)) & 0xffffu) + r_rank[i];
                 sm.ray_s[posn] = make_uint4(__byte_perm(r_sxy[i], 0, 0x1010), __byte_perm(r_sxy[i], 0, 0x3232),
                                             __byte_perm(r_sz[i], 0, 0x1010), (uint32_t)p);
-                sm.res[p] = KEY_NONE;
+                sm.res[p] = KEY_INIT;
             }
         }
     } else {
@@ -353,7 +349,7 @@ __global__ void __launch_bounds__(TT, 3) hm_tiled_kernel(const TiledParams q) {
                 sm.items[p] = make_uint2(cell, (uint32_t)p | (1u << 16));
                 sm.ray_s[p] = make_uint4(__byte_perm(r_sxy[i], 0, 0x1010), __byte_perm(r_sxy[i], 0, 0x3232),
                                          __byte_perm(r_sz[i], 0, 0x1010), (uint32_t)p);
-                sm.res[p] = KEY_NONE;
+                sm.res[p] = KEY_INIT;
             }
         }
         nitems = np;
@@ -362,53 +358,78 @@ __global__ void __launch_bounds__(TT, 3) hm_tiled_kernel(const TiledParams q) {
 
     // ---- phase 3: warps pull items; lanes own candidate pairs
     const int K = q.K;
-    const bool k_even = (K & 1) == 0;
+    const H3 dlit = {__low2half(dx2), __low2half(dy2), __low2half(dz2)};
+    uint2* wq = sm.wq + warp * WQ_CAP;
+    uint32_t q_head = 0, q_tail = 0;          // warp-uniform
+    const uint32_t lt_mask = (1u << lane) - 1u;
     int item = warp;
     while (item < nitems) {
         int next = 0;
         if (lane == 0) next = atomicAdd(&s_next, 1);
         next = __shfl_sync(0xffffffffu, next, 0);
         const uint2 it = sm.items[item];
-        const int32_t* row = q.index + (int64_t)it.x * K;
+        // this lane's id pairs of the cell's candidate row (rows are padded to an even length)
+        const int2* rowl = reinterpret_cast<const int2*>(q.index + (int64_t)it.x * q.Ks) + lane;
         if (next < nitems && lane * 32 < K) {
             // pull the next item's candidate list towards L2 while this one is being processed
-            const int32_t* nrow = q.index + (int64_t)sm.items[next].x * K + lane * 32;
+            const int32_t* nrow = q.index + (int64_t)sm.items[next].x * q.Ks + lane * 32;
             asm volatile("prefetch.global.L2 [%0];" ::"l"(nrow));
         }
         const int start = it.y & 0xffff, cnt = it.y >> 16;
+        int2 ids = (2 * lane < K) ? __ldg(rowl) : make_int2(0, 0);
         for (int c0 = 0; c0 < K; c0 += 64) {
             const int j0 = c0 + 2 * lane;
-            int id0 = 0, id1 = 0;
-            if (k_even) {
-                if (j0 < K) {
-                    const int2 v = __ldg(reinterpret_cast<const int2*>(row + j0));
-                    id0 = v.x; id1 = v.y;
-                }
-            } else {
-                if (j0 < K) id0 = __ldg(row + j0);
-                if (j0 + 1 < K) id1 = __ldg(row + j0 + 1);
-            }
-            const uint4* r0 = reinterpret_cast<const uint4*>(q.recs + id0);
-            const uint4* r1 = reinterpret_cast<const uint4*>(q.recs + id1);
+            const int2 ids_next = (j0 + 64 < K) ? __ldg(rowl + (c0 >> 1) + 32) : make_int2(0, 0);   // in flight during the ray loop
+            const uint4* r0 = reinterpret_cast<const uint4*>(q.recs + ids.x);
+            const uint4* r1 = reinterpret_cast<const uint4*>(q.recs + ids.y);
             const uint4 a0 = __ldg(r0), b0 = __ldg(r1);
             const uint2 a1 = __ldg(reinterpret_cast<const uint2*>(r0 + 1)), b1 = __ldg(reinterpret_cast<const uint2*>(r1 + 1));
             const Tri2 t = pack_tri2(a0, a1, b0, b1);
-            const Cand2 cd = make_cand2(t, dx2, dy2, dz2, j0, K);
+            const Cand2 cd = make_cand2(t, dx2, dy2, dz2, j0 < K, j0 + 1 < K);
             for (int r = 0; r < cnt; ++r) {
-                const uint4 rs = sm.ray_s[start + r];
-                uint32_t key = pair2_keys(u2h(rs.x), u2h(rs.y), u2h(rs.z), dx2, dy2, dz2, t, cd, (uint32_t)j0);
-                key = __reduce_min_sync(0xffffffffu, key);
-                if (lane == 0) atomicMin(&sm.res[rs.w], key);
+                const int pos = start + r;
+                const uint4 rs = sm.ray_s[pos];
+                const uint32_t f = prefilter2(u2h(rs.x), u2h(rs.y), u2h(rs.z), dx2, dy2, dz2, t, cd);
+                const uint32_t b0m = __ballot_sync(0xffffffffu, (f & 0xffffu) != 0u);
+                const uint32_t b1m = __ballot_sync(0xffffffffu, (f >> 16) != 0u);
+                if (b0m | b1m) {
+                    // about 1 candidate in 100 survives: queue it for a dense literal evaluation
+                    if (f & 0xffffu) wq[(q_tail + __popc(b0m & lt_mask)) & (WQ_CAP - 1)] = make_uint2(((uint32_t)pos << 16) | (uint32_t)j0, (uint32_t)ids.x);
+                    q_tail += __popc(b0m);
+                    if (f >> 16) wq[(q_tail + __popc(b1m & lt_mask)) & (WQ_CAP - 1)] = make_uint2(((uint32_t)pos << 16) | (uint32_t)(j0 + 1), (uint32_t)ids.y);
+                    q_tail += __popc(b1m);
+                    if (q_tail - q_head >= 32u) {
+                        __syncwarp();
+                        do {
+                            drain32(sm, wq, q_head, 32u, lane, q.recs, dlit);
+                            q_head += 32u;
+                        } while (q_tail - q_head >= 32u);
+                        __syncwarp();
+                    }
+                }
             }
+            ids = ids_next;
         }
         item = next;
     }
+    __syncwarp();
+    if (q_tail != q_head) drain32(sm, wq, q_head, q_tail - q_head, lane, q.recs, dlit);
     __syncthreads();
 
     // ---- phase 4: epilogue in ray order
     const bool want_geo = q.hit_tri || q.pt || q.sources;
     for (int p = tid; p < np; p += TT) {
-        const uint32_t key = sm.res[p];
+        uint32_t key = sm.res[p];
+        const bool far_hit = (sm.far[p >> 5] >> (p & 31)) & 1u;
+        if (far_hit && (key >> 16) == ORD_MISS) {
+            const double* pp = q.pattern + (int64_t)(p0 + p) * 3;
+            double xo, yo, zo;
+            body_transform<double>(pp[0], pp[1], pp[2], tr, tx, ty, tz, xo, yo, zo);
+            const H3 s = {h_from_double(xo), h_from_double(yo), h_from_double(zo)};
+            const int cx = cell_coord(s.x, q.shift_x, q.res, q.inv_res, q.G0 - 1, q.sem);
+            const int cy = min(cell_coord(s.y, q.shift_y, q.res, q.inv_res, q.G0 - 1, q.sem), q.G1 - 1);
+            key = literal_ray(q.index + ((int64_t)cx * q.G1 + cy) * q.Ks, K, q.recs, s, dlit);
+        }
         const unsigned short kb = key_bits(key);
         const int slot = (int)((key >> 1) & 0x7fffu);
         const int64_t o = n * q.P + p0 + p;
@@ -423,7 +444,7 @@ __global__ void __launch_bounds__(TT, 3) hm_tiled_kernel(const TiledParams q) {
             if (q.hit_tri) {
                 const int cx = cell_coord(hx, q.shift_x, q.res, q.inv_res, q.G0 - 1, q.sem);
                 const int cy = min(cell_coord(hy, q.shift_y, q.res, q.inv_res, q.G0 - 1, q.sem), q.G1 - 1);
-                q.hit_tri[o] = __ldg(q.index + ((int64_t)cx * q.G1 + cy) * K + slot);
+                q.hit_tri[o] = __ldg(q.index + ((int64_t)cx * q.G1 + cy) * q.Ks + slot);
             }
             if (q.pt) {
                 const __half k = h_from_bits(kb);
@@ -442,7 +463,8 @@ __global__ void __launch_bounds__(TT, 3) hm_tiled_kernel(const TiledParams q) {
 }
 
 size_t tiled_smem_bytes(int RT) {
-    return (size_t)RT * 16 + (size_t)((RT + 3) & ~3) * 4 + (size_t)((RT + 1) & ~1) * 8 + (size_t)BIN_CAP * 2;
+    return (size_t)RT * 16 + (size_t)((RT + 3) & ~3) * 4 + (size_t)((RT + 1) & ~1) * 8 + (size_t)BIN_CAP * 2 +
+           (size_t)NW * WQ_CAP * 8 + (size_t)((RT + 31) / 32) * 4;
 }
 
 }  // namespace
@@ -456,7 +478,7 @@ int launch_heightmap_tiled(const rvb_terrain* t, const float* pos, const float* 
     RVB_REQUIRE(t->G0 * t->G1 < ((int64_t)1 << 32), "heightmap ray-cast: more than 2^32 cells");
     TiledParams q;
     q.index = t->index; q.recs = t->recs;
-    q.G0 = (int)t->G0; q.G1 = (int)t->G1; q.K = (int)t->K;
+    q.G0 = (int)t->G0; q.G1 = (int)t->G1; q.K = (int)t->K; q.Ks = (int)t->Ks;
     q.res = t->res; q.inv_res = 1.0f / t->res; q.shift_x = t->shift_x; q.shift_y = t->shift_y; q.sem = t->sem;
     q.pos = pos; q.euler = euler; q.trig = trig; q.pattern = pattern;
     q.P = (int)P;

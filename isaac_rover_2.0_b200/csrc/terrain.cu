@@ -17,16 +17,19 @@ extern "C" int rvb_abi_version(void) { return RVB_ABI_VERSION; }
 // [G0,G1,K] strided view -> contiguous.  One thread per output element; consecutive threads walk K, so
 // the store is coalesced; the load is coalesced along whichever source stride is 1 only for K-major
 // inputs -- this runs once per terrain, bandwidth is irrelevant.
-__global__ void repack_index_kernel(const int32_t* __restrict__ src, int64_t G0, int64_t G1, int64_t K, int64_t s0,
-                                    int64_t s1, int64_t sk, int32_t T, int32_t* __restrict__ dst, int* bad) {
-    int64_t total = G0 * G1 * K;
+__global__ void repack_index_kernel(const int32_t* __restrict__ src, int64_t G0, int64_t G1, int64_t K, int64_t Ks,
+                                    int64_t s0, int64_t s1, int64_t sk, int32_t T, int32_t* __restrict__ dst, int* bad) {
+    int64_t total = G0 * G1 * Ks;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        int64_t k = i % K, c = i / K;
+        int64_t k = i % Ks, c = i / Ks;
         int64_t g1 = c % G1, g0 = c / G1;
-        int32_t v = src[g0 * s0 + g1 * s1 + k * sk];
-        if (v < 0 || v >= T) {
-            atomicExch(bad, 1);
-            v = 0;
+        int32_t v = 0;                                  // pad slot: a valid triangle id that is never evaluated
+        if (k < K) {
+            v = src[g0 * s0 + g1 * s1 + k * sk];
+            if (v < 0 || v >= T) {
+                atomicExch(bad, 1);
+                v = 0;
+            }
         }
         dst[i] = v;
     }
@@ -71,17 +74,17 @@ extern "C" int rvb_terrain_create(rvb_terrain** out, const int32_t* map_indices,
     rvb_terrain* t = new (std::nothrow) rvb_terrain();
     if (!t) return rvb_set_error(RVB_ERR_NOMEM, "rvb_terrain_create", "host allocation failed");
     memset(t, 0, sizeof(*t));
-    t->G0 = G0; t->G1 = G1; t->K = K; t->T = T; t->V = V;
+    t->G0 = G0; t->G1 = G1; t->K = K; t->Ks = (K + 1) & ~(int64_t)1; t->T = T; t->V = V;
     t->res = res; t->shift_x = shift_x; t->shift_y = shift_y; t->sem = sem;
     int* bad = nullptr;
     int hbad = 0;
     cudaError_t e = cudaGetDevice(&t->device);
-    if (e == cudaSuccess) e = cudaMalloc(&t->index, sizeof(int32_t) * G0 * G1 * K);
+    if (e == cudaSuccess) e = cudaMalloc(&t->index, sizeof(int32_t) * G0 * G1 * t->Ks);
     if (e == cudaSuccess) e = cudaMalloc(&t->recs, sizeof(TriRec) * T);
     if (e == cudaSuccess) e = cudaMalloc(&bad, sizeof(int));
     if (e == cudaSuccess) e = cudaMemsetAsync(bad, 0, sizeof(int), st);
     if (e == cudaSuccess) {
-        repack_index_kernel<<<148 * 8, 256, 0, st>>>(map_indices, G0, G1, K, stride_g0, stride_g1, stride_k, (int32_t)T,
+        repack_index_kernel<<<148 * 8, 256, 0, st>>>(map_indices, G0, G1, K, t->Ks, stride_g0, stride_g1, stride_k, (int32_t)T,
                                                      t->index, bad);
         build_records_kernel<<<(unsigned)ceil_div(T, 256), 256, 0, st>>>(triangles, T, (const __half*)vertices, V,
                                                                          t->recs, bad);
@@ -113,5 +116,5 @@ extern "C" int rvb_terrain_destroy(rvb_terrain* t) {
 
 extern "C" int64_t rvb_terrain_bytes(const rvb_terrain* t) {
     if (!t) return 0;
-    return (int64_t)sizeof(int32_t) * t->G0 * t->G1 * t->K + (int64_t)sizeof(TriRec) * t->T;
+    return (int64_t)sizeof(int32_t) * t->G0 * t->G1 * t->Ks + (int64_t)sizeof(TriRec) * t->T;
 }

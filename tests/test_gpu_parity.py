@@ -381,3 +381,66 @@ def test_knn_index_builder_matches_bruteforce(R, world20):
     ref = R.synth.knn_index_bruteforce(v, t, 200, 0.1, 128)
     got = R.build_knn_index(t, v, 200, 0.1, 128)
     assert torch.equal(got.cpu(), ref)
+
+
+@pytest.mark.parametrize("K", [1, 2, 37, 64, 65, 129])
+def test_candidate_count_variants(R, O, world20, K):
+    """Row lengths that are odd / straddle the 64-candidate chunks of the production kernel: production kernel ==
+    per-pair cross-check kernel == oracle, bit for bit (distances, hit slots, hit triangles)."""
+    w = world20
+    idx = R.build_knn_index(w.triangles, w.vertices, w.G, w.res, K).cpu()
+    N = 48
+    st = R.synth.make_env_state(w, N, seed=300 + K)
+    eul = O.quat_to_euler(st["quat"])
+    pat, _, _ = O.heightmap_pattern()
+    ref = O.get_depths(st["pos"], eul, pat, idx, w.triangles, w.vertices, torch.tensor([0, 0, 0.0]))
+    cam = R.Camera("cuda:0", torch.tensor([0, 0, 0.0]), assets=(idx, w.triangles, w.vertices), sem=R.SEM_TORCH_CPU)
+    for variant in (0, 1):
+        cam.variant = variant
+        dist, pt, src = cam.get_depths(st["pos"].cuda(), eul.cuda(), trig=_trig(eul).cuda(), want_hits=True)
+        assert_bits_equal(dist, ref["dist"], "dist K=%d v%d" % (K, variant))
+        assert_bits_equal(cam.last_hit_slot, ref["slot"].to(torch.int32), "slot K=%d v%d" % (K, variant))
+        assert_bits_equal(cam.last_hit_tri, ref["tri"].to(torch.int32), "tri K=%d v%d" % (K, variant))
+        assert_bits_equal(pt, ref["pt"], "pt K=%d v%d" % (K, variant))
+
+
+def test_far_hits_and_spread_rays(R, O, world20):
+    """(a) rays whose only hits lie beyond the 11.0 miss sentinel (torch.min then returns the first slot holding
+    <= 11.0, not necessarily slot 0); (b) a pattern spread over more cells than the kernel's cell histogram holds
+    (falls back to one work item per ray); (c) every ray of an env in one cell (heavy cell split into items)."""
+    w = world20
+    cam = R.Camera("cuda:0", torch.tensor([0, 0, 0.0]), assets=(w.map_indices, w.triangles, w.vertices), sem=R.SEM_TORCH_CPU)
+    pat, _, _ = O.heightmap_pattern()
+    g = torch.Generator().manual_seed(5)
+    pos = torch.cat((torch.rand(24, 2, generator=g) * 16 + 2, torch.rand(24, 1, generator=g) * 4 + 12.0), 1)     # 12 .. 16 m up, level:
+    eul = torch.cat((torch.zeros(24, 2), torch.rand(24, 1, generator=g) * 6.28 - 3.14), 1)     # rays hit their own cell's nearest triangles
+    pos[12:, 2] -= 2.2                                                                           # some hits on either side of 11.0
+    pos = torch.cat((pos, torch.tensor([[-40.0, -40.0, 1.0], [60.0, 8.0, 1.0]])))       # all rays clamp into one edge cell / one edge row
+    eul = torch.cat((eul, torch.zeros(2, 3)))
+    shift = torch.tensor([0, 0, 0.0])
+    ref = O.get_depths(pos, eul, pat, w.map_indices, w.triangles, w.vertices, shift)
+    far = (ref["dist"] == 11) & (ref["slot"] != 0)
+    for variant in (0, 1):
+        cam.variant = variant
+        d, pt, s = cam.get_depths(pos.cuda(), eul.cuda(), trig=_trig(eul).cuda(), want_hits=True)
+        assert_bits_equal(d, ref["dist"], "far dist v%d" % variant)
+        assert_bits_equal(cam.last_hit_slot, ref["slot"].to(torch.int32), "far slot v%d" % variant)
+    assert far.any(), "the case must exercise a first-miss slot other than 0"
+    # (b) a 40 m wide pattern: 4096 points on a 64 x 64 grid with 0.62 m spacing
+    lin = torch.arange(64, dtype=torch.float64) * 0.62 - 19.5
+    wide = torch.stack((lin[:, None].expand(64, 64).reshape(-1), lin[None, :].expand(64, 64).reshape(-1),
+                        torch.full((4096,), -0.2688, dtype=torch.float64)), 1)
+    pos2 = torch.tensor([[10.0, 10.0, 1.0], [3.0, 15.0, 1.2]])
+    eul2 = torch.tensor([[0.05, -0.03, 0.7], [0.0, 0.1, -2.0]])
+    ref2 = O.get_depths(pos2, eul2, wide, w.map_indices, w.triangles, w.vertices, shift)
+    lib = R._lib.load()
+    dist = torch.empty((2, 4096), dtype=torch.float16, device="cuda")
+    slot = torch.empty((2, 4096), dtype=torch.int32, device="cuda")
+    d_pos, d_eul, d_trig, d_pat = pos2.cuda(), eul2.cuda(), _trig(eul2).cuda(), wide.cuda()      # keep the buffers alive
+    for variant in (0, 1):
+        R._lib.check(lib.rvb_heightmap_raycast(cam.layer.handle, R._lib.ptr(d_pos), R._lib.ptr(d_eul), R._lib.ptr(d_trig),
+                                               R._lib.ptr(d_pat), 4096, 2, R._lib.ptr(dist), R._lib.ptr(slot), None, None, None,
+                                               None, 0, None, None, variant, None))
+        torch.cuda.synchronize()
+        assert_bits_equal(dist, ref2["dist"], "wide pattern dist v%d" % variant)
+        assert_bits_equal(slot, ref2["slot"].to(torch.int32), "wide pattern slot v%d" % variant)
