@@ -36,7 +36,18 @@ struct rvb_terrain {
     float res, shift_x, shift_y;
     int sem;
     int device;
+    // Block lists (built when K <= 255): the grid is cut into RVB_BLK x RVB_BLK cell blocks; a block's list is the
+    // union of its cells' K-lists, one entry per distinct triangle (sorted by id, padded to an even count): its id
+    // and, for each of the block's cells, the slot the triangle holds in that cell's list (0xFF = not in that list).
+    // Rays of neighbouring cells then share one fetch of every candidate record while each ray still sees exactly
+    // its own cell's list and slots.
+    int32_t nBx, nBy;
+    uint32_t* blk_off;   // [nBx*nBy + 1] entry offsets (even)
+    int32_t* blk_ids;    // [n_ent]  triangle ids (pad entries: 0)
+    uint4* blk_slots;    // [n_ent]  byte s = slot in sub-cell s (s = (cx % BLK) * BLK + cy % BLK), other bytes 0xFF
+    int64_t n_ent;
 };
+#define RVB_BLK 3
 
 // ---------------------------------------------------------------- fp16 arithmetic with torch's roundings
 // ATen computes every Half element-wise op as fp32 op + one rounding; for + - * that equals the

@@ -9,7 +9,7 @@
 int launch_heightmap_tiled(const rvb_terrain* t, const float* pos, const float* euler, const float* trig,
                            const double* pattern, int64_t P, int64_t N, uint16_t* dist, int32_t* hit_slot,
                            int32_t* hit_tri, uint16_t* pt, uint16_t* sources, float* obs, int64_t obs_ld,
-                           const int32_t* col_a, const int32_t* col_b, cudaStream_t st);
+                           const int32_t* col_a, const int32_t* col_b, bool per_cell, cudaStream_t st);
 
 // ------------------------------------------------------------------------------------------------
 // setup: sources (fp64 transform -> fp16), per-env direction, per-ray cell
@@ -141,12 +141,12 @@ extern "C" int rvb_heightmap_raycast(const rvb_terrain* t, const float* pos, con
     if (N == 0) return RVB_OK;
     RVB_REQUIRE(t && pos && euler && pattern && dist, "rvb_heightmap_raycast: null pointer");
     RVB_REQUIRE(!obs || (col_a && col_b && obs_ld > 0), "rvb_heightmap_raycast: obs needs col_a, col_b, obs_ld");
-    RVB_REQUIRE(variant == 0 || variant == 1, "rvb_heightmap_raycast: variant must be 0 or 1");
+    RVB_REQUIRE(variant >= 0 && variant <= 2, "rvb_heightmap_raycast: variant must be 0, 1 or 2");
     if (N == 0) return RVB_OK;
     cudaStream_t st = as_stream(stream);
-    if (variant == 0)
+    if (variant != 1)
         return launch_heightmap_tiled(t, pos, euler, trig, pattern, P, N, dist, hit_slot, hit_tri, pt, sources, obs,
-                                      obs_ld, col_a, col_b, st);
+                                      obs_ld, col_a, col_b, variant == 2, st);
     RVB_REQUIRE(N <= 65535, "rvb_heightmap_raycast: variant 1 handles at most 65535 envs per call");
     __half* src16 = (__half*)sources;
     __half* scratch = nullptr;

@@ -3,9 +3,11 @@
 // One CTA per (env, ray tile).  Phases, all inside the CTA:
 //   1. every thread transforms its rays (fp64 body transform -> fp16 sources, camera.py:165-212) and looks up
 //      their grid cell (camera.py:233-264);
-//   2. the tile's rays are grouped by cell with a counting sort over the tile's cell bounding box (shared-memory
-//      histogram + scan) -- the dense part of the pattern puts ~4 rays in a cell, so a cell's K-candidate list and
-//      its K triangle records are fetched once per cell instead of once per ray;
+//   2. the tile's rays are grouped by 3x3-cell BLOCK (terrain.cu builds, per block, the union of its cells' K-lists
+//      with the slot each triangle holds in each cell) with a counting sort over the tile's bounding box
+//      (shared-memory histogram + scan): ~10 rays share one fetch of every candidate record, while each ray is
+//      still answered from exactly its own cell's list (a survivor that is not in the ray's cell is dropped, its
+//      slot in that cell's list is the tie-break key).  Layers with K > 255 use the same kernel with 1x1 blocks;
 //   3. warps pull (cell, ray-range) items from a shared counter.  A lane owns TWO candidates of the cell's list:
 //      it gathers their pre-resolved 32-byte records (L2-resident table), packs them into half2 registers and
 //      then loops over the rays of the item.  All fp16 arithmetic of ray_casting.py:34-56 runs as packed
@@ -28,7 +30,7 @@ constexpr int NW = TT / 32;
 constexpr int RT_MAX = 2048;       // rays per tile (<= 8 per thread)
 constexpr int RPT = RT_MAX / TT;
 constexpr int BIN_CAP = 8192;      // cells in the tile's bounding box that can be histogrammed (u16 counters)
-constexpr int MAX_ITEM_RAYS = 16;  // rays per work item (heavy cells are split)
+constexpr int MAX_ITEM_RAYS = 32;  // rays per work item (heavier cells / blocks are split)
 constexpr int WQ_CAP = 128;        // per-warp survivor ring (<= 31 pending + 64 new per ray)
 
 constexpr uint32_t KEY_INIT = 0xC9800000u;     // (11.0, slot 0): the result when every candidate misses
@@ -37,6 +39,10 @@ constexpr uint32_t ORD_MISS = 0xC980u;        // order key of fp16 11.0 (0x4980 
 struct TiledParams {
     const int32_t* index;
     const TriRec* recs;
+    const uint32_t* blk_off;
+    const int32_t* blk_ids;
+    const uint4* blk_slots;
+    int nBy;
     int G0, G1, K, Ks;
     float res, inv_res, shift_x, shift_y;
     int sem;
@@ -177,8 +183,9 @@ __device__ __forceinline__ void drain32(const Smem& sm, const uint2* wq, uint32_
         const H3 s = {h_from_bits(rs.x & 0xffff), h_from_bits(rs.y & 0xffff), h_from_bits(rs.z & 0xffff)};
         const __half k = pair_test(s, d, a, b, c, nn);
         const uint32_t key = make_key(h_bits(k), e.x & 0xffffu);
-        if ((key >> 16) > ORD_MISS) atomicOr(&sm.far[rs.w >> 5], 1u << (rs.w & 31));      // k > 11: see epilogue
-        else atomicMin(&sm.res[rs.w], key);
+        const uint32_t p = rs.w & 0xffffu;
+        if ((key >> 16) > ORD_MISS) atomicOr(&sm.far[p >> 5], 1u << (p & 31));      // k > 11: see epilogue
+        else atomicMin(&sm.res[p], key);
     }
 }
 
@@ -195,6 +202,7 @@ __device__ __noinline__ uint32_t literal_ray(const int32_t* row, int K, const Tr
     return best;
 }
 
+template <int B>
 __global__ void __launch_bounds__(TT, 3) hm_tiled_kernel(const TiledParams q) {
     extern __shared__ uint4 smem_raw[];
     __shared__ int s_box[4];          // min cx, min cy, max cx, max cy
@@ -238,7 +246,7 @@ __global__ void __launch_bounds__(TT, 3) hm_tiled_kernel(const TiledParams q) {
 
     // ---- phase 1: sources + cells of this thread's rays (kept in registers across the sort)
     uint32_t r_sxy[RPT], r_sz[RPT];
-    int r_cell[RPT];                // cx << 16 | cy   (G <= 65535 checked on the host)
+    int r_cell[RPT];                // block (cell when B == 1) x << 16 | y   (G <= 65535 checked on the host)
     int mnx = 0x7fffffff, mny = 0x7fffffff, mxx = -1, mxy = -1;
 #pragma unroll
     for (int i = 0; i < RPT; ++i) {
@@ -250,9 +258,15 @@ __global__ void __launch_bounds__(TT, 3) hm_tiled_kernel(const TiledParams q) {
             body_transform<double>(pp[0], pp[1], pp[2], tr, tx, ty, tz, xo, yo, zo);
             const __half hx = h_from_double(xo), hy = h_from_double(yo), hz = h_from_double(zo);
             r_sxy[i] = (uint32_t)h_bits(hx) | ((uint32_t)h_bits(hy) << 16);
-            r_sz[i] = h_bits(hz);
-            const int cx = cell_coord(hx, q.shift_x, q.res, q.inv_res, q.G0 - 1, q.sem);
-            const int cy = min(cell_coord(hy, q.shift_y, q.res, q.inv_res, q.G0 - 1, q.sem), q.G1 - 1);   // camera.py:243
+            int cx = cell_coord(hx, q.shift_x, q.res, q.inv_res, q.G0 - 1, q.sem);
+            int cy = min(cell_coord(hy, q.shift_y, q.res, q.inv_res, q.G0 - 1, q.sem), q.G1 - 1);   // camera.py:243
+            uint32_t sub = 0;
+            if (B > 1) {
+                const int bx = cx / B, by = cy / B;
+                sub = (uint32_t)((cx - bx * B) * B + (cy - by * B));
+                cx = bx; cy = by;
+            }
+            r_sz[i] = (uint32_t)h_bits(hz) | (sub << 16);
             r_cell[i] = (cx << 16) | cy;
             mnx = min(mnx, cx); mxx = max(mxx, cx); mny = min(mny, cy); mxy = max(mxy, cy);
         }
@@ -316,7 +330,7 @@ __global__ void __launch_bounds__(TT, 3) hm_tiled_kernel(const TiledParams q) {
                 if (cnt) {
                     const int bin = 2 * w + h;
                     const int cx = bx0 + bin / BH, cy = by0 + bin % BH;
-                    const uint32_t cell = (uint32_t)cx * (uint32_t)q.G1 + (uint32_t)cy;
+                    const uint32_t cell = (uint32_t)cx * (uint32_t)(B > 1 ? q.nBy : q.G1) + (uint32_t)cy;
                     uint32_t it = run >> 16, start = run & 0xffffu;
                     for (uint32_t done = 0; done < cnt; done += MAX_ITEM_RAYS, ++it)
                         sm.items[it] = make_uint2(cell, (start + done) | (min(cnt - done, (uint32_t)MAX_ITEM_RAYS) << 16));
@@ -335,7 +349,7 @@ __global__ void __launch_bounds__(TT, 3) hm_tiled_kernel(const TiledParams q) {
                 const int bin = ((r_cell[i] >> 16) - bx0) * BH + ((r_cell[i] & 0xffff) - by0);
                 const uint32_t posn = ((sm.bins[bin >> 1] >> ((bin & 1) * 16)) & 0xffffu) + r_rank[i];
                 sm.ray_s[posn] = make_uint4(__byte_perm(r_sxy[i], 0, 0x1010), __byte_perm(r_sxy[i], 0, 0x3232),
-                                            __byte_perm(r_sz[i], 0, 0x1010), (uint32_t)p);
+                                            __byte_perm(r_sz[i], 0, 0x1010), (uint32_t)p | (r_sz[i] & 0xffff0000u));
                 sm.res[p] = KEY_INIT;
             }
         }
@@ -345,10 +359,10 @@ __global__ void __launch_bounds__(TT, 3) hm_tiled_kernel(const TiledParams q) {
         for (int i = 0; i < RPT; ++i) {
             if (r_cell[i] >= 0) {
                 const int p = tid + i * TT;
-                const uint32_t cell = (uint32_t)(r_cell[i] >> 16) * (uint32_t)q.G1 + (uint32_t)(r_cell[i] & 0xffff);
+                const uint32_t cell = (uint32_t)(r_cell[i] >> 16) * (uint32_t)(B > 1 ? q.nBy : q.G1) + (uint32_t)(r_cell[i] & 0xffff);
                 sm.items[p] = make_uint2(cell, (uint32_t)p | (1u << 16));
                 sm.ray_s[p] = make_uint4(__byte_perm(r_sxy[i], 0, 0x1010), __byte_perm(r_sxy[i], 0, 0x3232),
-                                         __byte_perm(r_sz[i], 0, 0x1010), (uint32_t)p);
+                                         __byte_perm(r_sz[i], 0, 0x1010), (uint32_t)p | (r_sz[i] & 0xffff0000u));
                 sm.res[p] = KEY_INIT;
             }
         }
@@ -357,46 +371,72 @@ __global__ void __launch_bounds__(TT, 3) hm_tiled_kernel(const TiledParams q) {
     __syncthreads();
 
     // ---- phase 3: warps pull items; lanes own candidate pairs
-    const int K = q.K;
     const H3 dlit = {__low2half(dx2), __low2half(dy2), __low2half(dz2)};
     uint2* wq = sm.wq + warp * WQ_CAP;
     uint32_t q_head = 0, q_tail = 0;          // warp-uniform
     const uint32_t lt_mask = (1u << lane) - 1u;
+    // candidate list of an item: the cell's row of the index (B == 1) or the block's union list
+    auto list_of = [&](uint32_t cell, const int32_t*& ids, const uint4*& slots) -> int {
+        if (B == 1) {
+            ids = q.index + (int64_t)cell * q.Ks;
+            slots = nullptr;
+            return q.K;
+        }
+        const uint32_t o0 = __ldg(q.blk_off + cell), o1 = __ldg(q.blk_off + cell + 1);
+        ids = q.blk_ids + o0;
+        slots = q.blk_slots + o0;
+        return (int)(o1 - o0);
+    };
     int item = warp;
     while (item < nitems) {
         int next = 0;
         if (lane == 0) next = atomicAdd(&s_next, 1);
         next = __shfl_sync(0xffffffffu, next, 0);
         const uint2 it = sm.items[item];
-        // this lane's id pairs of the cell's candidate row (rows are padded to an even length)
-        const int2* rowl = reinterpret_cast<const int2*>(q.index + (int64_t)it.x * q.Ks) + lane;
-        if (next < nitems && lane * 32 < K) {
-            // pull the next item's candidate list towards L2 while this one is being processed
-            const int32_t* nrow = q.index + (int64_t)sm.items[next].x * q.Ks + lane * 32;
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(nrow));
+        const int32_t* ids_base;
+        const uint4* slots_base;
+        const int U = list_of(it.x, ids_base, slots_base);
+        const int2* rowl = reinterpret_cast<const int2*>(ids_base) + lane;      // this lane's id pairs (lists have even length)
+        if (next < nitems) {
+            // pull the next item's candidate ids towards L2 while this one is being processed
+            const int32_t* nids;
+            const uint4* nsl;
+            const int nU = list_of(sm.items[next].x, nids, nsl);
+            if (lane * 32 < nU) asm volatile("prefetch.global.L2 [%0];" ::"l"(nids + lane * 32));
         }
         const int start = it.y & 0xffff, cnt = it.y >> 16;
-        int2 ids = (2 * lane < K) ? __ldg(rowl) : make_int2(0, 0);
-        for (int c0 = 0; c0 < K; c0 += 64) {
+        int2 ids = (2 * lane < U) ? __ldg(rowl) : make_int2(0, 0);
+        for (int c0 = 0; c0 < U; c0 += 64) {
             const int j0 = c0 + 2 * lane;
-            const int2 ids_next = (j0 + 64 < K) ? __ldg(rowl + (c0 >> 1) + 32) : make_int2(0, 0);   // in flight during the ray loop
+            const int2 ids_next = (j0 + 64 < U) ? __ldg(rowl + (c0 >> 1) + 32) : make_int2(0, 0);   // in flight during the ray loop
             const uint4* r0 = reinterpret_cast<const uint4*>(q.recs + ids.x);
             const uint4* r1 = reinterpret_cast<const uint4*>(q.recs + ids.y);
             const uint4 a0 = __ldg(r0), b0 = __ldg(r1);
             const uint2 a1 = __ldg(reinterpret_cast<const uint2*>(r0 + 1)), b1 = __ldg(reinterpret_cast<const uint2*>(r1 + 1));
             const Tri2 t = pack_tri2(a0, a1, b0, b1);
-            const Cand2 cd = make_cand2(t, dx2, dy2, dz2, j0 < K, j0 + 1 < K);
+            const Cand2 cd = make_cand2(t, dx2, dy2, dz2, j0 < U, j0 + 1 < U);
             for (int r = 0; r < cnt; ++r) {
                 const int pos = start + r;
                 const uint4 rs = sm.ray_s[pos];
                 const uint32_t f = prefilter2(u2h(rs.x), u2h(rs.y), u2h(rs.z), dx2, dy2, dz2, t, cd);
-                const uint32_t b0m = __ballot_sync(0xffffffffu, (f & 0xffffu) != 0u);
-                const uint32_t b1m = __ballot_sync(0xffffffffu, (f >> 16) != 0u);
-                if (b0m | b1m) {
-                    // about 1 candidate in 100 survives: queue it for a dense literal evaluation
-                    if (f & 0xffffu) wq[(q_tail + __popc(b0m & lt_mask)) & (WQ_CAP - 1)] = make_uint2(((uint32_t)pos << 16) | (uint32_t)j0, (uint32_t)ids.x);
+                if (__any_sync(0xffffffffu, f != 0u)) {
+                    // about 1 candidate in 100 survives: look up its slot in the ray's own cell and queue it for a
+                    // dense literal evaluation
+                    uint32_t s0 = 0xffu, s1 = 0xffu;
+                    if (B == 1) {
+                        if (f & 0xffffu) s0 = (uint32_t)j0;
+                        if (f >> 16) s1 = (uint32_t)(j0 + 1);
+                    } else {
+                        const uint32_t sub = rs.w >> 16;
+                        if (f & 0xffffu) s0 = __ldg(reinterpret_cast<const unsigned char*>(slots_base + j0) + sub);
+                        if (f >> 16) s1 = __ldg(reinterpret_cast<const unsigned char*>(slots_base + j0 + 1) + sub);
+                    }
+                    const bool m0 = B == 1 ? (f & 0xffffu) != 0u : s0 != 0xffu;
+                    const bool m1 = B == 1 ? (f >> 16) != 0u : s1 != 0xffu;
+                    const uint32_t b0m = __ballot_sync(0xffffffffu, m0), b1m = __ballot_sync(0xffffffffu, m1);
+                    if (m0) wq[(q_tail + __popc(b0m & lt_mask)) & (WQ_CAP - 1)] = make_uint2(((uint32_t)pos << 16) | s0, (uint32_t)ids.x);
                     q_tail += __popc(b0m);
-                    if (f >> 16) wq[(q_tail + __popc(b1m & lt_mask)) & (WQ_CAP - 1)] = make_uint2(((uint32_t)pos << 16) | (uint32_t)(j0 + 1), (uint32_t)ids.y);
+                    if (m1) wq[(q_tail + __popc(b1m & lt_mask)) & (WQ_CAP - 1)] = make_uint2(((uint32_t)pos << 16) | s1, (uint32_t)ids.y);
                     q_tail += __popc(b1m);
                     if (q_tail - q_head >= 32u) {
                         __syncwarp();
@@ -428,7 +468,7 @@ __global__ void __launch_bounds__(TT, 3) hm_tiled_kernel(const TiledParams q) {
             const H3 s = {h_from_double(xo), h_from_double(yo), h_from_double(zo)};
             const int cx = cell_coord(s.x, q.shift_x, q.res, q.inv_res, q.G0 - 1, q.sem);
             const int cy = min(cell_coord(s.y, q.shift_y, q.res, q.inv_res, q.G0 - 1, q.sem), q.G1 - 1);
-            key = literal_ray(q.index + ((int64_t)cx * q.G1 + cy) * q.Ks, K, q.recs, s, dlit);
+            key = literal_ray(q.index + ((int64_t)cx * q.G1 + cy) * q.Ks, q.K, q.recs, s, dlit);
         }
         const unsigned short kb = key_bits(key);
         const int slot = (int)((key >> 1) & 0x7fffu);
@@ -472,12 +512,14 @@ size_t tiled_smem_bytes(int RT) {
 int launch_heightmap_tiled(const rvb_terrain* t, const float* pos, const float* euler, const float* trig,
                            const double* pattern, int64_t P, int64_t N, uint16_t* dist, int32_t* hit_slot,
                            int32_t* hit_tri, uint16_t* pt, uint16_t* sources, float* obs, int64_t obs_ld,
-                           const int32_t* col_a, const int32_t* col_b, cudaStream_t st) {
+                           const int32_t* col_a, const int32_t* col_b, bool per_cell, cudaStream_t st) {
     RVB_REQUIRE(t->G0 <= 32767 && t->G1 <= 65535, "heightmap ray-cast: grid larger than 32767 x 65535 cells");
     RVB_REQUIRE(t->K <= 16383, "heightmap ray-cast: K > 16383");
     RVB_REQUIRE(t->G0 * t->G1 < ((int64_t)1 << 32), "heightmap ray-cast: more than 2^32 cells");
     TiledParams q;
     q.index = t->index; q.recs = t->recs;
+    q.blk_off = t->blk_off; q.blk_ids = t->blk_ids; q.blk_slots = t->blk_slots; q.nBy = t->nBy;
+    const bool blocks = t->blk_ids != nullptr && !per_cell;
     q.G0 = (int)t->G0; q.G1 = (int)t->G1; q.K = (int)t->K; q.Ks = (int)t->Ks;
     q.res = t->res; q.inv_res = 1.0f / t->res; q.shift_x = t->shift_x; q.shift_y = t->shift_y; q.sem = t->sem;
     q.pos = pos; q.euler = euler; q.trig = trig; q.pattern = pattern;
@@ -486,17 +528,19 @@ int launch_heightmap_tiled(const rvb_terrain* t, const float* pos, const float* 
     q.tile_size = (int)ceil_div(P, q.tiles);
     q.dist = (__half*)dist; q.hit_slot = hit_slot; q.hit_tri = hit_tri; q.pt = (__half*)pt; q.sources = (__half*)sources;
     q.obs = obs; q.obs_ld = obs_ld; q.col_a = col_a; q.col_b = col_b;
-    const int64_t blocks = N * q.tiles;
-    RVB_REQUIRE(blocks < ((int64_t)1 << 31), "heightmap ray-cast: too many (env, tile) blocks for one launch");
+    const int64_t nblocks = N * q.tiles;
+    RVB_REQUIRE(nblocks < ((int64_t)1 << 31), "heightmap ray-cast: too many (env, tile) blocks for one launch");
     const size_t smem = tiled_smem_bytes(q.tile_size);
     static thread_local int configured_device = -1;
     int dev = 0;
     RVB_CUDA(cudaGetDevice(&dev));
     if (configured_device != dev) {
-        RVB_CUDA(cudaFuncSetAttribute(hm_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tiled_smem_bytes(RT_MAX)));
+        RVB_CUDA(cudaFuncSetAttribute(hm_tiled_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tiled_smem_bytes(RT_MAX)));
+        RVB_CUDA(cudaFuncSetAttribute(hm_tiled_kernel<RVB_BLK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tiled_smem_bytes(RT_MAX)));
         configured_device = dev;
     }
-    hm_tiled_kernel<<<(unsigned)blocks, TT, smem, st>>>(q);
+    if (blocks) hm_tiled_kernel<RVB_BLK><<<(unsigned)nblocks, TT, smem, st>>>(q);
+    else hm_tiled_kernel<1><<<(unsigned)nblocks, TT, smem, st>>>(q);
     RVB_LAUNCH_CHECK();
     return RVB_OK;
 }

@@ -2,6 +2,8 @@
 #include <new>
 #include <string.h>
 
+#include <cub/device/device_scan.cuh>
+
 #include "common.cuh"
 
 static thread_local char g_err[512] = "";
@@ -59,6 +61,123 @@ __global__ void build_records_kernel(const int32_t* __restrict__ tri, int64_t T,
     recs[i] = r;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Block lists: one CTA per RVB_BLK x RVB_BLK block.  Keys (id << 16 | sub-cell << 8 | slot) of the block's cells are
+// sorted in shared memory; runs of equal id become one entry.  Run twice: count, then (after a scan) write.
+// ------------------------------------------------------------------------------------------------
+constexpr int BLK_THREADS = 256;
+constexpr int BLK_MAXKEYS = 4096;      // >= RVB_BLK^2 * 255
+
+__global__ void __launch_bounds__(BLK_THREADS)
+build_blocks_kernel(const int32_t* __restrict__ index, int G0, int G1, int K, int Ks, int nBy, const uint32_t* __restrict__ off,
+                    uint32_t* __restrict__ counts, int32_t* __restrict__ ids, uint4* __restrict__ slots) {
+    __shared__ unsigned long long keys[BLK_MAXKEYS];
+    __shared__ uint32_t s_warp[BLK_THREADS / 32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int I = blockIdx.x / nBy, J = blockIdx.x % nBy;
+    const int nk = RVB_BLK * RVB_BLK * K;
+    int n2 = 64;
+    while (n2 < nk) n2 <<= 1;
+    for (int t = tid; t < n2; t += BLK_THREADS) {
+        unsigned long long key = ~0ull;
+        if (t < nk) {
+            const int sub = t / K, slot = t % K;
+            const int ci = I * RVB_BLK + sub / RVB_BLK, cj = J * RVB_BLK + sub % RVB_BLK;
+            if (ci < G0 && cj < G1)
+                key = ((unsigned long long)(uint32_t)index[((int64_t)ci * G1 + cj) * Ks + slot] << 16) | (unsigned)(sub << 8) | (unsigned)slot;
+        }
+        keys[t] = key;
+    }
+    __syncthreads();
+    for (int k = 2; k <= n2; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = tid; i < n2; i += BLK_THREADS) {
+                const int ixj = i ^ j;
+                if (ixj > i) {
+                    const unsigned long long a = keys[i], b = keys[ixj];
+                    if ((a > b) == ((i & k) == 0)) {
+                        keys[i] = b;
+                        keys[ixj] = a;
+                    }
+                }
+            }
+            __syncthreads();
+        }
+    }
+    // entry number of key i = (number of id changes in [0, i]) - 1; thread t owns the contiguous keys [t*per, (t+1)*per)
+    const int per = n2 / BLK_THREADS > 0 ? n2 / BLK_THREADS : 1;
+    const int lo = tid * per, hi = min(lo + per, n2);
+    uint32_t mine = 0;
+    for (int i = lo; i < hi && lo < n2; ++i) {
+        const unsigned long long k = keys[i];
+        if (k != ~0ull && (i == 0 || (keys[i - 1] >> 16) != (k >> 16))) ++mine;
+    }
+    uint32_t inc = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t v = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += v;
+    }
+    if (lane == 31) s_warp[warp] = inc;
+    __syncthreads();
+    uint32_t base = 0, total = 0;
+    for (int w = 0; w < BLK_THREADS / 32; ++w) {
+        if (w < warp) base += s_warp[w];
+        total += s_warp[w];
+    }
+    if (!ids) {
+        if (tid == 0) counts[blockIdx.x] = (total + 1u) & ~1u;      // even: lanes fetch id pairs with 8-byte loads
+        return;
+    }
+    int32_t* out_id = ids + off[blockIdx.x];
+    uint4* out_sl = slots + off[blockIdx.x];
+    uint32_t e = base + inc - mine;          // entries started before this thread's first key
+    for (int i = lo; i < hi && lo < n2; ++i) {
+        const unsigned long long k = keys[i];
+        if (k == ~0ull) break;
+        const bool first = (i == 0 || (keys[i - 1] >> 16) != (k >> 16));
+        if (first) {
+            ++e;
+            out_id[e - 1] = (int32_t)(k >> 16);
+        }
+        // e - 1 is this key's entry (a run that started in an earlier thread's range keeps that thread's number)
+        reinterpret_cast<unsigned char*>(out_sl + (e - 1))[(k >> 8) & 0xff] = (unsigned char)(k & 0xff);
+    }
+}
+
+static int build_block_lists(rvb_terrain* t, cudaStream_t st) {
+    t->nBx = (int32_t)ceil_div(t->G0, RVB_BLK);
+    t->nBy = (int32_t)ceil_div(t->G1, RVB_BLK);
+    const int64_t nb = (int64_t)t->nBx * t->nBy;
+    if (t->K > 255 || nb >= ((int64_t)1 << 31)) return RVB_OK;      // per-cell path only
+    uint32_t* counts = nullptr;
+    RVB_CUDA(cudaMalloc(&t->blk_off, sizeof(uint32_t) * (nb + 1)));
+    RVB_CUDA(cudaMalloc(&counts, sizeof(uint32_t) * (nb + 1)));
+    RVB_CUDA(cudaMemsetAsync(counts, 0, sizeof(uint32_t) * (nb + 1), st));
+    build_blocks_kernel<<<(unsigned)nb, BLK_THREADS, 0, st>>>(t->index, (int)t->G0, (int)t->G1, (int)t->K, (int)t->Ks, t->nBy, nullptr,
+                                                             counts, nullptr, nullptr);
+    RVB_LAUNCH_CHECK();
+    void* tmp = nullptr;
+    size_t tmp_bytes = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, counts, t->blk_off, (int)(nb + 1), st);
+    RVB_CUDA(cudaMalloc(&tmp, tmp_bytes));
+    cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, counts, t->blk_off, (int)(nb + 1), st);
+    uint32_t total = 0;
+    RVB_CUDA(cudaMemcpyAsync(&total, t->blk_off + nb, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    RVB_CUDA(cudaStreamSynchronize(st));
+    cudaFree(tmp);
+    cudaFree(counts);
+    t->n_ent = total;
+    RVB_CUDA(cudaMalloc(&t->blk_ids, sizeof(int32_t) * (size_t)(total > 0 ? total : 1)));
+    RVB_CUDA(cudaMalloc(&t->blk_slots, sizeof(uint4) * (size_t)(total > 0 ? total : 1)));
+    RVB_CUDA(cudaMemsetAsync(t->blk_ids, 0, sizeof(int32_t) * (size_t)total, st));
+    RVB_CUDA(cudaMemsetAsync(t->blk_slots, 0xff, sizeof(uint4) * (size_t)total, st));
+    build_blocks_kernel<<<(unsigned)nb, BLK_THREADS, 0, st>>>(t->index, (int)t->G0, (int)t->G1, (int)t->K, (int)t->Ks, t->nBy, t->blk_off,
+                                                             nullptr, t->blk_ids, t->blk_slots);
+    RVB_LAUNCH_CHECK();
+    return RVB_OK;
+}
+
 extern "C" int rvb_terrain_create(rvb_terrain** out, const int32_t* map_indices, int64_t G0, int64_t G1, int64_t K,
                                   int64_t stride_g0, int64_t stride_g1, int64_t stride_k, const int32_t* triangles,
                                   int64_t T, const uint16_t* vertices, int64_t V, float res, float shift_x,
@@ -93,6 +212,19 @@ extern "C" int rvb_terrain_create(rvb_terrain** out, const int32_t* map_indices,
     if (e == cudaSuccess) e = cudaMemcpyAsync(&hbad, bad, sizeof(int), cudaMemcpyDeviceToHost, st);
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
     if (bad) cudaFree(bad);
+    if (e == cudaSuccess && !hbad) {
+        const int rc = build_block_lists(t, st);
+        if (rc == RVB_OK) e = cudaStreamSynchronize(st);
+        if (rc != RVB_OK || e != cudaSuccess) {
+            cudaFree(t->index);
+            cudaFree(t->recs);
+            cudaFree(t->blk_off);
+            cudaFree(t->blk_ids);
+            cudaFree(t->blk_slots);
+            delete t;
+            return rc != RVB_OK ? rc : rvb_set_error(RVB_ERR_CUDA, "rvb_terrain_create (block lists)", cudaGetErrorString(e));
+        }
+    }
     if (e != cudaSuccess || hbad) {
         cudaFree(t->index);
         cudaFree(t->recs);
@@ -110,11 +242,15 @@ extern "C" int rvb_terrain_destroy(rvb_terrain* t) {
     if (!t) return RVB_OK;
     cudaFree(t->index);
     cudaFree(t->recs);
+    cudaFree(t->blk_off);
+    cudaFree(t->blk_ids);
+    cudaFree(t->blk_slots);
     delete t;
     return RVB_OK;
 }
 
 extern "C" int64_t rvb_terrain_bytes(const rvb_terrain* t) {
     if (!t) return 0;
-    return (int64_t)sizeof(int32_t) * t->G0 * t->G1 * t->Ks + (int64_t)sizeof(TriRec) * t->T;
+    return (int64_t)sizeof(int32_t) * t->G0 * t->G1 * t->Ks + (int64_t)sizeof(TriRec) * t->T +
+           (t->blk_ids ? (int64_t)(sizeof(uint4) + sizeof(int32_t)) * t->n_ent + (int64_t)sizeof(uint32_t) * ((int64_t)t->nBx * t->nBy + 1) : 0);
 }

@@ -88,7 +88,7 @@ def test_golden_pattern(R, golden):
     assert (hm.get_num_sparse_vector(), hm.get_num_dense_vector()) == (634, 1112)      # teacher_loader.py:47-48
 
 
-@pytest.mark.parametrize("variant", [0, 1])
+@pytest.mark.parametrize("variant", [0, 1, 2])
 def test_golden_get_depths(R, golden, gcam, variant):
     gcam.variant = variant
     dist, pt, src = gcam.get_depths(golden["in_pos"].cuda(), golden["ref_euler"].cuda(), trig=golden["trig"].cuda(), want_hits=True)
@@ -241,7 +241,7 @@ def test_oracle_cpu_semantics_bit_exact(R, O, world20, N):
     pat, _, _ = O.heightmap_pattern()
     ref = O.get_depths(st["pos"], eul, pat, w.map_indices, w.triangles, w.vertices, torch.tensor([0, 0, 0.0]))
     cam = R.Camera("cuda:0", torch.tensor([0, 0, 0.0]), assets=(w.map_indices, w.triangles, w.vertices), sem=R.SEM_TORCH_CPU)
-    for variant in (0, 1):
+    for variant in (0, 1, 2):
         cam.variant = variant
         dist, pt, src = cam.get_depths(st["pos"].cuda(), eul.cuda(), trig=_trig(eul).cuda(), want_hits=True)
         assert_bits_equal(src, ref["sources"], "sources v%d" % variant)
@@ -328,7 +328,7 @@ def test_edge_cases(R, O, world20):
     eul = torch.tensor([[0.0, 0.0, 0.0], [0.1, -0.1, 2.0], [0.0, 0.0, 1.0], [3.1, 0.0, 0.0], [1.2, -1.2, -3.0]])
     pat, _, _ = O.heightmap_pattern()
     ref = O.get_depths(pos, eul, pat, w.map_indices, w.triangles, w.vertices, torch.tensor([0, 0, 0.0]))
-    for variant in (0, 1):
+    for variant in (0, 1, 2):
         cam.variant = variant
         d, pt, s = cam.get_depths(pos.cuda(), eul.cuda(), trig=_trig(eul).cuda(), want_hits=True)
         assert_bits_equal(d, ref["dist"], "edge dist v%d" % variant)
@@ -352,9 +352,10 @@ def test_full_size_properties(R, world20):
     cam = R.Camera("cuda:0", torch.tensor([0, 0, 0.0]), assets=(w.map_indices, w.triangles, w.vertices))
     d0, pt0, s0 = cam.get_depths(st["pos"], eul, want_hits=True)
     t0 = cam.last_hit_tri.clone()
-    cam.variant = 1
-    d1, pt1, s1 = cam.get_depths(st["pos"], eul, want_hits=True)
-    assert torch.equal(bits(d0), bits(d1)) and torch.equal(bits(pt0), bits(pt1)) and torch.equal(t0, cam.last_hit_tri)
+    for v in (1, 2):
+        cam.variant = v
+        d1, pt1, s1 = cam.get_depths(st["pos"], eul, want_hits=True)
+        assert torch.equal(bits(d0), bits(d1)) and torch.equal(bits(pt0), bits(pt1)) and torch.equal(t0, cam.last_hit_tri)
     cam.variant = 0
     d2, _, _ = cam.get_depths(st["pos"], eul)
     assert torch.equal(bits(d0), bits(d2))
@@ -395,7 +396,7 @@ def test_candidate_count_variants(R, O, world20, K):
     pat, _, _ = O.heightmap_pattern()
     ref = O.get_depths(st["pos"], eul, pat, idx, w.triangles, w.vertices, torch.tensor([0, 0, 0.0]))
     cam = R.Camera("cuda:0", torch.tensor([0, 0, 0.0]), assets=(idx, w.triangles, w.vertices), sem=R.SEM_TORCH_CPU)
-    for variant in (0, 1):
+    for variant in (0, 1, 2):
         cam.variant = variant
         dist, pt, src = cam.get_depths(st["pos"].cuda(), eul.cuda(), trig=_trig(eul).cuda(), want_hits=True)
         assert_bits_equal(dist, ref["dist"], "dist K=%d v%d" % (K, variant))
@@ -420,7 +421,7 @@ def test_far_hits_and_spread_rays(R, O, world20):
     shift = torch.tensor([0, 0, 0.0])
     ref = O.get_depths(pos, eul, pat, w.map_indices, w.triangles, w.vertices, shift)
     far = (ref["dist"] == 11) & (ref["slot"] != 0)
-    for variant in (0, 1):
+    for variant in (0, 1, 2):
         cam.variant = variant
         d, pt, s = cam.get_depths(pos.cuda(), eul.cuda(), trig=_trig(eul).cuda(), want_hits=True)
         assert_bits_equal(d, ref["dist"], "far dist v%d" % variant)
@@ -437,7 +438,7 @@ def test_far_hits_and_spread_rays(R, O, world20):
     dist = torch.empty((2, 4096), dtype=torch.float16, device="cuda")
     slot = torch.empty((2, 4096), dtype=torch.int32, device="cuda")
     d_pos, d_eul, d_trig, d_pat = pos2.cuda(), eul2.cuda(), _trig(eul2).cuda(), wide.cuda()      # keep the buffers alive
-    for variant in (0, 1):
+    for variant in (0, 1, 2):
         R._lib.check(lib.rvb_heightmap_raycast(cam.layer.handle, R._lib.ptr(d_pos), R._lib.ptr(d_eul), R._lib.ptr(d_trig),
                                                R._lib.ptr(d_pat), 4096, 2, R._lib.ptr(dist), R._lib.ptr(slot), None, None, None,
                                                None, 0, None, None, variant, None))
