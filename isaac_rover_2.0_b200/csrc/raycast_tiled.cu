@@ -173,16 +173,26 @@ struct Smem {
 };
 
 // Literal evaluation of up to 32 queued (ray, candidate) pairs, one per lane (ray_casting.py:34-59).
+// Queue entry: B == 1: (pos << 16 | slot, triangle id);  B > 1: (pos << 16, absolute entry of the block list) -- the
+// triangle id and the slot it holds in the ray's own cell are looked up here, where 32 lanes overlap the loads;
+// a candidate that is not in the ray's cell list (slot 0xFF) is dropped.
+template <int B>
 __device__ __forceinline__ void drain32(const Smem& sm, const uint2* wq, uint32_t head, uint32_t n, int lane, const TriRec* recs,
-                                        H3 d) {
+                                        const int32_t* blk_ids, const uint4* blk_slots, H3 d) {
     if ((uint32_t)lane < n) {
         const uint2 e = wq[(head + lane) & (WQ_CAP - 1)];
         const uint4 rs = sm.ray_s[e.x >> 16];
+        uint32_t slot = e.x & 0xffffu, id = e.y;
+        if (B > 1) {
+            id = (uint32_t)__ldg(blk_ids + e.y);
+            slot = __ldg(reinterpret_cast<const unsigned char*>(blk_slots + e.y) + (rs.w >> 16));
+            if (slot == 0xffu) return;
+        }
         H3 a, b, c, nn;
-        unpack_rec(recs + e.y, a, b, c, nn);
+        unpack_rec(recs + id, a, b, c, nn);
         const H3 s = {h_from_bits(rs.x & 0xffff), h_from_bits(rs.y & 0xffff), h_from_bits(rs.z & 0xffff)};
         const __half k = pair_test(s, d, a, b, c, nn);
-        const uint32_t key = make_key(h_bits(k), e.x & 0xffffu);
+        const uint32_t key = make_key(h_bits(k), slot);
         const uint32_t p = rs.w & 0xffffu;
         if ((key >> 16) > ORD_MISS) atomicOr(&sm.far[p >> 5], 1u << (p & 31));      // k > 11: see epilogue
         else atomicMin(&sm.res[p], key);
@@ -375,17 +385,36 @@ __global__ void __launch_bounds__(TT, 3) hm_tiled_kernel(const TiledParams q) {
     uint2* wq = sm.wq + warp * WQ_CAP;
     uint32_t q_head = 0, q_tail = 0;          // warp-uniform
     const uint32_t lt_mask = (1u << lane) - 1u;
+    const uint32_t ray_s_addr = (uint32_t)__cvta_generic_to_shared(sm.ray_s);
     // candidate list of an item: the cell's row of the index (B == 1) or the block's union list
-    auto list_of = [&](uint32_t cell, const int32_t*& ids, const uint4*& slots) -> int {
+    auto list_of = [&](uint32_t cell, const int32_t*& ids, uint32_t& o0) -> int {
         if (B == 1) {
             ids = q.index + (int64_t)cell * q.Ks;
-            slots = nullptr;
+            o0 = 0;
             return q.K;
         }
-        const uint32_t o0 = __ldg(q.blk_off + cell), o1 = __ldg(q.blk_off + cell + 1);
+        o0 = __ldg(q.blk_off + cell);
+        const uint32_t o1 = __ldg(q.blk_off + cell + 1);
         ids = q.blk_ids + o0;
-        slots = q.blk_slots + o0;
         return (int)(o1 - o0);
+    };
+    // survivors of one ray -> queue (warp-uniform control flow); returns with fewer than 32 pending
+    auto enqueue = [&](uint32_t f, int pos, int j0, int2 ids, uint32_t o0) {
+        const bool m0 = (f & 0xffffu) != 0u, m1 = (f >> 16) != 0u;
+        const uint32_t b0m = __ballot_sync(0xffffffffu, m0), b1m = __ballot_sync(0xffffffffu, m1);
+        const uint32_t x = (uint32_t)pos << 16;
+        if (m0) wq[(q_tail + __popc(b0m & lt_mask)) & (WQ_CAP - 1)] = B == 1 ? make_uint2(x | (uint32_t)j0, (uint32_t)ids.x) : make_uint2(x, o0 + (uint32_t)j0);
+        q_tail += __popc(b0m);
+        if (m1) wq[(q_tail + __popc(b1m & lt_mask)) & (WQ_CAP - 1)] = B == 1 ? make_uint2(x | (uint32_t)(j0 + 1), (uint32_t)ids.y) : make_uint2(x, o0 + (uint32_t)j0 + 1u);
+        q_tail += __popc(b1m);
+        if (q_tail - q_head >= 32u) {
+            __syncwarp();
+            do {
+                drain32<B>(sm, wq, q_head, 32u, lane, q.recs, q.blk_ids, q.blk_slots, dlit);
+                q_head += 32u;
+            } while (q_tail - q_head >= 32u);
+            __syncwarp();
+        }
     };
     int item = warp;
     while (item < nitems) {
@@ -394,17 +423,18 @@ __global__ void __launch_bounds__(TT, 3) hm_tiled_kernel(const TiledParams q) {
         next = __shfl_sync(0xffffffffu, next, 0);
         const uint2 it = sm.items[item];
         const int32_t* ids_base;
-        const uint4* slots_base;
-        const int U = list_of(it.x, ids_base, slots_base);
+        uint32_t o0;
+        const int U = list_of(it.x, ids_base, o0);
         const int2* rowl = reinterpret_cast<const int2*>(ids_base) + lane;      // this lane's id pairs (lists have even length)
         if (next < nitems) {
             // pull the next item's candidate ids towards L2 while this one is being processed
             const int32_t* nids;
-            const uint4* nsl;
-            const int nU = list_of(sm.items[next].x, nids, nsl);
+            uint32_t no0;
+            const int nU = list_of(sm.items[next].x, nids, no0);
             if (lane * 32 < nU) asm volatile("prefetch.global.L2 [%0];" ::"l"(nids + lane * 32));
         }
-        const int start = it.y & 0xffff, cnt = it.y >> 16;
+        const int cnt = it.y >> 16;
+        const uint32_t ray0 = ray_s_addr + (it.y & 0xffffu) * 16u;
         int2 ids = (2 * lane < U) ? __ldg(rowl) : make_int2(0, 0);
         for (int c0 = 0; c0 < U; c0 += 64) {
             const int j0 = c0 + 2 * lane;
@@ -415,45 +445,32 @@ __global__ void __launch_bounds__(TT, 3) hm_tiled_kernel(const TiledParams q) {
             const uint2 a1 = __ldg(reinterpret_cast<const uint2*>(r0 + 1)), b1 = __ldg(reinterpret_cast<const uint2*>(r1 + 1));
             const Tri2 t = pack_tri2(a0, a1, b0, b1);
             const Cand2 cd = make_cand2(t, dx2, dy2, dz2, j0 < U, j0 + 1 < U);
-            for (int r = 0; r < cnt; ++r) {
-                const int pos = start + r;
-                const uint4 rs = sm.ray_s[pos];
-                const uint32_t f = prefilter2(u2h(rs.x), u2h(rs.y), u2h(rs.z), dx2, dy2, dz2, t, cd);
-                if (__any_sync(0xffffffffu, f != 0u)) {
-                    // about 1 candidate in 100 survives: look up its slot in the ray's own cell and queue it for a
-                    // dense literal evaluation
-                    uint32_t s0 = 0xffu, s1 = 0xffu;
-                    if (B == 1) {
-                        if (f & 0xffffu) s0 = (uint32_t)j0;
-                        if (f >> 16) s1 = (uint32_t)(j0 + 1);
-                    } else {
-                        const uint32_t sub = rs.w >> 16;
-                        if (f & 0xffffu) s0 = __ldg(reinterpret_cast<const unsigned char*>(slots_base + j0) + sub);
-                        if (f >> 16) s1 = __ldg(reinterpret_cast<const unsigned char*>(slots_base + j0 + 1) + sub);
-                    }
-                    const bool m0 = B == 1 ? (f & 0xffffu) != 0u : s0 != 0xffu;
-                    const bool m1 = B == 1 ? (f >> 16) != 0u : s1 != 0xffu;
-                    const uint32_t b0m = __ballot_sync(0xffffffffu, m0), b1m = __ballot_sync(0xffffffffu, m1);
-                    if (m0) wq[(q_tail + __popc(b0m & lt_mask)) & (WQ_CAP - 1)] = make_uint2(((uint32_t)pos << 16) | s0, (uint32_t)ids.x);
-                    q_tail += __popc(b0m);
-                    if (m1) wq[(q_tail + __popc(b1m & lt_mask)) & (WQ_CAP - 1)] = make_uint2(((uint32_t)pos << 16) | s1, (uint32_t)ids.y);
-                    q_tail += __popc(b1m);
-                    if (q_tail - q_head >= 32u) {
-                        __syncwarp();
-                        do {
-                            drain32(sm, wq, q_head, 32u, lane, q.recs, dlit);
-                            q_head += 32u;
-                        } while (q_tail - q_head >= 32u);
-                        __syncwarp();
-                    }
+            uint32_t ra = ray0;
+            int r = 0;
+            for (; r + 2 <= cnt; r += 2, ra += 32u) {
+                uint32_t x0, y0, z0, w0, x1, y1, z1, w1;
+                asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(x0), "=r"(y0), "=r"(z0), "=r"(w0) : "r"(ra));
+                asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4+16];" : "=r"(x1), "=r"(y1), "=r"(z1), "=r"(w1) : "r"(ra));
+                const uint32_t f0 = prefilter2(u2h(x0), u2h(y0), u2h(z0), dx2, dy2, dz2, t, cd);
+                const uint32_t f1 = prefilter2(u2h(x1), u2h(y1), u2h(z1), dx2, dy2, dz2, t, cd);
+                if (__any_sync(0xffffffffu, (f0 | f1) != 0u)) {      // about 1 candidate in 100 survives
+                    const int pos = (int)((ra - ray_s_addr) >> 4);
+                    enqueue(f0, pos, j0, ids, o0);
+                    enqueue(f1, pos + 1, j0, ids, o0);
                 }
+            }
+            if (r < cnt) {
+                uint32_t x0, y0, z0, w0;
+                asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(x0), "=r"(y0), "=r"(z0), "=r"(w0) : "r"(ra));
+                const uint32_t f0 = prefilter2(u2h(x0), u2h(y0), u2h(z0), dx2, dy2, dz2, t, cd);
+                if (__any_sync(0xffffffffu, f0 != 0u)) enqueue(f0, (int)((ra - ray_s_addr) >> 4), j0, ids, o0);
             }
             ids = ids_next;
         }
         item = next;
     }
     __syncwarp();
-    if (q_tail != q_head) drain32(sm, wq, q_head, q_tail - q_head, lane, q.recs, dlit);
+    if (q_tail != q_head) drain32<B>(sm, wq, q_head, q_tail - q_head, lane, q.recs, q.blk_ids, q.blk_slots, dlit);
     __syncthreads();
 
     // ---- phase 4: epilogue in ray order

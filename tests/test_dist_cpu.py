@@ -1,0 +1,75 @@
+"""Host-side multi-process logic on CPU (gloo, world_size 2): env sharding, the per-step statistics all-reduce and the
+max-over-ranks timing helper used by bench.py.  The data path has no collective."""
+import os
+import socket
+import sys
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, total_envs, q):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    import isaac_rover_b200 as R
+    r, w, _ = R.dist.init_from_env(backend="gloo")
+    assert (r, w) == (rank, world)
+    lo, hi = R.dist.env_shard(total_envs, r, w)
+    # per-rank statistics of "its" envs: envs, reward sum, resets (stand-ins with a closed form)
+    ids = torch.arange(lo, hi, dtype=torch.float64)
+    stats = torch.zeros(16, dtype=torch.float64)
+    stats[0], stats[1], stats[8] = hi - lo, ids.sum(), (ids % 3 == 0).sum()
+    R.dist.reduce_stats(stats)
+    t = R.dist.max_over_ranks(1.0 + rank, torch.device("cpu"))
+    R.dist.barrier()
+    q.put((rank, lo, hi, stats.tolist(), t))
+    dist.destroy_process_group()
+
+
+def test_env_shard_partitions_exactly():
+    sys.path.insert(0, ROOT)
+    import isaac_rover_b200 as R
+    for total, world in ((1048576, 8), (4096, 1), (65536, 3), (7, 4), (0, 2)):
+        blocks = [R.dist.env_shard(total, r, world) for r in range(world)]
+        assert blocks[0][0] == 0 and blocks[-1][1] == total
+        assert all(a[1] == b[0] for a, b in zip(blocks, blocks[1:]))
+        sizes = [b[1] - b[0] for b in blocks]
+        assert max(sizes) - min(sizes) <= 1
+
+
+def test_two_rank_stats_reduction_gloo():
+    total, world, port = 1001, 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, total, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    out = sorted(q.get(timeout=120) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    ids = torch.arange(total, dtype=torch.float64)
+    for rank, lo, hi, stats, t in out:
+        assert stats[0] == total and stats[1] == ids.sum().item() and stats[8] == (ids % 3 == 0).sum().item()
+        assert t == 2.0                                        # max over ranks of (1 + rank)
+    assert out[0][1] == 0 and out[0][2] == out[1][1] and out[1][2] == total
+
+
+def test_single_process_helpers_are_noops():
+    sys.path.insert(0, ROOT)
+    import isaac_rover_b200 as R
+    s = torch.arange(16, dtype=torch.float64)
+    assert R.dist.reduce_stats(s) is None and torch.equal(s, torch.arange(16, dtype=torch.float64))
+    assert R.dist.max_over_ranks(3.5, torch.device("cpu")) == 3.5
+    R.dist.barrier()
