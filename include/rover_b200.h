@@ -77,8 +77,10 @@ int64_t rvb_terrain_bytes(const rvb_terrain* t);
  *   hit_tri      i32 [N,P]  triangle id        pt, sources f16 [N,P,3] (optional)
  *   obs/obs_ld/col_a/col_b: optional fused Heightmap.get_sparse_vector/get_dense_vector + rover.py:324-325:
  *        obs[n*obs_ld + col_a[p]] = obs[n*obs_ld + col_b[p]] = f32(fp16(dist/2))  for columns >= 0.
- * `variant`: 0 = production kernel (3x3-cell block lists when the layer has them, i.e. K <= 255), 1 = simple per-pair
- * kernel kept for cross-checking, 2 = production kernel forced onto per-cell lists.
+ * `variant`: 0 = production ("shadow" kernel: enumerates triangles, not (ray, candidate) pairs; needs the layer's block
+ * lists, i.e. K <= 255, otherwise the tiled kernel on per-cell lists runs), 1 = simple per-pair kernel kept for
+ * cross-checking, 2 = tiled kernel on per-cell lists, 3 = tiled kernel on 3x3-cell block lists.  All four are
+ * bit-identical by construction.
  * ---------------------------------------------------------------------------------------------- */
 int rvb_heightmap_raycast(const rvb_terrain* t, const float* pos, const float* euler, const float* trig,
                           const double* pattern, int64_t P, int64_t N,

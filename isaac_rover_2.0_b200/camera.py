@@ -66,8 +66,8 @@ class Camera():
                 _lib.ptr(dist), _lib.ptr(slot), _lib.ptr(tri), _lib.ptr(pt), _lib.ptr(src),
                 _lib.ptr(obs), 0 if obs is None else obs.stride(0), _lib.ptr(self._col_a if obs is not None else None),
                 _lib.ptr(self._col_b if obs is not None else None), self.variant, _lib.stream_of(pos)))
-        if self.variant == 1:
-            _lib.launch_count += 1          # the cross-check variant runs a set-up kernel + the cast kernel
+        if self.variant in (2, 3):
+            _lib.launch_count -= 1          # variants 0 (shadow + fall-back list) and 1 (set-up + cast) launch two kernels, 2/3 one
         if ev is not None:
             ev[1].record(torch.cuda.current_stream(dev))
             self.timing.append(ev)

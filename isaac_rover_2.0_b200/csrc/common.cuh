@@ -46,8 +46,16 @@ struct rvb_terrain {
     int32_t* blk_ids;    // [n_ent]  triangle ids (pad entries: 0)
     uint4* blk_slots;    // [n_ent]  byte s = slot in sub-cell s (s = (cx % BLK) * BLK + cy % BLK), other bytes 0xFF
     int64_t n_ent;
+    // Superblock lists (built with the block lists): the union of the K-lists of RVB_SB x RVB_SB blocks, sorted by id.
+    // The shadow ray-cast kernel enumerates these (a superset of every member cell's candidates) and looks the slot up
+    // in the block lists only for the few candidates a ray can actually hit.
+    int32_t nSBx, nSBy;
+    uint32_t* sb_off;    // [nSBx*nSBy + 1]
+    int32_t* sb_ids;     // [n_sb_ent]
+    int64_t n_sb_ent;
 };
 #define RVB_BLK 3
+#define RVB_SB 8
 
 // ---------------------------------------------------------------- fp16 arithmetic with torch's roundings
 // ATen computes every Half element-wise op as fp32 op + one rounding; for + - * that equals the

@@ -10,6 +10,13 @@ int launch_heightmap_tiled(const rvb_terrain* t, const float* pos, const float* 
                            const double* pattern, int64_t P, int64_t N, uint16_t* dist, int32_t* hit_slot,
                            int32_t* hit_tri, uint16_t* pt, uint16_t* sources, float* obs, int64_t obs_ld,
                            const int32_t* col_a, const int32_t* col_b, bool per_cell, cudaStream_t st);
+int launch_heightmap_shadow(const rvb_terrain* t, const float* pos, const float* euler, const float* trig,
+                           const double* pattern, int64_t P, int64_t N, uint16_t* dist, int32_t* hit_slot,
+                           int32_t* hit_tri, uint16_t* pt, uint16_t* sources, float* obs, int64_t obs_ld,
+                           const int32_t* col_a, const int32_t* col_b, float cos_steep, cudaStream_t st);
+// envs whose ray direction has |d_z| below this are ray-cast by the tiled kernel (their prisms are long slivers)
+#define RVB_COS_STEEP 0.0f
+
 
 // ------------------------------------------------------------------------------------------------
 // setup: sources (fp64 transform -> fp16), per-env direction, per-ray cell
@@ -141,9 +148,12 @@ extern "C" int rvb_heightmap_raycast(const rvb_terrain* t, const float* pos, con
     if (N == 0) return RVB_OK;
     RVB_REQUIRE(t && pos && euler && pattern && dist, "rvb_heightmap_raycast: null pointer");
     RVB_REQUIRE(!obs || (col_a && col_b && obs_ld > 0), "rvb_heightmap_raycast: obs needs col_a, col_b, obs_ld");
-    RVB_REQUIRE(variant >= 0 && variant <= 2, "rvb_heightmap_raycast: variant must be 0, 1 or 2");
+    RVB_REQUIRE(variant >= 0 && variant <= 3, "rvb_heightmap_raycast: variant must be 0, 1, 2 or 3");
     if (N == 0) return RVB_OK;
     cudaStream_t st = as_stream(stream);
+    if (variant == 0 && t->sb_ids != nullptr)
+        return launch_heightmap_shadow(t, pos, euler, trig, pattern, P, N, dist, hit_slot, hit_tri, pt, sources, obs,
+                                       obs_ld, col_a, col_b, RVB_COS_STEEP, st);
     if (variant != 1)
         return launch_heightmap_tiled(t, pos, euler, trig, pattern, P, N, dist, hit_slot, hit_tri, pt, sources, obs,
                                       obs_ld, col_a, col_b, variant == 2, st);

@@ -1,0 +1,136 @@
+// Pieces shared by the heightmap ray-cast kernels (raycast_tiled.cu, raycast_shadow.cu).
+#pragma once
+#include "common.cuh"
+
+namespace rc {
+
+constexpr uint32_t KEY_INIT = 0xC9800000u;     // (11.0, slot 0): the result when every candidate misses
+constexpr uint32_t ORD_MISS = 0xC980u;        // order key of fp16 11.0 (0x4980 | 0x8000)
+
+struct TiledParams {
+    const int32_t* index;
+    const TriRec* recs;
+    const uint32_t* blk_off;
+    const int32_t* blk_ids;
+    const uint4* blk_slots;
+    int nBy;
+    int G0, G1, K, Ks;
+    float res, inv_res, shift_x, shift_y;
+    int sem;
+    const float* pos;
+    const float* euler;
+    const float* trig;
+    const double* pattern;
+    int P, tiles, tile_size;
+    __half* dist;
+    int32_t* hit_slot;
+    int32_t* hit_tri;
+    __half* pt;
+    __half* sources;
+    float* obs;
+    int64_t obs_ld;
+    const int32_t* col_a;
+    const int32_t* col_b;
+    // shadow kernel (raycast_shadow.cu): superblock candidate lists + the list of (env, tile) work items it hands back
+    const uint32_t* sb_off;
+    const int32_t* sb_ids;
+    int nSBy;
+    float cos_steep;          // envs whose ray direction is flatter than this go to the fall-back list
+    int* fb_count;            // [1]
+    int32_t* fb_list;         // [N * tiles]  env * tiles + tile
+    // tiled kernel in work-list mode: CTAs loop over fb_list[0 .. *fb_count) instead of blockIdx
+    const int* work_count;
+    const int32_t* work_list;
+};
+
+// key of torch.min's total order: NaN < everything, -0 == +0, ties -> lower slot; bit 0 remembers a negative zero.
+__device__ __forceinline__ uint32_t make_key(unsigned short b, uint32_t slot) {
+    uint32_t ord, nz = 0;
+    if ((b & 0x7fffu) > 0x7c00u) ord = 0u;
+    else if ((b & 0x7fffu) == 0u) { ord = 0x8000u; nz = b >> 15; }
+    else ord = (b & 0x8000u) ? (uint32_t)(unsigned short)~b : (uint32_t)(b | 0x8000u);
+    return (ord << 16) | (slot << 1) | nz;
+}
+__device__ __forceinline__ unsigned short key_bits(uint32_t key) {
+    const uint32_t ord = key >> 16;
+    if (ord == 0u) return 0x7fffu;
+    if (ord == 0x8000u) return (key & 1u) ? 0x8000u : 0u;
+    return (ord & 0x8000u) ? (unsigned short)(ord & 0x7fffu) : (unsigned short)~ord;
+}
+
+__device__ __forceinline__ void unpack_rec(const TriRec* rec, H3& a, H3& b, H3& c, H3& n) {
+    const uint4 q0 = __ldg(reinterpret_cast<const uint4*>(rec));
+    const uint2 q1 = __ldg(reinterpret_cast<const uint2*>(rec) + 2);
+    a = {h_from_bits(q0.x & 0xffff), h_from_bits(q0.x >> 16), h_from_bits(q0.y & 0xffff)};
+    b = {h_from_bits(q0.y >> 16), h_from_bits(q0.z & 0xffff), h_from_bits(q0.z >> 16)};
+    c = {h_from_bits(q0.w & 0xffff), h_from_bits(q0.w >> 16), h_from_bits(q1.x & 0xffff)};
+    n = {h_from_bits(q1.x >> 16), h_from_bits(q1.y & 0xffff), h_from_bits(q1.y >> 16)};
+}
+
+// A ray that holds a hit with k > 11.0 and no nearer one: the first slot whose value is <= 11.0 (a miss, or a hit at
+// exactly 11.0) wins torch.min, and that slot is not necessarily 0.  Vanishingly rare (the rover would have to hover
+// 11 m above the mesh), so one thread simply walks the K candidates with the literal op sequence.
+static __device__ __noinline__ uint32_t literal_ray(const int32_t* row, int K, const TriRec* recs, H3 s, H3 d) {
+    uint32_t best = 0xffffffffu;
+    for (int j = 0; j < K; ++j) {
+        H3 a, b, c, nn;
+        unpack_rec(recs + __ldg(row + j), a, b, c, nn);
+        best = min(best, make_key(h_bits(pair_test(s, d, a, b, c, nn)), (uint32_t)j));
+    }
+    return best;
+}
+
+
+// Epilogue in ray order: coalesced stores of dist / hit slot / hit triangle / pt / sources and the fused sparse+dense
+// observation columns (heightmap_distribution.py:126-133, rover.py:324-325).  res[p] = best key of local ray p; a set bit
+// in far[] marks a ray that saw a hit beyond the 11.0 miss sentinel (resolved literally here).
+__device__ __forceinline__ void epilogue(const TiledParams& q, int64_t n, int p0, int np, const Trig& tr, double tx, double ty,
+                                         double tz, __half2 dx2, __half2 dy2, __half2 dz2, const uint32_t* res,
+                                         const uint32_t* far, int tid, int nthreads) {
+    const H3 dlit = {__low2half(dx2), __low2half(dy2), __low2half(dz2)};
+    const bool want_geo = q.hit_tri || q.pt || q.sources;
+    for (int p = tid; p < np; p += nthreads) {
+        uint32_t key = res[p];
+        const bool far_hit = (far[p >> 5] >> (p & 31)) & 1u;
+        if (far_hit && (key >> 16) == ORD_MISS) {
+            const double* pp = q.pattern + (int64_t)(p0 + p) * 3;
+            double xo, yo, zo;
+            body_transform<double>(pp[0], pp[1], pp[2], tr, tx, ty, tz, xo, yo, zo);
+            const H3 s = {h_from_double(xo), h_from_double(yo), h_from_double(zo)};
+            const int cx = cell_coord(s.x, q.shift_x, q.res, q.inv_res, q.G0 - 1, q.sem);
+            const int cy = min(cell_coord(s.y, q.shift_y, q.res, q.inv_res, q.G0 - 1, q.sem), q.G1 - 1);
+            key = literal_ray(q.index + ((int64_t)cx * q.G1 + cy) * q.Ks, q.K, q.recs, s, dlit);
+        }
+        const unsigned short kb = key_bits(key);
+        const int slot = (int)((key >> 1) & 0x7fffu);
+        const int64_t o = n * q.P + p0 + p;
+        q.dist[o] = h_from_bits(kb);
+        if (q.hit_slot) q.hit_slot[o] = slot;
+        if (want_geo) {
+            const double* pp = q.pattern + (int64_t)(p0 + p) * 3;
+            double xo, yo, zo;
+            body_transform<double>(pp[0], pp[1], pp[2], tr, tx, ty, tz, xo, yo, zo);
+            const __half hx = h_from_double(xo), hy = h_from_double(yo), hz = h_from_double(zo);
+            if (q.sources) { q.sources[o * 3 + 0] = hx; q.sources[o * 3 + 1] = hy; q.sources[o * 3 + 2] = hz; }
+            if (q.hit_tri) {
+                const int cx = cell_coord(hx, q.shift_x, q.res, q.inv_res, q.G0 - 1, q.sem);
+                const int cy = min(cell_coord(hy, q.shift_y, q.res, q.inv_res, q.G0 - 1, q.sem), q.G1 - 1);
+                q.hit_tri[o] = __ldg(q.index + ((int64_t)cx * q.G1 + cy) * q.Ks + slot);
+            }
+            if (q.pt) {
+                const __half k = h_from_bits(kb);
+                q.pt[o * 3 + 0] = h_sub(hx, h_mul(__low2half(dx2), k));     // ray_casting.py:63
+                q.pt[o * 3 + 1] = h_sub(hy, h_mul(__low2half(dy2), k));
+                q.pt[o * 3 + 2] = h_sub(hz, h_mul(__low2half(dz2), k));
+            }
+        }
+        if (q.obs) {
+            const float v = __half2float(h_mul(h_from_bits(kb), __float2half_rn(0.5f)));     // fp16(dist / 2) -> f32
+            const int ca = q.col_a[p0 + p], cb = q.col_b[p0 + p];
+            if (ca >= 0) q.obs[n * q.obs_ld + ca] = v;
+            if (cb >= 0) q.obs[n * q.obs_ld + cb] = v;
+        }
+    }
+}
+
+}  // namespace rc

@@ -1,0 +1,700 @@
+// Production heightmap ray-cast kernel ("shadow" culling): Camera.get_depths (camera.py:60-145) in one launch.
+//
+// The reference tests every ray against the K = 200 candidates of its cell; about 1.5 of them are hits.  All rays of
+// an env share ONE direction d (camera.py:202-207), so a triangle's pre-image under the test -- the set of sources s
+// that can pass `n >= -eps, m >= -eps, n + m <= 1 + eps` -- is a prism parallel to d, and the sources lie on a plane
+// (the pattern has constant z).  The kernel therefore enumerates TRIANGLES, not (ray, candidate) pairs:
+//
+//   phase 1/2  (as raycast_tiled.cu) fp64 body transform -> fp16 sources, cell lookup, counting sort of the tile's rays
+//              by 3x3-cell block (shared memory, column-major bins, so a block rectangle is a few contiguous ranges);
+//   stage 1    per (superblock, triangle of its list -- the union of the K-lists of 8x8 blocks): a bounding disc of the
+//              prism's cross-section on the source plane against the rectangle of the superblock's rays (~45 instr.);
+//   stage 2    survivors: exact corners of the cross-section -> xy box -> block columns -> ray ranges (tasks);
+//   stage 3a   rays of a task against the box (two packed-fp16 compares per ray);
+//   stage 3b   the (ray, triangle) pairs left (about 2.3 per hit): LITERAL evaluation of ray_casting.py:34-59 with its
+//              three IEEE divisions, membership + slot of the triangle in the ray's own cell list (binary search in the
+//              cell's 3x3 block list), atomicMin on (order-preserving fp16 bits, slot) = torch.min.
+//
+// Bit-exactness rests on stage 3b alone; stages 1-3a only have to be CONSERVATIVE (never drop a pair the literal test
+// would accept).  The bound: with g = s - a, the reference's numerators N = fl((g x c) . d), M = fl((b x g) . d) differ
+// from the exact N* = n det*, M* = m det* (det* = (b x c) . d, s = a + n b + m c + t d) by at most
+//     E = GAMMA * |g|_2 * sum_i aw_i + ALPHA,   aw_i = |c_j||d_k| + |c_k||d_j|,   GAMMA = 2^-8 >= (1 + 2^-11)^6 - 1
+// (six fp16 roundings per term, ALPHA for subnormal products), so a passing source satisfies
+//     n >= -(tlo + E_N)/|det*|,  m >= -(tlo + E_M)/|det*|,  n + m <= (thi' + E_N + E_M)/|det*|
+// with tlo/thi the outward-rounded fp16 thresholds of the packed pre-filter of raycast_tiled.cu (a superset of the
+// literal test).  |g| is bounded self-consistently from the disc of stage 1.  Triangles for which no bound holds
+// (|det*| within rounding of 0, fp16 overflow possible, NaN) are tested against every ray of the superblock.
+// tools/shadow_proto.py re-states stages 1-2 in numpy and checks them against a brute-force fp16 evaluation;
+// tests/test_shadow_bound_cpu.py runs it.  Envs this kernel cannot group (rays spread over more than 8192 blocks or
+// 128 superblocks) or whose rays are nearly parallel to the ground (cos < cos_steep: the prisms become long slivers)
+// are handed to the tiled kernel through a work list.
+#include <string.h>
+
+#include "raycast_common.cuh"
+
+int fill_tiled_params(const rvb_terrain* t, const float* pos, const float* euler, const float* trig, const double* pattern,
+                      int64_t P, int64_t N, uint16_t* dist, int32_t* hit_slot, int32_t* hit_tri, uint16_t* pt,
+                      uint16_t* sources, float* obs, int64_t obs_ld, const int32_t* col_a, const int32_t* col_b,
+                      rc::TiledParams& q);
+int launch_tiled(const rc::TiledParams& q, bool blocks, int64_t grid, cudaStream_t st);
+
+namespace {
+
+using namespace rc;
+
+constexpr int TT = 256;
+constexpr int NW = TT / 32;
+constexpr int RT_MAX = 2048;       // rays per tile; must equal raycast_tiled.cu's (shared tiling of the fall-back list)
+constexpr int RPT = RT_MAX / TT;
+constexpr int BIN_CAP = 8192;      // blocks in the tile's bounding box
+constexpr int SB = RVB_SB;
+constexpr int ITEM_CAP = 128;      // superblocks per tile (7 bits travel in the stage-1 queue)
+constexpr int CHUNK = 128;         // list entries per pulled work chunk
+constexpr int QCAP = 64;           // per-warp queues (each drained below 32 after every push of <= 32)
+constexpr int TASK_RAYS = 16;
+
+constexpr float GAMMA = 0.00390625f;            // 2^-8
+constexpr float ALPHA = 1.9073486328125e-06f;   // 2^-19
+constexpr float EPS0 = 0.1057f;
+constexpr float L_CAP = 64.0f;
+constexpr float OVF = 16000.0f;
+constexpr float SQ3 = 1.7320509f;
+
+struct Item {
+    uint32_t list_off, list_len;
+    float rlox, rhix, rloy, rhiy;   // rectangle holding the sources of the superblock's rays
+    uint32_t bx;                    // block columns with rays: lo | hi << 16 (absolute block coordinates)
+    uint32_t by;
+};
+static_assert(sizeof(Item) == 32, "Item");
+
+struct EnvC {
+    float dx, dy, dz;               // d = -normalize(dir) as the reference rounds it (fp16 values)
+    float nux, nuy, nuz;            // normal of the source plane
+    float inv_nd, hmid, hlo, hhi;   // nu . s in [hlo, hhi] for every source of the tile
+    float kappa, lam, dn, smax;
+};
+
+struct Smem {
+    uint2* rays;         // [RT]  sorted by block: (sx | sy << 16, sz | (p | sub << 11) << 16)
+    uint32_t* res;       // [RT]  best key per local ray id
+    uint32_t* bins;      // [BIN_CAP / 2 + 2]  u16 counters, then exclusive offsets (column-major bins)
+    Item* items;         // [ITEM_CAP]
+    uint32_t* cum;       // [ITEM_CAP + 1]  chunks before item i
+    uint2* q1;           // [NW][QCAP]  stage-1 survivors: (triangle, gball bits | item)
+    uint4* q2;           // [NW][QCAP]  tasks: (triangle, ray start | count << 16, box lo half2, box hi half2)
+    uint2* q3;           // [NW][QCAP]  pairs: (ray position, triangle)
+    uint32_t* far;       // [RT / 32]
+};
+
+__host__ __device__ inline size_t shadow_smem_bytes(int RT) {
+    return (size_t)RT * 8 + (size_t)((RT + 3) & ~3) * 4 + (size_t)(BIN_CAP / 2 + 4) * 4 + (size_t)ITEM_CAP * 32 +
+           (size_t)(ITEM_CAP + 4) * 4 + (size_t)NW * QCAP * (8 + 16 + 8) + (size_t)(((RT + 31) / 32 + 3) & ~3) * 4;
+}
+
+__device__ __forceinline__ float rcp_up(float x) { return __fdividef(1.0f, x) * 1.000001f; }
+__device__ __forceinline__ float hf(uint32_t bits16) { return __half2float(__ushort_as_half((unsigned short)bits16)); }
+__device__ __forceinline__ uint32_t off16(const uint32_t* bins, int bin) { return (bins[bin >> 1] >> ((bin & 1) * 16)) & 0xffffu; }
+
+// monotone non-decreasing in v (the arithmetic of cell_coord on an fp32 coordinate)
+__device__ __forceinline__ int cell_coord_f(float x, float shift, float res, float inv_res, int gmax, int sem) {
+    float v = __fsub_rn(x, shift);
+    v = (sem == RVB_SEM_TORCH_CPU) ? __fdiv_rn(v, res) : __fmul_rn(v, inv_res);
+    v = fminf(fmaxf(v, 0.0f), (float)gmax);
+    return (int)rintf(v);
+}
+
+struct TriF {
+    float ax, ay, az, bx, by, bz, cx, cy, cz;
+};
+__device__ __forceinline__ TriF tri_f(const uint4& q0, const uint2& q1) {
+    TriF t;
+    t.ax = hf(q0.x & 0xffff); t.ay = hf(q0.x >> 16); t.az = hf(q0.y & 0xffff);
+    t.bx = hf(q0.y >> 16); t.by = hf(q0.z & 0xffff); t.bz = hf(q0.z >> 16);
+    t.cx = hf(q0.w & 0xffff); t.cy = hf(q0.w >> 16); t.cz = hf(q1.x & 0xffff);
+    return t;
+}
+
+// Stage 1 (tools/shadow_proto.py: stage1).  Returns false if no source inside the rectangle can pass; gball >= |s - a|
+// for every passing source (+inf: no bound, the caller must test every ray of the item).
+__device__ __forceinline__ bool stage1(const TriF& t, const EnvC& e, float rlox, float rhix, float rloy, float rhiy, float& gball) {
+    const float third = 0.33333334f;
+    const float mx = __fmul_rn(__fadd_rn(t.bx, t.cx), third), my = __fmul_rn(__fadd_rn(t.by, t.cy), third),
+                mz = __fmul_rn(__fadd_rn(t.bz, t.cz), third);
+    const float qx0 = t.ax + mx, qy0 = t.ay + my, qz0 = t.az + mz;                    // centroid
+    const float ex = t.bx - t.cx, ey = t.by - t.cy, ez = t.bz - t.cz;
+    const float b2 = fmaf(t.bx, t.bx, fmaf(t.by, t.by, t.bz * t.bz)), c2 = fmaf(t.cx, t.cx, fmaf(t.cy, t.cy, t.cz * t.cz)),
+                e2 = fmaf(ex, ex, fmaf(ey, ey, ez * ez));
+    const float amax = fmaxf(fmaxf(fabsf(t.ax), fabsf(t.ay)), fabsf(t.az));
+    const float r = 0.6666667f * sqrtf(fmaxf(fmaxf(b2, c2), e2)) * 1.00001f + 1e-6f * amax;
+    const float nx = t.by * t.cz - t.bz * t.cy, ny = t.bz * t.cx - t.bx * t.cz, nz = t.bx * t.cy - t.by * t.cx;
+    const float adet = fabsf(fmaf(nx, e.dx, fmaf(ny, e.dy, nz * e.dz)));
+    const float cb = fmaxf(fmaxf(fmaxf(fabsf(t.bx), fabsf(t.by)), fabsf(t.bz)), fmaxf(fmaxf(fabsf(t.cx), fabsf(t.cy)), fabsf(t.cz)));
+    const float e_det = GAMMA * 6.1f * cb * cb + ALPHA;
+    const float rdet = rcp_up(adet);
+    const float eps0 = EPS0 + 1.3f * (e_det + 4.0f * ALPHA) * rdet;
+    const float rho = GAMMA * 2.01f * cb * rdet;
+    const float tc = (e.hmid - fmaf(qx0, e.nux, fmaf(qy0, e.nuy, qz0 * e.nuz))) * e.inv_nd;
+    const float atc = fabsf(tc) * e.dn;
+    const float kr = e.kappa * r;
+    const float Bn = SQ3 * (kr * (1.0f + 3.0f * eps0) + e.lam + atc + r);
+    const float den = 1.0f - 10.4f * kr * rho;
+    const float gsum = Bn * rcp_up(den);
+    const float eps = eps0 + 2.0f * rho * gsum;
+    const float R = kr * (1.0f + 3.0f * eps) + e.lam;
+    const bool fine = (den > 0.5f) && (adet > 4.0f * e_det) && (eps <= 16.0f) && ((e.smax + amax) * fmaxf(cb, 1.0f) <= OVF);
+    if (!fine) {                     // also every NaN case
+        gball = __int_as_float(0x7f800000);
+        return true;
+    }
+    gball = R + atc + r;
+    const float qx = fmaf(tc, e.dx, qx0), qy = fmaf(tc, e.dy, qy0);
+    const float Rs = R * 1.00001f + 1e-5f * (fabsf(qx) + fabsf(qy));
+    const bool out = (qx + Rs < rlox) || (qx - Rs > rhix) || (qy + Rs < rloy) || (qy - Rs > rhiy);
+    return !out;
+}
+
+// Stage 2 (tools/shadow_proto.py: stage2): xy box of the sources that can pass; full = no bound.
+__device__ __forceinline__ void stage2(const TriF& t, const uint2& q1, const EnvC& e, H3 d16, float gball, float& x0, float& x1,
+                                       float& y0, float& y1, bool& full) {
+    const __half n0 = h_from_bits(q1.x >> 16), n1 = h_from_bits(q1.y & 0xffff), n2 = h_from_bits(q1.y >> 16);
+    const __half det_h = h_add(h_add(h_mul(n0, d16.x), h_mul(n1, d16.y)), h_mul(n2, d16.z));           // ray_casting.py:41
+    const __half da = __habs(det_h);
+    const float tlo = __half2float(__hfma(da, h_from_bits(0x2E68u), h_from_bits(0x0002u)));              // = -tlo of the pre-filter
+    const float thi = __half2float(__hfma(da, h_from_bits(0x3C6Bu), h_from_bits(0x0002u)));
+    const float wx = t.cy * e.dz - t.cz * e.dy, wy = t.cz * e.dx - t.cx * e.dz, wz = t.cx * e.dy - t.cy * e.dx;    // c x d
+    const float dets = fmaf(t.bx, wx, fmaf(t.by, wy, t.bz * wz));
+    const float adx = fabsf(e.dx), ady = fabsf(e.dy), adz = fabsf(e.dz);
+    const float acx = fabsf(t.cx), acy = fabsf(t.cy), acz = fabsf(t.cz), abx = fabsf(t.bx), aby = fabsf(t.by), abz = fabsf(t.bz);
+    const float saw = fmaf(acy + acz, adx, fmaf(acz + acx, ady, (acx + acy) * adz));
+    const float sawp = fmaf(aby + abz, adx, fmaf(abz + abx, ady, (abx + aby) * adz));
+    const float rdet = __fdividef(1.0f, fabsf(dets)) * 1.001f;
+    const float EN = fmaf(GAMMA * gball, saw, ALPHA), EM = fmaf(GAMMA * gball, sawp, ALPHA);
+    const float l1 = (tlo + EN) * rdet, l2 = (tlo + EM) * rdet;
+    const float l3 = (fmaf(thi, 1.0009766f, 5.9604645e-08f) + EN + EM) * rdet;
+    const bool sign_ok = (__float_as_uint(dets) >> 31) == (uint32_t)(h_bits(det_h) >> 15);
+    const bool good = sign_ok && (fmaxf(fmaxf(l1, l2), l3) <= L_CAP) && (l1 == l1) && (l2 == l2) && (l3 == l3);
+    x0 = y0 = __int_as_float(0x7f800000);
+    x1 = y1 = __int_as_float(0xff800000);
+    float ext = 0.0f;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const float cn = (k == 1) ? (l3 + l2) : -l1, cm = (k == 2) ? (l3 + l1) : -l2;       // corners A, B, C in (n, m)
+        const float Px = fmaf(cn, t.bx, fmaf(cm, t.cx, t.ax)), Py = fmaf(cn, t.by, fmaf(cm, t.cy, t.ay)),
+                    Pz = fmaf(cn, t.bz, fmaf(cm, t.cz, t.az));
+        const float nP = fmaf(Px, e.nux, fmaf(Py, e.nuy, Pz * e.nuz));
+        const float t0 = (e.hlo - nP) * e.inv_nd, t1 = (e.hhi - nP) * e.inv_nd;
+        const float xa = fmaf(t0, e.dx, Px), xb = fmaf(t1, e.dx, Px), ya = fmaf(t0, e.dy, Py), yb = fmaf(t1, e.dy, Py);
+        x0 = fminf(x0, fminf(xa, xb)); x1 = fmaxf(x1, fmaxf(xa, xb));
+        y0 = fminf(y0, fminf(ya, yb)); y1 = fmaxf(y1, fmaxf(ya, yb));
+        ext = fmaxf(ext, fmaxf(fabsf(xa), fabsf(xb)) + fmaxf(fabsf(ya), fabsf(yb)));
+    }
+    const float sl = fmaf(ext, 7.6293945e-06f, 9.5367432e-07f);       // 2 * 2^-18 (ext is max |x| + |y| of one corner), 2^-20
+    x0 -= sl; x1 += sl; y0 -= sl; y1 += sl;
+    full = !good || !(x0 <= x1) || !(y0 <= y1);
+}
+
+__global__ void __launch_bounds__(TT, 3) hm_shadow_kernel(const TiledParams q) {
+    extern __shared__ uint4 smem_raw[];
+    __shared__ int s_box[4];
+    __shared__ float s_red[NW][12];
+    __shared__ uint32_t s_warp[NW];
+    __shared__ EnvC s_env;
+    __shared__ int s_next, s_nitems, s_nchunks, s_bail;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t n = blockIdx.x / q.tiles;
+    const int tile = blockIdx.x % q.tiles;
+    const int p0 = tile * q.tile_size;
+    const int np = min(q.tile_size, q.P - p0);
+    const int RT = q.tile_size;
+
+    Smem sm;
+    sm.rays = reinterpret_cast<uint2*>(smem_raw);
+    sm.res = reinterpret_cast<uint32_t*>(sm.rays + RT);
+    sm.bins = sm.res + ((RT + 3) & ~3);
+    sm.items = reinterpret_cast<Item*>(sm.bins + BIN_CAP / 2 + 4);
+    sm.cum = reinterpret_cast<uint32_t*>(sm.items + ITEM_CAP);
+    sm.q1 = reinterpret_cast<uint2*>(sm.cum + ITEM_CAP + 4);
+    sm.q2 = reinterpret_cast<uint4*>(sm.q1 + NW * QCAP);
+    sm.q3 = reinterpret_cast<uint2*>(sm.q2 + NW * QCAP);
+    sm.far = reinterpret_cast<uint32_t*>(sm.q3 + NW * QCAP);
+
+    // ---- phase 0
+    for (int i = tid; i < BIN_CAP / 2 + 4; i += TT) sm.bins[i] = 0u;
+    for (int i = tid; i < (RT + 31) / 32; i += TT) sm.far[i] = 0u;
+    if (tid == 0) {
+        s_box[0] = s_box[1] = 0x7fffffff;
+        s_box[2] = s_box[3] = -1;
+        s_next = 0;
+        s_bail = 0;
+    }
+    const Trig tr = make_trig(q.euler, q.trig, n);
+    const double tx = (double)q.pos[n * 3 + 0], ty = (double)q.pos[n * 3 + 1], tz = (double)q.pos[n * 3 + 2];
+    __half2 dx2, dy2, dz2;
+    H3 d16;
+    {
+        double xo, yo, zo;
+        body_transform<double>(0.0, 0.0, -1.0, tr, tx, ty, tz, xo, yo, zo);
+        d16 = neg_normalize({h_from_double(__dsub_rn(xo, tx)), h_from_double(__dsub_rn(yo, ty)), h_from_double(__dsub_rn(zo, tz))});
+        dx2 = __half2half2(d16.x); dy2 = __half2half2(d16.y); dz2 = __half2half2(d16.z);
+    }
+    __syncthreads();
+
+    // ---- phase 1: sources, cells, ranges
+    uint32_t r_sxy[RPT], r_sz[RPT];
+    int r_cell[RPT];
+    int mnx = 0x7fffffff, mny = 0x7fffffff, mxx = -1, mxy = -1;
+    float lo_x = __int_as_float(0x7f800000), lo_y = lo_x, hi_x = -lo_x, hi_y = -lo_x, amax_s = 0.0f;
+    float pz_lo = lo_x, pz_hi = -lo_x, pxy = 0.0f;
+    bool bad = false;
+#pragma unroll
+    for (int i = 0; i < RPT; ++i) {
+        const int p = tid + i * TT;
+        r_cell[i] = -1;
+        if (p < np) {
+            const double* pp = q.pattern + (int64_t)(p0 + p) * 3;
+            const double px = pp[0], py = pp[1], pz = pp[2];
+            double xo, yo, zo;
+            body_transform<double>(px, py, pz, tr, tx, ty, tz, xo, yo, zo);
+            const __half hx = h_from_double(xo), hy = h_from_double(yo), hz = h_from_double(zo);
+            r_sxy[i] = (uint32_t)h_bits(hx) | ((uint32_t)h_bits(hy) << 16);
+            int cx = cell_coord(hx, q.shift_x, q.res, q.inv_res, q.G0 - 1, q.sem);
+            int cy = min(cell_coord(hy, q.shift_y, q.res, q.inv_res, q.G0 - 1, q.sem), q.G1 - 1);   // camera.py:243
+            const int bx = cx / RVB_BLK, by = cy / RVB_BLK;
+            const uint32_t sub = (uint32_t)((cx - bx * RVB_BLK) * RVB_BLK + (cy - by * RVB_BLK));
+            r_sz[i] = (uint32_t)h_bits(hz) | (((uint32_t)p | (sub << 11)) << 16);
+            r_cell[i] = (bx << 16) | by;
+            mnx = min(mnx, bx); mxx = max(mxx, bx); mny = min(mny, by); mxy = max(mxy, by);
+            const float fx = __half2float(hx), fy = __half2float(hy), fz = __half2float(hz);
+            lo_x = fminf(lo_x, fx); hi_x = fmaxf(hi_x, fx); lo_y = fminf(lo_y, fy); hi_y = fmaxf(hi_y, fy);
+            amax_s = fmaxf(amax_s, fmaxf(fmaxf(fabsf(fx), fabsf(fy)), fabsf(fz)));
+            bad |= !(fabsf(fx) <= 65504.0f) || !(fabsf(fy) <= 65504.0f) || !(fabsf(fz) <= 65504.0f);
+            pz_lo = fminf(pz_lo, __double2float_rd(pz)); pz_hi = fmaxf(pz_hi, __double2float_ru(pz));
+            pxy = fmaxf(pxy, fmaxf(fabsf(__double2float_ru(fabs(px))), fabsf(__double2float_ru(fabs(py)))));
+        }
+    }
+    mnx = __reduce_min_sync(0xffffffffu, mnx); mny = __reduce_min_sync(0xffffffffu, mny);
+    mxx = __reduce_max_sync(0xffffffffu, mxx); mxy = __reduce_max_sync(0xffffffffu, mxy);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        lo_x = fminf(lo_x, __shfl_xor_sync(0xffffffffu, lo_x, o)); hi_x = fmaxf(hi_x, __shfl_xor_sync(0xffffffffu, hi_x, o));
+        lo_y = fminf(lo_y, __shfl_xor_sync(0xffffffffu, lo_y, o)); hi_y = fmaxf(hi_y, __shfl_xor_sync(0xffffffffu, hi_y, o));
+        amax_s = fmaxf(amax_s, __shfl_xor_sync(0xffffffffu, amax_s, o));
+        pz_lo = fminf(pz_lo, __shfl_xor_sync(0xffffffffu, pz_lo, o)); pz_hi = fmaxf(pz_hi, __shfl_xor_sync(0xffffffffu, pz_hi, o));
+        pxy = fmaxf(pxy, __shfl_xor_sync(0xffffffffu, pxy, o));
+    }
+    bad = __any_sync(0xffffffffu, bad);
+    if (lane == 0) {
+        atomicMin(&s_box[0], mnx); atomicMin(&s_box[1], mny);
+        atomicMax(&s_box[2], mxx); atomicMax(&s_box[3], mxy);
+        float* w = s_red[warp];
+        w[0] = lo_x; w[1] = hi_x; w[2] = lo_y; w[3] = hi_y; w[4] = amax_s; w[5] = pz_lo; w[6] = pz_hi; w[7] = pxy;
+        if (bad) s_bail = 1;
+    }
+    __syncthreads();
+    const int bx0 = s_box[0], by0 = s_box[1];
+    const int BW = s_box[2] - bx0 + 1, BH = s_box[3] - by0 + 1;
+    const int sbx0 = bx0 / SB, sby0 = by0 / SB;
+    const int nsx = s_box[2] / SB - sbx0 + 1, nsy = s_box[3] / SB - sby0 + 1;
+    float g_lox = s_red[0][0], g_hix = s_red[0][1], g_loy = s_red[0][2], g_hiy = s_red[0][3];
+    {
+        float a_s = s_red[0][4], z0 = s_red[0][5], z1 = s_red[0][6], pm = s_red[0][7];
+#pragma unroll
+        for (int w = 1; w < NW; ++w) {
+            g_lox = fminf(g_lox, s_red[w][0]); g_hix = fmaxf(g_hix, s_red[w][1]);
+            g_loy = fminf(g_loy, s_red[w][2]); g_hiy = fmaxf(g_hiy, s_red[w][3]);
+            a_s = fmaxf(a_s, s_red[w][4]); z0 = fminf(z0, s_red[w][5]); z1 = fmaxf(z1, s_red[w][6]); pm = fmaxf(pm, s_red[w][7]);
+        }
+        if (tid == 0) {
+            // source plane: s = t + x c1 + y c2 + z c3 (columns of camera.py:197-199), nu = c1 x c2 (tools/shadow_proto.py: EnvConsts)
+            const double sx = tr.sx, cx = tr.cx, sy = tr.sy, cy = tr.cy, sz = tr.sz, cz = tr.cz;
+            const double c1x = cz * cy, c1y = -sz * cy, c1z = sy;
+            const double c2x = sz * cx + cz * sy * sx, c2y = cz * cx - sz * sy * sx, c2z = -cy * sx;
+            const double c3x = sz * sx - cz * sy * cx, c3y = cz * sx + sz * sy * cx, c3z = cy * cx;
+            const float nux = (float)(c1y * c2z - c1z * c2y), nuy = (float)(c1z * c2x - c1x * c2z), nuz = (float)(c1x * c2y - c1y * c2x);
+            const double h0 = (double)nux * tx + (double)nuy * ty + (double)nuz * tz;
+            const double k1 = (double)nux * c1x + (double)nuy * c1y + (double)nuz * c1z;
+            const double k2 = (double)nux * c2x + (double)nuy * c2y + (double)nuz * c2z;
+            const double k3 = (double)nux * c3x + (double)nuy * c3y + (double)nuz * c3z;
+            const double ha = h0 + (double)z0 * k3, hb = h0 + (double)z1 * k3;
+            // half ulp of the largest source coordinate (sources are fp16 values); every coordinate moves by at most that
+            const uint32_t ab = __float_as_uint(a_s);
+            const int ex = (int)(ab >> 23) - 127;
+            const float qh = (ex >= -14) ? __uint_as_float((uint32_t)(ex - 11 + 127) << 23) : 2.9802322e-08f;
+            const double an = fabs((double)nux) + fabs((double)nuy) + fabs((double)nuz);
+            // tau: rounding of the sources + the fp32 evaluation of nu . P in the stages + pattern x/y leakage
+            const double tau = an * (double)qh * 1.01 + (double)pm * (fabs(k1) + fabs(k2)) +
+                               1e-6 * (fabs(ha) + fabs(hb) + an * ((double)a_s + 16.0)) + 1e-7;
+            EnvC e;
+            e.dx = __half2float(d16.x); e.dy = __half2float(d16.y); e.dz = __half2float(d16.z);
+            e.nux = nux; e.nuy = nuy; e.nuz = nuz;
+            const float nd = fmaf(nux, e.dx, fmaf(nuy, e.dy, nuz * e.dz));
+            e.inv_nd = 1.0f / nd;
+            e.hlo = __double2float_rd(fmin(ha, hb) - tau);
+            e.hhi = __double2float_ru(fmax(ha, hb) + tau);
+            e.hmid = 0.5f * (e.hlo + e.hhi);
+            const float dn = sqrtf(fmaf(e.dx, e.dx, fmaf(e.dy, e.dy, e.dz * e.dz))) * 1.000001f;
+            const float nn = sqrtf(fmaf(nux, nux, fmaf(nuy, nuy, nuz * nuz))) * 1.000001f;
+            e.dn = dn;
+            e.kappa = dn * nn / fabsf(nd) * 1.00001f;
+            e.lam = dn * (0.5f * (e.hhi - e.hlo) + 1e-6f * (fabsf(e.hlo) + fabsf(e.hhi))) / fabsf(nd) * 1.00001f + 1e-7f;
+            e.smax = a_s;
+            s_env = e;
+            // cos of the angle between the rays and the plane normal ~ 1; steep = rays nearly horizontal in the WORLD
+            const bool steep = !(fabsf(e.dz) >= q.cos_steep);
+            const bool ungrouped = (int64_t)BW * BH > BIN_CAP || (int64_t)nsx * nsy > ITEM_CAP;
+            const bool degenerate = !(fabsf(nd) > 0.5f) || !(e.kappa < 2.0f) || !(e.lam < 1e4f) || !(a_s <= 65504.0f);
+            if (steep || ungrouped || degenerate) s_bail = 1;
+        }
+    }
+    __syncthreads();
+    if (s_bail) {
+        // hand this (env, tile) to the tiled kernel
+        if (tid == 0) q.fb_list[atomicAdd(q.fb_count, 1)] = (int32_t)blockIdx.x;
+        return;
+    }
+
+    // ---- phase 2: counting sort by block, column-major bins
+    {
+        uint32_t r_rank[RPT];
+#pragma unroll
+        for (int i = 0; i < RPT; ++i) {
+            if (r_cell[i] >= 0) {
+                const int bin = ((r_cell[i] >> 16) - bx0) * BH + ((r_cell[i] & 0xffff) - by0);
+                const uint32_t old = atomicAdd(&sm.bins[bin >> 1], 1u << ((bin & 1) * 16));
+                r_rank[i] = (old >> ((bin & 1) * 16)) & 0xffffu;
+            }
+        }
+        __syncthreads();
+        // exclusive scan in bin order: thread t owns the contiguous words [t * wpt, (t + 1) * wpt)
+        const int nwords = ((BW * BH) >> 1) + 1;                 // covers bins 0 .. BW*BH (sentinel = total)
+        const int wpt = (nwords + TT - 1) / TT;
+        const int w0 = tid * wpt, w1 = min(w0 + wpt, nwords);
+        uint32_t tot = 0;
+        for (int w = w0; w < w1; ++w) {
+            const uint32_t v = sm.bins[w];
+            tot += (v & 0xffffu) + (v >> 16);
+        }
+        uint32_t inc = tot;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t v = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += v;
+        }
+        if (lane == 31) s_warp[warp] = inc;
+        __syncthreads();
+        uint32_t run = inc - tot;
+#pragma unroll
+        for (int w = 0; w < NW; ++w)
+            if (w < warp) run += s_warp[w];
+        for (int w = w0; w < w1; ++w) {
+            const uint32_t v = sm.bins[w];
+            const uint32_t a = v & 0xffffu, b = v >> 16;
+            sm.bins[w] = run | ((run + a) << 16);
+            run += a + b;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < RPT; ++i) {
+            if (r_cell[i] >= 0) {
+                const int p = tid + i * TT;
+                const int bin = ((r_cell[i] >> 16) - bx0) * BH + ((r_cell[i] & 0xffff) - by0);
+                sm.rays[off16(sm.bins, bin) + r_rank[i]] = make_uint2(r_sxy[i], r_sz[i]);
+                sm.res[p] = KEY_INIT;
+            }
+        }
+    }
+    // ---- superblock items: block rectangle with rays, source rectangle, candidate list
+    const int nsb = nsx * nsy;
+    int* it_red = reinterpret_cast<int*>(sm.q2);          // [4][ITEM_CAP] bx lo, bx hi, by lo, by hi (queues are idle here)
+    for (int i = tid; i < nsb; i += TT) {
+        it_red[i] = 0x7fffffff; it_red[ITEM_CAP + i] = -1;
+        it_red[2 * ITEM_CAP + i] = 0x7fffffff; it_red[3 * ITEM_CAP + i] = -1;
+    }
+    if (tid == 0) s_nitems = 0;
+    __syncthreads();
+    for (int i = tid; i < nsb * SB; i += TT) {
+        const int sbi = i / SB, col = i % SB;
+        const int SX = sbx0 + sbi / nsy, SY = sby0 + sbi % nsy;
+        const int bx = SX * SB + col;
+        if (bx < bx0 || bx >= bx0 + BW) continue;
+        const int rlo = max(by0, SY * SB), rhi = min(by0 + BH - 1, SY * SB + SB - 1);
+        const int base = (bx - bx0) * BH - by0;
+        int ylo = 0x7fffffff, yhi = -1;
+        for (int y = rlo; y <= rhi; ++y) {
+            if (off16(sm.bins, base + y + 1) > off16(sm.bins, base + y)) {
+                ylo = min(ylo, y);
+                yhi = y;
+            }
+        }
+        if (yhi >= 0) {
+            atomicMin(&it_red[sbi], bx); atomicMax(&it_red[ITEM_CAP + sbi], bx);
+            atomicMin(&it_red[2 * ITEM_CAP + sbi], ylo); atomicMax(&it_red[3 * ITEM_CAP + sbi], yhi);
+        }
+    }
+    __syncthreads();
+    {
+        const float slop = 1e-6f * (fmaxf(fabsf(q.shift_x), fabsf(q.shift_y)) + (float)max(q.G0, q.G1) * q.res) + 1e-4f * q.res;
+        const float inf = __int_as_float(0x7f800000);
+        for (int i = tid; i < nsb; i += TT) {
+            const int bxl = it_red[i], bxh = it_red[ITEM_CAP + i], byl = it_red[2 * ITEM_CAP + i], byh = it_red[3 * ITEM_CAP + i];
+            if (bxh < 0) continue;
+            const int SX = sbx0 + i / nsy, SY = sby0 + i % nsy;
+            const uint32_t sb = (uint32_t)SX * (uint32_t)q.nSBy + (uint32_t)SY;
+            Item it;
+            it.list_off = __ldg(q.sb_off + sb);
+            it.list_len = __ldg(q.sb_off + sb + 1) - it.list_off;
+            const int cxl = bxl * RVB_BLK, cxh = bxh * RVB_BLK + RVB_BLK - 1, cyl = byl * RVB_BLK, cyh = byh * RVB_BLK + RVB_BLK - 1;
+            // a source whose cell is >= c lies above shift + (c - 0.5) res (minus slop); clamped border cells hold everything beyond
+            it.rlox = fmaxf(g_lox, cxl <= 0 ? -inf : q.shift_x + ((float)cxl - 0.52f) * q.res - slop);
+            it.rhix = fminf(g_hix, cxh >= q.G0 - 1 ? inf : q.shift_x + ((float)cxh + 0.52f) * q.res + slop);
+            it.rloy = fmaxf(g_loy, cyl <= 0 ? -inf : q.shift_y + ((float)cyl - 0.52f) * q.res - slop);
+            it.rhiy = fminf(g_hiy, cyh >= min(q.G0, q.G1) - 1 ? inf : q.shift_y + ((float)cyh + 0.52f) * q.res + slop);
+            it.bx = (uint32_t)bxl | ((uint32_t)bxh << 16);
+            it.by = (uint32_t)byl | ((uint32_t)byh << 16);
+            sm.items[atomicAdd(&s_nitems, 1)] = it;
+        }
+    }
+    __syncthreads();
+    if (tid == 0) {
+        const int ni = s_nitems;
+        uint32_t c = 0;
+        for (int i = 0; i < ni; ++i) {
+            sm.cum[i] = c;
+            c += (sm.items[i].list_len + CHUNK - 1) / CHUNK;
+        }
+        sm.cum[ni] = c;
+        s_nchunks = (int)c;
+    }
+    __syncthreads();
+
+    // ---- phase 3: warps pull (superblock, chunk of its list); stage 1 -> q1 -> stage 2 -> q2 -> stage 3a -> q3 -> stage 3b
+    const EnvC e = s_env;
+    const int nitems = s_nitems, nchunks = s_nchunks;
+    uint2* q1 = sm.q1 + warp * QCAP;
+    uint4* q2 = sm.q2 + warp * QCAP;
+    uint2* q3 = sm.q3 + warp * QCAP;
+    uint32_t h1 = 0, t1 = 0, h2 = 0, t2 = 0, h3 = 0, t3 = 0;          // warp-uniform
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    const uint32_t FULLM = 0xffffffffu;
+
+    // stage 3b: literal evaluation + slot lookup of up to 32 queued (ray, triangle) pairs, one per lane
+    auto run3b = [&](uint32_t cnt) {
+        if ((uint32_t)lane < cnt) {
+            const uint2 pr = q3[(h3 + lane) & (QCAP - 1)];
+            const uint2 ray = sm.rays[pr.x];
+            const H3 s = {h_from_bits(ray.x & 0xffff), h_from_bits(ray.x >> 16), h_from_bits(ray.y & 0xffff)};
+            H3 a, b, c, nn;
+            unpack_rec(q.recs + pr.y, a, b, c, nn);
+            const __half k = pair_test(s, d16, a, b, c, nn);
+            if (h_bits(k) != RVB_H_MISS) {      // a hit at exactly 11.0 equals the all-miss result (slot 0)
+                const uint32_t meta = ray.y >> 16, p = meta & 0x7ffu, sub = meta >> 11;
+                const int cx = cell_coord(s.x, q.shift_x, q.res, q.inv_res, q.G0 - 1, q.sem);
+                const int cy = min(cell_coord(s.y, q.shift_y, q.res, q.inv_res, q.G0 - 1, q.sem), q.G1 - 1);
+                const uint32_t blk = (uint32_t)(cx / RVB_BLK) * (uint32_t)q.nBy + (uint32_t)(cy / RVB_BLK);
+                const uint32_t o0 = __ldg(q.blk_off + blk), o1 = __ldg(q.blk_off + blk + 1);
+                uint32_t lo = o0, hi = o1;
+                while (lo < hi) {                       // block lists are sorted by triangle id
+                    const uint32_t mid = (lo + hi) >> 1;
+                    if (__ldg(q.blk_ids + mid) < (int32_t)pr.y) lo = mid + 1; else hi = mid;
+                }
+                if (lo < o1 && __ldg(q.blk_ids + lo) == (int32_t)pr.y) {
+                    const uint32_t slot = __ldg(reinterpret_cast<const unsigned char*>(q.blk_slots + lo) + sub);
+                    if (slot != 0xffu) {                // the triangle is in the ray's own cell list
+                        const uint32_t key = make_key(h_bits(k), slot);
+                        if ((key >> 16) > ORD_MISS) atomicOr(&sm.far[p >> 5], 1u << (p & 31));      // k > 11: see epilogue
+                        else atomicMin(&sm.res[p], key);
+                    }
+                }
+            }
+        }
+        h3 += cnt;
+    };
+
+    // stage 3a: up to 32 tasks (triangle, <= 16 consecutive sorted rays, box), one per lane
+    auto run3a = [&](uint32_t cnt) {
+        uint4 tk = make_uint4(0, 0, 0, 0);
+        int c = 0;
+        if ((uint32_t)lane < cnt) {
+            tk = q2[(h2 + lane) & (QCAP - 1)];
+            c = (int)(tk.y >> 16);
+        }
+        h2 += cnt;
+        const int cmax = __reduce_max_sync(FULLM, c);
+        const uint32_t start = tk.y & 0xffffu;
+        for (int i = 0; i < cmax; ++i) {
+            bool in = false;
+            if (i < c) {
+                const uint32_t w0 = sm.rays[start + i].x;
+                in = (__hge2_mask(*reinterpret_cast<const __half2*>(&w0), *reinterpret_cast<const __half2*>(&tk.z)) &
+                      __hle2_mask(*reinterpret_cast<const __half2*>(&w0), *reinterpret_cast<const __half2*>(&tk.w))) == 0xffffffffu;
+            }
+            const uint32_t m = __ballot_sync(FULLM, in);
+            if (m) {
+                if (in) q3[(t3 + __popc(m & lt_mask)) & (QCAP - 1)] = make_uint2(start + (uint32_t)i, tk.x);
+                t3 += __popc(m);
+                if (t3 - h3 >= 32u) {
+                    __syncwarp();
+                    run3b(32u);
+                    __syncwarp();
+                }
+            }
+        }
+    };
+
+    // stage 2: up to 32 surviving triangles, one per lane -> tasks
+    auto run2 = [&](uint32_t cnt) {
+        uint32_t tri = 0, lo16 = 0, hi16 = 0;
+        int col = 1, cx1 = 0, r_lo = 0, r_hi = 0;          // empty column range
+        if ((uint32_t)lane < cnt) {
+            const uint2 en = q1[(h1 + lane) & (QCAP - 1)];
+            tri = en.x;
+            const float gball = __uint_as_float(en.y & ~0x7fu);
+            const Item it = sm.items[en.y & 0x7fu];
+            const uint4 r0 = __ldg(reinterpret_cast<const uint4*>(q.recs + tri));
+            const uint2 r1 = __ldg(reinterpret_cast<const uint2*>(q.recs + tri) + 2);
+            const TriF t = tri_f(r0, r1);
+            float x0, x1, y0, y1;
+            bool full;
+            stage2(t, r1, e, d16, gball, x0, x1, y0, y1, full);
+            int bxl = (int)(it.bx & 0xffffu), bxh = (int)(it.bx >> 16), byl = (int)(it.by & 0xffffu), byh = (int)(it.by >> 16);
+            if (!full) {
+                bxl = max(bxl, cell_coord_f(x0, q.shift_x, q.res, q.inv_res, q.G0 - 1, q.sem) / RVB_BLK);
+                bxh = min(bxh, cell_coord_f(x1, q.shift_x, q.res, q.inv_res, q.G0 - 1, q.sem) / RVB_BLK);
+                byl = max(byl, min(cell_coord_f(y0, q.shift_y, q.res, q.inv_res, q.G0 - 1, q.sem), q.G1 - 1) / RVB_BLK);
+                byh = min(byh, min(cell_coord_f(y1, q.shift_y, q.res, q.inv_res, q.G0 - 1, q.sem), q.G1 - 1) / RVB_BLK);
+                lo16 = (uint32_t)h_bits(__float2half_ru(x0)) | ((uint32_t)h_bits(__float2half_ru(y0)) << 16);
+                hi16 = (uint32_t)h_bits(__float2half_rd(x1)) | ((uint32_t)h_bits(__float2half_rd(y1)) << 16);
+            } else {
+                lo16 = 0xFC00FC00u;
+                hi16 = 0x7C007C00u;
+            }
+            if (bxl <= bxh && byl <= byh) {
+                col = bxl; cx1 = bxh;
+                r_lo = byl - by0; r_hi = byh - by0 + 1;
+            }
+        }
+        h1 += cnt;
+        uint32_t cur = 0, end = 0;
+        while (true) {
+            while (cur >= end && col <= cx1) {
+                const int b = (col - bx0) * BH;
+                cur = off16(sm.bins, b + r_lo);
+                end = off16(sm.bins, b + r_hi);
+                ++col;
+            }
+            const bool have = cur < end;
+            const uint32_t m = __ballot_sync(FULLM, have);
+            if (!m) break;
+            if (have) {
+                const uint32_t c = min(end - cur, (uint32_t)TASK_RAYS);
+                q2[(t2 + __popc(m & lt_mask)) & (QCAP - 1)] = make_uint4(tri, cur | (c << 16), lo16, hi16);
+                cur += c;
+            }
+            t2 += __popc(m);
+            if (t2 - h2 >= 32u) {
+                __syncwarp();
+                run3a(32u);
+                __syncwarp();
+            }
+        }
+    };
+
+    while (true) {
+        int g = 0;
+        if (lane == 0) g = atomicAdd(&s_next, 1);
+        g = __shfl_sync(FULLM, g, 0);
+        if (g >= nchunks) break;
+        int ilo = 0, ihi = nitems;                       // largest i with cum[i] <= g
+        while (ihi - ilo > 1) {
+            const int mid = (ilo + ihi) >> 1;
+            if (sm.cum[mid] <= (uint32_t)g) ilo = mid; else ihi = mid;
+        }
+        const Item it = sm.items[ilo];
+        const uint32_t cbeg = ((uint32_t)g - sm.cum[ilo]) * CHUNK;
+        const int cn = (int)min((uint32_t)CHUNK, it.list_len - cbeg);
+        const int32_t* ids = q.sb_ids + it.list_off + cbeg;
+        int32_t id[CHUNK / 32];
+        uint4 r0[CHUNK / 32];
+        uint2 r1[CHUNK / 32];
+#pragma unroll
+        for (int j = 0; j < CHUNK / 32; ++j) id[j] = (lane + 32 * j < cn) ? __ldg(ids + lane + 32 * j) : -1;
+#pragma unroll
+        for (int j = 0; j < CHUNK / 32; ++j) {
+            if (id[j] >= 0) {
+                r0[j] = __ldg(reinterpret_cast<const uint4*>(q.recs + id[j]));
+                r1[j] = __ldg(reinterpret_cast<const uint2*>(q.recs + id[j]) + 2);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < CHUNK / 32; ++j) {
+            if (32 * j < cn) {
+                bool keep = false;
+                float gball = 0.0f;
+                if (id[j] >= 0) keep = stage1(tri_f(r0[j], r1[j]), e, it.rlox, it.rhix, it.rloy, it.rhiy, gball);
+                const uint32_t m = __ballot_sync(FULLM, keep);
+                if (m) {
+                    if (keep)
+                        q1[(t1 + __popc(m & lt_mask)) & (QCAP - 1)] =
+                            make_uint2((uint32_t)id[j], ((__float_as_uint(gball) + 0x7fu) & ~0x7fu) | (uint32_t)ilo);
+                    t1 += __popc(m);
+                    if (t1 - h1 >= 32u) {
+                        __syncwarp();
+                        run2(32u);
+                        __syncwarp();
+                    }
+                }
+            }
+        }
+    }
+    __syncwarp();
+    if (t1 != h1) run2(t1 - h1);
+    __syncwarp();
+    if (t2 != h2) run3a(t2 - h2);
+    __syncwarp();
+    if (t3 != h3) run3b(t3 - h3);
+    __syncthreads();
+
+    // ---- phase 4
+    epilogue(q, n, p0, np, tr, tx, ty, tz, dx2, dy2, dz2, sm.res, sm.far, tid, TT);
+}
+
+}  // namespace
+
+int launch_heightmap_shadow(const rvb_terrain* t, const float* pos, const float* euler, const float* trig,
+                            const double* pattern, int64_t P, int64_t N, uint16_t* dist, int32_t* hit_slot,
+                            int32_t* hit_tri, uint16_t* pt, uint16_t* sources, float* obs, int64_t obs_ld,
+                            const int32_t* col_a, const int32_t* col_b, float cos_steep, cudaStream_t st) {
+    RVB_REQUIRE(t->sb_ids != nullptr && t->blk_ids != nullptr, "heightmap ray-cast (shadow): layer has no block lists");
+    rc::TiledParams q;
+    int rc_ = fill_tiled_params(t, pos, euler, trig, pattern, P, N, dist, hit_slot, hit_tri, pt, sources, obs, obs_ld, col_a,
+                                col_b, q);
+    if (rc_ != RVB_OK) return rc_;
+    RVB_REQUIRE(q.tile_size <= 2047, "heightmap ray-cast (shadow): tile larger than 2047 rays");
+    const int64_t nblocks = N * q.tiles;
+    int* scratch = nullptr;
+    RVB_CUDA(cudaMallocAsync(&scratch, sizeof(int) * (size_t)(nblocks + 1), st));
+    RVB_CUDA(cudaMemsetAsync(scratch, 0, sizeof(int), st));
+    q.fb_count = scratch;
+    q.fb_list = scratch + 1;
+    q.cos_steep = cos_steep;
+    static thread_local int configured_device = -1;
+    int dev = 0;
+    RVB_CUDA(cudaGetDevice(&dev));
+    if (configured_device != dev) {
+        RVB_CUDA(cudaFuncSetAttribute(hm_shadow_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shadow_smem_bytes(RT_MAX)));
+        configured_device = dev;
+    }
+    hm_shadow_kernel<<<(unsigned)nblocks, TT, shadow_smem_bytes(q.tile_size), st>>>(q);
+    rc_ = RVB_OK;
+    if (cudaGetLastError() != cudaSuccess) rc_ = rvb_set_error(RVB_ERR_CUDA, "hm_shadow_kernel", "launch failed");
+    if (rc_ == RVB_OK) {
+        // (env, tile) items the shadow kernel handed back: the tiled kernel loops over the list (usually empty)
+        q.work_count = q.fb_count;
+        q.work_list = q.fb_list;
+        rc_ = launch_tiled(q, true, nblocks < 148 * 3 ? nblocks : 148 * 3, st);
+    }
+    cudaFreeAsync(scratch, st);
+    return rc_;
+}

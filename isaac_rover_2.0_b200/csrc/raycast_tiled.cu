@@ -21,9 +21,13 @@
 //      (NaN first, ties -> lowest slot), merged across candidate chunks with a shared-memory atomicMin;
 //   6. epilogue in ray order: coalesced stores of dist / hit slot / hit triangle / pt / sources and the fused
 //      sparse+dense observation columns (heightmap_distribution.py:126-133, rover.py:324-325).
-#include "common.cuh"
+#include <string.h>
+
+#include "raycast_common.cuh"
 
 namespace {
+
+using namespace rc;
 
 constexpr int TT = 256;            // threads per CTA
 constexpr int NW = TT / 32;
@@ -32,35 +36,6 @@ constexpr int RPT = RT_MAX / TT;
 constexpr int BIN_CAP = 8192;      // cells in the tile's bounding box that can be histogrammed (u16 counters)
 constexpr int MAX_ITEM_RAYS = 32;  // rays per work item (heavier cells / blocks are split)
 constexpr int WQ_CAP = 128;        // per-warp survivor ring (<= 31 pending + 64 new per ray)
-
-constexpr uint32_t KEY_INIT = 0xC9800000u;     // (11.0, slot 0): the result when every candidate misses
-constexpr uint32_t ORD_MISS = 0xC980u;        // order key of fp16 11.0 (0x4980 | 0x8000)
-
-struct TiledParams {
-    const int32_t* index;
-    const TriRec* recs;
-    const uint32_t* blk_off;
-    const int32_t* blk_ids;
-    const uint4* blk_slots;
-    int nBy;
-    int G0, G1, K, Ks;
-    float res, inv_res, shift_x, shift_y;
-    int sem;
-    const float* pos;
-    const float* euler;
-    const float* trig;
-    const double* pattern;
-    int P, tiles, tile_size;
-    __half* dist;
-    int32_t* hit_slot;
-    int32_t* hit_tri;
-    __half* pt;
-    __half* sources;
-    float* obs;
-    int64_t obs_ld;
-    const int32_t* col_a;
-    const int32_t* col_b;
-};
 
 // two candidates of one cell, component-wise packed: .x = candidate j, .y = candidate j+1
 struct Tri2 {
@@ -83,21 +58,6 @@ __device__ __forceinline__ Tri2 pack_tri2(const uint4& p0, const uint2& p1, cons
     t.cz = u2h(__byte_perm(p1.x, q1.x, 0x5410)); t.nx = u2h(__byte_perm(p1.x, q1.x, 0x7632));
     t.ny = u2h(__byte_perm(p1.y, q1.y, 0x5410)); t.nz = u2h(__byte_perm(p1.y, q1.y, 0x7632));
     return t;
-}
-
-// key of torch.min's total order: NaN < everything, -0 == +0, ties -> lower slot; bit 0 remembers a negative zero.
-__device__ __forceinline__ uint32_t make_key(unsigned short b, uint32_t slot) {
-    uint32_t ord, nz = 0;
-    if ((b & 0x7fffu) > 0x7c00u) ord = 0u;
-    else if ((b & 0x7fffu) == 0u) { ord = 0x8000u; nz = b >> 15; }
-    else ord = (b & 0x8000u) ? (uint32_t)(unsigned short)~b : (uint32_t)(b | 0x8000u);
-    return (ord << 16) | (slot << 1) | nz;
-}
-__device__ __forceinline__ unsigned short key_bits(uint32_t key) {
-    const uint32_t ord = key >> 16;
-    if (ord == 0u) return 0x7fffu;
-    if (ord == 0x8000u) return (key & 1u) ? 0x8000u : 0u;
-    return (ord & 0x8000u) ? (unsigned short)(ord & 0x7fffu) : (unsigned short)~ord;
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -154,15 +114,6 @@ __device__ __forceinline__ uint32_t prefilter2(__half2 sx, __half2 sy, __half2 s
     return __hge2_mask(Ns, c.tlo) & __hge2_mask(Ms, c.tlo) & __hle2_mask(add2(Ns, Ms), c.thi);
 }
 
-__device__ __forceinline__ void unpack_rec(const TriRec* rec, H3& a, H3& b, H3& c, H3& n) {
-    const uint4 q0 = __ldg(reinterpret_cast<const uint4*>(rec));
-    const uint2 q1 = __ldg(reinterpret_cast<const uint2*>(rec) + 2);
-    a = {h_from_bits(q0.x & 0xffff), h_from_bits(q0.x >> 16), h_from_bits(q0.y & 0xffff)};
-    b = {h_from_bits(q0.y >> 16), h_from_bits(q0.z & 0xffff), h_from_bits(q0.z >> 16)};
-    c = {h_from_bits(q0.w & 0xffff), h_from_bits(q0.w >> 16), h_from_bits(q1.x & 0xffff)};
-    n = {h_from_bits(q1.x >> 16), h_from_bits(q1.y & 0xffff), h_from_bits(q1.y >> 16)};
-}
-
 struct Smem {
     uint4* ray_s;        // [RT]  sorted by cell: (sx2, sy2, sz2 duplicated halves, local ray id)
     uint32_t* res;       // [RT]  best key per local ray id
@@ -199,29 +150,16 @@ __device__ __forceinline__ void drain32(const Smem& sm, const uint2* wq, uint32_
     }
 }
 
-// A ray that holds a hit with k > 11.0 and no nearer one: the first slot whose value is <= 11.0 (a miss, or a hit at
-// exactly 11.0) wins torch.min, and that slot is not necessarily 0.  Vanishingly rare (the rover would have to hover
-// 11 m above the mesh), so one thread simply walks the K candidates with the literal op sequence.
-__device__ __noinline__ uint32_t literal_ray(const int32_t* row, int K, const TriRec* recs, H3 s, H3 d) {
-    uint32_t best = 0xffffffffu;
-    for (int j = 0; j < K; ++j) {
-        H3 a, b, c, nn;
-        unpack_rec(recs + __ldg(row + j), a, b, c, nn);
-        best = min(best, make_key(h_bits(pair_test(s, d, a, b, c, nn)), (uint32_t)j));
-    }
-    return best;
-}
-
 template <int B>
-__global__ void __launch_bounds__(TT, 3) hm_tiled_kernel(const TiledParams q) {
+__device__ __forceinline__ void hm_tiled_body(const TiledParams& q, const int work) {
     extern __shared__ uint4 smem_raw[];
     __shared__ int s_box[4];          // min cx, min cy, max cx, max cy
     __shared__ uint32_t s_warp[NW];
     __shared__ int s_nitems, s_next;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int64_t n = blockIdx.x / q.tiles;
-    const int tile = blockIdx.x % q.tiles;
+    const int64_t n = work / q.tiles;
+    const int tile = work % q.tiles;
     const int p0 = tile * q.tile_size;
     const int np = min(q.tile_size, q.P - p0);
     const int RT = q.tile_size;
@@ -474,48 +412,20 @@ __global__ void __launch_bounds__(TT, 3) hm_tiled_kernel(const TiledParams q) {
     __syncthreads();
 
     // ---- phase 4: epilogue in ray order
-    const bool want_geo = q.hit_tri || q.pt || q.sources;
-    for (int p = tid; p < np; p += TT) {
-        uint32_t key = sm.res[p];
-        const bool far_hit = (sm.far[p >> 5] >> (p & 31)) & 1u;
-        if (far_hit && (key >> 16) == ORD_MISS) {
-            const double* pp = q.pattern + (int64_t)(p0 + p) * 3;
-            double xo, yo, zo;
-            body_transform<double>(pp[0], pp[1], pp[2], tr, tx, ty, tz, xo, yo, zo);
-            const H3 s = {h_from_double(xo), h_from_double(yo), h_from_double(zo)};
-            const int cx = cell_coord(s.x, q.shift_x, q.res, q.inv_res, q.G0 - 1, q.sem);
-            const int cy = min(cell_coord(s.y, q.shift_y, q.res, q.inv_res, q.G0 - 1, q.sem), q.G1 - 1);
-            key = literal_ray(q.index + ((int64_t)cx * q.G1 + cy) * q.Ks, q.K, q.recs, s, dlit);
+    epilogue(q, n, p0, np, tr, tx, ty, tz, dx2, dy2, dz2, sm.res, sm.far, tid, TT);
+}
+
+// One CTA per (env, tile); in work-list mode (the shadow kernel's fall-back list) CTAs loop over the listed items.
+template <int B>
+__global__ void __launch_bounds__(TT, 3) hm_tiled_kernel(const TiledParams q) {
+    if (q.work_list) {
+        const int cnt = *q.work_count;
+        for (int w = blockIdx.x; w < cnt; w += gridDim.x) {
+            hm_tiled_body<B>(q, q.work_list[w]);
+            __syncthreads();
         }
-        const unsigned short kb = key_bits(key);
-        const int slot = (int)((key >> 1) & 0x7fffu);
-        const int64_t o = n * q.P + p0 + p;
-        q.dist[o] = h_from_bits(kb);
-        if (q.hit_slot) q.hit_slot[o] = slot;
-        if (want_geo) {
-            const double* pp = q.pattern + (int64_t)(p0 + p) * 3;
-            double xo, yo, zo;
-            body_transform<double>(pp[0], pp[1], pp[2], tr, tx, ty, tz, xo, yo, zo);
-            const __half hx = h_from_double(xo), hy = h_from_double(yo), hz = h_from_double(zo);
-            if (q.sources) { q.sources[o * 3 + 0] = hx; q.sources[o * 3 + 1] = hy; q.sources[o * 3 + 2] = hz; }
-            if (q.hit_tri) {
-                const int cx = cell_coord(hx, q.shift_x, q.res, q.inv_res, q.G0 - 1, q.sem);
-                const int cy = min(cell_coord(hy, q.shift_y, q.res, q.inv_res, q.G0 - 1, q.sem), q.G1 - 1);
-                q.hit_tri[o] = __ldg(q.index + ((int64_t)cx * q.G1 + cy) * q.Ks + slot);
-            }
-            if (q.pt) {
-                const __half k = h_from_bits(kb);
-                q.pt[o * 3 + 0] = h_sub(hx, h_mul(__low2half(dx2), k));     // ray_casting.py:63
-                q.pt[o * 3 + 1] = h_sub(hy, h_mul(__low2half(dy2), k));
-                q.pt[o * 3 + 2] = h_sub(hz, h_mul(__low2half(dz2), k));
-            }
-        }
-        if (q.obs) {
-            const float v = __half2float(h_mul(h_from_bits(kb), __float2half_rn(0.5f)));     // fp16(dist / 2) -> f32
-            const int ca = q.col_a[p0 + p], cb = q.col_b[p0 + p];
-            if (ca >= 0) q.obs[n * q.obs_ld + ca] = v;
-            if (cb >= 0) q.obs[n * q.obs_ld + cb] = v;
-        }
+    } else {
+        hm_tiled_body<B>(q, (int)blockIdx.x);
     }
 }
 
@@ -526,28 +436,7 @@ size_t tiled_smem_bytes(int RT) {
 
 }  // namespace
 
-int launch_heightmap_tiled(const rvb_terrain* t, const float* pos, const float* euler, const float* trig,
-                           const double* pattern, int64_t P, int64_t N, uint16_t* dist, int32_t* hit_slot,
-                           int32_t* hit_tri, uint16_t* pt, uint16_t* sources, float* obs, int64_t obs_ld,
-                           const int32_t* col_a, const int32_t* col_b, bool per_cell, cudaStream_t st) {
-    RVB_REQUIRE(t->G0 <= 32767 && t->G1 <= 65535, "heightmap ray-cast: grid larger than 32767 x 65535 cells");
-    RVB_REQUIRE(t->K <= 16383, "heightmap ray-cast: K > 16383");
-    RVB_REQUIRE(t->G0 * t->G1 < ((int64_t)1 << 32), "heightmap ray-cast: more than 2^32 cells");
-    TiledParams q;
-    q.index = t->index; q.recs = t->recs;
-    q.blk_off = t->blk_off; q.blk_ids = t->blk_ids; q.blk_slots = t->blk_slots; q.nBy = t->nBy;
-    const bool blocks = t->blk_ids != nullptr && !per_cell;
-    q.G0 = (int)t->G0; q.G1 = (int)t->G1; q.K = (int)t->K; q.Ks = (int)t->Ks;
-    q.res = t->res; q.inv_res = 1.0f / t->res; q.shift_x = t->shift_x; q.shift_y = t->shift_y; q.sem = t->sem;
-    q.pos = pos; q.euler = euler; q.trig = trig; q.pattern = pattern;
-    q.P = (int)P;
-    q.tiles = (int)ceil_div(P, RT_MAX);
-    q.tile_size = (int)ceil_div(P, q.tiles);
-    q.dist = (__half*)dist; q.hit_slot = hit_slot; q.hit_tri = hit_tri; q.pt = (__half*)pt; q.sources = (__half*)sources;
-    q.obs = obs; q.obs_ld = obs_ld; q.col_a = col_a; q.col_b = col_b;
-    const int64_t nblocks = N * q.tiles;
-    RVB_REQUIRE(nblocks < ((int64_t)1 << 31), "heightmap ray-cast: too many (env, tile) blocks for one launch");
-    const size_t smem = tiled_smem_bytes(q.tile_size);
+static int configure_tiled() {
     static thread_local int configured_device = -1;
     int dev = 0;
     RVB_CUDA(cudaGetDevice(&dev));
@@ -556,8 +445,50 @@ int launch_heightmap_tiled(const rvb_terrain* t, const float* pos, const float* 
         RVB_CUDA(cudaFuncSetAttribute(hm_tiled_kernel<RVB_BLK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tiled_smem_bytes(RT_MAX)));
         configured_device = dev;
     }
-    if (blocks) hm_tiled_kernel<RVB_BLK><<<(unsigned)nblocks, TT, smem, st>>>(q);
-    else hm_tiled_kernel<1><<<(unsigned)nblocks, TT, smem, st>>>(q);
+    return RVB_OK;
+}
+
+int fill_tiled_params(const rvb_terrain* t, const float* pos, const float* euler, const float* trig, const double* pattern,
+                      int64_t P, int64_t N, uint16_t* dist, int32_t* hit_slot, int32_t* hit_tri, uint16_t* pt,
+                      uint16_t* sources, float* obs, int64_t obs_ld, const int32_t* col_a, const int32_t* col_b,
+                      rc::TiledParams& q) {
+    RVB_REQUIRE(t->G0 <= 32767 && t->G1 <= 65535, "heightmap ray-cast: grid larger than 32767 x 65535 cells");
+    RVB_REQUIRE(t->K <= 16383, "heightmap ray-cast: K > 16383");
+    RVB_REQUIRE(t->G0 * t->G1 < ((int64_t)1 << 32), "heightmap ray-cast: more than 2^32 cells");
+    memset(&q, 0, sizeof(q));
+    q.index = t->index; q.recs = t->recs;
+    q.blk_off = t->blk_off; q.blk_ids = t->blk_ids; q.blk_slots = t->blk_slots; q.nBy = t->nBy;
+    q.sb_off = t->sb_off; q.sb_ids = t->sb_ids; q.nSBy = t->nSBy;
+    q.G0 = (int)t->G0; q.G1 = (int)t->G1; q.K = (int)t->K; q.Ks = (int)t->Ks;
+    q.res = t->res; q.inv_res = 1.0f / t->res; q.shift_x = t->shift_x; q.shift_y = t->shift_y; q.sem = t->sem;
+    q.pos = pos; q.euler = euler; q.trig = trig; q.pattern = pattern;
+    q.P = (int)P;
+    q.tiles = (int)ceil_div(P, RT_MAX);
+    q.tile_size = (int)ceil_div(P, q.tiles);
+    q.dist = (__half*)dist; q.hit_slot = hit_slot; q.hit_tri = hit_tri; q.pt = (__half*)pt; q.sources = (__half*)sources;
+    q.obs = obs; q.obs_ld = obs_ld; q.col_a = col_a; q.col_b = col_b;
+    RVB_REQUIRE(N * q.tiles < ((int64_t)1 << 31), "heightmap ray-cast: too many (env, tile) blocks for one launch");
+    return RVB_OK;
+}
+
+// q.work_list / q.work_count set: `grid` CTAs loop over the list; otherwise one CTA per (env, tile).
+int launch_tiled(const rc::TiledParams& q, bool blocks, int64_t grid, cudaStream_t st) {
+    const int rc_ = configure_tiled();
+    if (rc_ != RVB_OK) return rc_;
+    const size_t smem = tiled_smem_bytes(q.tile_size);
+    if (blocks) hm_tiled_kernel<RVB_BLK><<<(unsigned)grid, TT, smem, st>>>(q);
+    else hm_tiled_kernel<1><<<(unsigned)grid, TT, smem, st>>>(q);
     RVB_LAUNCH_CHECK();
     return RVB_OK;
+}
+
+int launch_heightmap_tiled(const rvb_terrain* t, const float* pos, const float* euler, const float* trig,
+                           const double* pattern, int64_t P, int64_t N, uint16_t* dist, int32_t* hit_slot,
+                           int32_t* hit_tri, uint16_t* pt, uint16_t* sources, float* obs, int64_t obs_ld,
+                           const int32_t* col_a, const int32_t* col_b, bool per_cell, cudaStream_t st) {
+    rc::TiledParams q;
+    const int rc_ = fill_tiled_params(t, pos, euler, trig, pattern, P, N, dist, hit_slot, hit_tri, pt, sources, obs, obs_ld,
+                                      col_a, col_b, q);
+    if (rc_ != RVB_OK) return rc_;
+    return launch_tiled(q, t->blk_ids != nullptr && !per_cell, N * q.tiles, st);
 }

@@ -2,7 +2,9 @@
 #include <new>
 #include <string.h>
 
+#include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
+#include <cub/device/device_select.cuh>
 
 #include "common.cuh"
 
@@ -131,6 +133,11 @@ build_blocks_kernel(const int32_t* __restrict__ index, int G0, int G1, int K, in
     }
     int32_t* out_id = ids + off[blockIdx.x];
     uint4* out_sl = slots + off[blockIdx.x];
+    if (tid == 0 && (total & 1u)) {
+        // pad entry of an odd list: the largest id again (keeps the list sorted and the id valid; its slots stay 0xFF)
+        const int nci = min(RVB_BLK, G0 - I * RVB_BLK), ncj = min(RVB_BLK, G1 - J * RVB_BLK);
+        out_id[total] = (int32_t)(keys[nci * ncj * K - 1] >> 16);
+    }
     uint32_t e = base + inc - mine;          // entries started before this thread's first key
     for (int i = lo; i < hi && lo < n2; ++i) {
         const unsigned long long k = keys[i];
@@ -140,9 +147,88 @@ build_blocks_kernel(const int32_t* __restrict__ index, int G0, int G1, int K, in
             ++e;
             out_id[e - 1] = (int32_t)(k >> 16);
         }
-        // e - 1 is this key's entry (a run that started in an earlier thread's range keeps that thread's number)
-        reinterpret_cast<unsigned char*>(out_sl + (e - 1))[(k >> 8) & 0xff] = (unsigned char)(k & 0xff);
+        // e - 1 is this key's entry (a run that started in an earlier thread's range keeps that thread's number).
+        // A cell list that repeats a triangle keeps the LOWEST slot (torch.min returns the first index on ties).
+        if (i == 0 || (keys[i - 1] >> 8) != (k >> 8))
+            reinterpret_cast<unsigned char*>(out_sl + (e - 1))[(k >> 8) & 0xff] = (unsigned char)(k & 0xff);
     }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Superblock lists: keys (superblock << 32 | id) of every block-list entry, radix-sorted and made unique.
+// ------------------------------------------------------------------------------------------------
+__global__ void sb_keys_kernel(const uint32_t* __restrict__ blk_off, const int32_t* __restrict__ blk_ids, int nBy, int nSBy,
+                               unsigned long long* __restrict__ keys) {
+    const int I = blockIdx.x / nBy, J = blockIdx.x % nBy;
+    const unsigned long long sb = (unsigned long long)((I / RVB_SB) * nSBy + (J / RVB_SB)) << 32;
+    const uint32_t o0 = blk_off[blockIdx.x], o1 = blk_off[blockIdx.x + 1];
+    for (uint32_t e = o0 + threadIdx.x; e < o1; e += blockDim.x) keys[e] = sb | (uint32_t)blk_ids[e];
+}
+
+__global__ void sb_offsets_kernel(const unsigned long long* __restrict__ keys, int64_t n, int64_t nsb, uint32_t* __restrict__ off) {
+    const int64_t s = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (s > nsb) return;
+    const unsigned long long want = (unsigned long long)s << 32;       // first key >= want
+    int64_t lo = 0, hi = n;
+    while (lo < hi) {
+        const int64_t mid = (lo + hi) >> 1;
+        if (keys[mid] < want) lo = mid + 1; else hi = mid;
+    }
+    off[s] = (uint32_t)lo;
+}
+
+__global__ void sb_ids_kernel(const unsigned long long* __restrict__ keys, int64_t n, int32_t* __restrict__ ids) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n) ids[i] = (int32_t)(uint32_t)keys[i];
+}
+
+static int build_superblock_lists(rvb_terrain* t, cudaStream_t st) {
+    t->nSBx = (int32_t)ceil_div(t->nBx, RVB_SB);
+    t->nSBy = (int32_t)ceil_div(t->nBy, RVB_SB);
+    const int64_t nb = (int64_t)t->nBx * t->nBy, nsb = (int64_t)t->nSBx * t->nSBy, n = t->n_ent;
+    if (!t->blk_ids || n <= 0 || n >= ((int64_t)1 << 31)) return RVB_OK;
+    unsigned long long *k0 = nullptr, *k1 = nullptr;
+    int64_t* d_num = nullptr;
+    void* tmp = nullptr;
+    int rc = RVB_OK;
+    cudaError_t e = cudaMalloc(&k0, sizeof(unsigned long long) * n);
+    if (e == cudaSuccess) e = cudaMalloc(&k1, sizeof(unsigned long long) * n);
+    if (e == cudaSuccess) e = cudaMalloc(&d_num, sizeof(int64_t));
+    int64_t n_u = 0;
+    if (e == cudaSuccess) {
+        sb_keys_kernel<<<(unsigned)nb, 128, 0, st>>>(t->blk_off, t->blk_ids, t->nBy, t->nSBy, k0);
+        int sb_bits = 1;
+        while (((int64_t)1 << sb_bits) < nsb) ++sb_bits;
+        size_t b0 = 0, b1 = 0;
+        cub::DeviceRadixSort::SortKeys(nullptr, b0, k0, k1, (int)n, 0, 32 + sb_bits, st);
+        cub::DeviceSelect::Unique(nullptr, b1, k1, k0, d_num, (int)n, st);
+        e = cudaMalloc(&tmp, b0 > b1 ? b0 : b1);
+        if (e == cudaSuccess) {
+            size_t b = b0;
+            cub::DeviceRadixSort::SortKeys(tmp, b, k0, k1, (int)n, 0, 32 + sb_bits, st);
+            b = b1;
+            cub::DeviceSelect::Unique(tmp, b, k1, k0, d_num, (int)n, st);
+            e = cudaMemcpyAsync(&n_u, d_num, sizeof(int64_t), cudaMemcpyDeviceToHost, st);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        }
+    }
+    if (e == cudaSuccess) {
+        t->n_sb_ent = n_u;
+        e = cudaMalloc(&t->sb_off, sizeof(uint32_t) * (nsb + 1));
+        if (e == cudaSuccess) e = cudaMalloc(&t->sb_ids, sizeof(int32_t) * (size_t)(n_u > 0 ? n_u : 1));
+        if (e == cudaSuccess) {
+            sb_offsets_kernel<<<(unsigned)ceil_div(nsb + 1, 256), 256, 0, st>>>(k0, n_u, nsb, t->sb_off);
+            sb_ids_kernel<<<(unsigned)ceil_div(n_u > 0 ? n_u : 1, 256), 256, 0, st>>>(k0, n_u, t->sb_ids);
+            e = cudaGetLastError();
+            if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        }
+    }
+    cudaFree(tmp);
+    cudaFree(d_num);
+    cudaFree(k1);
+    cudaFree(k0);
+    if (e != cudaSuccess) rc = rvb_set_error(RVB_ERR_CUDA, "rvb_terrain_create (superblock lists)", cudaGetErrorString(e));
+    return rc;
 }
 
 static int build_block_lists(rvb_terrain* t, cudaStream_t st) {
@@ -175,7 +261,7 @@ static int build_block_lists(rvb_terrain* t, cudaStream_t st) {
     build_blocks_kernel<<<(unsigned)nb, BLK_THREADS, 0, st>>>(t->index, (int)t->G0, (int)t->G1, (int)t->K, (int)t->Ks, t->nBy, t->blk_off,
                                                              nullptr, t->blk_ids, t->blk_slots);
     RVB_LAUNCH_CHECK();
-    return RVB_OK;
+    return build_superblock_lists(t, st);
 }
 
 extern "C" int rvb_terrain_create(rvb_terrain** out, const int32_t* map_indices, int64_t G0, int64_t G1, int64_t K,
@@ -221,6 +307,8 @@ extern "C" int rvb_terrain_create(rvb_terrain** out, const int32_t* map_indices,
             cudaFree(t->blk_off);
             cudaFree(t->blk_ids);
             cudaFree(t->blk_slots);
+            cudaFree(t->sb_off);
+            cudaFree(t->sb_ids);
             delete t;
             return rc != RVB_OK ? rc : rvb_set_error(RVB_ERR_CUDA, "rvb_terrain_create (block lists)", cudaGetErrorString(e));
         }
@@ -245,6 +333,8 @@ extern "C" int rvb_terrain_destroy(rvb_terrain* t) {
     cudaFree(t->blk_off);
     cudaFree(t->blk_ids);
     cudaFree(t->blk_slots);
+    cudaFree(t->sb_off);
+    cudaFree(t->sb_ids);
     delete t;
     return RVB_OK;
 }
@@ -252,5 +342,6 @@ extern "C" int rvb_terrain_destroy(rvb_terrain* t) {
 extern "C" int64_t rvb_terrain_bytes(const rvb_terrain* t) {
     if (!t) return 0;
     return (int64_t)sizeof(int32_t) * t->G0 * t->G1 * t->Ks + (int64_t)sizeof(TriRec) * t->T +
-           (t->blk_ids ? (int64_t)(sizeof(uint4) + sizeof(int32_t)) * t->n_ent + (int64_t)sizeof(uint32_t) * ((int64_t)t->nBx * t->nBy + 1) : 0);
+           (t->blk_ids ? (int64_t)(sizeof(uint4) + sizeof(int32_t)) * t->n_ent + (int64_t)sizeof(uint32_t) * ((int64_t)t->nBx * t->nBy + 1) : 0) +
+           (t->sb_ids ? (int64_t)sizeof(int32_t) * t->n_sb_ent + (int64_t)sizeof(uint32_t) * ((int64_t)t->nSBx * t->nSBy + 1) : 0);
 }

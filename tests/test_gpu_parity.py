@@ -88,7 +88,7 @@ def test_golden_pattern(R, golden):
     assert (hm.get_num_sparse_vector(), hm.get_num_dense_vector()) == (634, 1112)      # teacher_loader.py:47-48
 
 
-@pytest.mark.parametrize("variant", [0, 1, 2])
+@pytest.mark.parametrize("variant", [0, 1, 2, 3])
 def test_golden_get_depths(R, golden, gcam, variant):
     gcam.variant = variant
     dist, pt, src = gcam.get_depths(golden["in_pos"].cuda(), golden["ref_euler"].cuda(), trig=golden["trig"].cuda(), want_hits=True)
@@ -241,7 +241,7 @@ def test_oracle_cpu_semantics_bit_exact(R, O, world20, N):
     pat, _, _ = O.heightmap_pattern()
     ref = O.get_depths(st["pos"], eul, pat, w.map_indices, w.triangles, w.vertices, torch.tensor([0, 0, 0.0]))
     cam = R.Camera("cuda:0", torch.tensor([0, 0, 0.0]), assets=(w.map_indices, w.triangles, w.vertices), sem=R.SEM_TORCH_CPU)
-    for variant in (0, 1, 2):
+    for variant in (0, 1, 2, 3):
         cam.variant = variant
         dist, pt, src = cam.get_depths(st["pos"].cuda(), eul.cuda(), trig=_trig(eul).cuda(), want_hits=True)
         assert_bits_equal(src, ref["sources"], "sources v%d" % variant)
@@ -328,7 +328,7 @@ def test_edge_cases(R, O, world20):
     eul = torch.tensor([[0.0, 0.0, 0.0], [0.1, -0.1, 2.0], [0.0, 0.0, 1.0], [3.1, 0.0, 0.0], [1.2, -1.2, -3.0]])
     pat, _, _ = O.heightmap_pattern()
     ref = O.get_depths(pos, eul, pat, w.map_indices, w.triangles, w.vertices, torch.tensor([0, 0, 0.0]))
-    for variant in (0, 1, 2):
+    for variant in (0, 1, 2, 3):
         cam.variant = variant
         d, pt, s = cam.get_depths(pos.cuda(), eul.cuda(), trig=_trig(eul).cuda(), want_hits=True)
         assert_bits_equal(d, ref["dist"], "edge dist v%d" % variant)
@@ -352,7 +352,7 @@ def test_full_size_properties(R, world20):
     cam = R.Camera("cuda:0", torch.tensor([0, 0, 0.0]), assets=(w.map_indices, w.triangles, w.vertices))
     d0, pt0, s0 = cam.get_depths(st["pos"], eul, want_hits=True)
     t0 = cam.last_hit_tri.clone()
-    for v in (1, 2):
+    for v in (1, 2, 3):
         cam.variant = v
         d1, pt1, s1 = cam.get_depths(st["pos"], eul, want_hits=True)
         assert torch.equal(bits(d0), bits(d1)) and torch.equal(bits(pt0), bits(pt1)) and torch.equal(t0, cam.last_hit_tri)
@@ -396,7 +396,7 @@ def test_candidate_count_variants(R, O, world20, K):
     pat, _, _ = O.heightmap_pattern()
     ref = O.get_depths(st["pos"], eul, pat, idx, w.triangles, w.vertices, torch.tensor([0, 0, 0.0]))
     cam = R.Camera("cuda:0", torch.tensor([0, 0, 0.0]), assets=(idx, w.triangles, w.vertices), sem=R.SEM_TORCH_CPU)
-    for variant in (0, 1, 2):
+    for variant in (0, 1, 2, 3):
         cam.variant = variant
         dist, pt, src = cam.get_depths(st["pos"].cuda(), eul.cuda(), trig=_trig(eul).cuda(), want_hits=True)
         assert_bits_equal(dist, ref["dist"], "dist K=%d v%d" % (K, variant))
@@ -421,7 +421,7 @@ def test_far_hits_and_spread_rays(R, O, world20):
     shift = torch.tensor([0, 0, 0.0])
     ref = O.get_depths(pos, eul, pat, w.map_indices, w.triangles, w.vertices, shift)
     far = (ref["dist"] == 11) & (ref["slot"] != 0)
-    for variant in (0, 1, 2):
+    for variant in (0, 1, 2, 3):
         cam.variant = variant
         d, pt, s = cam.get_depths(pos.cuda(), eul.cuda(), trig=_trig(eul).cuda(), want_hits=True)
         assert_bits_equal(d, ref["dist"], "far dist v%d" % variant)
@@ -438,10 +438,47 @@ def test_far_hits_and_spread_rays(R, O, world20):
     dist = torch.empty((2, 4096), dtype=torch.float16, device="cuda")
     slot = torch.empty((2, 4096), dtype=torch.int32, device="cuda")
     d_pos, d_eul, d_trig, d_pat = pos2.cuda(), eul2.cuda(), _trig(eul2).cuda(), wide.cuda()      # keep the buffers alive
-    for variant in (0, 1, 2):
+    for variant in (0, 1, 2, 3):
         R._lib.check(lib.rvb_heightmap_raycast(cam.layer.handle, R._lib.ptr(d_pos), R._lib.ptr(d_eul), R._lib.ptr(d_trig),
                                                R._lib.ptr(d_pat), 4096, 2, R._lib.ptr(dist), R._lib.ptr(slot), None, None, None,
                                                None, 0, None, None, variant, None))
         torch.cuda.synchronize()
         assert_bits_equal(dist, ref2["dist"], "wide pattern dist v%d" % variant)
         assert_bits_equal(slot, ref2["slot"].to(torch.int32), "wide pattern slot v%d" % variant)
+
+
+@pytest.fixture(scope="module")
+def world200(R):
+    """The benchmark world (BASELINE.json configs[1]): 200 x 200 m, 999 698 triangles, K = 200, index built on the device.
+    fp16 coordinates up to 200 m (grid spacing 0.125 m above 128 m) are where the shadow kernel's bounds are loosest."""
+    w = R.synth.make_world(length=200.0, nv=708, K=200, n_stones=2000, seed=42, build_index=None)
+    w.map_indices = R.build_knn_index(w.triangles, w.vertices, w.G, w.res, w.K, device="cuda:0")
+    return w
+
+
+def test_large_world_all_variants_agree(R, world200):
+    """2048 envs on the 200 m world (1 % strongly tilted, some on the map border): the production kernel (triangle
+    enumeration with conservative culling) == tiled kernels == the per-pair kernel that evaluates every (ray, candidate)
+    pair literally; distances, hit slots, hit triangles and intersection points bit for bit."""
+    w = world200
+    N = 2048
+    st = R.synth.make_env_state(w, N, seed=9)
+    g = torch.Generator().manual_seed(4)
+    st["pos"][:64, :2] = torch.rand(64, 2, generator=g) * 6 - 3 + torch.tensor([0.0, 100.0])         # across the x = 0 border
+    st["pos"][64:128, :2] = torch.rand(64, 2, generator=g) * 6 + torch.tensor([196.0, 196.0])        # around the far corner
+    rp = torch.rand(128, 2, generator=g) * 2.9 - 1.45                                               # up to 83 degrees of tilt
+    yaw = torch.rand(128, generator=g) * 6.28 - 3.14
+    st["quat"][128:256] = R.synth.euler_to_quat_wxyz(rp[:, 0], rp[:, 1], yaw)
+    st["pos"][256:288, 2] += torch.rand(32, generator=g) * 12                                       # hovering up to 12 m
+    st = {k: v.cuda() for k, v in st.items()}
+    eul = R.tensor_quat_to_eul(st["quat"])
+    cam = R.Camera("cuda:0", torch.tensor([0, 0, 0.0]), assets=(w.map_indices, w.triangles, w.vertices))
+    out = {}
+    for v in (1, 0, 2, 3):
+        cam.variant = v
+        d, pt, s = cam.get_depths(st["pos"], eul, want_hits=True)
+        out[v] = (d.clone(), pt.clone(), cam.last_hit_slot.clone(), cam.last_hit_tri.clone())
+    for v in (0, 2, 3):
+        for i, what in enumerate(("dist", "pt", "slot", "tri")):
+            assert_bits_equal(out[v][i], out[1][i], "200 m world %s variant %d vs 1" % (what, v))
+    assert (out[0][0] != 11).float().mean() > 0.5

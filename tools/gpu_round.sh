@@ -1,16 +1,19 @@
 #!/bin/bash
-# one GPU call: parity tests, bench line, ncu launch list, ncu full capture of the ray-cast kernel
+# one GPU call: diagnostic, parity tests, bench line, ncu launch list, ncu full capture of the ray-cast kernel
 cd "$GRAFT_REPO_ROOT" 2>/dev/null || true
 mkdir -p gpurun_out
 TAG=${1:-run}
-python -m pytest tests -m gpu -q -x --timeout 900 > gpurun_out/pytest_gpu_$TAG.txt 2>&1
+KERN=${3:-hm_shadow}
+timeout 600 python tools/shadow_diag.py 4096 > gpurun_out/diag_$TAG.txt 2>&1
+tail -25 gpurun_out/diag_$TAG.txt
+timeout 1500 python -m pytest tests -m gpu -q -x --timeout 900 > gpurun_out/pytest_gpu_$TAG.txt 2>&1
 tail -15 gpurun_out/pytest_gpu_$TAG.txt
-python bench.py --steps 20 --warmup 3 > gpurun_out/bench_$TAG.json 2> gpurun_out/bench_$TAG.err
+timeout 600 python bench.py --steps 20 --warmup 3 > gpurun_out/bench_$TAG.json 2> gpurun_out/bench_$TAG.err
 tail -3 gpurun_out/bench_$TAG.err; cat gpurun_out/bench_$TAG.json
 if [ "$2" != "noprof" ]; then
-ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_$TAG.csv \
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_$TAG.csv \
     python bench.py --steps 2 --warmup 3 --no-cpu > gpurun_out/ncu_launches_$TAG.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:hm_tiled -s 3 -c 2 -f -o gpurun_out/prof_$TAG \
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:$KERN -s 3 -c 2 -f -o gpurun_out/prof_$TAG \
     python bench.py --steps 2 --warmup 3 --no-cpu > gpurun_out/ncu_full_$TAG.log 2>&1
 tail -3 gpurun_out/ncu_full_$TAG.log
 fi

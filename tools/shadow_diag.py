@@ -1,0 +1,53 @@
+"""GPU diagnostic: production (shadow) ray-cast vs the tiled and per-pair kernels on the benchmark world; prints
+mismatch statistics and per-variant timings.  python tools/shadow_diag.py [N]"""
+import os
+import sys
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import isaac_rover_b200 as R      # noqa: E402
+
+N = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
+w = R.synth.make_world(length=200.0, nv=708, K=200, n_stones=2000, seed=42, build_index=None)
+t0 = time.perf_counter()
+w.map_indices = R.build_knn_index(w.triangles, w.vertices, w.G, w.res, w.K, device="cuda:0")
+torch.cuda.synchronize()
+print("index build %.2f s" % (time.perf_counter() - t0))
+t0 = time.perf_counter()
+cam = R.Camera("cuda:0", torch.tensor([0, 0, 0.0]), assets=(w.map_indices, w.triangles, w.vertices))
+torch.cuda.synchronize()
+print("layer create %.2f s, %.2f GB" % (time.perf_counter() - t0, cam.layer.bytes() / 1e9))
+st = {k: v.cuda() for k, v in R.synth.make_env_state(w, N, seed=100).items()}
+eul = R.tensor_quat_to_eul(st["quat"])
+out = {}
+for v in (3, 0, 2):
+    cam.variant = v
+    for _ in range(2):
+        d, pt, s = cam.get_depths(st["pos"], eul, want_hits=True, want_pt=False)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(5):
+        d, pt, s = cam.get_depths(st["pos"], eul, want_hits=False, want_pt=False)
+    e1.record()
+    torch.cuda.synchronize()
+    print("variant %d: %.3f ms per launch (%d envs)" % (v, e0.elapsed_time(e1) / 5, N))
+    d, pt, s = cam.get_depths(st["pos"], eul, want_hits=True, want_pt=False)
+    out[v] = (d.clone(), cam.last_hit_slot.clone(), cam.last_hit_tri.clone())
+ref = out[3]
+for v in (0, 2):
+    neq = out[v][0].view(torch.int16) != ref[0].view(torch.int16)
+    nslot = out[v][1] != ref[1]
+    print("variant %d vs 3: %d / %d distances differ (%d envs), %d slots differ" % (
+        v, int(neq.sum()), neq.numel(), int(neq.any(1).sum()), int(nslot.sum())))
+    if neq.any():
+        idx = neq.nonzero()[:10]
+        for e, p in idx.tolist():
+            print("   env %d ray %d: got %s (slot %d tri %d) want %s (slot %d tri %d)  roll/pitch %.2f %.2f pos %s" % (
+                e, p, out[v][0][e, p].item(), out[v][1][e, p].item(), out[v][2][e, p].item(), ref[0][e, p].item(),
+                ref[1][e, p].item(), ref[2][e, p].item(), eul[e, 0].item(), eul[e, 1].item(), st["pos"][e].tolist()))
+        miss_not_hit = (neq & (out[v][0] == 11)).sum().item()
+        print("   of those, %d are misses where the reference kernel hits" % miss_not_hit)
