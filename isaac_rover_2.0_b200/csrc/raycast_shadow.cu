@@ -49,7 +49,8 @@ constexpr int RPT = RT_MAX / TT;
 constexpr int BIN_CAP = 8192;      // blocks in the tile's bounding box
 constexpr int SB = RVB_SB;
 constexpr int ITEM_CAP = 128;      // superblocks per tile (7 bits travel in the stage-1 queue)
-constexpr int CHUNK = 128;         // list entries per pulled work chunk
+constexpr int CHUNK = 32;          // list entries per pulled work chunk (one stage-1 batch)
+constexpr int CHUNK_CAP = 4096;    // chunks per tile (u8 chunk -> item table)
 constexpr int QCAP = 64;           // per-warp queues (each drained below 32 after every push of <= 32)
 constexpr int TASK_RAYS = 16;
 
@@ -81,6 +82,7 @@ struct Smem {
     uint32_t* bins;      // [BIN_CAP / 2 + 2]  u16 counters, then exclusive offsets (column-major bins)
     Item* items;         // [ITEM_CAP]
     uint32_t* cum;       // [ITEM_CAP + 1]  chunks before item i
+    unsigned char* chunk_item;   // [CHUNK_CAP]
     uint2* q1;           // [NW][QCAP]  stage-1 survivors: (triangle, gball bits | item)
     uint4* q2;           // [NW][QCAP]  tasks: (triangle, ray start | count << 16, box lo half2, box hi half2)
     uint2* q3;           // [NW][QCAP]  pairs: (ray position, triangle)
@@ -89,7 +91,7 @@ struct Smem {
 
 __host__ __device__ inline size_t shadow_smem_bytes(int RT) {
     return (size_t)RT * 8 + (size_t)((RT + 3) & ~3) * 4 + (size_t)(BIN_CAP / 2 + 4) * 4 + (size_t)ITEM_CAP * 32 +
-           (size_t)(ITEM_CAP + 4) * 4 + (size_t)NW * QCAP * (8 + 16 + 8) + (size_t)(((RT + 31) / 32 + 3) & ~3) * 4;
+           (size_t)(ITEM_CAP + 4) * 4 + (size_t)CHUNK_CAP + (size_t)NW * QCAP * (8 + 16 + 8) + (size_t)(((RT + 31) / 32 + 3) & ~3) * 4;
 }
 
 __device__ __forceinline__ float rcp_up(float x) { return __fdividef(1.0f, x) * 1.000001f; }
@@ -215,7 +217,8 @@ __global__ void __launch_bounds__(TT, 3) hm_shadow_kernel(const TiledParams q) {
     sm.bins = sm.res + ((RT + 3) & ~3);
     sm.items = reinterpret_cast<Item*>(sm.bins + BIN_CAP / 2 + 4);
     sm.cum = reinterpret_cast<uint32_t*>(sm.items + ITEM_CAP);
-    sm.q1 = reinterpret_cast<uint2*>(sm.cum + ITEM_CAP + 4);
+    sm.chunk_item = reinterpret_cast<unsigned char*>(sm.cum + ITEM_CAP + 4);
+    sm.q1 = reinterpret_cast<uint2*>(sm.chunk_item + CHUNK_CAP);
     sm.q2 = reinterpret_cast<uint4*>(sm.q1 + NW * QCAP);
     sm.q3 = reinterpret_cast<uint2*>(sm.q2 + NW * QCAP);
     sm.far = reinterpret_cast<uint32_t*>(sm.q3 + NW * QCAP);
@@ -457,203 +460,255 @@ __global__ void __launch_bounds__(TT, 3) hm_shadow_kernel(const TiledParams q) {
         }
     }
     __syncthreads();
-    if (tid == 0) {
+    {
+        // chunks before each item (warp 0: 4 items per lane), then the chunk -> item table
         const int ni = s_nitems;
-        uint32_t c = 0;
-        for (int i = 0; i < ni; ++i) {
-            sm.cum[i] = c;
-            c += (sm.items[i].list_len + CHUNK - 1) / CHUNK;
+        if (warp == 0) {
+            uint32_t c[4], tot = 0;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int i = lane * 4 + j;
+                c[j] = i < ni ? (sm.items[i].list_len + CHUNK - 1) / CHUNK : 0u;
+                tot += c[j];
+            }
+            uint32_t inc = tot;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t v = __shfl_up_sync(0xffffffffu, inc, o);
+                if (lane >= o) inc += v;
+            }
+            uint32_t run = inc - tot;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int i = lane * 4 + j;
+                if (i <= ni) sm.cum[i] = run;
+                run += c[j];
+            }
+            if (lane == 31) s_nchunks = (int)inc;
         }
-        sm.cum[ni] = c;
-        s_nchunks = (int)c;
+        __syncthreads();
+        if (s_nchunks > CHUNK_CAP) {
+            if (tid == 0) q.fb_list[atomicAdd(q.fb_count, 1)] = (int32_t)blockIdx.x;
+            return;
+        }
+        for (int i = tid; i < ni; i += TT)
+            for (uint32_t c = sm.cum[i]; c < sm.cum[i + 1]; ++c) sm.chunk_item[c] = (unsigned char)i;
     }
     __syncthreads();
 
-    // ---- phase 3: warps pull (superblock, chunk of its list); stage 1 -> q1 -> stage 2 -> q2 -> stage 3a -> q3 -> stage 3b
+    // ---- phase 3: warps pull (superblock, 32 list entries); stage 1 -> q1 -> stage 2 -> q2 -> stage 3a -> q3 -> stage 3b.
+    // One dispatcher loop per warp; every stage's code exists once (the kernel must stay inside the instruction cache).
     const EnvC e = s_env;
-    const int nitems = s_nitems, nchunks = s_nchunks;
+    const int nchunks = s_nchunks;
     uint2* q1 = sm.q1 + warp * QCAP;
     uint4* q2 = sm.q2 + warp * QCAP;
     uint2* q3 = sm.q3 + warp * QCAP;
     uint32_t h1 = 0, t1 = 0, h2 = 0, t2 = 0, h3 = 0, t3 = 0;          // warp-uniform
     const uint32_t lt_mask = (1u << lane) - 1u;
     const uint32_t FULLM = 0xffffffffu;
+    enum { A1 = 0, A2_START, A2_EMIT, A3A_START, A3A_RUN, A3B };
 
-    // stage 3b: literal evaluation + slot lookup of up to 32 queued (ray, triangle) pairs, one per lane
-    auto run3b = [&](uint32_t cnt) {
-        if ((uint32_t)lane < cnt) {
-            const uint2 pr = q3[(h3 + lane) & (QCAP - 1)];
-            const uint2 ray = sm.rays[pr.x];
-            const H3 s = {h_from_bits(ray.x & 0xffff), h_from_bits(ray.x >> 16), h_from_bits(ray.y & 0xffff)};
-            H3 a, b, c, nn;
-            unpack_rec(q.recs + pr.y, a, b, c, nn);
-            const __half k = pair_test(s, d16, a, b, c, nn);
-            if (h_bits(k) != RVB_H_MISS) {      // a hit at exactly 11.0 equals the all-miss result (slot 0)
-                const uint32_t meta = ray.y >> 16, p = meta & 0x7ffu, sub = meta >> 11;
-                const int cx = cell_coord(s.x, q.shift_x, q.res, q.inv_res, q.G0 - 1, q.sem);
-                const int cy = min(cell_coord(s.y, q.shift_y, q.res, q.inv_res, q.G0 - 1, q.sem), q.G1 - 1);
-                const uint32_t blk = (uint32_t)(cx / RVB_BLK) * (uint32_t)q.nBy + (uint32_t)(cy / RVB_BLK);
-                const uint32_t o0 = __ldg(q.blk_off + blk), o1 = __ldg(q.blk_off + blk + 1);
-                uint32_t lo = o0, hi = o1;
-                while (lo < hi) {                       // block lists are sorted by triangle id
-                    const uint32_t mid = (lo + hi) >> 1;
-                    if (__ldg(q.blk_ids + mid) < (int32_t)pr.y) lo = mid + 1; else hi = mid;
-                }
-                if (lo < o1 && __ldg(q.blk_ids + lo) == (int32_t)pr.y) {
-                    const uint32_t slot = __ldg(reinterpret_cast<const unsigned char*>(q.blk_slots + lo) + sub);
-                    if (slot != 0xffu) {                // the triangle is in the ray's own cell list
-                        const uint32_t key = make_key(h_bits(k), slot);
-                        if ((key >> 16) > ORD_MISS) atomicOr(&sm.far[p >> 5], 1u << (p & 31));      // k > 11: see epilogue
-                        else atomicMin(&sm.res[p], key);
-                    }
-                }
-            }
-        }
-        h3 += cnt;
-    };
-
-    // stage 3a: up to 32 tasks (triangle, <= 16 consecutive sorted rays, box), one per lane
-    auto run3a = [&](uint32_t cnt) {
-        uint4 tk = make_uint4(0, 0, 0, 0);
-        int c = 0;
-        if ((uint32_t)lane < cnt) {
-            tk = q2[(h2 + lane) & (QCAP - 1)];
-            c = (int)(tk.y >> 16);
-        }
-        h2 += cnt;
-        const int cmax = __reduce_max_sync(FULLM, c);
-        const uint32_t start = tk.y & 0xffffu;
-        for (int i = 0; i < cmax; ++i) {
-            bool in = false;
-            if (i < c) {
-                const uint32_t w0 = sm.rays[start + i].x;
-                in = (__hge2_mask(*reinterpret_cast<const __half2*>(&w0), *reinterpret_cast<const __half2*>(&tk.z)) &
-                      __hle2_mask(*reinterpret_cast<const __half2*>(&w0), *reinterpret_cast<const __half2*>(&tk.w))) == 0xffffffffu;
-            }
-            const uint32_t m = __ballot_sync(FULLM, in);
-            if (m) {
-                if (in) q3[(t3 + __popc(m & lt_mask)) & (QCAP - 1)] = make_uint2(start + (uint32_t)i, tk.x);
-                t3 += __popc(m);
-                if (t3 - h3 >= 32u) {
-                    __syncwarp();
-                    run3b(32u);
-                    __syncwarp();
-                }
-            }
-        }
-    };
-
-    // stage 2: up to 32 surviving triangles, one per lane -> tasks
-    auto run2 = [&](uint32_t cnt) {
-        uint32_t tri = 0, lo16 = 0, hi16 = 0;
-        int col = 1, cx1 = 0, r_lo = 0, r_hi = 0;          // empty column range
-        if ((uint32_t)lane < cnt) {
-            const uint2 en = q1[(h1 + lane) & (QCAP - 1)];
-            tri = en.x;
-            const float gball = __uint_as_float(en.y & ~0x7fu);
-            const Item it = sm.items[en.y & 0x7fu];
-            const uint4 r0 = __ldg(reinterpret_cast<const uint4*>(q.recs + tri));
-            const uint2 r1 = __ldg(reinterpret_cast<const uint2*>(q.recs + tri) + 2);
-            const TriF t = tri_f(r0, r1);
-            float x0, x1, y0, y1;
-            bool full;
-            stage2(t, r1, e, d16, gball, x0, x1, y0, y1, full);
-            int bxl = (int)(it.bx & 0xffffu), bxh = (int)(it.bx >> 16), byl = (int)(it.by & 0xffffu), byh = (int)(it.by >> 16);
-            if (!full) {
-                bxl = max(bxl, cell_coord_f(x0, q.shift_x, q.res, q.inv_res, q.G0 - 1, q.sem) / RVB_BLK);
-                bxh = min(bxh, cell_coord_f(x1, q.shift_x, q.res, q.inv_res, q.G0 - 1, q.sem) / RVB_BLK);
-                byl = max(byl, min(cell_coord_f(y0, q.shift_y, q.res, q.inv_res, q.G0 - 1, q.sem), q.G1 - 1) / RVB_BLK);
-                byh = min(byh, min(cell_coord_f(y1, q.shift_y, q.res, q.inv_res, q.G0 - 1, q.sem), q.G1 - 1) / RVB_BLK);
-                lo16 = (uint32_t)h_bits(__float2half_ru(x0)) | ((uint32_t)h_bits(__float2half_ru(y0)) << 16);
-                hi16 = (uint32_t)h_bits(__float2half_rd(x1)) | ((uint32_t)h_bits(__float2half_rd(y1)) << 16);
-            } else {
-                lo16 = 0xFC00FC00u;
-                hi16 = 0x7C007C00u;
-            }
-            if (bxl <= bxh && byl <= byh) {
-                col = bxl; cx1 = bxh;
-                r_lo = byl - by0; r_hi = byh - by0 + 1;
-            }
-        }
-        h1 += cnt;
-        uint32_t cur = 0, end = 0;
-        while (true) {
-            while (cur >= end && col <= cx1) {
-                const int b = (col - bx0) * BH;
-                cur = off16(sm.bins, b + r_lo);
-                end = off16(sm.bins, b + r_hi);
-                ++col;
-            }
-            const bool have = cur < end;
-            const uint32_t m = __ballot_sync(FULLM, have);
-            if (!m) break;
-            if (have) {
-                const uint32_t c = min(end - cur, (uint32_t)TASK_RAYS);
-                q2[(t2 + __popc(m & lt_mask)) & (QCAP - 1)] = make_uint4(tri, cur | (c << 16), lo16, hi16);
-                cur += c;
-            }
-            t2 += __popc(m);
-            if (t2 - h2 >= 32u) {
-                __syncwarp();
-                run3a(32u);
-                __syncwarp();
-            }
-        }
-    };
-
-    while (true) {
+    // stage-1 pipeline: ids of chunk k+2 and records of chunk k+1 are in flight while chunk k is tested
+    int32_t idA = -1, idB = -1;            // idA: records loaded (r0A, r1A); idB: id loaded
+    int itemA = -1, itemB = -1;            // -1: no chunk
+    uint4 r0A = make_uint4(0, 0, 0, 0);
+    uint2 r1A = make_uint2(0, 0);
+    auto pull = [&](int32_t& id, int& item) {
         int g = 0;
         if (lane == 0) g = atomicAdd(&s_next, 1);
         g = __shfl_sync(FULLM, g, 0);
-        if (g >= nchunks) break;
-        int ilo = 0, ihi = nitems;                       // largest i with cum[i] <= g
-        while (ihi - ilo > 1) {
-            const int mid = (ilo + ihi) >> 1;
-            if (sm.cum[mid] <= (uint32_t)g) ilo = mid; else ihi = mid;
+        item = -1;
+        id = -1;
+        if (g < nchunks) {
+            item = sm.chunk_item[g];
+            const Item& it = sm.items[item];
+            const uint32_t cbeg = ((uint32_t)g - sm.cum[item]) * CHUNK;
+            if (cbeg + lane < it.list_len) id = __ldg(q.sb_ids + it.list_off + cbeg + lane);
         }
-        const Item it = sm.items[ilo];
-        const uint32_t cbeg = ((uint32_t)g - sm.cum[ilo]) * CHUNK;
-        const int cn = (int)min((uint32_t)CHUNK, it.list_len - cbeg);
-        const int32_t* ids = q.sb_ids + it.list_off + cbeg;
-        int32_t id[CHUNK / 32];
-        uint4 r0[CHUNK / 32];
-        uint2 r1[CHUNK / 32];
-#pragma unroll
-        for (int j = 0; j < CHUNK / 32; ++j) id[j] = (lane + 32 * j < cn) ? __ldg(ids + lane + 32 * j) : -1;
-#pragma unroll
-        for (int j = 0; j < CHUNK / 32; ++j) {
-            if (id[j] >= 0) {
-                r0[j] = __ldg(reinterpret_cast<const uint4*>(q.recs + id[j]));
-                r1[j] = __ldg(reinterpret_cast<const uint2*>(q.recs + id[j]) + 2);
+    };
+    pull(idA, itemA);
+    if (idA >= 0) {
+        r0A = __ldg(reinterpret_cast<const uint4*>(q.recs + idA));
+        r1A = __ldg(reinterpret_cast<const uint2*>(q.recs + idA) + 2);
+    }
+    pull(idB, itemB);
+    bool more = true, in2 = false, in3a = false;
+    // stage-2 emission state (per lane)
+    uint32_t e_tri = 0, e_lo16 = 0, e_hi16 = 0, e_cur = 0, e_end = 0;
+    int e_col = 1, e_cx1 = 0, e_rlo = 0, e_rhi = 0;
+    // stage-3a state (per lane)
+    uint4 tk = make_uint4(0, 0, 0, 0);
+    int a_c = 0, a_i = 0, a_cmax = 0;
+
+    while (true) {
+        const uint32_t n1 = t1 - h1, n2 = t2 - h2, n3 = t3 - h3;
+        int action;
+        uint32_t cnt = 32u;
+        if (n3 >= 32u) action = A3B;
+        else if (in3a) action = A3A_RUN;
+        else if (n2 >= 32u) action = A3A_START;
+        else if (in2) action = A2_EMIT;
+        else if (n1 >= 32u) action = A2_START;
+        else if (more) action = A1;
+        else if (n1) { action = A2_START; cnt = n1; }
+        else if (n2) { action = A3A_START; cnt = n2; }
+        else if (n3) { action = A3B; cnt = n3; }
+        else break;
+        __syncwarp();
+        switch (action) {
+        case A1: {
+            if (itemA < 0) {
+                more = false;
+                break;
             }
+            const int32_t id = idA;
+            const int item = itemA;
+            const uint4 r0 = r0A;
+            const uint2 r1 = r1A;
+            idA = idB; itemA = itemB;
+            if (idA >= 0) {
+                r0A = __ldg(reinterpret_cast<const uint4*>(q.recs + idA));
+                r1A = __ldg(reinterpret_cast<const uint2*>(q.recs + idA) + 2);
+            }
+            pull(idB, itemB);
+            const Item& it = sm.items[item];
+            bool keep = false;
+            float gball = 0.0f;
+            if (id >= 0) keep = stage1(tri_f(r0, r1), e, it.rlox, it.rhix, it.rloy, it.rhiy, gball);
+            const uint32_t m = __ballot_sync(FULLM, keep);
+            if (keep)
+                q1[(t1 + __popc(m & lt_mask)) & (QCAP - 1)] =
+                    make_uint2((uint32_t)id, ((__float_as_uint(gball) + 0x7fu) & ~0x7fu) | (uint32_t)item);
+            t1 += __popc(m);
+            break;
         }
-#pragma unroll
-        for (int j = 0; j < CHUNK / 32; ++j) {
-            if (32 * j < cn) {
-                bool keep = false;
-                float gball = 0.0f;
-                if (id[j] >= 0) keep = stage1(tri_f(r0[j], r1[j]), e, it.rlox, it.rhix, it.rloy, it.rhiy, gball);
-                const uint32_t m = __ballot_sync(FULLM, keep);
-                if (m) {
-                    if (keep)
-                        q1[(t1 + __popc(m & lt_mask)) & (QCAP - 1)] =
-                            make_uint2((uint32_t)id[j], ((__float_as_uint(gball) + 0x7fu) & ~0x7fu) | (uint32_t)ilo);
-                    t1 += __popc(m);
-                    if (t1 - h1 >= 32u) {
-                        __syncwarp();
-                        run2(32u);
-                        __syncwarp();
+        case A2_START: {
+            // up to 32 surviving triangles, one per lane -> box -> block columns
+            e_col = 1; e_cx1 = 0; e_cur = 0; e_end = 0;                   // empty column range
+            if ((uint32_t)lane < cnt) {
+                const uint2 en = q1[(h1 + lane) & (QCAP - 1)];
+                e_tri = en.x;
+                const float gball = __uint_as_float(en.y & ~0x7fu);
+                const Item& it = sm.items[en.y & 0x7fu];
+                const uint4 r0 = __ldg(reinterpret_cast<const uint4*>(q.recs + e_tri));
+                const uint2 r1 = __ldg(reinterpret_cast<const uint2*>(q.recs + e_tri) + 2);
+                float x0, x1, y0, y1;
+                bool full;
+                stage2(tri_f(r0, r1), r1, e, d16, gball, x0, x1, y0, y1, full);
+                int bxl = (int)(it.bx & 0xffffu), bxh = (int)(it.bx >> 16), byl = (int)(it.by & 0xffffu), byh = (int)(it.by >> 16);
+                if (!full) {
+                    bxl = max(bxl, cell_coord_f(x0, q.shift_x, q.res, q.inv_res, q.G0 - 1, q.sem) / RVB_BLK);
+                    bxh = min(bxh, cell_coord_f(x1, q.shift_x, q.res, q.inv_res, q.G0 - 1, q.sem) / RVB_BLK);
+                    byl = max(byl, min(cell_coord_f(y0, q.shift_y, q.res, q.inv_res, q.G0 - 1, q.sem), q.G1 - 1) / RVB_BLK);
+                    byh = min(byh, min(cell_coord_f(y1, q.shift_y, q.res, q.inv_res, q.G0 - 1, q.sem), q.G1 - 1) / RVB_BLK);
+                    e_lo16 = (uint32_t)h_bits(__float2half_ru(x0)) | ((uint32_t)h_bits(__float2half_ru(y0)) << 16);
+                    e_hi16 = (uint32_t)h_bits(__float2half_rd(x1)) | ((uint32_t)h_bits(__float2half_rd(y1)) << 16);
+                } else {
+                    e_lo16 = 0xFC00FC00u;
+                    e_hi16 = 0x7C007C00u;
+                }
+                if (bxl <= bxh && byl <= byh) {
+                    e_col = bxl; e_cx1 = bxh;
+                    e_rlo = byl - by0; e_rhi = byh - by0 + 1;
+                }
+            }
+            h1 += cnt;
+            in2 = true;
+            break;
+        }
+        case A2_EMIT: {
+            // tasks of <= TASK_RAYS consecutive sorted rays; runs until q2 holds a batch or the lanes are done
+            while (true) {
+                while (e_cur >= e_end && e_col <= e_cx1) {
+                    const int b = (e_col - bx0) * BH;
+                    e_cur = off16(sm.bins, b + e_rlo);
+                    e_end = off16(sm.bins, b + e_rhi);
+                    ++e_col;
+                }
+                const bool have = e_cur < e_end;
+                const uint32_t m = __ballot_sync(FULLM, have);
+                if (!m) {
+                    in2 = false;
+                    break;
+                }
+                if (have) {
+                    const uint32_t c = min(e_end - e_cur, (uint32_t)TASK_RAYS);
+                    q2[(t2 + __popc(m & lt_mask)) & (QCAP - 1)] = make_uint4(e_tri, e_cur | (c << 16), e_lo16, e_hi16);
+                    e_cur += c;
+                }
+                t2 += __popc(m);
+                if (t2 - h2 >= 32u) break;
+            }
+            break;
+        }
+        case A3A_START: {
+            tk = make_uint4(0, 0, 0, 0);
+            a_c = 0;
+            if ((uint32_t)lane < cnt) {
+                tk = q2[(h2 + lane) & (QCAP - 1)];
+                a_c = (int)(tk.y >> 16);
+            }
+            h2 += cnt;
+            a_cmax = __reduce_max_sync(FULLM, a_c);
+            a_i = 0;
+            in3a = true;
+            break;
+        }
+        case A3A_RUN: {
+            // rays of the tasks against the boxes; runs until q3 holds a batch or the tasks are done
+            const uint32_t start = tk.y & 0xffffu;
+            while (a_i < a_cmax && t3 - h3 < 32u) {
+                bool in = false;
+                if (a_i < a_c) {
+                    const uint32_t w0 = sm.rays[start + a_i].x;
+                    in = (__hge2_mask(*reinterpret_cast<const __half2*>(&w0), *reinterpret_cast<const __half2*>(&tk.z)) &
+                          __hle2_mask(*reinterpret_cast<const __half2*>(&w0), *reinterpret_cast<const __half2*>(&tk.w))) == 0xffffffffu;
+                }
+                const uint32_t m = __ballot_sync(FULLM, in);
+                if (in) q3[(t3 + __popc(m & lt_mask)) & (QCAP - 1)] = make_uint2(start + (uint32_t)a_i, tk.x);
+                t3 += __popc(m);
+                ++a_i;
+            }
+            if (a_i >= a_cmax) in3a = false;
+            break;
+        }
+        case A3B: {
+            // literal evaluation + slot lookup of up to 32 queued (ray, triangle) pairs, one per lane
+            if ((uint32_t)lane < cnt) {
+                const uint2 pr = q3[(h3 + lane) & (QCAP - 1)];
+                const uint2 ray = sm.rays[pr.x];
+                const H3 s = {h_from_bits(ray.x & 0xffff), h_from_bits(ray.x >> 16), h_from_bits(ray.y & 0xffff)};
+                H3 a, b, c, nn;
+                unpack_rec(q.recs + pr.y, a, b, c, nn);
+                const __half k = pair_test(s, d16, a, b, c, nn);
+                const uint32_t meta = ray.y >> 16, p = meta & 0x7ffu, sub = meta >> 11;
+                const uint32_t ord = make_key(h_bits(k), 0u) >> 16;
+                // a hit at exactly 11.0 equals the all-miss result (slot 0); a hit farther than a confirmed one cannot win
+                if (h_bits(k) != RVB_H_MISS && (ord > ORD_MISS || ord <= (sm.res[p] >> 16))) {
+                    const int cx = cell_coord(s.x, q.shift_x, q.res, q.inv_res, q.G0 - 1, q.sem);
+                    const int cy = min(cell_coord(s.y, q.shift_y, q.res, q.inv_res, q.G0 - 1, q.sem), q.G1 - 1);
+                    const uint32_t blk = (uint32_t)(cx / RVB_BLK) * (uint32_t)q.nBy + (uint32_t)(cy / RVB_BLK);
+                    const uint32_t o0 = __ldg(q.blk_off + blk), o1 = __ldg(q.blk_off + blk + 1);
+                    uint32_t lo = o0, hi = o1;
+                    while (lo < hi) {                       // block lists are sorted by triangle id
+                        const uint32_t mid = (lo + hi) >> 1;
+                        if (__ldg(q.blk_ids + mid) < (int32_t)pr.y) lo = mid + 1; else hi = mid;
+                    }
+                    if (lo < o1 && __ldg(q.blk_ids + lo) == (int32_t)pr.y) {
+                        const uint32_t slot = __ldg(reinterpret_cast<const unsigned char*>(q.blk_slots + lo) + sub);
+                        if (slot != 0xffu) {                // the triangle is in the ray's own cell list
+                            const uint32_t key = make_key(h_bits(k), slot);
+                            if ((key >> 16) > ORD_MISS) atomicOr(&sm.far[p >> 5], 1u << (p & 31));      // k > 11: see epilogue
+                            else atomicMin(&sm.res[p], key);
+                        }
                     }
                 }
             }
+            h3 += cnt;
+            break;
+        }
         }
     }
-    __syncwarp();
-    if (t1 != h1) run2(t1 - h1);
-    __syncwarp();
-    if (t2 != h2) run3a(t2 - h2);
-    __syncwarp();
-    if (t3 != h3) run3b(t3 - h3);
     __syncthreads();
 
     // ---- phase 4
@@ -671,7 +726,7 @@ int launch_heightmap_shadow(const rvb_terrain* t, const float* pos, const float*
     int rc_ = fill_tiled_params(t, pos, euler, trig, pattern, P, N, dist, hit_slot, hit_tri, pt, sources, obs, obs_ld, col_a,
                                 col_b, q);
     if (rc_ != RVB_OK) return rc_;
-    RVB_REQUIRE(q.tile_size <= 2047, "heightmap ray-cast (shadow): tile larger than 2047 rays");
+    RVB_REQUIRE(q.tile_size <= 2048, "heightmap ray-cast (shadow): tile larger than 2048 rays");
     const int64_t nblocks = N * q.tiles;
     int* scratch = nullptr;
     RVB_CUDA(cudaMallocAsync(&scratch, sizeof(int) * (size_t)(nblocks + 1), st));
