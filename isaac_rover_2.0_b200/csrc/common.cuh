@@ -52,6 +52,7 @@ struct rvb_terrain {
     int32_t nSBx, nSBy;
     uint32_t* sb_off;    // [nSBx*nSBy + 1]
     int32_t* sb_ids;     // [n_sb_ent]
+    uint16_t* sb_pos;    // [n_sb_ent][RVB_SB*RVB_SB]  position of the triangle in the list of block (i % SB, j % SB); 0xFFFF = absent
     int64_t n_sb_ent;
 };
 #define RVB_BLK 3

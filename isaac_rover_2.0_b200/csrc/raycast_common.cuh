@@ -34,6 +34,7 @@ struct TiledParams {
     // shadow kernel (raycast_shadow.cu): superblock candidate lists + the list of (env, tile) work items it hands back
     const uint32_t* sb_off;
     const int32_t* sb_ids;
+    const uint16_t* sb_pos;
     int nSBy;
     float cos_steep;          // envs whose ray direction is flatter than this go to the fall-back list
     int* fb_count;            // [1]

@@ -83,9 +83,9 @@ struct Smem {
     Item* items;         // [ITEM_CAP]
     uint32_t* cum;       // [ITEM_CAP + 1]  chunks before item i
     unsigned char* chunk_item;   // [CHUNK_CAP]
-    uint2* q1;           // [NW][QCAP]  stage-1 survivors: (triangle, gball bits | item)
-    uint4* q2;           // [NW][QCAP]  tasks: (triangle, ray start | count << 16, box lo half2, box hi half2)
-    uint2* q3;           // [NW][QCAP]  pairs: (ray position, triangle)
+    uint2* q1;           // [NW][QCAP]  stage-1 survivors: (superblock-list entry, gball bits | item)
+    uint4* q2;           // [NW][QCAP]  tasks: (entry, ray start | count << 16 | item << 24, box lo half2, box hi half2)
+    uint2* q3;           // [NW][QCAP]  pairs: (ray position | item << 16, superblock-list entry)
     uint32_t* far;       // [RT / 32]
 };
 
@@ -410,10 +410,11 @@ __global__ void __launch_bounds__(TT, 3) hm_shadow_kernel(const TiledParams q) {
     }
     // ---- superblock items: block rectangle with rays, source rectangle, candidate list
     const int nsb = nsx * nsy;
-    int* it_red = reinterpret_cast<int*>(sm.q2);          // [4][ITEM_CAP] bx lo, bx hi, by lo, by hi (queues are idle here)
+    int* it_red = reinterpret_cast<int*>(sm.q2);          // [5][ITEM_CAP] bx lo, bx hi, by lo, by hi, rays (queues are idle here)
     for (int i = tid; i < nsb; i += TT) {
         it_red[i] = 0x7fffffff; it_red[ITEM_CAP + i] = -1;
         it_red[2 * ITEM_CAP + i] = 0x7fffffff; it_red[3 * ITEM_CAP + i] = -1;
+        it_red[4 * ITEM_CAP + i] = 0;
     }
     if (tid == 0) s_nitems = 0;
     __syncthreads();
@@ -434,6 +435,7 @@ __global__ void __launch_bounds__(TT, 3) hm_shadow_kernel(const TiledParams q) {
         if (yhi >= 0) {
             atomicMin(&it_red[sbi], bx); atomicMax(&it_red[ITEM_CAP + sbi], bx);
             atomicMin(&it_red[2 * ITEM_CAP + sbi], ylo); atomicMax(&it_red[3 * ITEM_CAP + sbi], yhi);
+            atomicAdd(&it_red[4 * ITEM_CAP + sbi], (int)(off16(sm.bins, base + rhi + 1) - off16(sm.bins, base + rlo)));
         }
     }
     __syncthreads();
@@ -443,6 +445,14 @@ __global__ void __launch_bounds__(TT, 3) hm_shadow_kernel(const TiledParams q) {
         for (int i = tid; i < nsb; i += TT) {
             const int bxl = it_red[i], bxh = it_red[ITEM_CAP + i], byl = it_red[2 * ITEM_CAP + i], byh = it_red[3 * ITEM_CAP + i];
             if (bxh < 0) continue;
+            // heavy superblocks first: the warps' last chunks are then cheap ones (the CTA ends at its slowest warp)
+            const int mine = it_red[4 * ITEM_CAP + i];
+            int rank = 0;
+            for (int j = 0; j < nsb; ++j) {
+                const int cj = it_red[4 * ITEM_CAP + j];
+                rank += (cj > mine || (cj == mine && j < i && cj > 0)) ? 1 : 0;
+            }
+            atomicAdd(&s_nitems, 1);
             const int SX = sbx0 + i / nsy, SY = sby0 + i % nsy;
             const uint32_t sb = (uint32_t)SX * (uint32_t)q.nSBy + (uint32_t)SY;
             Item it;
@@ -456,7 +466,7 @@ __global__ void __launch_bounds__(TT, 3) hm_shadow_kernel(const TiledParams q) {
             it.rhiy = fminf(g_hiy, cyh >= min(q.G0, q.G1) - 1 ? inf : q.shift_y + ((float)cyh + 0.52f) * q.res + slop);
             it.bx = (uint32_t)bxl | ((uint32_t)bxh << 16);
             it.by = (uint32_t)byl | ((uint32_t)byh << 16);
-            sm.items[atomicAdd(&s_nitems, 1)] = it;
+            sm.items[rank] = it;
         }
     }
     __syncthreads();
@@ -510,10 +520,11 @@ __global__ void __launch_bounds__(TT, 3) hm_shadow_kernel(const TiledParams q) {
 
     // stage-1 pipeline: ids of chunk k+2 and records of chunk k+1 are in flight while chunk k is tested
     int32_t idA = -1, idB = -1;            // idA: records loaded (r0A, r1A); idB: id loaded
+    uint32_t entA = 0, entB = 0;           // superblock-list entry of the lane's triangle
     int itemA = -1, itemB = -1;            // -1: no chunk
     uint4 r0A = make_uint4(0, 0, 0, 0);
     uint2 r1A = make_uint2(0, 0);
-    auto pull = [&](int32_t& id, int& item) {
+    auto pull = [&](int32_t& id, uint32_t& ent, int& item) {
         int g = 0;
         if (lane == 0) g = atomicAdd(&s_next, 1);
         g = __shfl_sync(FULLM, g, 0);
@@ -523,22 +534,22 @@ __global__ void __launch_bounds__(TT, 3) hm_shadow_kernel(const TiledParams q) {
             item = sm.chunk_item[g];
             const Item& it = sm.items[item];
             const uint32_t cbeg = ((uint32_t)g - sm.cum[item]) * CHUNK;
-            if (cbeg + lane < it.list_len) id = __ldg(q.sb_ids + it.list_off + cbeg + lane);
+            ent = it.list_off + cbeg + lane;
+            if (cbeg + lane < it.list_len) id = __ldg(q.sb_ids + ent);
         }
     };
-    pull(idA, itemA);
+    pull(idA, entA, itemA);
     if (idA >= 0) {
         r0A = __ldg(reinterpret_cast<const uint4*>(q.recs + idA));
         r1A = __ldg(reinterpret_cast<const uint2*>(q.recs + idA) + 2);
     }
-    pull(idB, itemB);
+    pull(idB, entB, itemB);
     bool more = true, in2 = false, in3a = false;
     // stage-2 emission state (per lane)
-    uint32_t e_tri = 0, e_lo16 = 0, e_hi16 = 0, e_cur = 0, e_end = 0;
+    uint32_t e_ent = 0, e_lo16 = 0, e_hi16 = 0, e_cur = 0, e_end = 0;
     int e_col = 1, e_cx1 = 0, e_rlo = 0, e_rhi = 0;
-    // stage-3a state (per lane)
-    uint4 tk = make_uint4(0, 0, 0, 0);
-    int a_c = 0, a_i = 0, a_cmax = 0;
+    // stage-3a state (per lane): task + bit i set = ray start + i lies in the box
+    uint32_t a_ent = 0, a_start = 0, a_mask = 0;
 
     while (true) {
         const uint32_t n1 = t1 - h1, n2 = t2 - h2, n3 = t3 - h3;
@@ -557,29 +568,32 @@ __global__ void __launch_bounds__(TT, 3) hm_shadow_kernel(const TiledParams q) {
         __syncwarp();
         switch (action) {
         case A1: {
-            if (itemA < 0) {
-                more = false;
-                break;
-            }
-            const int32_t id = idA;
-            const int item = itemA;
-            const uint4 r0 = r0A;
-            const uint2 r1 = r1A;
-            idA = idB; itemA = itemB;
-            if (idA >= 0) {
-                r0A = __ldg(reinterpret_cast<const uint4*>(q.recs + idA));
-                r1A = __ldg(reinterpret_cast<const uint2*>(q.recs + idA) + 2);
-            }
-            pull(idB, itemB);
-            const Item& it = sm.items[item];
-            bool keep = false;
-            float gball = 0.0f;
-            if (id >= 0) keep = stage1(tri_f(r0, r1), e, it.rlox, it.rhix, it.rloy, it.rhiy, gball);
-            const uint32_t m = __ballot_sync(FULLM, keep);
-            if (keep)
-                q1[(t1 + __popc(m & lt_mask)) & (QCAP - 1)] =
-                    make_uint2((uint32_t)id, ((__float_as_uint(gball) + 0x7fu) & ~0x7fu) | (uint32_t)item);
-            t1 += __popc(m);
+            do {
+                if (itemA < 0) {
+                    more = false;
+                    break;
+                }
+                const int32_t id = idA;
+                const uint32_t ent = entA;
+                const int item = itemA;
+                const uint4 r0 = r0A;
+                const uint2 r1 = r1A;
+                idA = idB; itemA = itemB; entA = entB;
+                if (idA >= 0) {
+                    r0A = __ldg(reinterpret_cast<const uint4*>(q.recs + idA));
+                    r1A = __ldg(reinterpret_cast<const uint2*>(q.recs + idA) + 2);
+                }
+                pull(idB, entB, itemB);
+                const Item& it = sm.items[item];
+                bool keep = false;
+                float gball = 0.0f;
+                if (id >= 0) keep = stage1(tri_f(r0, r1), e, it.rlox, it.rhix, it.rloy, it.rhiy, gball);
+                const uint32_t m = __ballot_sync(FULLM, keep);
+                if (keep)
+                    q1[(t1 + __popc(m & lt_mask)) & (QCAP - 1)] =
+                        make_uint2(ent, ((__float_as_uint(gball) + 0x7fu) & ~0x7fu) | (uint32_t)item);
+                t1 += __popc(m);
+            } while (t1 - h1 < 32u);
             break;
         }
         case A2_START: {
@@ -587,11 +601,12 @@ __global__ void __launch_bounds__(TT, 3) hm_shadow_kernel(const TiledParams q) {
             e_col = 1; e_cx1 = 0; e_cur = 0; e_end = 0;                   // empty column range
             if ((uint32_t)lane < cnt) {
                 const uint2 en = q1[(h1 + lane) & (QCAP - 1)];
-                e_tri = en.x;
+                e_ent = en.x;
+                const int32_t tri = __ldg(q.sb_ids + e_ent);
                 const float gball = __uint_as_float(en.y & ~0x7fu);
                 const Item& it = sm.items[en.y & 0x7fu];
-                const uint4 r0 = __ldg(reinterpret_cast<const uint4*>(q.recs + e_tri));
-                const uint2 r1 = __ldg(reinterpret_cast<const uint2*>(q.recs + e_tri) + 2);
+                const uint4 r0 = __ldg(reinterpret_cast<const uint4*>(q.recs + tri));
+                const uint2 r1 = __ldg(reinterpret_cast<const uint2*>(q.recs + tri) + 2);
                 float x0, x1, y0, y1;
                 bool full;
                 stage2(tri_f(r0, r1), r1, e, d16, gball, x0, x1, y0, y1, full);
@@ -633,7 +648,7 @@ __global__ void __launch_bounds__(TT, 3) hm_shadow_kernel(const TiledParams q) {
                 }
                 if (have) {
                     const uint32_t c = min(e_end - e_cur, (uint32_t)TASK_RAYS);
-                    q2[(t2 + __popc(m & lt_mask)) & (QCAP - 1)] = make_uint4(e_tri, e_cur | (c << 16), e_lo16, e_hi16);
+                    q2[(t2 + __popc(m & lt_mask)) & (QCAP - 1)] = make_uint4(e_ent, e_cur | (c << 16), e_lo16, e_hi16);
                     e_cur += c;
                 }
                 t2 += __popc(m);
@@ -642,60 +657,66 @@ __global__ void __launch_bounds__(TT, 3) hm_shadow_kernel(const TiledParams q) {
             break;
         }
         case A3A_START: {
-            tk = make_uint4(0, 0, 0, 0);
-            a_c = 0;
+            // one task per lane: its rays against the box -> bit mask (no warp-level work inside the loop)
+            a_mask = 0u;
             if ((uint32_t)lane < cnt) {
-                tk = q2[(h2 + lane) & (QCAP - 1)];
-                a_c = (int)(tk.y >> 16);
+                const uint4 tk = q2[(h2 + lane) & (QCAP - 1)];
+                a_ent = tk.x;
+                a_start = tk.y & 0xffffu;
+                const int c = (int)(tk.y >> 16);
+                const __half2 lo = *reinterpret_cast<const __half2*>(&tk.z), hi = *reinterpret_cast<const __half2*>(&tk.w);
+                for (int i = 0; i < c; ++i) {
+                    const uint32_t w0 = sm.rays[a_start + i].x;
+                    const bool in = (__hge2_mask(*reinterpret_cast<const __half2*>(&w0), lo) &
+                                     __hle2_mask(*reinterpret_cast<const __half2*>(&w0), hi)) == 0xffffffffu;
+                    a_mask |= (in ? 1u : 0u) << i;
+                }
             }
             h2 += cnt;
-            a_cmax = __reduce_max_sync(FULLM, a_c);
-            a_i = 0;
-            in3a = true;
+            in3a = __any_sync(FULLM, a_mask != 0u);
             break;
         }
         case A3A_RUN: {
-            // rays of the tasks against the boxes; runs until q3 holds a batch or the tasks are done
-            const uint32_t start = tk.y & 0xffffu;
-            while (a_i < a_cmax && t3 - h3 < 32u) {
-                bool in = false;
-                if (a_i < a_c) {
-                    const uint32_t w0 = sm.rays[start + a_i].x;
-                    in = (__hge2_mask(*reinterpret_cast<const __half2*>(&w0), *reinterpret_cast<const __half2*>(&tk.z)) &
-                          __hle2_mask(*reinterpret_cast<const __half2*>(&w0), *reinterpret_cast<const __half2*>(&tk.w))) == 0xffffffffu;
+            // expand the masks into (ray, entry) pairs; runs until q3 holds a batch or the masks are empty
+            while (true) {
+                const bool have = a_mask != 0u;
+                const uint32_t m = __ballot_sync(FULLM, have);
+                if (!m) {
+                    in3a = false;
+                    break;
                 }
-                const uint32_t m = __ballot_sync(FULLM, in);
-                if (in) q3[(t3 + __popc(m & lt_mask)) & (QCAP - 1)] = make_uint2(start + (uint32_t)a_i, tk.x);
+                if (have) {
+                    const uint32_t bit = (uint32_t)__ffs((int)a_mask) - 1u;
+                    a_mask &= a_mask - 1u;
+                    q3[(t3 + __popc(m & lt_mask)) & (QCAP - 1)] = make_uint2(a_start + bit, a_ent);
+                }
                 t3 += __popc(m);
-                ++a_i;
+                if (t3 - h3 >= 32u) break;
             }
-            if (a_i >= a_cmax) in3a = false;
             break;
         }
         case A3B: {
             // literal evaluation + slot lookup of up to 32 queued (ray, triangle) pairs, one per lane
-            if ((uint32_t)lane < cnt) {
-                const uint2 pr = q3[(h3 + lane) & (QCAP - 1)];
-                const uint2 ray = sm.rays[pr.x];
-                const H3 s = {h_from_bits(ray.x & 0xffff), h_from_bits(ray.x >> 16), h_from_bits(ray.y & 0xffff)};
-                H3 a, b, c, nn;
-                unpack_rec(q.recs + pr.y, a, b, c, nn);
-                const __half k = pair_test(s, d16, a, b, c, nn);
-                const uint32_t meta = ray.y >> 16, p = meta & 0x7ffu, sub = meta >> 11;
-                const uint32_t ord = make_key(h_bits(k), 0u) >> 16;
-                // a hit at exactly 11.0 equals the all-miss result (slot 0); a hit farther than a confirmed one cannot win
-                if (h_bits(k) != RVB_H_MISS && (ord > ORD_MISS || ord <= (sm.res[p] >> 16))) {
+            do {
+                if ((uint32_t)lane < cnt) {
+                    const uint2 pr = q3[(h3 + lane) & (QCAP - 1)];
+                    const uint2 ray = sm.rays[pr.x];
+                    const int32_t tri = __ldg(q.sb_ids + pr.y);
+                    const H3 s = {h_from_bits(ray.x & 0xffff), h_from_bits(ray.x >> 16), h_from_bits(ray.y & 0xffff)};
+                    const uint32_t meta = ray.y >> 16, p = meta & 0x7ffu, sub = meta >> 11;
+                    // position of the triangle in the list of the ray's 3x3 block (0xFFFF: in none of its nine cell lists)
                     const int cx = cell_coord(s.x, q.shift_x, q.res, q.inv_res, q.G0 - 1, q.sem);
                     const int cy = min(cell_coord(s.y, q.shift_y, q.res, q.inv_res, q.G0 - 1, q.sem), q.G1 - 1);
-                    const uint32_t blk = (uint32_t)(cx / RVB_BLK) * (uint32_t)q.nBy + (uint32_t)(cy / RVB_BLK);
-                    const uint32_t o0 = __ldg(q.blk_off + blk), o1 = __ldg(q.blk_off + blk + 1);
-                    uint32_t lo = o0, hi = o1;
-                    while (lo < hi) {                       // block lists are sorted by triangle id
-                        const uint32_t mid = (lo + hi) >> 1;
-                        if (__ldg(q.blk_ids + mid) < (int32_t)pr.y) lo = mid + 1; else hi = mid;
-                    }
-                    if (lo < o1 && __ldg(q.blk_ids + lo) == (int32_t)pr.y) {
-                        const uint32_t slot = __ldg(reinterpret_cast<const unsigned char*>(q.blk_slots + lo) + sub);
+                    const int bx = cx / RVB_BLK, by = cy / RVB_BLK;
+                    const uint32_t pos16 = __ldg(q.sb_pos + (size_t)pr.y * (SB * SB) + (uint32_t)((bx % SB) * SB + (by % SB)));
+                    const uint32_t o0 = __ldg(q.blk_off + (uint32_t)bx * (uint32_t)q.nBy + (uint32_t)by);
+                    H3 a, b, c, nn;
+                    unpack_rec(q.recs + tri, a, b, c, nn);
+                    const __half k = pair_test(s, d16, a, b, c, nn);
+                    const uint32_t ord = make_key(h_bits(k), 0u) >> 16;
+                    // a hit at exactly 11.0 equals the all-miss result (slot 0); a hit farther than a confirmed one cannot win
+                    if (h_bits(k) != RVB_H_MISS && pos16 != 0xffffu && (ord > ORD_MISS || ord <= (sm.res[p] >> 16))) {
+                        const uint32_t slot = __ldg(reinterpret_cast<const unsigned char*>(q.blk_slots + o0 + pos16) + sub);
                         if (slot != 0xffu) {                // the triangle is in the ray's own cell list
                             const uint32_t key = make_key(h_bits(k), slot);
                             if ((key >> 16) > ORD_MISS) atomicOr(&sm.far[p >> 5], 1u << (p & 31));      // k > 11: see epilogue
@@ -703,8 +724,8 @@ __global__ void __launch_bounds__(TT, 3) hm_shadow_kernel(const TiledParams q) {
                         }
                     }
                 }
-            }
-            h3 += cnt;
+                h3 += cnt;
+            } while (cnt == 32u && t3 - h3 >= 32u);
             break;
         }
         }
@@ -721,7 +742,7 @@ int launch_heightmap_shadow(const rvb_terrain* t, const float* pos, const float*
                             const double* pattern, int64_t P, int64_t N, uint16_t* dist, int32_t* hit_slot,
                             int32_t* hit_tri, uint16_t* pt, uint16_t* sources, float* obs, int64_t obs_ld,
                             const int32_t* col_a, const int32_t* col_b, float cos_steep, cudaStream_t st) {
-    RVB_REQUIRE(t->sb_ids != nullptr && t->blk_ids != nullptr, "heightmap ray-cast (shadow): layer has no block lists");
+    RVB_REQUIRE(t->sb_ids != nullptr && t->sb_pos != nullptr && t->blk_ids != nullptr, "heightmap ray-cast (shadow): layer has no block lists");
     rc::TiledParams q;
     int rc_ = fill_tiled_params(t, pos, euler, trig, pattern, P, N, dist, hit_slot, hit_tri, pt, sources, obs, obs_ld, col_a,
                                 col_b, q);

@@ -182,6 +182,30 @@ __global__ void sb_ids_kernel(const unsigned long long* __restrict__ keys, int64
     if (i < n) ids[i] = (int32_t)(uint32_t)keys[i];
 }
 
+// position of every superblock-list triangle in each of the superblock's block lists (binary search; lists sorted by id)
+__global__ void sb_pos_kernel(const uint32_t* __restrict__ sb_off, const int32_t* __restrict__ sb_ids, const uint32_t* __restrict__ blk_off,
+                              const int32_t* __restrict__ blk_ids, int nBx, int nBy, int nSBy, uint16_t* __restrict__ pos) {
+    const int SX = blockIdx.x / nSBy, SY = blockIdx.x % nSBy;
+    const uint32_t e0 = sb_off[blockIdx.x], e1 = sb_off[blockIdx.x + 1];
+    const uint32_t total = (e1 - e0) * (RVB_SB * RVB_SB);
+    for (uint32_t w = threadIdx.x; w < total; w += blockDim.x) {
+        const uint32_t ent = e0 + w / (RVB_SB * RVB_SB), b = w % (RVB_SB * RVB_SB);
+        const int I = SX * RVB_SB + (int)(b / RVB_SB), J = SY * RVB_SB + (int)(b % RVB_SB);
+        uint16_t out = 0xffffu;
+        if (I < nBx && J < nBy) {
+            const int32_t id = sb_ids[ent];
+            const uint32_t o0 = blk_off[(uint32_t)I * nBy + J], o1 = blk_off[(uint32_t)I * nBy + J + 1];
+            uint32_t lo = o0, hi = o1;
+            while (lo < hi) {
+                const uint32_t mid = (lo + hi) >> 1;
+                if (blk_ids[mid] < id) lo = mid + 1; else hi = mid;
+            }
+            if (lo < o1 && blk_ids[lo] == id && lo - o0 < 0xffffu) out = (uint16_t)(lo - o0);
+        }
+        pos[(size_t)ent * (RVB_SB * RVB_SB) + b] = out;
+    }
+}
+
 static int build_superblock_lists(rvb_terrain* t, cudaStream_t st) {
     t->nSBx = (int32_t)ceil_div(t->nBx, RVB_SB);
     t->nSBy = (int32_t)ceil_div(t->nBy, RVB_SB);
@@ -220,6 +244,11 @@ static int build_superblock_lists(rvb_terrain* t, cudaStream_t st) {
             sb_offsets_kernel<<<(unsigned)ceil_div(nsb + 1, 256), 256, 0, st>>>(k0, n_u, nsb, t->sb_off);
             sb_ids_kernel<<<(unsigned)ceil_div(n_u > 0 ? n_u : 1, 256), 256, 0, st>>>(k0, n_u, t->sb_ids);
             e = cudaGetLastError();
+            if (e == cudaSuccess) e = cudaMalloc(&t->sb_pos, sizeof(uint16_t) * RVB_SB * RVB_SB * (size_t)(n_u > 0 ? n_u : 1));
+            if (e == cudaSuccess) {
+                sb_pos_kernel<<<(unsigned)nsb, 256, 0, st>>>(t->sb_off, t->sb_ids, t->blk_off, t->blk_ids, t->nBx, t->nBy, t->nSBy, t->sb_pos);
+                e = cudaGetLastError();
+            }
             if (e == cudaSuccess) e = cudaStreamSynchronize(st);
         }
     }
@@ -309,6 +338,7 @@ extern "C" int rvb_terrain_create(rvb_terrain** out, const int32_t* map_indices,
             cudaFree(t->blk_slots);
             cudaFree(t->sb_off);
             cudaFree(t->sb_ids);
+            cudaFree(t->sb_pos);
             delete t;
             return rc != RVB_OK ? rc : rvb_set_error(RVB_ERR_CUDA, "rvb_terrain_create (block lists)", cudaGetErrorString(e));
         }
@@ -335,6 +365,7 @@ extern "C" int rvb_terrain_destroy(rvb_terrain* t) {
     cudaFree(t->blk_slots);
     cudaFree(t->sb_off);
     cudaFree(t->sb_ids);
+    cudaFree(t->sb_pos);
     delete t;
     return RVB_OK;
 }
@@ -343,5 +374,5 @@ extern "C" int64_t rvb_terrain_bytes(const rvb_terrain* t) {
     if (!t) return 0;
     return (int64_t)sizeof(int32_t) * t->G0 * t->G1 * t->Ks + (int64_t)sizeof(TriRec) * t->T +
            (t->blk_ids ? (int64_t)(sizeof(uint4) + sizeof(int32_t)) * t->n_ent + (int64_t)sizeof(uint32_t) * ((int64_t)t->nBx * t->nBy + 1) : 0) +
-           (t->sb_ids ? (int64_t)sizeof(int32_t) * t->n_sb_ent + (int64_t)sizeof(uint32_t) * ((int64_t)t->nSBx * t->nSBy + 1) : 0);
+           (t->sb_ids ? (int64_t)(sizeof(int32_t) + sizeof(uint16_t) * RVB_SB * RVB_SB) * t->n_sb_ent + (int64_t)sizeof(uint32_t) * ((int64_t)t->nSBx * t->nSBy + 1) : 0);
 }
