@@ -4,6 +4,8 @@
 // variant 1 ("simple"): one warp per ray, lanes stride over the K candidates of the ray's cell, every
 // (ray, candidate) pair evaluated with the literal op sequence of ray_casting.py.  Kept as the on-device
 // cross-check for the production kernel (raycast_tiled.cu).
+#include <stdlib.h>
+
 #include "common.cuh"
 
 int launch_heightmap_tiled(const rvb_terrain* t, const float* pos, const float* euler, const float* trig,
@@ -15,7 +17,7 @@ int launch_heightmap_shadow(const rvb_terrain* t, const float* pos, const float*
                            int32_t* hit_tri, uint16_t* pt, uint16_t* sources, float* obs, int64_t obs_ld,
                            const int32_t* col_a, const int32_t* col_b, float cos_steep, cudaStream_t st);
 // envs whose ray direction has |d_z| below this are ray-cast by the tiled kernel (their prisms are long slivers)
-#define RVB_COS_STEEP 0.0f
+#define RVB_COS_STEEP 0.8f
 
 
 // ------------------------------------------------------------------------------------------------
@@ -151,9 +153,12 @@ extern "C" int rvb_heightmap_raycast(const rvb_terrain* t, const float* pos, con
     RVB_REQUIRE(variant >= 0 && variant <= 3, "rvb_heightmap_raycast: variant must be 0, 1, 2 or 3");
     if (N == 0) return RVB_OK;
     cudaStream_t st = as_stream(stream);
-    if (variant == 0 && t->sb_ids != nullptr)
+    if (variant == 0 && t->sb_ids != nullptr) {
+        float cos_steep = RVB_COS_STEEP;
+        if (const char* ev = getenv("RVB_COS_STEEP")) cos_steep = (float)atof(ev);      // tuning hook; results do not depend on it
         return launch_heightmap_shadow(t, pos, euler, trig, pattern, P, N, dist, hit_slot, hit_tri, pt, sources, obs,
-                                       obs_ld, col_a, col_b, RVB_COS_STEEP, st);
+                                       obs_ld, col_a, col_b, cos_steep, st);
+    }
     if (variant != 1)
         return launch_heightmap_tiled(t, pos, euler, trig, pattern, P, N, dist, hit_slot, hit_tri, pt, sources, obs,
                                       obs_ld, col_a, col_b, variant == 2, st);

@@ -42,6 +42,7 @@ struct TiledParams {
     // tiled kernel in work-list mode: CTAs loop over fb_list[0 .. *fb_count) instead of blockIdx
     const int* work_count;
     const int32_t* work_list;
+    int work_slices;
 };
 
 // key of torch.min's total order: NaN < everything, -0 == +0, ties -> lower slot; bit 0 remembers a negative zero.

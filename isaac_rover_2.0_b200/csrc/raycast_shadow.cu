@@ -769,6 +769,7 @@ int launch_heightmap_shadow(const rvb_terrain* t, const float* pos, const float*
         // (env, tile) items the shadow kernel handed back: the tiled kernel loops over the list (usually empty)
         q.work_count = q.fb_count;
         q.work_list = q.fb_list;
+        q.work_slices = 8;
         rc_ = launch_tiled(q, true, nblocks < 148 * 3 ? nblocks : 148 * 3, st);
     }
     cudaFreeAsync(scratch, st);

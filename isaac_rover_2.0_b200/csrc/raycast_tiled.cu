@@ -151,7 +151,7 @@ __device__ __forceinline__ void drain32(const Smem& sm, const uint2* wq, uint32_
 }
 
 template <int B>
-__device__ __forceinline__ void hm_tiled_body(const TiledParams& q, const int work) {
+__device__ __forceinline__ void hm_tiled_body(const TiledParams& q, const int work, const int sub, const int nsub) {
     extern __shared__ uint4 smem_raw[];
     __shared__ int s_box[4];          // min cx, min cy, max cx, max cy
     __shared__ uint32_t s_warp[NW];
@@ -160,8 +160,12 @@ __device__ __forceinline__ void hm_tiled_body(const TiledParams& q, const int wo
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int64_t n = work / q.tiles;
     const int tile = work % q.tiles;
-    const int p0 = tile * q.tile_size;
-    const int np = min(q.tile_size, q.P - p0);
+    // work-list mode cuts a tile into nsub slices (one CTA each): the few listed envs then finish in a fraction of the time
+    const int tile_np = min(q.tile_size, q.P - tile * q.tile_size);
+    const int slice = (tile_np + nsub - 1) / nsub;
+    const int p0 = tile * q.tile_size + sub * slice;
+    const int np = min(slice, tile_np - sub * slice);
+    if (np <= 0) return;
     const int RT = q.tile_size;
 
     Smem sm;
@@ -420,12 +424,12 @@ template <int B>
 __global__ void __launch_bounds__(TT, 3) hm_tiled_kernel(const TiledParams q) {
     if (q.work_list) {
         const int cnt = *q.work_count;
-        for (int w = blockIdx.x; w < cnt; w += gridDim.x) {
-            hm_tiled_body<B>(q, q.work_list[w]);
+        for (int w = blockIdx.x; w < cnt * q.work_slices; w += gridDim.x) {
+            hm_tiled_body<B>(q, q.work_list[w / q.work_slices], w % q.work_slices, q.work_slices);
             __syncthreads();
         }
     } else {
-        hm_tiled_body<B>(q, (int)blockIdx.x);
+        hm_tiled_body<B>(q, (int)blockIdx.x, 0, 1);
     }
 }
 

@@ -37,6 +37,38 @@ for v in (3, 0, 2):
     print("variant %d: %.3f ms per launch (%d envs)" % (v, e0.elapsed_time(e1) / 5, N))
     d, pt, s = cam.get_depths(st["pos"], eul, want_hits=True, want_pt=False)
     out[v] = (d.clone(), cam.last_hit_slot.clone(), cam.last_hit_tri.clone())
+import os as _os
+for cs in ("0", "0.5", "0.7", "0.8", "0.9", "0.95"):
+    _os.environ["RVB_COS_STEEP"] = cs
+    cam.variant = 0
+    for _ in range(2):
+        cam.get_depths(st["pos"], eul, want_pt=False)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(5):
+        cam.get_depths(st["pos"], eul, want_pt=False)
+    e1.record()
+    torch.cuda.synchronize()
+    d, _, _ = cam.get_depths(st["pos"], eul, want_pt=False)
+    print("cos_steep %s: %.3f ms, equal to variant 3: %s" % (cs, e0.elapsed_time(e1) / 5, bool(torch.equal(d.view(torch.int16), out[3][0].view(torch.int16)))))
+_os.environ.pop("RVB_COS_STEEP")
+# the same without the 1 % strongly tilted envs
+st2 = dict(st)
+eul2 = eul.clone()
+eul2[:, :2] = eul2[:, :2].clamp(-0.25, 0.25)
+for v in (3, 0):
+    cam.variant = v
+    for _ in range(2):
+        cam.get_depths(st["pos"], eul2, want_pt=False)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(5):
+        cam.get_depths(st["pos"], eul2, want_pt=False)
+    e1.record()
+    torch.cuda.synchronize()
+    print("no tilted envs, variant %d: %.3f ms" % (v, e0.elapsed_time(e1) / 5))
 ref = out[3]
 for v in (0, 2):
     neq = out[v][0].view(torch.int16) != ref[0].view(torch.int16)
