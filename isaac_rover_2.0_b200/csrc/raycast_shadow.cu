@@ -6,7 +6,7 @@
 // (the pattern has constant z).  The kernel therefore enumerates TRIANGLES, not (ray, candidate) pairs:
 //
 //   phase 1/2  (as raycast_tiled.cu) fp64 body transform -> fp16 sources, cell lookup, counting sort of the tile's rays
-//              by 3x3-cell block (shared memory, column-major bins, so a block rectangle is a few contiguous ranges);
+//              by cell (shared memory, column-major bins, so a cell rectangle is a few contiguous ranges);
 //   stage 1    per (superblock, triangle of its list -- the union of the K-lists of 8x8 blocks): a bounding disc of the
 //              prism's cross-section on the source plane against the rectangle of the superblock's rays (~45 instr.);
 //   stage 2    survivors: exact corners of the cross-section -> xy box -> block columns -> ray ranges (tasks);
@@ -25,9 +25,10 @@
 // literal test).  |g| is bounded self-consistently from the disc of stage 1.  Triangles for which no bound holds
 // (|det*| within rounding of 0, fp16 overflow possible, NaN) are tested against every ray of the superblock.
 // tools/shadow_proto.py re-states stages 1-2 in numpy and checks them against a brute-force fp16 evaluation;
-// tests/test_shadow_bound_cpu.py runs it.  Envs this kernel cannot group (rays spread over more than 8192 blocks or
+// tests/test_shadow_bound_cpu.py runs it.  Envs this kernel cannot group (rays spread over more than 8192 cells or
 // 128 superblocks) or whose rays are nearly parallel to the ground (cos < cos_steep: the prisms become long slivers)
 // are handed to the tiled kernel through a work list.
+#include <stdlib.h>
 #include <string.h>
 
 #include "raycast_common.cuh"
@@ -46,12 +47,14 @@ constexpr int TT = 256;
 constexpr int NW = TT / 32;
 constexpr int RT_MAX = 2048;       // rays per tile; must equal raycast_tiled.cu's (shared tiling of the fall-back list)
 constexpr int RPT = RT_MAX / TT;
-constexpr int BIN_CAP = 8192;      // blocks in the tile's bounding box
-constexpr int SB = RVB_SB;
+constexpr int BIN_CAP = 8192;      // cells in the tile's bounding box
+constexpr int SB = RVB_SB;          // blocks per superblock side
+constexpr int SBC = RVB_SB * RVB_BLK;   // cells per superblock side
 constexpr int ITEM_CAP = 128;      // superblocks per tile (7 bits travel in the stage-1 queue)
 constexpr int CHUNK = 32;          // list entries per pulled work chunk (one stage-1 batch)
-constexpr int CHUNK_CAP = 4096;    // chunks per tile (u8 chunk -> item table)
-constexpr int QCAP = 64;           // per-warp queues (each drained below 32 after every push of <= 32)
+constexpr int CHUNK_CAP = 2048;    // chunks per tile (u8 chunk -> item table)
+constexpr int QCAP = 64;           // per-warp queues q1, q2 (each drained below 32 after every push of <= 32)
+constexpr int QCAP3 = 128;         // q3 (drained in batches of 64), q4 (receives up to 64 per batch)
 constexpr int TASK_RAYS = 16;
 
 constexpr float GAMMA = 0.00390625f;            // 2^-8
@@ -64,7 +67,7 @@ constexpr float SQ3 = 1.7320509f;
 struct Item {
     uint32_t list_off, list_len;
     float rlox, rhix, rloy, rhiy;   // rectangle holding the sources of the superblock's rays
-    uint32_t bx;                    // block columns with rays: lo | hi << 16 (absolute block coordinates)
+    uint32_t bx;                    // bin columns with rays: lo | hi << 16 (absolute bin coordinates)
     uint32_t by;
 };
 static_assert(sizeof(Item) == 32, "Item");
@@ -85,13 +88,14 @@ struct Smem {
     unsigned char* chunk_item;   // [CHUNK_CAP]
     uint2* q1;           // [NW][QCAP]  stage-1 survivors: (superblock-list entry, gball bits | item)
     uint4* q2;           // [NW][QCAP]  tasks: (entry, ray start | count << 16 | item << 24, box lo half2, box hi half2)
-    uint2* q3;           // [NW][QCAP]  pairs: (ray position | item << 16, superblock-list entry)
+    uint2* q3;           // [NW][QCAP3]  pairs inside the box: (ray position, superblock-list entry)
+    uint2* q4;           // [NW][QCAP3]  pairs that passed the packed fp16 pre-filter
     uint32_t* far;       // [RT / 32]
 };
 
 __host__ __device__ inline size_t shadow_smem_bytes(int RT) {
     return (size_t)RT * 8 + (size_t)((RT + 3) & ~3) * 4 + (size_t)(BIN_CAP / 2 + 4) * 4 + (size_t)ITEM_CAP * 32 +
-           (size_t)(ITEM_CAP + 4) * 4 + (size_t)CHUNK_CAP + (size_t)NW * QCAP * (8 + 16 + 8) + (size_t)(((RT + 31) / 32 + 3) & ~3) * 4;
+           (size_t)(ITEM_CAP + 4) * 4 + (size_t)CHUNK_CAP + (size_t)NW * (QCAP * (8 + 16) + QCAP3 * (8 + 8)) + (size_t)(((RT + 31) / 32 + 3) & ~3) * 4;
 }
 
 __device__ __forceinline__ float rcp_up(float x) { return __fdividef(1.0f, x) * 1.000001f; }
@@ -196,6 +200,7 @@ __device__ __forceinline__ void stage2(const TriF& t, const uint2& q1, const Env
     full = !good || !(x0 <= x1) || !(y0 <= y1);
 }
 
+template <bool DBGK>
 __global__ void __launch_bounds__(TT, 3) hm_shadow_kernel(const TiledParams q) {
     extern __shared__ uint4 smem_raw[];
     __shared__ int s_box[4];
@@ -221,7 +226,8 @@ __global__ void __launch_bounds__(TT, 3) hm_shadow_kernel(const TiledParams q) {
     sm.q1 = reinterpret_cast<uint2*>(sm.chunk_item + CHUNK_CAP);
     sm.q2 = reinterpret_cast<uint4*>(sm.q1 + NW * QCAP);
     sm.q3 = reinterpret_cast<uint2*>(sm.q2 + NW * QCAP);
-    sm.far = reinterpret_cast<uint32_t*>(sm.q3 + NW * QCAP);
+    sm.q4 = sm.q3 + NW * QCAP3;
+    sm.far = reinterpret_cast<uint32_t*>(sm.q4 + NW * QCAP3);
 
     // ---- phase 0
     for (int i = tid; i < BIN_CAP / 2 + 4; i += TT) sm.bins[i] = 0u;
@@ -267,8 +273,8 @@ __global__ void __launch_bounds__(TT, 3) hm_shadow_kernel(const TiledParams q) {
             const int bx = cx / RVB_BLK, by = cy / RVB_BLK;
             const uint32_t sub = (uint32_t)((cx - bx * RVB_BLK) * RVB_BLK + (cy - by * RVB_BLK));
             r_sz[i] = (uint32_t)h_bits(hz) | (((uint32_t)p | (sub << 11)) << 16);
-            r_cell[i] = (bx << 16) | by;
-            mnx = min(mnx, bx); mxx = max(mxx, bx); mny = min(mny, by); mxy = max(mxy, by);
+            r_cell[i] = (cx << 16) | cy;
+            mnx = min(mnx, cx); mxx = max(mxx, cx); mny = min(mny, cy); mxy = max(mxy, cy);
             const float fx = __half2float(hx), fy = __half2float(hy), fz = __half2float(hz);
             lo_x = fminf(lo_x, fx); hi_x = fmaxf(hi_x, fx); lo_y = fminf(lo_y, fy); hi_y = fmaxf(hi_y, fy);
             amax_s = fmaxf(amax_s, fmaxf(fmaxf(fabsf(fx), fabsf(fy)), fabsf(fz)));
@@ -296,10 +302,15 @@ __global__ void __launch_bounds__(TT, 3) hm_shadow_kernel(const TiledParams q) {
         if (bad) s_bail = 1;
     }
     __syncthreads();
-    const int bx0 = s_box[0], by0 = s_box[1];
-    const int BW = s_box[2] - bx0 + 1, BH = s_box[3] - by0 + 1;
-    const int sbx0 = bx0 / SB, sby0 = by0 / SB;
-    const int nsx = s_box[2] / SB - sbx0 + 1, nsy = s_box[3] / SB - sby0 + 1;
+    // bins: 2^sh x 2^sh cells, the finest that lets the tile's bounding box fit the histogram (sh = 0 for a rover on its wheels);
+    // 2^sh divides the superblock side (24 cells), so bins never straddle superblocks
+    int sh = 0;
+    while (sh < 3 && (int64_t)((s_box[2] >> sh) - (s_box[0] >> sh) + 1) * ((s_box[3] >> sh) - (s_box[1] >> sh) + 1) > BIN_CAP) ++sh;
+    const int bx0 = s_box[0] >> sh, by0 = s_box[1] >> sh;          // (bx0, by0, BW, BH: bounding box of the tile's rays in BINS)
+    const int BW = (s_box[2] >> sh) - bx0 + 1, BH = (s_box[3] >> sh) - by0 + 1;
+    const int SBB = SBC >> sh;                                       // bins per superblock side
+    const int sbx0 = bx0 / SBB, sby0 = by0 / SBB;
+    const int nsx = (s_box[2] >> sh) / SBB - sbx0 + 1, nsy = (s_box[3] >> sh) / SBB - sby0 + 1;
     float g_lox = s_red[0][0], g_hix = s_red[0][1], g_loy = s_red[0][2], g_hiy = s_red[0][3];
     {
         float a_s = s_red[0][4], z0 = s_red[0][5], z1 = s_red[0][6], pm = s_red[0][7];
@@ -358,13 +369,13 @@ __global__ void __launch_bounds__(TT, 3) hm_shadow_kernel(const TiledParams q) {
         return;
     }
 
-    // ---- phase 2: counting sort by block, column-major bins
+    // ---- phase 2: counting sort by cell, column-major bins
     {
         uint32_t r_rank[RPT];
 #pragma unroll
         for (int i = 0; i < RPT; ++i) {
             if (r_cell[i] >= 0) {
-                const int bin = ((r_cell[i] >> 16) - bx0) * BH + ((r_cell[i] & 0xffff) - by0);
+                const int bin = (((r_cell[i] >> 16) >> sh) - bx0) * BH + (((r_cell[i] & 0xffff) >> sh) - by0);
                 const uint32_t old = atomicAdd(&sm.bins[bin >> 1], 1u << ((bin & 1) * 16));
                 r_rank[i] = (old >> ((bin & 1) * 16)) & 0xffffu;
             }
@@ -402,7 +413,7 @@ __global__ void __launch_bounds__(TT, 3) hm_shadow_kernel(const TiledParams q) {
         for (int i = 0; i < RPT; ++i) {
             if (r_cell[i] >= 0) {
                 const int p = tid + i * TT;
-                const int bin = ((r_cell[i] >> 16) - bx0) * BH + ((r_cell[i] & 0xffff) - by0);
+                const int bin = (((r_cell[i] >> 16) >> sh) - bx0) * BH + (((r_cell[i] & 0xffff) >> sh) - by0);
                 sm.rays[off16(sm.bins, bin) + r_rank[i]] = make_uint2(r_sxy[i], r_sz[i]);
                 sm.res[p] = KEY_INIT;
             }
@@ -418,13 +429,14 @@ __global__ void __launch_bounds__(TT, 3) hm_shadow_kernel(const TiledParams q) {
     }
     if (tid == 0) s_nitems = 0;
     __syncthreads();
-    for (int i = tid; i < nsb * SB; i += TT) {
-        const int sbi = i / SB, col = i % SB;
+    for (int i = tid; i < nsb * SBB; i += TT) {
+        const int sbi = i / SBB, col = i % SBB;
         const int SX = sbx0 + sbi / nsy, SY = sby0 + sbi % nsy;
-        const int bx = SX * SB + col;
+        const int bx = SX * SBB + col;
         if (bx < bx0 || bx >= bx0 + BW) continue;
-        const int rlo = max(by0, SY * SB), rhi = min(by0 + BH - 1, SY * SB + SB - 1);
+        const int rlo = max(by0, SY * SBB), rhi = min(by0 + BH - 1, SY * SBB + SBB - 1);
         const int base = (bx - bx0) * BH - by0;
+        if (off16(sm.bins, base + rhi + 1) == off16(sm.bins, base + rlo)) continue;       // no ray in this cell column
         int ylo = 0x7fffffff, yhi = -1;
         for (int y = rlo; y <= rhi; ++y) {
             if (off16(sm.bins, base + y + 1) > off16(sm.bins, base + y)) {
@@ -458,7 +470,7 @@ __global__ void __launch_bounds__(TT, 3) hm_shadow_kernel(const TiledParams q) {
             Item it;
             it.list_off = __ldg(q.sb_off + sb);
             it.list_len = __ldg(q.sb_off + sb + 1) - it.list_off;
-            const int cxl = bxl * RVB_BLK, cxh = bxh * RVB_BLK + RVB_BLK - 1, cyl = byl * RVB_BLK, cyh = byh * RVB_BLK + RVB_BLK - 1;
+            const int cxl = bxl << sh, cxh = ((bxh + 1) << sh) - 1, cyl = byl << sh, cyh = ((byh + 1) << sh) - 1;          // cells
             // a source whose cell is >= c lies above shift + (c - 0.5) res (minus slop); clamped border cells hold everything beyond
             it.rlox = fmaxf(g_lox, cxl <= 0 ? -inf : q.shift_x + ((float)cxl - 0.52f) * q.res - slop);
             it.rhix = fminf(g_hix, cxh >= q.G0 - 1 ? inf : q.shift_x + ((float)cxh + 0.52f) * q.res + slop);
@@ -512,11 +524,13 @@ __global__ void __launch_bounds__(TT, 3) hm_shadow_kernel(const TiledParams q) {
     const int nchunks = s_nchunks;
     uint2* q1 = sm.q1 + warp * QCAP;
     uint4* q2 = sm.q2 + warp * QCAP;
-    uint2* q3 = sm.q3 + warp * QCAP;
-    uint32_t h1 = 0, t1 = 0, h2 = 0, t2 = 0, h3 = 0, t3 = 0;          // warp-uniform
+    uint2* q3 = sm.q3 + warp * QCAP3;
+    uint2* q4 = sm.q4 + warp * QCAP3;
+    uint32_t h1 = 0, t1 = 0, h2 = 0, t2 = 0, h3 = 0, t3 = 0, h4 = 0, t4 = 0;          // warp-uniform
     const uint32_t lt_mask = (1u << lane) - 1u;
     const uint32_t FULLM = 0xffffffffu;
-    enum { A1 = 0, A2_START, A2_EMIT, A3A_START, A3A_RUN, A3B };
+    enum { A1 = 0, A2_START, A2_EMIT, A3A_START, A3A_RUN, A3P, A3B };
+#define DBG(i, v) do { if (DBGK) { const unsigned long long v_ = (unsigned long long)(v); if (lane == 0) atomicAdd(q.dbg + (i), v_); } } while (0)
 
     // stage-1 pipeline: ids of chunk k+2 and records of chunk k+1 are in flight while chunk k is tested
     int32_t idA = -1, idB = -1;            // idA: records loaded (r0A, r1A); idB: id loaded
@@ -552,10 +566,11 @@ __global__ void __launch_bounds__(TT, 3) hm_shadow_kernel(const TiledParams q) {
     uint32_t a_ent = 0, a_start = 0, a_mask = 0;
 
     while (true) {
-        const uint32_t n1 = t1 - h1, n2 = t2 - h2, n3 = t3 - h3;
+        const uint32_t n1 = t1 - h1, n2 = t2 - h2, n3 = t3 - h3, n4 = t4 - h4;
         int action;
         uint32_t cnt = 32u;
-        if (n3 >= 32u) action = A3B;
+        if (n4 >= 32u) action = A3B;
+        else if (n3 >= 64u) { action = A3P; cnt = 64u; }
         else if (in3a) action = A3A_RUN;
         else if (n2 >= 32u) action = A3A_START;
         else if (in2) action = A2_EMIT;
@@ -563,9 +578,11 @@ __global__ void __launch_bounds__(TT, 3) hm_shadow_kernel(const TiledParams q) {
         else if (more) action = A1;
         else if (n1) { action = A2_START; cnt = n1; }
         else if (n2) { action = A3A_START; cnt = n2; }
-        else if (n3) { action = A3B; cnt = n3; }
+        else if (n3) { action = A3P; cnt = n3; }
+        else if (n4) { action = A3B; cnt = n4; }
         else break;
         __syncwarp();
+        DBG(12, 1);
         switch (action) {
         case A1: {
             do {
@@ -593,6 +610,7 @@ __global__ void __launch_bounds__(TT, 3) hm_shadow_kernel(const TiledParams q) {
                     q1[(t1 + __popc(m & lt_mask)) & (QCAP - 1)] =
                         make_uint2(ent, ((__float_as_uint(gball) + 0x7fu) & ~0x7fu) | (uint32_t)item);
                 t1 += __popc(m);
+                DBG(0, 1); DBG(1, __popc(m));
             } while (t1 - h1 < 32u);
             break;
         }
@@ -612,10 +630,10 @@ __global__ void __launch_bounds__(TT, 3) hm_shadow_kernel(const TiledParams q) {
                 stage2(tri_f(r0, r1), r1, e, d16, gball, x0, x1, y0, y1, full);
                 int bxl = (int)(it.bx & 0xffffu), bxh = (int)(it.bx >> 16), byl = (int)(it.by & 0xffffu), byh = (int)(it.by >> 16);
                 if (!full) {
-                    bxl = max(bxl, cell_coord_f(x0, q.shift_x, q.res, q.inv_res, q.G0 - 1, q.sem) / RVB_BLK);
-                    bxh = min(bxh, cell_coord_f(x1, q.shift_x, q.res, q.inv_res, q.G0 - 1, q.sem) / RVB_BLK);
-                    byl = max(byl, min(cell_coord_f(y0, q.shift_y, q.res, q.inv_res, q.G0 - 1, q.sem), q.G1 - 1) / RVB_BLK);
-                    byh = min(byh, min(cell_coord_f(y1, q.shift_y, q.res, q.inv_res, q.G0 - 1, q.sem), q.G1 - 1) / RVB_BLK);
+                    bxl = max(bxl, cell_coord_f(x0, q.shift_x, q.res, q.inv_res, q.G0 - 1, q.sem) >> sh);
+                    bxh = min(bxh, cell_coord_f(x1, q.shift_x, q.res, q.inv_res, q.G0 - 1, q.sem) >> sh);
+                    byl = max(byl, min(cell_coord_f(y0, q.shift_y, q.res, q.inv_res, q.G0 - 1, q.sem), q.G1 - 1) >> sh);
+                    byh = min(byh, min(cell_coord_f(y1, q.shift_y, q.res, q.inv_res, q.G0 - 1, q.sem), q.G1 - 1) >> sh);
                     e_lo16 = (uint32_t)h_bits(__float2half_ru(x0)) | ((uint32_t)h_bits(__float2half_ru(y0)) << 16);
                     e_hi16 = (uint32_t)h_bits(__float2half_rd(x1)) | ((uint32_t)h_bits(__float2half_rd(y1)) << 16);
                 } else {
@@ -629,6 +647,7 @@ __global__ void __launch_bounds__(TT, 3) hm_shadow_kernel(const TiledParams q) {
             }
             h1 += cnt;
             in2 = true;
+            DBG(2, cnt); DBG(13, __popc(__ballot_sync(FULLM, e_lo16 == 0xFC00FC00u && (uint32_t)lane < cnt)));
             break;
         }
         case A2_EMIT: {
@@ -652,6 +671,7 @@ __global__ void __launch_bounds__(TT, 3) hm_shadow_kernel(const TiledParams q) {
                     e_cur += c;
                 }
                 t2 += __popc(m);
+                DBG(3, __popc(m)); DBG(10, 1);
                 if (t2 - h2 >= 32u) break;
             }
             break;
@@ -667,13 +687,17 @@ __global__ void __launch_bounds__(TT, 3) hm_shadow_kernel(const TiledParams q) {
                 const __half2 lo = *reinterpret_cast<const __half2*>(&tk.z), hi = *reinterpret_cast<const __half2*>(&tk.w);
                 for (int i = 0; i < c; ++i) {
                     const uint32_t w0 = sm.rays[a_start + i].x;
-                    const bool in = (__hge2_mask(*reinterpret_cast<const __half2*>(&w0), lo) &
-                                     __hle2_mask(*reinterpret_cast<const __half2*>(&w0), hi)) == 0xffffffffu;
+                    const bool in = __hbge2(*reinterpret_cast<const __half2*>(&w0), lo) && __hble2(*reinterpret_cast<const __half2*>(&w0), hi);
                     a_mask |= (in ? 1u : 0u) << i;
                 }
             }
             h2 += cnt;
             in3a = __any_sync(FULLM, a_mask != 0u);
+            if (DBGK) {
+                const int c = (uint32_t)lane < cnt ? (int)(q2[(h2 - cnt + lane) & (QCAP - 1)].y >> 16) : 0;
+                const int cm = __reduce_max_sync(FULLM, c), cs = __reduce_add_sync(FULLM, c), ib = __reduce_add_sync(FULLM, __popc(a_mask));
+                DBG(4, cm); DBG(5, cs); DBG(6, ib);
+            }
             break;
         }
         case A3A_RUN: {
@@ -688,18 +712,48 @@ __global__ void __launch_bounds__(TT, 3) hm_shadow_kernel(const TiledParams q) {
                 if (have) {
                     const uint32_t bit = (uint32_t)__ffs((int)a_mask) - 1u;
                     a_mask &= a_mask - 1u;
-                    q3[(t3 + __popc(m & lt_mask)) & (QCAP - 1)] = make_uint2(a_start + bit, a_ent);
+                    q3[(t3 + __popc(m & lt_mask)) & (QCAP3 - 1)] = make_uint2(a_start + bit, a_ent);
                 }
                 t3 += __popc(m);
-                if (t3 - h3 >= 32u) break;
+                DBG(11, 1);
+                if (t3 - h3 >= 64u) break;
             }
+            break;
+        }
+        case A3P: {
+            // packed fp16 pre-filter (raycast_common.cuh: prefilter2, conservative) on up to 64 pairs, two per lane
+            const bool v0 = (uint32_t)(2 * lane) < cnt, v1 = (uint32_t)(2 * lane + 1) < cnt;
+            uint4 pp = make_uint4(0, 0, 0, 0);          // (pos A, entry A, pos B, entry B); h3 stays even until the last batch
+            if (v0) pp = *reinterpret_cast<const uint4*>(q3 + ((h3 + 2 * lane) & (QCAP3 - 1)));
+            if (!v1) { pp.z = pp.x; pp.w = pp.y; }
+            if (v0) {
+                const uint2 ra = sm.rays[pp.x], rb = sm.rays[pp.z];
+                const int32_t ta = __ldg(q.sb_ids + pp.y), tb = __ldg(q.sb_ids + pp.w);
+                const uint4* pa = reinterpret_cast<const uint4*>(q.recs + ta);
+                const uint4* pb = reinterpret_cast<const uint4*>(q.recs + tb);
+                const uint4 a0 = __ldg(pa), b0 = __ldg(pb);
+                const uint2 a1 = __ldg(reinterpret_cast<const uint2*>(pa + 1)), b1 = __ldg(reinterpret_cast<const uint2*>(pb + 1));
+                const Tri2 t = pack_tri2(a0, a1, b0, b1);
+                const Cand2 cd = make_cand2(t, dx2, dy2, dz2, v0, v1);
+                const uint32_t f = prefilter2(u2h(__byte_perm(ra.x, rb.x, 0x5410)), u2h(__byte_perm(ra.x, rb.x, 0x7632)),
+                                              u2h(__byte_perm(ra.y, rb.y, 0x5410)), dx2, dy2, dz2, t, cd);
+                pp.x |= (f & 0xffffu) ? 0x80000000u : 0u;
+                pp.z |= (f >> 16) ? 0x80000000u : 0u;
+            }
+            h3 += cnt;
+            const uint32_t m0 = __ballot_sync(FULLM, (pp.x >> 31) != 0u), m1 = __ballot_sync(FULLM, (pp.z >> 31) != 0u);
+            if (pp.x >> 31) q4[(t4 + __popc(m0 & lt_mask)) & (QCAP3 - 1)] = make_uint2(pp.x & 0x7fffffffu, pp.y);
+            t4 += __popc(m0);
+            if (pp.z >> 31) q4[(t4 + __popc(m1 & lt_mask)) & (QCAP3 - 1)] = make_uint2(pp.z & 0x7fffffffu, pp.w);
+            t4 += __popc(m1);
+            DBG(14, 1); DBG(15, __popc(m0) + __popc(m1));
             break;
         }
         case A3B: {
             // literal evaluation + slot lookup of up to 32 queued (ray, triangle) pairs, one per lane
             do {
                 if ((uint32_t)lane < cnt) {
-                    const uint2 pr = q3[(h3 + lane) & (QCAP - 1)];
+                    const uint2 pr = q4[(h4 + lane) & (QCAP3 - 1)];
                     const uint2 ray = sm.rays[pr.x];
                     const int32_t tri = __ldg(q.sb_ids + pr.y);
                     const H3 s = {h_from_bits(ray.x & 0xffff), h_from_bits(ray.x >> 16), h_from_bits(ray.y & 0xffff)};
@@ -713,19 +767,22 @@ __global__ void __launch_bounds__(TT, 3) hm_shadow_kernel(const TiledParams q) {
                     H3 a, b, c, nn;
                     unpack_rec(q.recs + tri, a, b, c, nn);
                     const __half k = pair_test(s, d16, a, b, c, nn);
-                    const uint32_t ord = make_key(h_bits(k), 0u) >> 16;
+                    const uint32_t key0 = make_key(h_bits(k), 0u), ord = key0 >> 16;
                     // a hit at exactly 11.0 equals the all-miss result (slot 0); a hit farther than a confirmed one cannot win
+                    if (DBGK && h_bits(k) != RVB_H_MISS) atomicAdd(q.dbg + 8, 1ull);
                     if (h_bits(k) != RVB_H_MISS && pos16 != 0xffffu && (ord > ORD_MISS || ord <= (sm.res[p] >> 16))) {
+                        if (DBGK) atomicAdd(q.dbg + 9, 1ull);
                         const uint32_t slot = __ldg(reinterpret_cast<const unsigned char*>(q.blk_slots + o0 + pos16) + sub);
                         if (slot != 0xffu) {                // the triangle is in the ray's own cell list
-                            const uint32_t key = make_key(h_bits(k), slot);
-                            if ((key >> 16) > ORD_MISS) atomicOr(&sm.far[p >> 5], 1u << (p & 31));      // k > 11: see epilogue
+                            const uint32_t key = key0 | (slot << 1);
+                            if (ord > ORD_MISS) atomicOr(&sm.far[p >> 5], 1u << (p & 31));      // k > 11: see epilogue
                             else atomicMin(&sm.res[p], key);
                         }
                     }
                 }
-                h3 += cnt;
-            } while (cnt == 32u && t3 - h3 >= 32u);
+                h4 += cnt;
+                DBG(7, 1);
+            } while (cnt == 32u && t4 - h4 >= 32u);
             break;
         }
         }
@@ -759,10 +816,32 @@ int launch_heightmap_shadow(const rvb_terrain* t, const float* pos, const float*
     int dev = 0;
     RVB_CUDA(cudaGetDevice(&dev));
     if (configured_device != dev) {
-        RVB_CUDA(cudaFuncSetAttribute(hm_shadow_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shadow_smem_bytes(RT_MAX)));
+        RVB_CUDA(cudaFuncSetAttribute(hm_shadow_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shadow_smem_bytes(RT_MAX)));
+        RVB_CUDA(cudaFuncSetAttribute(hm_shadow_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shadow_smem_bytes(RT_MAX)));
         configured_device = dev;
     }
-    hm_shadow_kernel<<<(unsigned)nblocks, TT, shadow_smem_bytes(q.tile_size), st>>>(q);
+    const bool dbg = getenv("RVB_SHADOW_DBG") != nullptr;
+    if (dbg) {
+        cudaMalloc(&q.dbg, 16 * sizeof(unsigned long long));
+        cudaMemset(q.dbg, 0, 16 * sizeof(unsigned long long));
+    }
+    if (dbg) hm_shadow_kernel<true><<<(unsigned)nblocks, TT, shadow_smem_bytes(q.tile_size), st>>>(q);
+    else hm_shadow_kernel<false><<<(unsigned)nblocks, TT, shadow_smem_bytes(q.tile_size), st>>>(q);
+    if (dbg) {
+        unsigned long long h[16];
+        int fb = 0;
+        cudaStreamSynchronize(st);
+        cudaMemcpy(h, q.dbg, sizeof(h), cudaMemcpyDeviceToHost);
+        cudaMemcpy(&fb, q.fb_count, sizeof(int), cudaMemcpyDeviceToHost);
+        cudaFree(q.dbg);
+        q.dbg = nullptr;
+        const double ne = (double)(nblocks - fb);
+        fprintf(stderr, "[shadow dbg] tiles %lld, handed back %d; per tile: chunks %.1f, stage-1 keeps %.1f, stage-2 triangles %.1f (no bound: %.2f), "
+                        "tasks %.1f (emit iterations %.1f), box loop iterations %.1f, rays box-tested %.1f, in box %.1f (expand iterations %.1f), "
+                        "pre-filter batches %.1f (passed %.1f), 3b batches %.1f, literal hits %.1f, slot lookups %.1f, dispatches %.1f\n",
+                (long long)nblocks, fb, h[0] / ne, h[1] / ne, h[2] / ne, h[13] / ne, h[3] / ne, h[10] / ne, h[4] / ne, h[5] / ne, h[6] / ne,
+                h[11] / ne, h[14] / ne, h[15] / ne, h[7] / ne, h[8] / ne, h[9] / ne, h[12] / ne);
+    }
     rc_ = RVB_OK;
     if (cudaGetLastError() != cudaSuccess) rc_ = rvb_set_error(RVB_ERR_CUDA, "hm_shadow_kernel", "launch failed");
     if (rc_ == RVB_OK) {

@@ -37,83 +37,6 @@ constexpr int BIN_CAP = 8192;      // cells in the tile's bounding box that can 
 constexpr int MAX_ITEM_RAYS = 32;  // rays per work item (heavier cells / blocks are split)
 constexpr int WQ_CAP = 128;        // per-warp survivor ring (<= 31 pending + 64 new per ray)
 
-// two candidates of one cell, component-wise packed: .x = candidate j, .y = candidate j+1
-struct Tri2 {
-    __half2 ax, ay, az, bx, by, bz, cx, cy, cz, nx, ny, nz;
-};
-
-__device__ __forceinline__ __half2 u2h(uint32_t u) { return *reinterpret_cast<__half2*>(&u); }
-__device__ __forceinline__ uint32_t h2u(__half2 h) { return *reinterpret_cast<uint32_t*>(&h); }
-__device__ __forceinline__ __half2 add2(__half2 a, __half2 b) { return __hadd2_rn(a, b); }
-__device__ __forceinline__ __half2 sub2(__half2 a, __half2 b) { return __hsub2_rn(a, b); }
-__device__ __forceinline__ __half2 mul2(__half2 a, __half2 b) { return __hmul2_rn(a, b); }
-
-__device__ __forceinline__ Tri2 pack_tri2(const uint4& p0, const uint2& p1, const uint4& q0, const uint2& q1) {
-    // record halves: q0 = [a.x a.y | a.z b.x | b.y b.z | c.x c.y], q1 = [c.z n.x | n.y n.z]
-    Tri2 t;
-    t.ax = u2h(__byte_perm(p0.x, q0.x, 0x5410)); t.ay = u2h(__byte_perm(p0.x, q0.x, 0x7632));
-    t.az = u2h(__byte_perm(p0.y, q0.y, 0x5410)); t.bx = u2h(__byte_perm(p0.y, q0.y, 0x7632));
-    t.by = u2h(__byte_perm(p0.z, q0.z, 0x5410)); t.bz = u2h(__byte_perm(p0.z, q0.z, 0x7632));
-    t.cx = u2h(__byte_perm(p0.w, q0.w, 0x5410)); t.cy = u2h(__byte_perm(p0.w, q0.w, 0x7632));
-    t.cz = u2h(__byte_perm(p1.x, q1.x, 0x5410)); t.nx = u2h(__byte_perm(p1.x, q1.x, 0x7632));
-    t.ny = u2h(__byte_perm(p1.y, q1.y, 0x5410)); t.nz = u2h(__byte_perm(p1.y, q1.y, 0x7632));
-    return t;
-}
-
-// ------------------------------------------------------------------------------------------------------------
-// Conservative fp16 pre-filter.  With q_n = N/det, q_m = M/det (exact rationals of fp16 values), n = fp16(q_n),
-// m = fp16(q_m), a candidate passes ray_casting.py:59 only if
-//     n >= fp16(-0.1)        <=>  q_n >= -3277/32768   (rounding boundary below -0x1.998p-4, tie -> even = -0.1)
-//     m >= fp16(-0.1)        <=>  q_m >= -3277/32768
-//     fp16(n + m) <= fp16(1.1) =>  q_n + q_m < 2253/2048 + 2^-9   (n, m are within 2^-11 relative of q_n, q_m, both
-//                                                                   in [-0.11, 1.31] there, so n + m moves by < 2^-9)
-// Multiplying by |det| (N' = N*sgn(det), M' likewise):  N' >= -C_LO*|det|,  M' >= -C_LO*|det|,  N'+M' < C_FAIL*|det|.
-// The filter evaluates these in packed fp16 against thresholds rounded OUTWARDS:
-//     tlo = -RN(|det| * 0x2E68 + 2^-23)   <= -C_LO*|det|      (0x2E68 = 0.10009766 >= C_LO / (1 - 2^-11))
-//     thi =  RN(|det| * 0x3C6B + 2^-23)   >= RN16(x) for every x < C_FAIL*|det|   (0x3C6B = 1.10449 >= C_FAIL*(1+2^-11)^2)
-// (the 2^-23 term covers the absolute rounding error 2^-25 of subnormal results).  NaN thresholds or numerators
-// compare false -- exactly the cases the reference rejects (det = 0/NaN gives n, m = +-inf/NaN; a NaN numerator
-// gives a NaN quotient).  Every candidate the filter lets through is re-evaluated with the literal op sequence
-// (pair_test, divisions included), so the filter only has to be conservative, never exact.
-// ------------------------------------------------------------------------------------------------------------
-#define H_C1 0x2E68u
-#define H_C2 0x3C6Bu
-#define H_TINY 0x0002u
-
-struct Cand2 {
-    uint32_t sgn;      // sign bits of det = (b x c) . d in both halves   (ray_casting.py:41; d is per env)
-    __half2 tlo, thi;  // outward-rounded thresholds; NaN for a slot beyond K
-};
-
-__device__ __forceinline__ Cand2 make_cand2(const Tri2& t, __half2 dx, __half2 dy, __half2 dz, bool v0, bool v1) {
-    Cand2 c;
-    const __half2 det = add2(add2(mul2(t.nx, dx), mul2(t.ny, dy)), mul2(t.nz, dz));
-    c.sgn = h2u(det) & 0x80008000u;
-    const __half2 da = u2h(h2u(det) & 0x7fff7fffu);
-    const __half2 tiny = u2h(H_TINY | (H_TINY << 16));
-    c.tlo = __hneg2(__hfma2(da, u2h(H_C1 | (H_C1 << 16)), tiny));
-    c.thi = __hfma2(da, u2h(H_C2 | (H_C2 << 16)), tiny);
-    if (!v0) c.tlo = u2h((h2u(c.tlo) & 0xffff0000u) | 0x7fffu);
-    if (!v1) c.tlo = u2h((h2u(c.tlo) & 0x0000ffffu) | 0x7fff0000u);
-    return c;
-}
-
-// 0xffff in the half of every candidate that may pass
-__device__ __forceinline__ uint32_t prefilter2(__half2 sx, __half2 sy, __half2 sz, __half2 dx, __half2 dy, __half2 dz,
-                                               const Tri2& t, const Cand2& c) {
-    const __half2 gx = sub2(sx, t.ax), gy = sub2(sy, t.ay), gz = sub2(sz, t.az);                 // ray_casting.py:37
-    const __half2 ux = sub2(mul2(gy, t.cz), mul2(gz, t.cy));                                     // g x c  (:44)
-    const __half2 uy = sub2(mul2(gz, t.cx), mul2(gx, t.cz));
-    const __half2 uz = sub2(mul2(gx, t.cy), mul2(gy, t.cx));
-    const __half2 Nn = add2(add2(mul2(ux, dx), mul2(uy, dy)), mul2(uz, dz));                     // :45 numerator
-    const __half2 vx = sub2(mul2(t.by, gz), mul2(t.bz, gy));                                     // b x g  (:49)
-    const __half2 vy = sub2(mul2(t.bz, gx), mul2(t.bx, gz));
-    const __half2 vz = sub2(mul2(t.bx, gy), mul2(t.by, gx));
-    const __half2 Mn = add2(add2(mul2(vx, dx), mul2(vy, dy)), mul2(vz, dz));                     // :50 numerator
-    const __half2 Ns = u2h(h2u(Nn) ^ c.sgn), Ms = u2h(h2u(Mn) ^ c.sgn);
-    return __hge2_mask(Ns, c.tlo) & __hge2_mask(Ms, c.tlo) & __hle2_mask(add2(Ns, Ms), c.thi);
-}
-
 struct Smem {
     uint4* ray_s;        // [RT]  sorted by cell: (sx2, sy2, sz2 duplicated halves, local ray id)
     uint32_t* res;       // [RT]  best key per local ray id

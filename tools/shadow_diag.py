@@ -53,6 +53,7 @@ for cs in ("0", "0.5", "0.7", "0.8", "0.9", "0.95"):
     d, _, _ = cam.get_depths(st["pos"], eul, want_pt=False)
     print("cos_steep %s: %.3f ms, equal to variant 3: %s" % (cs, e0.elapsed_time(e1) / 5, bool(torch.equal(d.view(torch.int16), out[3][0].view(torch.int16)))))
 _os.environ.pop("RVB_COS_STEEP")
+
 # the same without the 1 % strongly tilted envs
 st2 = dict(st)
 eul2 = eul.clone()
@@ -83,3 +84,10 @@ for v in (0, 2):
                 ref[1][e, p].item(), ref[2][e, p].item(), eul[e, 0].item(), eul[e, 1].item(), st["pos"][e].tolist()))
         miss_not_hit = (neq & (out[v][0] == 11)).sum().item()
         print("   of those, %d are misses where the reference kernel hits" % miss_not_hit)
+
+sys.stdout.flush()
+os.environ["RVB_SHADOW_DBG"] = "1"
+cam.variant = 0
+cam.get_depths(st["pos"], eul, want_pt=False)
+torch.cuda.synchronize()
+os.environ.pop("RVB_SHADOW_DBG")
