@@ -46,7 +46,7 @@ class ClockSampler:
         self.proc = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                                          "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", "50"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except Exception:
             self.proc = None
 
@@ -158,7 +158,7 @@ def run_b200(args, rank, world, local):
         return s["actions"]
 
     def step(i):
-        task.hot_step(set_state(i))
+        task.hot_step(set_state(i), fused=not args.unfused)
         R.dist.reduce_stats(task.stats)
 
     task.Camera.variant = args.variant
@@ -190,11 +190,20 @@ def run_b200(args, rank, world, local):
         pipe.step(h["pos"], h["quat"], h["joints"], h["actions"])
     torch.cuda.synchronize()
     R.dist.barrier()
+    # every step: inputs copied from pinned host memory, results (obs, rew, reset) read back and touched on the host;
+    # two slots, so the read-back of step i overlaps the kernels of step i+1
     t0 = time.perf_counter()
+    prev, checksum = None, 0.0
     for i in range(args.steps):
         h = hstates[i % n_sets]
-        obs_h, rew_h, reset_h = pipe.step(h["pos"], h["quat"], h["joints"], h["actions"])
+        k = pipe.submit(h["pos"], h["quat"], h["joints"], h["actions"])
         R.dist.reduce_stats(task.stats)
+        if prev is not None:
+            obs_h, rew_h, reset_h = pipe.result(prev)
+            checksum += float(rew_h[0]) + float(obs_h[-1, -1]) + int(reset_h[0])
+        prev = k
+    obs_h, rew_h, reset_h = pipe.result(prev)
+    checksum += float(rew_h[0]) + float(obs_h[-1, -1]) + int(reset_h[0])
     torch.cuda.synchronize()
     dt_e2e = R.dist.max_over_ranks(time.perf_counter() - t0, dev)
     clk = clocks.stop() if clocks else None
@@ -221,7 +230,7 @@ def run_b200(args, rank, world, local):
                        "l2": "inputs larger than L2: %d pose sets cycled, %.1f GB of index rows touched per step, index %.1f GB"
                              % (n_sets, N * 785 * w.K * 4 / 1e9, w.G * w.G * w.K * 4 / 1e9),
                        "parallelism": "env shards x%d, terrain replicated, 1 all-reduce of 16 f64 per step" % world,
-                       "raycast_variant": args.variant, "index_build_s": round(t_index, 3)},
+                       "raycast_variant": args.variant, "fused_step": not args.unfused, "index_build_s": round(t_index, 3)},
             "rays_per_s": value * P_RAYS,
             "raycast_ms": ray_s * 1e3,
             "raycast_share_of_step": ray_s / (dt / args.steps),
@@ -230,7 +239,8 @@ def run_b200(args, rank, world, local):
                          "algorithmic_bytes_per_launch": ALGO_BYTES_PER_ENV_STEP * N,
                          "kernel": "heightmap ray-cast (Camera.get_depths)"},
             "e2e": {"value": total_envs * args.steps / dt_e2e, "unit": "env-steps/s", "h2d_bytes_per_step": pipe.h2d_bytes * world,
-                    "d2h_bytes_per_step": pipe.d2h_bytes * world, "ms_per_step": dt_e2e / args.steps * 1e3},
+                    "d2h_bytes_per_step": pipe.d2h_bytes * world, "ms_per_step": dt_e2e / args.steps * 1e3,
+                    "api": "HostPipeline.submit/result (2 slots: read-back of step i overlaps step i+1)", "checksum": checksum},
             "gpu_launches": launches,
             "clocks": clk}
     if world == 1 and not args.no_cpu:
@@ -245,8 +255,8 @@ def run_b200(args, rank, world, local):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--envs", type=int, default=4096, help="envs per GPU")
     ap.add_argument("--length", type=float, default=200.0)
@@ -256,6 +266,7 @@ def main():
     ap.add_argument("--variant", type=int, default=0)
     ap.add_argument("--cpu-envs", type=int, default=16)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--unfused", action="store_true", help="one library call per reference call instead of rvb_env_step")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 1 if args.impl == "reference" else 3)
     rank = int(os.environ.get("RANK", "0"))

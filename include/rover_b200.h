@@ -166,6 +166,32 @@ int rvb_reward_reset(const rvb_reward_params* p,
                      double* stats, double* stats_scratch, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * One env step with a single host call: the action half of RoverTask.pre_physics_step (rover.py:366-414: Memory.input_state,
+ * Ackermann, joint targets) followed by RLTask.post_physics_step (rl_task.py:239-259: progress += 1, get_observations,
+ * calculate_metrics, is_done) on the poses in `pos`/`quat` (PhysX is outside this library).  Equivalent to calling
+ * rvb_quat_to_euler, rvb_history_push x2, rvb_ackermann, rvb_obs_proprio, rvb_heightmap_raycast (obs fused),
+ * rvb_rock_collision and rvb_reward_reset in that order; the rock layer is cast on an internal forked stream, concurrently
+ * with the heightmap.  rover_rot of is_done (rover.py:343,615) is taken from the same poses.
+ *   lin_hist/ang_hist f32 [N,H] (Memory.tracker, newest first; shifted in place)   progress i64 [N] (incremented in place)
+ *   euler f32 [N,3]  heading f32 [N]  steer/vel [N,6]  pos_targets [N,4]  vel_targets [N,6] (the last four optional)
+ *   obs f32 [N,obs_ld>=4+sparse+dense]  dist f16 [N,P]  wheel_dist f16 [N,24]  body_dist f16 [N,2]  rock_collision i64 [N]
+ *   (rock outputs and the `rocks` layer may be NULL when curriculum_level < 2); rew, reset, ex_*, stats as rvb_reward_reset.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct rvb_step_io {
+    const float* pos; const float* quat; const float* joints; const float* actions; const float* target;
+    float* lin_hist; float* ang_hist; int64_t* progress;
+    float* euler; float* heading; float* steer; float* vel; float* pos_targets; float* vel_targets;
+    float* obs; int64_t obs_ld;
+    uint16_t* dist; uint16_t* wheel_dist; uint16_t* body_dist; int64_t* rock_collision;
+    float* rew; int64_t* reset;
+    float* ex_pos_reward; int64_t* ex_collision; float* ex_uprightness; float* ex_heading; float* ex_motion; float* ex_goal_angle;
+    double* stats; double* stats_scratch;
+} rvb_step_io;
+int rvb_env_step(const rvb_terrain* terrain, const rvb_terrain* rocks, const rvb_reward_params* p, const rvb_step_io* io,
+                 const double* pattern, int64_t P, const int32_t* col_a, const int32_t* col_b, int64_t N, int64_t H,
+                 void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * stone_info validation (rover.py:533-542 check_goal_collision, :649-661 avoid_pos_rock_collision):
  * nearest[m] = min_s(cdist(xy[m], stone[s].xy) - stone[s].radius), flag[m] = nearest <= thr.
  *   xy f32 with row stride xy_ld; stones f32 [S,7]; nearest/flag/count optional; count i32 [1] += #flags.

@@ -28,6 +28,14 @@ class RewardParams(C.Structure):
                 ("sem", i32), ("reserved", i32)]
 
 
+class StepIO(C.Structure):
+    """rvb_step_io (include/rover_b200.h)."""
+    _fields_ = [(n, p) for n in ("pos", "quat", "joints", "actions", "target", "lin_hist", "ang_hist", "progress", "euler", "heading",
+                                 "steer", "vel", "pos_targets", "vel_targets", "obs")] + [("obs_ld", i64)] + \
+               [(n, p) for n in ("dist", "wheel_dist", "body_dist", "rock_collision", "rew", "reset", "ex_pos_reward", "ex_collision",
+                                 "ex_uprightness", "ex_heading", "ex_motion", "ex_goal_angle", "stats", "stats_scratch")]
+
+
 _SIGNATURES = {
     "rvb_abi_version": (C.c_int, []),
     "rvb_last_error": (C.c_char_p, []),
@@ -46,6 +54,7 @@ _SIGNATURES = {
     "rvb_obs_gather": (C.c_int, [p, i64, i64, p, i64, p, i64, i64, p]),
     "rvb_stats_scratch_len": (i64, [i64]),
     "rvb_reward_reset": (C.c_int, [C.POINTER(RewardParams)] + [p] * 11 + [i64] + [p] * 10 + [p]),
+    "rvb_env_step": (C.c_int, [p, p, C.POINTER(RewardParams), C.POINTER(StepIO), p, i64, p, p, i64, i64, p]),
     "rvb_stone_validate": (C.c_int, [p, i64, i64, p, i64, f32, C.c_int, p, p, p, p]),
     "rvb_spawn_validate": (C.c_int, [p, i64, p, i64, i32, p, p]),
     "rvb_height_lookup": (C.c_int, [p, i64, i64, p, i64, i64, f32, f32, f32, f32, p, C.c_int, p]),
@@ -62,8 +71,9 @@ def lib_path():
 # kernels launched per entry point (for bench.py's `gpu_launches` claim)
 KERNELS_PER_CALL = {"rvb_terrain_create": 2, "rvb_heightmap_raycast": 2, "rvb_cast_rays": 2, "rvb_ray_distance": 1,
                     "rvb_rock_collision": 1, "rvb_check_collision": 1, "rvb_quat_to_euler": 1, "rvb_ackermann": 1,
-                    "rvb_history_push": 1, "rvb_obs_proprio": 1, "rvb_obs_gather": 1, "rvb_reward_reset": 2,
-                    "rvb_stone_validate": 1, "rvb_spawn_validate": 1, "rvb_height_lookup": 1, "rvb_build_knn_index": 6}
+                    "rvb_history_push": 1, "rvb_obs_proprio": 1, "rvb_obs_gather": 1, "rvb_reward_reset": 2, "rvb_env_step": 6,
+                    "rvb_env_step": (C.c_int, [p, p, C.POINTER(RewardParams), C.POINTER(StepIO), p, i64, p, p, i64, i64, p]),
+    "rvb_stone_validate": 1, "rvb_spawn_validate": 1, "rvb_height_lookup": 1, "rvb_build_knn_index": 6}
 launch_count = 0
 
 

@@ -1,33 +1,7 @@
 // Per-env fp32 task arithmetic: tensor_quat_to_eul, Ackermann + joint-target mapping, Memory.input_state,
 // the proprioceptive observation columns, calculate_metrics + is_done with fused episode statistics.
 // All of it is HBM-streaming SoA/AoS work: one thread per env, coalesced loads, no FMA contraction.
-#include <math_constants.h>
-
-#include "common.cuh"
-
-#define PI_F32 3.1415927410125732f   // tensor_quat_to_euler.py:4
-
-using F = Ops<float>;
-
-// torch divides a tensor by a Python scalar with a true division on the CPU and with a multiplication by
-// fp32(1/scalar) on CUDA (ATen div_true_kernel_cuda); `inv` must be 1.0f / c computed in fp32.
-__device__ __forceinline__ float div_scalar(float v, float c, float inv, int sem) {
-    return sem == RVB_SEM_TORCH_CPU ? __fdiv_rn(v, c) : __fmul_rn(v, inv);
-}
-
-// ---------------------------------------------------------------- tensor_quat_to_eul
-__device__ __forceinline__ void quat_to_euler_dev(float w, float x, float y, float z, float& roll, float& pitch,
-                                                  float& yaw) {
-    const float sinr = F::mul(2.f, F::add(F::mul(w, x), F::mul(y, z)));
-    const float cosr = F::sub(1.f, F::mul(2.f, F::add(F::mul(x, x), F::mul(y, y))));
-    roll = atan2f(sinr, cosr);
-    const float sinp = F::mul(2.f, F::sub(F::mul(w, y), F::mul(z, x)));
-    // sign(sinp - 1) >= 0  <=>  sinp - 1 >= 0 (NaN -> false)   (:23)
-    pitch = (F::sub(sinp, 1.f) >= 0.f) ? copysignf(F::mul(PI_F32, 0.5f), sinp) : asinf(sinp);
-    const float siny = F::mul(2.f, F::add(F::mul(w, z), F::mul(x, y)));
-    const float cosy = F::sub(1.f, F::mul(2.f, F::add(F::mul(y, y), F::mul(z, z))));
-    yaw = atan2f(siny, cosy);
-}
+#include "task_dev.cuh"
 
 __global__ void quat_to_euler_kernel(const float4* __restrict__ quat, int64_t N, float* __restrict__ euler) {
     int64_t n = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
@@ -50,47 +24,14 @@ extern "C" int rvb_quat_to_euler(const float* quat, int64_t N, float* euler, voi
 }
 
 // ---------------------------------------------------------------- Ackermann
-__constant__ float c_wheel_xy[6][2] = {{-0.385f, 0.438f}, {0.385f, 0.438f},   {-0.447f, 0.0f},
-                                       {0.447f, 0.0f},    {-0.385f, -0.411f}, {0.385f, -0.411f}};   // kinematics.py:20-25
-
 __global__ void ackermann_kernel(const float* __restrict__ lin_p, int64_t lin_stride, const float* __restrict__ ang_p,
                                  int64_t ang_stride, int64_t N, float* __restrict__ steer, float* __restrict__ vel,
                                  float* __restrict__ pos_t, float* __restrict__ vel_t, int sem) {
     int64_t n = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (n >= N) return;
-    float lin = lin_p[n * lin_stride];
-    const float ang = ang_p[n * ang_stride];
-    float P = copysignf(__fdiv_rn(lin, ang), -ang);                      // :34-35
-    P = (fabsf(P) > 0.45f) ? P : 0.f;                                    // :38
-    lin = (P != 0.f) ? lin : 0.f;                                        // :39
     float st[6], ve[6];
-#pragma unroll
-    for (int w = 0; w < 6; ++w) {
-        const float wx = c_wheel_xy[w][0], wy = c_wheel_xy[w][1];
-        const float ddx = F::sub(P, wx), ddy = F::sub(0.f, wy);
-        const float dist = __fsqrt_rn(F::add(F::mul(ddx, ddx), F::mul(ddy, ddy)));   // :43
-        const float side = (w & 1) ? 1.f : -1.f;
-        const float omega = (lin != 0.f) ? copysignf(ang, lin) : F::mul(ang, side);  // :49-52
-        float v = F::mul(dist, omega);
-        v = (dist > 1000.f) ? lin : v;                                   // :58
-        ve[w] = div_scalar(v, 0.2f, 1.0f / 0.2f, sem);                   // :61
-        float a = atan2f(wy, F::sub(wx, P));                             // :63
-        a = (a < (float)(-3.14 / 2)) ? F::add(a, (float)M_PI) : a;       // :64
-        a = (a > (float)(3.14 / 2)) ? F::sub(a, (float)M_PI) : a;        // :65
-        st[w] = a;
-    }
-#pragma unroll
-    for (int w = 0; w < 6; ++w) {
-        steer[n * 6 + w] = st[w];
-        vel[n * 6 + w] = ve[w];
-    }
-    if (pos_t) {   // rover.py:400-403  FR, RR, FL, RL
-        pos_t[n * 4 + 0] = st[1]; pos_t[n * 4 + 1] = st[5]; pos_t[n * 4 + 2] = st[0]; pos_t[n * 4 + 3] = st[4];
-    }
-    if (vel_t) {   // rover.py:404-409  FR, CR, RR, FL, CL, RL
-        vel_t[n * 6 + 0] = ve[1]; vel_t[n * 6 + 1] = ve[3]; vel_t[n * 6 + 2] = ve[5];
-        vel_t[n * 6 + 3] = ve[0]; vel_t[n * 6 + 4] = ve[2]; vel_t[n * 6 + 5] = ve[4];
-    }
+    ackermann_dev(lin_p[n * lin_stride], ang_p[n * ang_stride], sem, st, ve);
+    ackermann_store(n, st, ve, steer, vel, pos_t, vel_t);
 }
 
 extern "C" int rvb_ackermann(const float* lin, int64_t lin_stride, const float* ang, int64_t ang_stride, int64_t N,
@@ -131,16 +72,8 @@ __global__ void obs_proprio_kernel(const float* __restrict__ pos, const float* _
                                    float* __restrict__ heading, int sem) {
     int64_t n = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (n >= N) return;
-    const float yaw = euler[n * 3 + 2];
-    const float dx = cosf(yaw), dy = sinf(yaw);                                    // rover.py:280-281
-    const float tx = F::sub(target[n * 3 + 0], pos[n * 3 + 0]), ty = F::sub(target[n * 3 + 1], pos[n * 3 + 1]);
-    const float h = -atan2f(F::sub(F::mul(tx, dy), F::mul(ty, dx)), F::add(F::mul(tx, dx), F::mul(ty, dy)));   // :283
-    if (heading) heading[n] = h;
-    const float nrm = __fsqrt_rn(F::add(F::mul(tx, tx), F::mul(ty, ty)));
-    obs[n * ld + 0] = div_scalar(nrm, 9.f, 1.0f / 9.f, sem);                       // :320
-    obs[n * ld + 1] = div_scalar(h, (float)M_PI, 1.0f / (float)M_PI, sem);         // :321
-    obs[n * ld + 2] = lin_now[n];
-    obs[n * ld + 3] = ang_now[n];
+    obs_proprio_dev(pos[n * 3 + 0], pos[n * 3 + 1], euler[n * 3 + 2], target[n * 3 + 0], target[n * 3 + 1], lin_now[n], ang_now[n],
+                    sem, obs + n * ld, heading ? heading + n : nullptr);
 }
 
 extern "C" int rvb_obs_proprio(const float* pos, const float* euler, const float* target, const float* lin_now,
@@ -185,7 +118,7 @@ reward_reset_kernel(rvb_reward_params p, const float* __restrict__ pos, const fl
                     const float* __restrict__ heading, const float* __restrict__ rover_rot,
                     const float* __restrict__ lin_p, const float* __restrict__ lin_prev_p, const float* __restrict__ ang_p,
                     const float* __restrict__ ang_prev_p, const float* __restrict__ joints,
-                    const int64_t* __restrict__ progress, const int64_t* __restrict__ rock, int64_t N,
+                    const int64_t* __restrict__ progress, const int64_t* __restrict__ rock, int64_t N, int64_t hs,
                     float* __restrict__ rew, int64_t* __restrict__ reset, float* __restrict__ ex_pos,
                     int64_t* __restrict__ ex_col, float* __restrict__ ex_up, float* __restrict__ ex_head,
                     float* __restrict__ ex_motion, float* __restrict__ ex_goal, double* __restrict__ partial) {
@@ -194,7 +127,7 @@ reward_reset_kernel(rvb_reward_params p, const float* __restrict__ pos, const fl
 #pragma unroll
     for (int i = 0; i < RVB_N_STATS; ++i) s[i] = 0.0;
     if (n < N) {
-        const float lin = lin_p[n], lin_prev = lin_prev_p[n], ang = ang_p[n], ang_prev = ang_prev_p[n];
+        const float lin = lin_p[n * hs], lin_prev = lin_prev_p[n * hs], ang = ang_p[n * hs], ang_prev = ang_prev_p[n * hs];
         const float ddx = F::sub(target[n * 3 + 0], pos[n * 3 + 0]), ddy = F::sub(target[n * 3 + 1], pos[n * 3 + 1]);
         const float td = __fsqrt_rn(F::add(F::mul(ddx, ddx), F::mul(ddy, ddy)));                 // rover.py:482
         const float head_pen = F::mul(lin < 0.f ? -1.f : 0.f, p.heading_contraint_reward);       // :486
@@ -266,24 +199,24 @@ __global__ void stats_final_kernel(const double* __restrict__ partial, int64_t n
     }
 }
 
-extern "C" int rvb_reward_reset(const rvb_reward_params* p, const float* pos, const float* target, const float* heading,
-                                const float* rover_rot, const float* lin, const float* lin_prev, const float* ang,
-                                const float* ang_prev, const float* joints, const int64_t* progress,
-                                const int64_t* rock_collision, int64_t N, float* rew, int64_t* reset, float* ex_pos_reward,
-                                int64_t* ex_collision, float* ex_uprightness, float* ex_heading, float* ex_motion,
-                                float* ex_goal_angle, double* stats, double* stats_scratch, void* stream) {
+// hs: element stride between consecutive envs in lin / lin_prev / ang / ang_prev (1 for packed columns, H for [N,H] histories)
+int launch_reward_reset(const rvb_reward_params* p, const float* pos, const float* target, const float* heading,
+                        const float* rover_rot, const float* lin, const float* lin_prev, const float* ang,
+                        const float* ang_prev, int64_t hs, const float* joints, const int64_t* progress,
+                        const int64_t* rock_collision, int64_t N, float* rew, int64_t* reset, float* ex_pos_reward,
+                        int64_t* ex_collision, float* ex_uprightness, float* ex_heading, float* ex_motion,
+                        float* ex_goal_angle, double* stats, double* stats_scratch, cudaStream_t st) {
     RVB_REQUIRE(p && pos && target && heading && rover_rot && lin && lin_prev && ang && ang_prev && joints && progress &&
                     rew && reset, "rvb_reward_reset: null pointer");
     RVB_REQUIRE(p->curriculum_level < 2 || rock_collision, "rvb_reward_reset: curriculum_level >= 2 needs rock_collision");
     RVB_REQUIRE(!stats || stats_scratch, "rvb_reward_reset: stats needs stats_scratch");
-    cudaStream_t st = as_stream(stream);
     if (N <= 0) {
         if (stats) RVB_CUDA(cudaMemsetAsync(stats, 0, sizeof(double) * RVB_N_STATS, st));
         return RVB_OK;
     }
     const int64_t blocks = ceil_div(N, RR_THREADS);
     reward_reset_kernel<<<(unsigned)blocks, RR_THREADS, 0, st>>>(*p, pos, target, heading, rover_rot, lin, lin_prev, ang,
-                                                                ang_prev, joints, progress, rock_collision, N, rew, reset,
+                                                                ang_prev, joints, progress, rock_collision, N, hs, rew, reset,
                                                                 ex_pos_reward, ex_collision, ex_uprightness, ex_heading,
                                                                 ex_motion, ex_goal_angle, stats ? stats_scratch : nullptr);
     RVB_LAUNCH_CHECK();
@@ -292,4 +225,15 @@ extern "C" int rvb_reward_reset(const rvb_reward_params* p, const float* pos, co
         RVB_LAUNCH_CHECK();
     }
     return RVB_OK;
+}
+
+extern "C" int rvb_reward_reset(const rvb_reward_params* p, const float* pos, const float* target, const float* heading,
+                                const float* rover_rot, const float* lin, const float* lin_prev, const float* ang,
+                                const float* ang_prev, const float* joints, const int64_t* progress,
+                                const int64_t* rock_collision, int64_t N, float* rew, int64_t* reset, float* ex_pos_reward,
+                                int64_t* ex_collision, float* ex_uprightness, float* ex_heading, float* ex_motion,
+                                float* ex_goal_angle, double* stats, double* stats_scratch, void* stream) {
+    return launch_reward_reset(p, pos, target, heading, rover_rot, lin, lin_prev, ang, ang_prev, 1, joints, progress,
+                               rock_collision, N, rew, reset, ex_pos_reward, ex_collision, ex_uprightness, ex_heading, ex_motion,
+                               ex_goal_angle, stats, stats_scratch, as_stream(stream));
 }

@@ -123,6 +123,7 @@ class RoverTask():
                         goal_angle_penalty=torch.zeros(num_envs, device=device))
         self._count = torch.zeros(1, device=device, dtype=torch.int32)
         self._reset_next = None
+        self._fused = None
         self.joint_position_targets = None
         self.joint_velocity_targets = None
 
@@ -138,14 +139,68 @@ class RoverTask():
         self.is_done()
         return self.obs_buf, self.rew_buf, self.reset_buf, self.extras
 
-    def hot_step(self, actions):
+    def hot_step(self, actions, fused=True):
         """One env-step of the hot path with PhysX excluded: the action half of pre_physics_step (history,
         Ackermann, joint targets; rover.py:343,366-414) followed by post_physics_step (rl_task.py:239-259).
-        Reset poses / goal re-sampling (rover.py:356-361) are the caller's (simulator-side) business."""
+        Reset poses / goal re-sampling (rover.py:356-361) are the caller's (simulator-side) business.
+        fused=True enqueues the whole step with ONE library call (rvb_env_step); fused=False makes the reference's
+        sequence of calls (same results, ~25 host round trips)."""
+        if fused:
+            return self._hot_step_fused(actions)
         _, quat = self._rover.get_world_poses()
         self.rover_rot = tensor_quat_to_eul(quat)
         self.apply_actions(actions)
         return self.post_physics_step()
+
+    def _hot_step_fused(self, actions):
+        N, dev = self.num_envs, torch.device(self._device)
+        pos, quat = self._rover.get_world_poses()
+        joints = self._rover.get_joint_positions()
+        f32 = torch.float32
+        pos = pos if (pos.dtype == f32 and pos.is_contiguous()) else pos.to(f32).contiguous()
+        quat = quat if (quat.dtype == f32 and quat.is_contiguous()) else quat.to(f32).contiguous()
+        joints = joints if (joints.dtype == f32 and joints.is_contiguous()) else joints.to(f32).contiguous()
+        act = actions if (actions.dtype == f32 and actions.is_contiguous() and actions.device == dev) else actions.to(dev, f32).contiguous()
+        _lib.require_cuda(pos, quat, joints, act)
+        if self._fused is None:
+            P = self.num_exteroceptive
+            self._fused = dict(
+                euler=torch.empty((N, 3), device=dev), dist=torch.empty((N, P), device=dev, dtype=torch.float16),
+                wheel=torch.empty((N, 24), device=dev, dtype=torch.float16), body=torch.empty((N, 2), device=dev, dtype=torch.float16),
+                pos_t=torch.empty((N, 4), device=dev), vel_t=torch.empty((N, 6), device=dev))
+        fb = self._fused
+        want_rocks = self.curriculum_level >= 2
+        e = self._ex
+        io = _lib.StepIO(*[_lib.ptr(t) for t in (pos, quat, joints, act, self.target_positions, self.linear_velocity.tracker,
+                                                  self.angular_velocity.tracker, self.progress_buf, fb["euler"], self.heading_diff,
+                                                  None, None, fb["pos_t"], fb["vel_t"], self.obs_buf)],
+                         self.obs_buf.stride(0),
+                         *[_lib.ptr(t) for t in (fb["dist"], fb["wheel"] if want_rocks else None, fb["body"] if want_rocks else None,
+                                                  self.rock_collison if want_rocks else None, self.rew_buf, self.reset_buf,
+                                                  e["pos_reward"], e["collision_penalty"], e["uprightness_penalty"],
+                                                  e["heading_contraint_penalty"], e["motion_contraint_penalty"],
+                                                  e["goal_angle_penalty"], self.stats, self._stats_scratch)])
+        prm = self._params()
+        cam = self.Camera
+        with torch.cuda.device(dev):
+            _lib.check(self._lib.rvb_env_step(cam.layer.handle, self.Rock_detector.layer.handle if want_rocks else None,
+                                              C.byref(prm), C.byref(io), _lib.ptr(cam.heightmap_distribution), self.num_exteroceptive,
+                                              _lib.ptr(cam._col_a), _lib.ptr(cam._col_b), N, self.linear_velocity.horizon,
+                                              self._stream()))
+        if not want_rocks:
+            _lib.launch_count -= 1
+        self.rover_positions, self.rover_rotation, self.rover_rot = pos, fb["euler"], fb["euler"]
+        self.rock_wheel_dist, self.rock_body_dist = (fb["wheel"], fb["body"]) if want_rocks else (None, None)
+        self.joint_position_targets, self.joint_velocity_targets = fb["pos_t"], fb["vel_t"]
+        if hasattr(self._rover, "set_joint_position_targets"):
+            self._rover.set_joint_position_targets(fb["pos_t"], indices=None,
+                                                   joint_indices=getattr(self._rover, "actuated_pos_indices", None))
+            self._rover.set_joint_velocity_targets(fb["vel_t"], indices=None,
+                                                   joint_indices=getattr(self._rover, "actuated_vel_indices", None))
+        self.extras.update(self._ex)
+        self.extras["torque_penalty_driving"] = self.linear_velocity.tracker[:, 0, 0]      # rover.py:530-531
+        self.extras["torque_penalty_steering"] = self.angular_velocity.tracker[:, 0, 0]
+        return self.obs_buf, self.rew_buf, self.reset_buf, self.extras
 
     # ------------------------------------------------------------------ get_observations (rover.py:272-336)
     def get_observations(self) -> dict:

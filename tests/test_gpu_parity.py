@@ -482,3 +482,41 @@ def test_large_world_all_variants_agree(R, world200):
         for i, what in enumerate(("dist", "pt", "slot", "tri")):
             assert_bits_equal(out[v][i], out[1][i], "200 m world %s variant %d vs 1" % (what, v))
     assert (out[0][0] != 11).float().mean() > 0.5
+
+
+def test_fused_step_equals_call_sequence(R, world20):
+    """rvb_env_step (one host call, rock layer on a forked stream) == the reference-shaped sequence of calls, for three
+    consecutive steps (history shift, progress counter and statistics included); then the pipelined host front end."""
+    w = world20
+    N = 300
+    st = R.synth.make_env_state(w, N, seed=21)
+    tasks = [R.synth.make_task(w, st, device="cuda:0", level=2) for _ in range(2)]
+    g = torch.Generator().manual_seed(1)
+    for step in range(3):
+        act = (torch.rand(N, 2, generator=g) * 2 - 1).cuda()
+        outs = []
+        for t, fused in zip(tasks, (True, False)):
+            obs, rew, reset, extras = t.hot_step(act, fused=fused)
+            torch.cuda.synchronize()
+            outs.append((obs.clone(), rew.clone(), reset.clone(), t.progress_buf.clone(), t.stats.clone(), t.rock_collison.clone(),
+                         t.linear_velocity.tracker.clone(), t.joint_position_targets.clone(), t.joint_velocity_targets.clone(),
+                         t.heading_diff.clone(), extras["motion_contraint_penalty"].clone(), extras["collision_penalty"].clone()))
+        for a, b in zip(*outs):
+            assert torch.equal(a, b)
+    # host pipeline: two slots, results of every step equal to the synchronous device path
+    t_ref, t_pipe = tasks
+    pipe = R.HostPipeline(t_pipe)
+    hs = {k: v.clone() for k, v in st.items()}
+    view = t_ref._rover
+    slots = []
+    for step in range(4):
+        act = torch.rand(N, 2, generator=g) * 2 - 1
+        hs["pos"][:, 0] += 0.01
+        view.pos = hs["pos"].cuda()
+        obs, rew, reset, _ = t_ref.hot_step(act.cuda())
+        torch.cuda.synchronize()
+        want = (obs.cpu().clone(), rew.cpu().clone(), reset.cpu().clone())
+        k = pipe.submit(hs["pos"], hs["quat"], hs["joints"], act)
+        got = pipe.result(k)
+        for a, b in zip(got, want):
+            assert torch.equal(a, b)
