@@ -191,6 +191,11 @@ int rvb_env_step(const rvb_terrain* terrain, const rvb_terrain* rocks, const rvb
                  const double* pattern, int64_t P, const int32_t* col_a, const int32_t* col_b, int64_t N, int64_t H,
                  void* stream);
 
+/* Device timing of the heightmap ray-cast inside rvb_env_step (CUDA events on the caller's stream, calling thread only):
+ * enable, run steps, then read the per-step durations in ms (host array; returns the count or <0; synchronises). */
+int rvb_timing_enable(int on);
+int rvb_timing_read(float* ms_host, int cap);
+
 /* ------------------------------------------------------------------------------------------------
  * stone_info validation (rover.py:533-542 check_goal_collision, :649-661 avoid_pos_rock_collision):
  * nearest[m] = min_s(cdist(xy[m], stone[s].xy) - stone[s].radius), flag[m] = nearest <= thr.

@@ -55,6 +55,8 @@ _SIGNATURES = {
     "rvb_stats_scratch_len": (i64, [i64]),
     "rvb_reward_reset": (C.c_int, [C.POINTER(RewardParams)] + [p] * 11 + [i64] + [p] * 10 + [p]),
     "rvb_env_step": (C.c_int, [p, p, C.POINTER(RewardParams), C.POINTER(StepIO), p, i64, p, p, i64, i64, p]),
+    "rvb_timing_enable": (C.c_int, [C.c_int]),
+    "rvb_timing_read": (C.c_int, [C.POINTER(f32), C.c_int]),
     "rvb_stone_validate": (C.c_int, [p, i64, i64, p, i64, f32, C.c_int, p, p, p, p]),
     "rvb_spawn_validate": (C.c_int, [p, i64, p, i64, i32, p, p]),
     "rvb_height_lookup": (C.c_int, [p, i64, i64, p, i64, i64, f32, f32, f32, f32, p, C.c_int, p]),

@@ -41,7 +41,17 @@ int launch_reward_reset(const rvb_reward_params* p, const float* pos, const floa
                         int64_t* ex_collision, float* ex_uprightness, float* ex_heading, float* ex_motion,
                         float* ex_goal_angle, double* stats, double* stats_scratch, cudaStream_t st);
 
+#include <vector>
+
 namespace {
+// optional device timing of the heightmap ray-cast inside rvb_env_step (bench.py's roofline figure)
+struct Timing {
+    bool on = false;
+    std::vector<cudaEvent_t> ev;     // start, end, start, end, ...
+    size_t used = 0;
+};
+thread_local Timing g_timing;
+
 struct SideStream {
     int dev = -1;
     cudaStream_t side = nullptr;
@@ -83,13 +93,45 @@ extern "C" int rvb_env_step(const rvb_terrain* terrain, const rvb_terrain* rocks
         if (rc != RVB_OK) return rc;
         RVB_CUDA(cudaEventRecord(g_side.join, g_side.side));
     }
+    cudaEvent_t t0 = nullptr, t1 = nullptr;
+    if (g_timing.on) {
+        if (g_timing.used + 2 > g_timing.ev.size()) {
+            cudaEvent_t a, b;
+            RVB_CUDA(cudaEventCreate(&a));
+            RVB_CUDA(cudaEventCreate(&b));
+            g_timing.ev.push_back(a);
+            g_timing.ev.push_back(b);
+        }
+        t0 = g_timing.ev[g_timing.used];
+        t1 = g_timing.ev[g_timing.used + 1];
+        g_timing.used += 2;
+        RVB_CUDA(cudaEventRecord(t0, st));
+    }
     int rc = rvb_heightmap_raycast(terrain, io.pos, io.euler, nullptr, pattern, P, N, io.dist, nullptr, nullptr, nullptr, nullptr,
                                    io.obs, io.obs_ld, col_a, col_b, 0, st);
     if (rc != RVB_OK) return rc;
+    if (t1) RVB_CUDA(cudaEventRecord(t1, st));
     if (with_rocks) RVB_CUDA(cudaStreamWaitEvent(st, g_side.join, 0));
     // hist[:, 0] = this step's action, hist[:, 1] = the previous one (rover.py:498-501); rover_rot = euler (no physics in between)
     return launch_reward_reset(p, io.pos, io.target, io.heading, io.euler, io.lin_hist, io.lin_hist + 1, io.ang_hist, io.ang_hist + 1, H,
                             io.joints, io.progress, p->curriculum_level >= 2 ? io.rock_collision : nullptr, N, io.rew, io.reset,
                             io.ex_pos_reward, io.ex_collision, io.ex_uprightness, io.ex_heading, io.ex_motion, io.ex_goal_angle,
                             io.stats, io.stats_scratch, st);
+}
+
+extern "C" int rvb_timing_enable(int on) {
+    g_timing.on = on != 0;
+    g_timing.used = 0;
+    return RVB_OK;
+}
+
+extern "C" int rvb_timing_read(float* ms_host, int cap) {
+    int n = 0;
+    for (size_t i = 0; i + 1 < g_timing.used && n < cap; i += 2, ++n) {
+        if (cudaEventSynchronize(g_timing.ev[i + 1]) != cudaSuccess) return rvb_set_error(RVB_ERR_CUDA, "rvb_timing_read", "event sync failed");
+        if (cudaEventElapsedTime(ms_host + n, g_timing.ev[i], g_timing.ev[i + 1]) != cudaSuccess)
+            return rvb_set_error(RVB_ERR_CUDA, "rvb_timing_read", "elapsed time failed");
+    }
+    g_timing.used = 0;
+    return n;
 }
