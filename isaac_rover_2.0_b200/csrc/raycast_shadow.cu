@@ -93,7 +93,8 @@ struct Smem {
     uint32_t* far;       // [RT / 32]
 };
 
-__host__ __device__ inline size_t shadow_smem_bytes(int RT) {
+__host__ __device__ inline size_t shadow_smem_bytes(int) {
+    const int RT = RT_MAX;
     return (size_t)RT * 8 + (size_t)((RT + 3) & ~3) * 4 + (size_t)(BIN_CAP / 2 + 4) * 4 + (size_t)ITEM_CAP * 32 +
            (size_t)(ITEM_CAP + 4) * 4 + (size_t)CHUNK_CAP + (size_t)NW * (QCAP * (8 + 16) + QCAP3 * (8 + 8)) + (size_t)(((RT + 31) / 32 + 3) & ~3) * 4;
 }
@@ -217,9 +218,10 @@ __global__ void __launch_bounds__(TT, 3) hm_shadow_kernel(const TiledParams q) {
     const int RT = q.tile_size;
 
     Smem sm;
+    // fixed layout (sized for RT_MAX): every shared-memory address is base + constant, nothing to keep in registers
     sm.rays = reinterpret_cast<uint2*>(smem_raw);
-    sm.res = reinterpret_cast<uint32_t*>(sm.rays + RT);
-    sm.bins = sm.res + ((RT + 3) & ~3);
+    sm.res = reinterpret_cast<uint32_t*>(sm.rays + RT_MAX);
+    sm.bins = sm.res + RT_MAX;
     sm.items = reinterpret_cast<Item*>(sm.bins + BIN_CAP / 2 + 4);
     sm.cum = reinterpret_cast<uint32_t*>(sm.items + ITEM_CAP);
     sm.chunk_item = reinterpret_cast<unsigned char*>(sm.cum + ITEM_CAP + 4);
@@ -648,8 +650,8 @@ __global__ void __launch_bounds__(TT, 3) hm_shadow_kernel(const TiledParams q) {
             h1 += cnt;
             in2 = true;
             DBG(2, cnt); DBG(13, __popc(__ballot_sync(FULLM, e_lo16 == 0xFC00FC00u && (uint32_t)lane < cnt)));
-            break;
         }
+        // fall through: nothing of higher priority became ready
         case A2_EMIT: {
             // tasks of <= TASK_RAYS consecutive sorted rays; runs until q2 holds a batch or the lanes are done
             while (true) {
@@ -698,8 +700,9 @@ __global__ void __launch_bounds__(TT, 3) hm_shadow_kernel(const TiledParams q) {
                 const int cm = __reduce_max_sync(FULLM, c), cs = __reduce_add_sync(FULLM, c), ib = __reduce_add_sync(FULLM, __popc(a_mask));
                 DBG(4, cm); DBG(5, cs); DBG(6, ib);
             }
-            break;
+            if (!in3a) break;
         }
+        // fall through
         case A3A_RUN: {
             // expand the masks into (ray, entry) pairs; runs until q3 holds a batch or the masks are empty
             while (true) {

@@ -16,6 +16,7 @@ def main():
     lib = sys.argv[3] if len(sys.argv) > 3 else os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
                                                              "isaac_rover_2.0_b200", "librover_b200.so")
     top = int(sys.argv[4]) if len(sys.argv) > 4 else 40
+    kre = sys.argv[5] if len(sys.argv) > 5 else kern          # kernel-name regex for ncu (demangled), kern matches the cubin symbol
     tmp = tempfile.mkdtemp()
     subprocess.run(["cuobjdump", "-xelf", "all", lib], cwd=tmp, capture_output=True)
     lines = None
@@ -44,7 +45,7 @@ def main():
             break
     if not lines:
         sys.exit("kernel not found in " + lib)
-    raw = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "sass", "--kernel-name", "regex:" + kern],
+    raw = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "sass", "--kernel-name", "regex:" + kre],
                          capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(raw)))
     h = rows[1]
