@@ -25,8 +25,8 @@
 // literal test).  |g| is bounded self-consistently from the disc of stage 1.  Triangles for which no bound holds
 // (|det*| within rounding of 0, fp16 overflow possible, NaN) are tested against every ray of the superblock.
 // tools/shadow_proto.py re-states stages 1-2 in numpy and checks them against a brute-force fp16 evaluation;
-// tests/test_shadow_bound_cpu.py runs it.  Envs this kernel cannot group (rays spread over more than 8192 cells or
-// 128 superblocks) or whose rays are nearly parallel to the ground (cos < cos_steep: the prisms become long slivers)
+// tests/test_shadow_bound_cpu.py runs it.  Envs this kernel cannot group (rays spread over more than 8192 bins or
+// 64 superblocks) or whose rays are nearly parallel to the ground (cos < cos_steep: the prisms become long slivers)
 // are handed to the tiled kernel through a work list.
 #include <stdlib.h>
 #include <string.h>
@@ -50,9 +50,9 @@ constexpr int RPT = RT_MAX / TT;
 constexpr int BIN_CAP = 8192;      // cells in the tile's bounding box
 constexpr int SB = RVB_SB;          // blocks per superblock side
 constexpr int SBC = RVB_SB * RVB_BLK;   // cells per superblock side
-constexpr int ITEM_CAP = 128;      // superblocks per tile (7 bits travel in the stage-1 queue)
+constexpr int ITEM_CAP = 64;       // superblocks per tile (7 bits travel in the stage-1 queue)
 constexpr int CHUNK = 32;          // list entries per pulled work chunk (one stage-1 batch)
-constexpr int CHUNK_CAP = 2048;    // chunks per tile (u8 chunk -> item table)
+constexpr int CHUNK_CAP = 1024;    // chunks per tile (u8 chunk -> item table)
 constexpr int QCAP = 64;           // per-warp queues q1, q2 (each drained below 32 after every push of <= 32)
 constexpr int QCAP3 = 128;         // q3 (drained in batches of 64), q4 (receives up to 64 per batch)
 constexpr int TASK_RAYS = 16;
