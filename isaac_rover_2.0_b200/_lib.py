@@ -71,9 +71,9 @@ def lib_path():
 
 
 # kernels launched per entry point (for bench.py's `gpu_launches` claim)
-KERNELS_PER_CALL = {"rvb_terrain_create": 2, "rvb_heightmap_raycast": 2, "rvb_cast_rays": 2, "rvb_ray_distance": 1,
+KERNELS_PER_CALL = {"rvb_terrain_create": 2, "rvb_heightmap_raycast": 4, "rvb_cast_rays": 2, "rvb_ray_distance": 1,
                     "rvb_rock_collision": 1, "rvb_check_collision": 1, "rvb_quat_to_euler": 1, "rvb_ackermann": 1,
-                    "rvb_history_push": 1, "rvb_obs_proprio": 1, "rvb_obs_gather": 1, "rvb_reward_reset": 2, "rvb_env_step": 6,
+                    "rvb_history_push": 1, "rvb_obs_proprio": 1, "rvb_obs_gather": 1, "rvb_reward_reset": 2, "rvb_env_step": 8,
     "rvb_stone_validate": 1, "rvb_spawn_validate": 1, "rvb_height_lookup": 1, "rvb_build_knn_index": 6}
 launch_count = 0
 

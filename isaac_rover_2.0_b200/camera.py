@@ -66,8 +66,10 @@ class Camera():
                 _lib.ptr(dist), _lib.ptr(slot), _lib.ptr(tri), _lib.ptr(pt), _lib.ptr(src),
                 _lib.ptr(obs), 0 if obs is None else obs.stride(0), _lib.ptr(self._col_a if obs is not None else None),
                 _lib.ptr(self._col_b if obs is not None else None), self.variant, _lib.stream_of(pos)))
-        if self.variant in (2, 3):
-            _lib.launch_count -= 1          # variants 0 (shadow + fall-back list) and 1 (set-up + cast) launch two kernels, 2/3 one
+        # variant 0 launches four kernels (classify, tiled kernel on the steep list, shadow, tiled kernel on the hand-back list),
+        # variant 1 two (set-up + cast), variants 2/3 one
+        if self.variant != 0:
+            _lib.launch_count -= 2 if self.variant == 1 else 3
         if ev is not None:
             ev[1].record(torch.cuda.current_stream(dev))
             self.timing.append(ev)

@@ -43,6 +43,10 @@ struct TiledParams {
     const int* work_count;
     const int32_t* work_list;
     int work_slices;
+    // shadow kernel: env order (envs with tilted rays first: they are the slow CTAs, so they must not start last) and the
+    // pre-sorted steep envs (cast by the tiled kernel on a second stream, concurrently); both written by hm_classify_kernel
+    const int32_t* order;     // [N] or NULL
+    int presorted;            // steep envs are already on a work list: the shadow kernel just skips them
     unsigned long long* dbg;  // optional [16] work counters of the shadow kernel (RVB_SHADOW_DBG=1)
 };
 

@@ -46,8 +46,7 @@ using namespace rc;
 constexpr int TT = 256;
 constexpr int NW = TT / 32;
 constexpr int RT_MAX = 2048;       // rays per tile; must equal raycast_tiled.cu's (shared tiling of the fall-back list)
-constexpr int RPT = RT_MAX / TT;
-constexpr int BIN_CAP = 8192;      // cells in the tile's bounding box
+constexpr int BIN_CAP = 6144;      // bins in the tile's bounding box (a 3.4 m x 6.6 m pattern at 45 degrees of yaw needs ~5000)
 constexpr int SB = RVB_SB;          // blocks per superblock side
 constexpr int SBC = RVB_SB * RVB_BLK;   // cells per superblock side
 constexpr int ITEM_CAP = 64;       // superblocks per tile (7 bits travel in the stage-1 queue)
@@ -56,6 +55,8 @@ constexpr int CHUNK_CAP = 1024;    // chunks per tile (u8 chunk -> item table)
 constexpr int QCAP = 64;           // per-warp queues q1, q2 (each drained below 32 after every push of <= 32)
 constexpr int QCAP3 = 128;         // q3 (drained in batches of 64), q4 (receives up to 64 per batch)
 constexpr int TASK_RAYS = 16;
+constexpr int REL_BITS = 15;        // queue entries name a triangle as item << 15 | position in the item's list
+constexpr int RT_SMALL = 1664;      // ray capacity of the 4-CTAs-per-SM instantiation (the reference pattern has 1634 rays)
 
 constexpr float GAMMA = 0.00390625f;            // 2^-8
 constexpr float ALPHA = 1.9073486328125e-06f;   // 2^-19
@@ -87,16 +88,15 @@ struct Smem {
     uint32_t* cum;       // [ITEM_CAP + 1]  chunks before item i
     unsigned char* chunk_item;   // [CHUNK_CAP]
     uint2* q1;           // [NW][QCAP]  stage-1 survivors: (superblock-list entry, gball bits | item)
-    uint4* q2;           // [NW][QCAP]  tasks: (entry, ray start | count << 16 | item << 24, box lo half2, box hi half2)
-    uint2* q3;           // [NW][QCAP3]  pairs inside the box: (ray position, superblock-list entry)
-    uint2* q4;           // [NW][QCAP3]  pairs that passed the packed fp16 pre-filter
+    uint4* q2;           // [NW][QCAP]  tasks: (item << 15 | list position, ray start | count << 16, box lo half2, box hi half2)
+    uint32_t* q3;        // [NW][QCAP3]  pairs inside the box: ray position | (item << 15 | list position) << 11
+    uint32_t* q4;        // [NW][QCAP3]  pairs that passed the packed fp16 pre-filter
     uint32_t* far;       // [RT / 32]
 };
 
-__host__ __device__ inline size_t shadow_smem_bytes(int) {
-    const int RT = RT_MAX;
+__host__ __device__ inline size_t shadow_smem_bytes(int RT) {       // RT = ray capacity of the instantiation
     return (size_t)RT * 8 + (size_t)((RT + 3) & ~3) * 4 + (size_t)(BIN_CAP / 2 + 4) * 4 + (size_t)ITEM_CAP * 32 +
-           (size_t)(ITEM_CAP + 4) * 4 + (size_t)CHUNK_CAP + (size_t)NW * (QCAP * (8 + 16) + QCAP3 * (8 + 8)) + (size_t)(((RT + 31) / 32 + 3) & ~3) * 4;
+           (size_t)(ITEM_CAP + 4) * 4 + (size_t)CHUNK_CAP + (size_t)NW * (QCAP * (8 + 16) + QCAP3 * (4 + 4)) + (size_t)(((RT + 31) / 32 + 3) & ~3) * 4;
 }
 
 __device__ __forceinline__ float rcp_up(float x) { return __fdividef(1.0f, x) * 1.000001f; }
@@ -201,8 +201,31 @@ __device__ __forceinline__ void stage2(const TriF& t, const uint2& q1, const Env
     full = !good || !(x0 <= x1) || !(y0 <= y1);
 }
 
-template <bool DBGK>
-__global__ void __launch_bounds__(TT, 3) hm_shadow_kernel(const TiledParams q) {
+__device__ __forceinline__ bool is_steep(const H3& d16, float cos_steep) { return !(fabsf(__half2float(d16.z)) >= cos_steep); }
+
+// One thread per env: the ray direction as the kernels compute it -> steep envs onto the tiled kernel's work list (every tile),
+// and the env order of the shadow kernel: tilted envs (long shadows = slow CTAs) from the front, the rest from the back.
+__global__ void hm_classify_kernel(const TiledParams q, int64_t N, int32_t* __restrict__ order, int* __restrict__ counters,
+                                   int32_t* __restrict__ steep_list) {
+    const int64_t n = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    const Trig tr = make_trig(q.euler, q.trig, n);
+    const double tx = (double)q.pos[n * 3 + 0], ty = (double)q.pos[n * 3 + 1], tz = (double)q.pos[n * 3 + 2];
+    double xo, yo, zo;
+    body_transform<double>(0.0, 0.0, -1.0, tr, tx, ty, tz, xo, yo, zo);
+    const H3 d16 = neg_normalize({h_from_double(__dsub_rn(xo, tx)), h_from_double(__dsub_rn(yo, ty)), h_from_double(__dsub_rn(zo, tz))});
+    const bool steep = is_steep(d16, q.cos_steep);
+    if (steep) {
+        const int at = atomicAdd(counters + 0, q.tiles);
+        for (int t = 0; t < q.tiles; ++t) steep_list[at + t] = (int32_t)(n * q.tiles + t);
+    }
+    const bool tilted = !steep && !(fabsf(__half2float(d16.z)) >= 0.97f);
+    if (tilted) order[atomicAdd(counters + 1, 1)] = (int32_t)n;
+    else order[N - 1 - atomicAdd(counters + 2, 1)] = (int32_t)n;
+}
+
+template <bool DBGK, int RTC>
+__global__ void __launch_bounds__(TT, RTC <= RT_SMALL ? 4 : 3) hm_shadow_kernel(const TiledParams q) {
     extern __shared__ uint4 smem_raw[];
     __shared__ int s_box[4];
     __shared__ float s_red[NW][12];
@@ -211,23 +234,24 @@ __global__ void __launch_bounds__(TT, 3) hm_shadow_kernel(const TiledParams q) {
     __shared__ int s_next, s_nitems, s_nchunks, s_bail;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int64_t n = blockIdx.x / q.tiles;
+    const int64_t n = q.order ? (int64_t)__ldg(q.order + blockIdx.x / q.tiles) : (int64_t)(blockIdx.x / q.tiles);
     const int tile = blockIdx.x % q.tiles;
+    const int32_t work_id = (int32_t)(n * q.tiles + tile);
     const int p0 = tile * q.tile_size;
     const int np = min(q.tile_size, q.P - p0);
     const int RT = q.tile_size;
 
     Smem sm;
-    // fixed layout (sized for RT_MAX): every shared-memory address is base + constant, nothing to keep in registers
+    // fixed layout (sized for RTC rays): every shared-memory address is base + constant, nothing to keep in registers
     sm.rays = reinterpret_cast<uint2*>(smem_raw);
-    sm.res = reinterpret_cast<uint32_t*>(sm.rays + RT_MAX);
-    sm.bins = sm.res + RT_MAX;
+    sm.res = reinterpret_cast<uint32_t*>(sm.rays + RTC);
+    sm.bins = sm.res + RTC;
     sm.items = reinterpret_cast<Item*>(sm.bins + BIN_CAP / 2 + 4);
     sm.cum = reinterpret_cast<uint32_t*>(sm.items + ITEM_CAP);
     sm.chunk_item = reinterpret_cast<unsigned char*>(sm.cum + ITEM_CAP + 4);
     sm.q1 = reinterpret_cast<uint2*>(sm.chunk_item + CHUNK_CAP);
     sm.q2 = reinterpret_cast<uint4*>(sm.q1 + NW * QCAP);
-    sm.q3 = reinterpret_cast<uint2*>(sm.q2 + NW * QCAP);
+    sm.q3 = reinterpret_cast<uint32_t*>(sm.q2 + NW * QCAP);
     sm.q4 = sm.q3 + NW * QCAP3;
     sm.far = reinterpret_cast<uint32_t*>(sm.q4 + NW * QCAP3);
 
@@ -250,9 +274,12 @@ __global__ void __launch_bounds__(TT, 3) hm_shadow_kernel(const TiledParams q) {
         d16 = neg_normalize({h_from_double(__dsub_rn(xo, tx)), h_from_double(__dsub_rn(yo, ty)), h_from_double(__dsub_rn(zo, tz))});
         dx2 = __half2half2(d16.x); dy2 = __half2half2(d16.y); dz2 = __half2half2(d16.z);
     }
+    // rays nearly horizontal in the WORLD (steep env): hm_classify_kernel put this env on the tiled kernel's list already
+    if (q.presorted && is_steep(d16, q.cos_steep)) return;
     __syncthreads();
 
     // ---- phase 1: sources, cells, ranges
+    constexpr int RPT = (RTC + TT - 1) / TT;
     uint32_t r_sxy[RPT], r_sz[RPT];
     int r_cell[RPT];
     int mnx = 0x7fffffff, mny = 0x7fffffff, mxx = -1, mxy = -1;
@@ -358,7 +385,7 @@ __global__ void __launch_bounds__(TT, 3) hm_shadow_kernel(const TiledParams q) {
             e.smax = a_s;
             s_env = e;
             // cos of the angle between the rays and the plane normal ~ 1; steep = rays nearly horizontal in the WORLD
-            const bool steep = !(fabsf(e.dz) >= q.cos_steep);
+            const bool steep = is_steep(d16, q.cos_steep);
             const bool ungrouped = (int64_t)BW * BH > BIN_CAP || (int64_t)nsx * nsy > ITEM_CAP;
             const bool degenerate = !(fabsf(nd) > 0.5f) || !(e.kappa < 2.0f) || !(e.lam < 1e4f) || !(a_s <= 65504.0f);
             if (steep || ungrouped || degenerate) s_bail = 1;
@@ -367,7 +394,7 @@ __global__ void __launch_bounds__(TT, 3) hm_shadow_kernel(const TiledParams q) {
     __syncthreads();
     if (s_bail) {
         // hand this (env, tile) to the tiled kernel
-        if (tid == 0) q.fb_list[atomicAdd(q.fb_count, 1)] = (int32_t)blockIdx.x;
+        if (tid == 0) q.fb_list[atomicAdd(q.fb_count, 1)] = work_id;
         return;
     }
 
@@ -472,6 +499,7 @@ __global__ void __launch_bounds__(TT, 3) hm_shadow_kernel(const TiledParams q) {
             Item it;
             it.list_off = __ldg(q.sb_off + sb);
             it.list_len = __ldg(q.sb_off + sb + 1) - it.list_off;
+            if (it.list_len > (1u << REL_BITS)) s_bail = 1;          // queue entries keep REL_BITS bits of list position
             const int cxl = bxl << sh, cxh = ((bxh + 1) << sh) - 1, cyl = byl << sh, cyh = ((byh + 1) << sh) - 1;          // cells
             // a source whose cell is >= c lies above shift + (c - 0.5) res (minus slop); clamped border cells hold everything beyond
             it.rlox = fmaxf(g_lox, cxl <= 0 ? -inf : q.shift_x + ((float)cxl - 0.52f) * q.res - slop);
@@ -511,8 +539,8 @@ __global__ void __launch_bounds__(TT, 3) hm_shadow_kernel(const TiledParams q) {
             if (lane == 31) s_nchunks = (int)inc;
         }
         __syncthreads();
-        if (s_nchunks > CHUNK_CAP) {
-            if (tid == 0) q.fb_list[atomicAdd(q.fb_count, 1)] = (int32_t)blockIdx.x;
+        if (s_nchunks > CHUNK_CAP || s_bail) {
+            if (tid == 0) q.fb_list[atomicAdd(q.fb_count, 1)] = work_id;
             return;
         }
         for (int i = tid; i < ni; i += TT)
@@ -526,8 +554,8 @@ __global__ void __launch_bounds__(TT, 3) hm_shadow_kernel(const TiledParams q) {
     const int nchunks = s_nchunks;
     uint2* q1 = sm.q1 + warp * QCAP;
     uint4* q2 = sm.q2 + warp * QCAP;
-    uint2* q3 = sm.q3 + warp * QCAP3;
-    uint2* q4 = sm.q4 + warp * QCAP3;
+    uint32_t* q3 = sm.q3 + warp * QCAP3;
+    uint32_t* q4 = sm.q4 + warp * QCAP3;
     uint32_t h1 = 0, t1 = 0, h2 = 0, t2 = 0, h3 = 0, t3 = 0, h4 = 0, t4 = 0;          // warp-uniform
     const uint32_t lt_mask = (1u << lane) - 1u;
     const uint32_t FULLM = 0xffffffffu;
@@ -625,6 +653,7 @@ __global__ void __launch_bounds__(TT, 3) hm_shadow_kernel(const TiledParams q) {
                 const int32_t tri = __ldg(q.sb_ids + e_ent);
                 const float gball = __uint_as_float(en.y & ~0x7fu);
                 const Item& it = sm.items[en.y & 0x7fu];
+                e_ent = ((en.y & 0x7fu) << REL_BITS) | (e_ent - it.list_off);
                 const uint4 r0 = __ldg(reinterpret_cast<const uint4*>(q.recs + tri));
                 const uint2 r1 = __ldg(reinterpret_cast<const uint2*>(q.recs + tri) + 2);
                 float x0, x1, y0, y1;
@@ -715,7 +744,7 @@ __global__ void __launch_bounds__(TT, 3) hm_shadow_kernel(const TiledParams q) {
                 if (have) {
                     const uint32_t bit = (uint32_t)__ffs((int)a_mask) - 1u;
                     a_mask &= a_mask - 1u;
-                    q3[(t3 + __popc(m & lt_mask)) & (QCAP3 - 1)] = make_uint2(a_start + bit, a_ent);
+                    q3[(t3 + __popc(m & lt_mask)) & (QCAP3 - 1)] = (a_start + bit) | (a_ent << 11);
                 }
                 t3 += __popc(m);
                 DBG(11, 1);
@@ -726,12 +755,15 @@ __global__ void __launch_bounds__(TT, 3) hm_shadow_kernel(const TiledParams q) {
         case A3P: {
             // packed fp16 pre-filter (raycast_common.cuh: prefilter2, conservative) on up to 64 pairs, two per lane
             const bool v0 = (uint32_t)(2 * lane) < cnt, v1 = (uint32_t)(2 * lane + 1) < cnt;
-            uint4 pp = make_uint4(0, 0, 0, 0);          // (pos A, entry A, pos B, entry B); h3 stays even until the last batch
-            if (v0) pp = *reinterpret_cast<const uint4*>(q3 + ((h3 + 2 * lane) & (QCAP3 - 1)));
-            if (!v1) { pp.z = pp.x; pp.w = pp.y; }
+            uint2 pq = make_uint2(0, 0);                // pairs A, B; h3 stays even until the last batch
+            if (v0) pq = *reinterpret_cast<const uint2*>(q3 + ((h3 + 2 * lane) & (QCAP3 - 1)));
+            if (!v1) pq.y = pq.x;
+            bool passA = false, passB = false;
             if (v0) {
-                const uint2 ra = sm.rays[pp.x], rb = sm.rays[pp.z];
-                const int32_t ta = __ldg(q.sb_ids + pp.y), tb = __ldg(q.sb_ids + pp.w);
+                const uint2 ra = sm.rays[pq.x & 0x7ffu], rb = sm.rays[pq.y & 0x7ffu];
+                const uint32_t ea = sm.items[pq.x >> (11 + REL_BITS)].list_off + ((pq.x >> 11) & ((1u << REL_BITS) - 1u));
+                const uint32_t eb = sm.items[pq.y >> (11 + REL_BITS)].list_off + ((pq.y >> 11) & ((1u << REL_BITS) - 1u));
+                const int32_t ta = __ldg(q.sb_ids + ea), tb = __ldg(q.sb_ids + eb);
                 const uint4* pa = reinterpret_cast<const uint4*>(q.recs + ta);
                 const uint4* pb = reinterpret_cast<const uint4*>(q.recs + tb);
                 const uint4 a0 = __ldg(pa), b0 = __ldg(pb);
@@ -740,14 +772,14 @@ __global__ void __launch_bounds__(TT, 3) hm_shadow_kernel(const TiledParams q) {
                 const Cand2 cd = make_cand2(t, dx2, dy2, dz2, v0, v1);
                 const uint32_t f = prefilter2(u2h(__byte_perm(ra.x, rb.x, 0x5410)), u2h(__byte_perm(ra.x, rb.x, 0x7632)),
                                               u2h(__byte_perm(ra.y, rb.y, 0x5410)), dx2, dy2, dz2, t, cd);
-                pp.x |= (f & 0xffffu) ? 0x80000000u : 0u;
-                pp.z |= (f >> 16) ? 0x80000000u : 0u;
+                passA = (f & 0xffffu) != 0u;
+                passB = (f >> 16) != 0u;
             }
             h3 += cnt;
-            const uint32_t m0 = __ballot_sync(FULLM, (pp.x >> 31) != 0u), m1 = __ballot_sync(FULLM, (pp.z >> 31) != 0u);
-            if (pp.x >> 31) q4[(t4 + __popc(m0 & lt_mask)) & (QCAP3 - 1)] = make_uint2(pp.x & 0x7fffffffu, pp.y);
+            const uint32_t m0 = __ballot_sync(FULLM, passA), m1 = __ballot_sync(FULLM, passB);
+            if (passA) q4[(t4 + __popc(m0 & lt_mask)) & (QCAP3 - 1)] = pq.x;
             t4 += __popc(m0);
-            if (pp.z >> 31) q4[(t4 + __popc(m1 & lt_mask)) & (QCAP3 - 1)] = make_uint2(pp.z & 0x7fffffffu, pp.w);
+            if (passB) q4[(t4 + __popc(m1 & lt_mask)) & (QCAP3 - 1)] = pq.y;
             t4 += __popc(m1);
             DBG(14, 1); DBG(15, __popc(m0) + __popc(m1));
             break;
@@ -756,16 +788,17 @@ __global__ void __launch_bounds__(TT, 3) hm_shadow_kernel(const TiledParams q) {
             // literal evaluation + slot lookup of up to 32 queued (ray, triangle) pairs, one per lane
             do {
                 if ((uint32_t)lane < cnt) {
-                    const uint2 pr = q4[(h4 + lane) & (QCAP3 - 1)];
-                    const uint2 ray = sm.rays[pr.x];
-                    const int32_t tri = __ldg(q.sb_ids + pr.y);
+                    const uint32_t pc = q4[(h4 + lane) & (QCAP3 - 1)];
+                    const uint2 ray = sm.rays[pc & 0x7ffu];
+                    const uint32_t ent = sm.items[pc >> (11 + REL_BITS)].list_off + ((pc >> 11) & ((1u << REL_BITS) - 1u));
+                    const int32_t tri = __ldg(q.sb_ids + ent);
                     const H3 s = {h_from_bits(ray.x & 0xffff), h_from_bits(ray.x >> 16), h_from_bits(ray.y & 0xffff)};
                     const uint32_t meta = ray.y >> 16, p = meta & 0x7ffu, sub = meta >> 11;
                     // position of the triangle in the list of the ray's 3x3 block (0xFFFF: in none of its nine cell lists)
                     const int cx = cell_coord(s.x, q.shift_x, q.res, q.inv_res, q.G0 - 1, q.sem);
                     const int cy = min(cell_coord(s.y, q.shift_y, q.res, q.inv_res, q.G0 - 1, q.sem), q.G1 - 1);
                     const int bx = cx / RVB_BLK, by = cy / RVB_BLK;
-                    const uint32_t pos16 = __ldg(q.sb_pos + (size_t)pr.y * (SB * SB) + (uint32_t)((bx % SB) * SB + (by % SB)));
+                    const uint32_t pos16 = __ldg(q.sb_pos + (size_t)ent * (SB * SB) + (uint32_t)((bx % SB) * SB + (by % SB)));
                     const uint32_t o0 = __ldg(q.blk_off + (uint32_t)bx * (uint32_t)q.nBy + (uint32_t)by);
                     H3 a, b, c, nn;
                     unpack_rec(q.recs + tri, a, b, c, nn);
@@ -809,18 +842,52 @@ int launch_heightmap_shadow(const rvb_terrain* t, const float* pos, const float*
     if (rc_ != RVB_OK) return rc_;
     RVB_REQUIRE(q.tile_size <= 2048, "heightmap ray-cast (shadow): tile larger than 2048 rays");
     const int64_t nblocks = N * q.tiles;
+    // scratch: [0] steep count, [1] tilted envs placed, [2] other envs placed, [3] handed-back count, then the steep list
+    // [nblocks], the hand-back list [nblocks] and the env order [N]
     int* scratch = nullptr;
-    RVB_CUDA(cudaMallocAsync(&scratch, sizeof(int) * (size_t)(nblocks + 1), st));
-    RVB_CUDA(cudaMemsetAsync(scratch, 0, sizeof(int), st));
-    q.fb_count = scratch;
-    q.fb_list = scratch + 1;
+    RVB_CUDA(cudaMallocAsync(&scratch, sizeof(int) * (size_t)(4 + 2 * nblocks + N), st));
+    RVB_CUDA(cudaMemsetAsync(scratch, 0, sizeof(int) * 4, st));
+    int32_t* steep_list = scratch + 4;
+    q.fb_count = scratch + 3;
+    q.fb_list = scratch + 4 + nblocks;
+    int32_t* order = scratch + 4 + 2 * nblocks;
     q.cos_steep = cos_steep;
+    q.order = order;
+    q.presorted = 1;
+    struct Side {
+        int dev = -1;
+        cudaStream_t s = nullptr;
+        cudaEvent_t fork = nullptr, join = nullptr;
+    };
+    static thread_local Side side;
     static thread_local int configured_device = -1;
     int dev = 0;
     RVB_CUDA(cudaGetDevice(&dev));
+    if (side.dev != dev) {
+        RVB_CUDA(cudaStreamCreateWithFlags(&side.s, cudaStreamNonBlocking));
+        RVB_CUDA(cudaEventCreateWithFlags(&side.fork, cudaEventDisableTiming));
+        RVB_CUDA(cudaEventCreateWithFlags(&side.join, cudaEventDisableTiming));
+        side.dev = dev;
+    }
+    hm_classify_kernel<<<(unsigned)ceil_div(N, 256), 256, 0, st>>>(q, N, order, scratch, steep_list);
+    // steep envs: the tiled kernel on the second stream, concurrently with the shadow kernel
+    const int64_t tgrid = nblocks < 148 * 3 ? nblocks : 148 * 3;
+    {
+        rc::TiledParams qs = q;
+        qs.work_count = scratch;
+        qs.work_list = steep_list;
+        qs.work_slices = 8;
+        RVB_CUDA(cudaEventRecord(side.fork, st));
+        RVB_CUDA(cudaStreamWaitEvent(side.s, side.fork, 0));
+        const int rcs = launch_tiled(qs, true, tgrid, side.s);
+        if (rcs != RVB_OK) return rcs;
+        RVB_CUDA(cudaEventRecord(side.join, side.s));
+    }
     if (configured_device != dev) {
-        RVB_CUDA(cudaFuncSetAttribute(hm_shadow_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shadow_smem_bytes(RT_MAX)));
-        RVB_CUDA(cudaFuncSetAttribute(hm_shadow_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shadow_smem_bytes(RT_MAX)));
+        RVB_CUDA(cudaFuncSetAttribute(hm_shadow_kernel<false, RT_MAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shadow_smem_bytes(RT_MAX) + 48 * 1024));
+        RVB_CUDA(cudaFuncSetAttribute(hm_shadow_kernel<true, RT_MAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shadow_smem_bytes(RT_MAX) + 48 * 1024));
+        RVB_CUDA(cudaFuncSetAttribute(hm_shadow_kernel<false, RT_SMALL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shadow_smem_bytes(RT_SMALL) + 48 * 1024));
+        RVB_CUDA(cudaFuncSetAttribute(hm_shadow_kernel<true, RT_SMALL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shadow_smem_bytes(RT_SMALL) + 48 * 1024));
         configured_device = dev;
     }
     const bool dbg = getenv("RVB_SHADOW_DBG") != nullptr;
@@ -828,8 +895,19 @@ int launch_heightmap_shadow(const rvb_terrain* t, const float* pos, const float*
         cudaMalloc(&q.dbg, 16 * sizeof(unsigned long long));
         cudaMemset(q.dbg, 0, 16 * sizeof(unsigned long long));
     }
-    if (dbg) hm_shadow_kernel<true><<<(unsigned)nblocks, TT, shadow_smem_bytes(q.tile_size), st>>>(q);
-    else hm_shadow_kernel<false><<<(unsigned)nblocks, TT, shadow_smem_bytes(q.tile_size), st>>>(q);
+    // RVB_SHADOW_PAD (bytes, <= 48 KB): extra dynamic shared memory, to measure the kernel at a lower occupancy (tuning hook);
+    // RVB_SHADOW_BIG: force the 2048-ray instantiation (3 CTAs per SM) where the 1664-ray one (4 CTAs per SM) would run
+    const char* pad_s = getenv("RVB_SHADOW_PAD");
+    const size_t pad = pad_s ? (size_t)min(max(atoi(pad_s), 0), 48 * 1024) : 0;
+    const bool small = q.tile_size <= RT_SMALL && getenv("RVB_SHADOW_BIG") == nullptr;
+    const unsigned grid = (unsigned)nblocks;
+    if (small) {
+        if (dbg) hm_shadow_kernel<true, RT_SMALL><<<grid, TT, shadow_smem_bytes(RT_SMALL) + pad, st>>>(q);
+        else hm_shadow_kernel<false, RT_SMALL><<<grid, TT, shadow_smem_bytes(RT_SMALL) + pad, st>>>(q);
+    } else {
+        if (dbg) hm_shadow_kernel<true, RT_MAX><<<grid, TT, shadow_smem_bytes(RT_MAX) + pad, st>>>(q);
+        else hm_shadow_kernel<false, RT_MAX><<<grid, TT, shadow_smem_bytes(RT_MAX) + pad, st>>>(q);
+    }
     if (dbg) {
         unsigned long long h[16];
         int fb = 0;
@@ -852,8 +930,9 @@ int launch_heightmap_shadow(const rvb_terrain* t, const float* pos, const float*
         q.work_count = q.fb_count;
         q.work_list = q.fb_list;
         q.work_slices = 8;
-        rc_ = launch_tiled(q, true, nblocks < 148 * 3 ? nblocks : 148 * 3, st);
+        rc_ = launch_tiled(q, true, tgrid, st);
     }
+    cudaStreamWaitEvent(st, side.join, 0);
     cudaFreeAsync(scratch, st);
     return rc_;
 }

@@ -8,7 +8,7 @@ timeout 600 python tools/shadow_diag.py 4096 > gpurun_out/diag_$TAG.txt 2>&1
 tail -25 gpurun_out/diag_$TAG.txt
 timeout 1500 python -m pytest tests -m gpu -q -x --timeout 900 > gpurun_out/pytest_gpu_$TAG.txt 2>&1
 tail -15 gpurun_out/pytest_gpu_$TAG.txt
-timeout 600 python bench.py --steps 20 --warmup 3 > gpurun_out/bench_$TAG.json 2> gpurun_out/bench_$TAG.err
+timeout 600 python bench.py --steps 100 --warmup 5 > gpurun_out/bench_$TAG.json 2> gpurun_out/bench_$TAG.err
 tail -3 gpurun_out/bench_$TAG.err; cat gpurun_out/bench_$TAG.json
 if [ "$2" != "noprof" ]; then
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_$TAG.csv \

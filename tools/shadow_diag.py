@@ -11,6 +11,21 @@ sys.path.insert(0, ROOT)
 import isaac_rover_b200 as R      # noqa: E402
 
 N = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
+
+
+def timed(fn, reps=30, warm=3):
+    """median / min of per-launch CUDA-event times [ms]"""
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
+    for a, b in ev:
+        a.record()
+        fn()
+        b.record()
+    torch.cuda.synchronize()
+    t = sorted(a.elapsed_time(b) for a, b in ev)
+    return t[len(t) // 2], t[0]
 w = R.synth.make_world(length=200.0, nv=708, K=200, n_stones=2000, seed=42, build_index=None)
 t0 = time.perf_counter()
 w.map_indices = R.build_knn_index(w.triangles, w.vertices, w.G, w.res, w.K, device="cuda:0")
@@ -38,20 +53,22 @@ for v in (3, 0, 2):
     d, pt, s = cam.get_depths(st["pos"], eul, want_hits=True, want_pt=False)
     out[v] = (d.clone(), cam.last_hit_slot.clone(), cam.last_hit_tri.clone())
 import os as _os
-for cs in ("0", "0.5", "0.7", "0.8", "0.9", "0.95"):
+for big in ("1", None):
+    if big:
+        _os.environ["RVB_SHADOW_BIG"] = big
+    else:
+        _os.environ.pop("RVB_SHADOW_BIG", None)
+    cam.variant = 0
+    med, mn = timed(lambda: cam.get_depths(st["pos"], eul, want_pt=False))
+    d, _, _ = cam.get_depths(st["pos"], eul, want_pt=False)
+    print("shadow %s instantiation: median %.3f ms, min %.3f ms, equal to variant 3: %s" % ("2048-ray (3 CTAs/SM)" if big else "1664-ray (4 CTAs/SM)", med, mn,
+                                                                        bool(torch.equal(d.view(torch.int16), out[3][0].view(torch.int16)))))
+for cs in ("0.7", "0.9"):
     _os.environ["RVB_COS_STEEP"] = cs
     cam.variant = 0
-    for _ in range(2):
-        cam.get_depths(st["pos"], eul, want_pt=False)
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(5):
-        cam.get_depths(st["pos"], eul, want_pt=False)
-    e1.record()
-    torch.cuda.synchronize()
+    med, mn = timed(lambda: cam.get_depths(st["pos"], eul, want_pt=False), reps=15)
     d, _, _ = cam.get_depths(st["pos"], eul, want_pt=False)
-    print("cos_steep %s: %.3f ms, equal to variant 3: %s" % (cs, e0.elapsed_time(e1) / 5, bool(torch.equal(d.view(torch.int16), out[3][0].view(torch.int16)))))
+    print("cos_steep %s: median %.3f ms, min %.3f, equal to variant 3: %s" % (cs, med, mn, bool(torch.equal(d.view(torch.int16), out[3][0].view(torch.int16)))))
 _os.environ.pop("RVB_COS_STEEP")
 
 # the same without the 1 % strongly tilted envs
@@ -60,16 +77,8 @@ eul2 = eul.clone()
 eul2[:, :2] = eul2[:, :2].clamp(-0.25, 0.25)
 for v in (3, 0):
     cam.variant = v
-    for _ in range(2):
-        cam.get_depths(st["pos"], eul2, want_pt=False)
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(5):
-        cam.get_depths(st["pos"], eul2, want_pt=False)
-    e1.record()
-    torch.cuda.synchronize()
-    print("no tilted envs, variant %d: %.3f ms" % (v, e0.elapsed_time(e1) / 5))
+    med, mn = timed(lambda: cam.get_depths(st["pos"], eul2, want_pt=False), reps=15)
+    print("no tilted envs, variant %d: median %.3f ms, min %.3f" % (v, med, mn))
 ref = out[3]
 for v in (0, 2):
     neq = out[v][0].view(torch.int16) != ref[0].view(torch.int16)
