@@ -21,6 +21,11 @@ int rvb_set_error(int code, const char* what, const char* detail);
     } while (0)
 #define RVB_LAUNCH_CHECK() RVB_CUDA(cudaGetLastError())
 
+// Stream-ordered scratch memory from the library's own per-device pool.  The pool keeps what it has been given (release
+// threshold = max): the default pool hands its memory back at every synchronisation, and a caller that synchronises once
+// per env step (the host pipeline) then pays a driver re-allocation of several ms inside the next call.
+cudaError_t rvb_scratch_alloc(void** p, size_t bytes, cudaStream_t st);
+
 // ---------------------------------------------------------------- terrain handle
 // One pre-resolved record per triangle, 32 B = one L2 sector, two 16-byte loads.
 // halves: a.xyz | b.xyz | c.xyz | n.xyz (n = b x c) | 4 x pad      (ray_casting.py:34-40)

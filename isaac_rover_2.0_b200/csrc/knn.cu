@@ -198,8 +198,8 @@ extern "C" int rvb_build_knn_index(const int32_t* triangles, int64_t T, const ui
     auto fail = [&](const char* what, cudaError_t e) { rc = rvb_set_error(RVB_ERR_CUDA, what, cudaGetErrorString(e)); };
     cudaError_t e;
     do {
-        if ((e = cudaMallocAsync(&cen, sizeof(__half2) * T, st)) != cudaSuccess) { fail("alloc centroids", e); break; }
-        if ((e = cudaMallocAsync(&bbox, sizeof(unsigned) * 4 + sizeof(int), st)) != cudaSuccess) { fail("alloc bbox", e); break; }
+        if ((e = rvb_scratch_alloc((void**)&cen, sizeof(__half2) * T, st)) != cudaSuccess) { fail("alloc centroids", e); break; }
+        if ((e = rvb_scratch_alloc((void**)&bbox, sizeof(unsigned) * 4 + sizeof(int), st)) != cudaSuccess) { fail("alloc bbox", e); break; }
         bad = reinterpret_cast<int*>(bbox + 4);
         const unsigned init[5] = {0xffffffffu, 0u, 0xffffffffu, 0u, 0u};
         cudaMemcpyAsync(bbox, init, sizeof(init), cudaMemcpyHostToDevice, st);
@@ -217,14 +217,14 @@ extern "C" int rvb_build_knn_index(const int32_t* triangles, int64_t T, const ui
         g.x0 = x0; g.y0 = y0; g.b = b; g.inv_b = 1.0f / b;
         g.nx = (int)floorf(w / b) + 1; g.ny = (int)floorf(h / b) + 1;
         const int64_t NB = (int64_t)g.nx * g.ny;
-        if ((e = cudaMallocAsync(&counts, sizeof(int) * (NB + 1) * 2, st)) != cudaSuccess) { fail("alloc buckets", e); break; }
+        if ((e = rvb_scratch_alloc((void**)&counts, sizeof(int) * (NB + 1) * 2, st)) != cudaSuccess) { fail("alloc buckets", e); break; }
         offsets = counts + NB + 1;
-        if ((e = cudaMallocAsync(&items, sizeof(int) * T, st)) != cudaSuccess) { fail("alloc items", e); break; }
+        if ((e = rvb_scratch_alloc((void**)&items, sizeof(int) * T, st)) != cudaSuccess) { fail("alloc items", e); break; }
         cudaMemsetAsync(counts, 0, sizeof(int) * (NB + 1), st);
         bucket_count_kernel<<<(unsigned)ceil_div(T, 256), 256, 0, st>>>(cen, T, g, counts);
         size_t tmp_bytes = 0;
         cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, counts, offsets, (int)(NB + 1), st);
-        if ((e = cudaMallocAsync(&tmp, tmp_bytes, st)) != cudaSuccess) { fail("alloc scan", e); break; }
+        if ((e = rvb_scratch_alloc((void**)&tmp, tmp_bytes, st)) != cudaSuccess) { fail("alloc scan", e); break; }
         cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, counts, offsets, (int)(NB + 1), st);
         cudaMemsetAsync(counts, 0, sizeof(int) * (NB + 1), st);
         bucket_fill_kernel<<<(unsigned)ceil_div(T, 256), 256, 0, st>>>(cen, T, g, offsets, counts, items);

@@ -166,7 +166,7 @@ extern "C" int rvb_heightmap_raycast(const rvb_terrain* t, const float* pos, con
     __half* src16 = (__half*)sources;
     __half* scratch = nullptr;
     const size_t src_bytes = sizeof(__half) * 3 * (size_t)N * P, d_bytes = sizeof(__half) * 3 * (size_t)N;
-    RVB_CUDA(cudaMallocAsync(&scratch, d_bytes + (sources ? 0 : src_bytes), st));
+    RVB_CUDA(rvb_scratch_alloc((void**)&scratch, d_bytes + (sources ? 0 : src_bytes), st));
     __half* dneg = scratch;
     if (!sources) src16 = scratch + 3 * N;
     dim3 grid((unsigned)ceil_div(P, 256), (unsigned)N);
@@ -189,7 +189,7 @@ extern "C" int rvb_cast_rays(const rvb_terrain* t, const uint16_t* sources, cons
     if (R == 0) return RVB_OK;
     cudaStream_t st = as_stream(stream);
     __half* dneg = nullptr;
-    RVB_CUDA(cudaMallocAsync(&dneg, sizeof(__half) * 3 * (size_t)R, st));
+    RVB_CUDA(rvb_scratch_alloc((void**)&dneg, sizeof(__half) * 3 * (size_t)R, st));
     normalize_dirs_kernel<<<(unsigned)ceil_div(R, 256), 256, 0, st>>>((const __half*)directions, R, dneg);
     int rc = launch_cast_simple(t, (const __half*)sources, dneg, R, 1, dist, hit_slot, hit_tri, pt, nullptr, 0, nullptr,
                                 nullptr, st);

@@ -101,7 +101,8 @@ __host__ __device__ inline size_t shadow_smem_bytes(int RT) {       // RT = ray 
 
 __device__ __forceinline__ float rcp_up(float x) { return __fdividef(1.0f, x) * 1.000001f; }
 __device__ __forceinline__ float hf(uint32_t bits16) { return __half2float(__ushort_as_half((unsigned short)bits16)); }
-__device__ __forceinline__ uint32_t off16(const uint32_t* bins, int bin) { return (bins[bin >> 1] >> ((bin & 1) * 16)) & 0xffffu; }
+// bins are u16 pairs packed into the u32 words the histogram's atomicAdd works on (little endian: even bin = low half)
+__device__ __forceinline__ uint32_t off16(const uint32_t* bins, int bin) { return reinterpret_cast<const unsigned short*>(bins)[bin]; }
 
 // monotone non-decreasing in v (the arithmetic of cell_coord on an fp32 coordinate)
 __device__ __forceinline__ int cell_coord_f(float x, float shift, float res, float inv_res, int gmax, int sem) {
@@ -733,20 +734,31 @@ __global__ void __launch_bounds__(TT, RTC <= RT_SMALL ? 4 : 3) hm_shadow_kernel(
         }
         // fall through
         case A3A_RUN: {
-            // expand the masks into (ray, entry) pairs; runs until q3 holds a batch or the masks are empty
+            // expand the masks into (ray, entry) pairs: a warp scan gives every lane the queue position of its first pair, so the
+            // lanes write their pairs without any warp-level work inside the loop; runs until q3 holds a batch or the masks are empty
             while (true) {
-                const bool have = a_mask != 0u;
-                const uint32_t m = __ballot_sync(FULLM, have);
-                if (!m) {
+                const uint32_t c = (uint32_t)__popc(a_mask);
+                uint32_t inc = c;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const uint32_t v = __shfl_up_sync(FULLM, inc, o);
+                    if (lane >= o) inc += v;
+                }
+                const uint32_t total = __shfl_sync(FULLM, inc, 31);
+                if (!total) {
                     in3a = false;
                     break;
                 }
-                if (have) {
+                const uint32_t room = (uint32_t)QCAP3 - (t3 - h3);        // >= 64: this stage only runs while q3 holds < 64 pairs
+                uint32_t at = inc - c;                                    // queue position of this lane's next pair, relative to t3
+                const uint32_t code = a_ent << 11;
+                while (a_mask != 0u && at < room) {
                     const uint32_t bit = (uint32_t)__ffs((int)a_mask) - 1u;
                     a_mask &= a_mask - 1u;
-                    q3[(t3 + __popc(m & lt_mask)) & (QCAP3 - 1)] = (a_start + bit) | (a_ent << 11);
+                    q3[(t3 + at) & (QCAP3 - 1)] = (a_start + bit) | code;
+                    ++at;
                 }
-                t3 += __popc(m);
+                t3 += min(total, room);
                 DBG(11, 1);
                 if (t3 - h3 >= 64u) break;
             }
@@ -845,7 +857,7 @@ int launch_heightmap_shadow(const rvb_terrain* t, const float* pos, const float*
     // scratch: [0] steep count, [1] tilted envs placed, [2] other envs placed, [3] handed-back count, then the steep list
     // [nblocks], the hand-back list [nblocks] and the env order [N]
     int* scratch = nullptr;
-    RVB_CUDA(cudaMallocAsync(&scratch, sizeof(int) * (size_t)(4 + 2 * nblocks + N), st));
+    RVB_CUDA(rvb_scratch_alloc((void**)&scratch, sizeof(int) * (size_t)(4 + 2 * nblocks + N), st));
     RVB_CUDA(cudaMemsetAsync(scratch, 0, sizeof(int) * 4, st));
     int32_t* steep_list = scratch + 4;
     q.fb_count = scratch + 3;

@@ -16,6 +16,32 @@ int rvb_set_error(int code, const char* what, const char* detail) {
 }
 
 extern "C" const char* rvb_last_error(void) { return g_err; }
+
+#include <mutex>
+cudaError_t rvb_scratch_alloc(void** p, size_t bytes, cudaStream_t st) {
+    static std::mutex mu;
+    static cudaMemPool_t pools[64] = {};
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev < 0 || dev >= 64) return cudaMallocAsync(p, bytes, st);
+    cudaMemPool_t pool;
+    {
+        std::lock_guard<std::mutex> lk(mu);
+        if (!pools[dev]) {
+            cudaMemPoolProps props = {};
+            props.allocType = cudaMemAllocationTypePinned;
+            props.handleTypes = cudaMemHandleTypeNone;
+            props.location.type = cudaMemLocationTypeDevice;
+            props.location.id = dev;
+            if ((e = cudaMemPoolCreate(&pools[dev], &props)) != cudaSuccess) return e;
+            uint64_t keep = UINT64_MAX;
+            if ((e = cudaMemPoolSetAttribute(pools[dev], cudaMemPoolAttrReleaseThreshold, &keep)) != cudaSuccess) return e;
+        }
+        pool = pools[dev];
+    }
+    return cudaMallocFromPoolAsync(p, bytes, pool, st);
+}
 extern "C" int rvb_abi_version(void) { return RVB_ABI_VERSION; }
 
 // [G0,G1,K] strided view -> contiguous.  One thread per output element; consecutive threads walk K, so
