@@ -19,24 +19,60 @@ def _nvcc():
     raise RuntimeError("nvcc not found")
 
 
+HASH_FILE = LIB + ".srchash"
+LOCK_FILE = LIB + ".lock"
+
+
+def source_hash():
+    """sha256 over the sources, the public header and the compiler flags (mtimes do not survive a copy of the tree)."""
+    import hashlib
+    h = hashlib.sha256(" ".join(NVCC_FLAGS).encode())
+    files = sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh")))
+    files.append(os.path.join(HERE, "..", "include", "rover_b200.h"))
+    for f in files:
+        h.update(os.path.basename(f).encode())
+        with open(f, "rb") as fh:
+            h.update(fh.read())
+    return h.hexdigest()
+
+
 def needs_build():
     if not os.path.exists(LIB):
         return True
-    t = os.path.getmtime(LIB)
-    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(HERE, "..", "include", "rover_b200.h")]
-    return any(os.path.getmtime(d) > t for d in deps)
+    try:
+        with open(HASH_FILE) as fh:
+            return fh.read().strip() != source_hash()
+    except OSError:
+        return True
 
 
 def build(force=False, verbose=False):
+    """Compile under an exclusive file lock into a temporary file and rename it into place: the ranks of a multi-GPU
+    launch never see a half-written library, and only one of them compiles."""
+    import fcntl
     if not force and not needs_build():
         return LIB
-    cmd = [_nvcc()] + NVCC_FLAGS + ["-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
-    if verbose:
-        cmd.insert(1, "-Xptxas")
-        cmd.insert(2, "-v")
-    r = subprocess.run(cmd, capture_output=True, text=True)
-    if r.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + r.stdout + r.stderr)
-    if verbose:
-        print(r.stderr)
+    with open(LOCK_FILE, "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and not needs_build():          # another process built it while we waited
+                return LIB
+            tmp = LIB + ".tmp.%d" % os.getpid()
+            cmd = [_nvcc()] + NVCC_FLAGS + ["-o", tmp] + [os.path.join(CSRC, s) for s in SOURCES]
+            if verbose:
+                cmd.insert(1, "-Xptxas")
+                cmd.insert(2, "-v")
+            r = subprocess.run(cmd, capture_output=True, text=True)
+            if r.returncode != 0:
+                if os.path.exists(tmp):
+                    os.remove(tmp)
+                raise RuntimeError("nvcc failed:\n" + r.stdout + r.stderr)
+            if verbose:
+                print(r.stderr)
+            os.replace(tmp, LIB)
+            with open(HASH_FILE + ".tmp", "w") as fh:
+                fh.write(source_hash())
+            os.replace(HASH_FILE + ".tmp", HASH_FILE)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
     return LIB

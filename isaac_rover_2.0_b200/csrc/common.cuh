@@ -34,9 +34,20 @@ struct __align__(16) TriRec {
 };
 static_assert(sizeof(TriRec) == 32, "TriRec must be one 32-byte sector");
 
+// Per-triangle inputs of the shadow kernel's stage 1 (raycast_shadow.cu), pre-computed once per layer with the very fp32
+// operations the kernel used to run per (env, triangle): centroid, bounding radius, b x c, and the two magnitudes the
+// error bounds scale with (rounded UP to fp16: a larger value only widens the bounds).
+struct __align__(16) S1Rec {
+    float qx, qy, qz, r;      // centroid a + (b + c) / 3; 2/3 of the longest edge (+ slack)
+    float nx, ny, nz;         // b x c in fp32
+    uint32_t cb_amax;         // fp16 bits: max |b_i|, |c_i|  |  max |a_i| << 16
+};
+static_assert(sizeof(S1Rec) == 32, "S1Rec must be one 32-byte sector");
+
 struct rvb_terrain {
     int32_t* index;    // [G0,G1,Ks] device; row stride Ks = K rounded up to even (8-byte aligned id pairs), pad ids = 0
     TriRec* recs;      // [T], device
+    S1Rec* s1recs;     // [T], device
     int64_t G0, G1, K, Ks, T, V;
     float res, shift_x, shift_y;
     int sem;

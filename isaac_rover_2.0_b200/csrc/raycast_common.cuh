@@ -10,6 +10,7 @@ constexpr uint32_t ORD_MISS = 0xC980u;        // order key of fp16 11.0 (0x4980 
 struct TiledParams {
     const int32_t* index;
     const TriRec* recs;
+    const S1Rec* s1;          // stage-1 records of the shadow kernel
     const uint32_t* blk_off;
     const int32_t* blk_ids;
     const uint4* blk_slots;

@@ -125,19 +125,12 @@ __device__ __forceinline__ TriF tri_f(const uint4& q0, const uint2& q1) {
 
 // Stage 1 (tools/shadow_proto.py: stage1).  Returns false if no source inside the rectangle can pass; gball >= |s - a|
 // for every passing source (+inf: no bound, the caller must test every ray of the item).
-__device__ __forceinline__ bool stage1(const TriF& t, const EnvC& e, float rlox, float rhix, float rloy, float rhiy, float& gball) {
-    const float third = 0.33333334f;
-    const float mx = __fmul_rn(__fadd_rn(t.bx, t.cx), third), my = __fmul_rn(__fadd_rn(t.by, t.cy), third),
-                mz = __fmul_rn(__fadd_rn(t.bz, t.cz), third);
-    const float qx0 = t.ax + mx, qy0 = t.ay + my, qz0 = t.az + mz;                    // centroid
-    const float ex = t.bx - t.cx, ey = t.by - t.cy, ez = t.bz - t.cz;
-    const float b2 = fmaf(t.bx, t.bx, fmaf(t.by, t.by, t.bz * t.bz)), c2 = fmaf(t.cx, t.cx, fmaf(t.cy, t.cy, t.cz * t.cz)),
-                e2 = fmaf(ex, ex, fmaf(ey, ey, ez * ez));
-    const float amax = fmaxf(fmaxf(fabsf(t.ax), fabsf(t.ay)), fabsf(t.az));
-    const float r = 0.6666667f * sqrtf(fmaxf(fmaxf(b2, c2), e2)) * 1.00001f + 1e-6f * amax;
-    const float nx = t.by * t.cz - t.bz * t.cy, ny = t.bz * t.cx - t.bx * t.cz, nz = t.bx * t.cy - t.by * t.cx;
+__device__ __forceinline__ bool stage1(const uint4& s0, const uint4& s1, const EnvC& e, float rlox, float rhix, float rloy, float rhiy, float& gball) {
+    // S1Rec (common.cuh): centroid, radius, b x c, magnitudes -- computed once per layer by build_records_kernel (terrain.cu)
+    const float qx0 = __uint_as_float(s0.x), qy0 = __uint_as_float(s0.y), qz0 = __uint_as_float(s0.z), r = __uint_as_float(s0.w);
+    const float nx = __uint_as_float(s1.x), ny = __uint_as_float(s1.y), nz = __uint_as_float(s1.z);
+    const float cb = hf(s1.w & 0xffffu), amax = hf(s1.w >> 16);
     const float adet = fabsf(fmaf(nx, e.dx, fmaf(ny, e.dy, nz * e.dz)));
-    const float cb = fmaxf(fmaxf(fmaxf(fabsf(t.bx), fabsf(t.by)), fabsf(t.bz)), fmaxf(fmaxf(fabsf(t.cx), fabsf(t.cy)), fabsf(t.cz)));
     const float e_det = GAMMA * 6.1f * cb * cb + ALPHA;
     const float rdet = rcp_up(adet);
     const float eps0 = EPS0 + 1.3f * (e_det + 4.0f * ALPHA) * rdet;
@@ -551,7 +544,7 @@ __global__ void __launch_bounds__(TT, RTC <= RT_SMALL ? 4 : 3) hm_shadow_kernel(
 
     // ---- phase 3: warps pull (superblock, 32 list entries); stage 1 -> q1 -> stage 2 -> q2 -> stage 3a -> q3 -> stage 3b.
     // One dispatcher loop per warp; every stage's code exists once (the kernel must stay inside the instruction cache).
-    const EnvC e = s_env;
+    const EnvC& e = s_env;            // read from shared memory where used (stages 1 and 2), not held in registers
     const int nchunks = s_nchunks;
     uint2* q1 = sm.q1 + warp * QCAP;
     uint4* q2 = sm.q2 + warp * QCAP;
@@ -563,12 +556,11 @@ __global__ void __launch_bounds__(TT, RTC <= RT_SMALL ? 4 : 3) hm_shadow_kernel(
     enum { A1 = 0, A2_START, A2_EMIT, A3A_START, A3A_RUN, A3P, A3B };
 #define DBG(i, v) do { if (DBGK) { const unsigned long long v_ = (unsigned long long)(v); if (lane == 0) atomicAdd(q.dbg + (i), v_); } } while (0)
 
-    // stage-1 pipeline: ids of chunk k+2 and records of chunk k+1 are in flight while chunk k is tested
-    int32_t idA = -1, idB = -1;            // idA: records loaded (r0A, r1A); idB: id loaded
+    // stage-1 pipeline: the ids of chunk k+1 are in flight while chunk k is tested (its stage-1 records are loaded on the spot:
+    // holding them across the dispatcher loop costs eight registers the 64-register instantiation does not have)
+    int32_t idA = -1, idB = -1;
     uint32_t entA = 0, entB = 0;           // superblock-list entry of the lane's triangle
     int itemA = -1, itemB = -1;            // -1: no chunk
-    uint4 r0A = make_uint4(0, 0, 0, 0);
-    uint2 r1A = make_uint2(0, 0);
     auto pull = [&](int32_t& id, uint32_t& ent, int& item) {
         int g = 0;
         if (lane == 0) g = atomicAdd(&s_next, 1);
@@ -584,10 +576,6 @@ __global__ void __launch_bounds__(TT, RTC <= RT_SMALL ? 4 : 3) hm_shadow_kernel(
         }
     };
     pull(idA, entA, itemA);
-    if (idA >= 0) {
-        r0A = __ldg(reinterpret_cast<const uint4*>(q.recs + idA));
-        r1A = __ldg(reinterpret_cast<const uint2*>(q.recs + idA) + 2);
-    }
     pull(idB, entB, itemB);
     bool more = true, in2 = false, in3a = false;
     // stage-2 emission state (per lane)
@@ -624,18 +612,17 @@ __global__ void __launch_bounds__(TT, RTC <= RT_SMALL ? 4 : 3) hm_shadow_kernel(
                 const int32_t id = idA;
                 const uint32_t ent = entA;
                 const int item = itemA;
-                const uint4 r0 = r0A;
-                const uint2 r1 = r1A;
-                idA = idB; itemA = itemB; entA = entB;
-                if (idA >= 0) {
-                    r0A = __ldg(reinterpret_cast<const uint4*>(q.recs + idA));
-                    r1A = __ldg(reinterpret_cast<const uint2*>(q.recs + idA) + 2);
+                uint4 r0 = make_uint4(0, 0, 0, 0), r1 = r0;
+                if (id >= 0) {
+                    r0 = __ldg(reinterpret_cast<const uint4*>(q.s1 + id));
+                    r1 = __ldg(reinterpret_cast<const uint4*>(q.s1 + id) + 1);
                 }
+                idA = idB; itemA = itemB; entA = entB;
                 pull(idB, entB, itemB);
                 const Item& it = sm.items[item];
                 bool keep = false;
                 float gball = 0.0f;
-                if (id >= 0) keep = stage1(tri_f(r0, r1), e, it.rlox, it.rhix, it.rloy, it.rhiy, gball);
+                if (id >= 0) keep = stage1(r0, r1, e, it.rlox, it.rhix, it.rloy, it.rhiy, gball);
                 const uint32_t m = __ballot_sync(FULLM, keep);
                 if (keep)
                     q1[(t1 + __popc(m & lt_mask)) & (QCAP - 1)] =
@@ -838,7 +825,22 @@ __global__ void __launch_bounds__(TT, RTC <= RT_SMALL ? 4 : 3) hm_shadow_kernel(
     __syncthreads();
 
     // ---- phase 4
-    epilogue(q, n, p0, np, tr, tx, ty, tz, dx2, dy2, dz2, sm.res, sm.far, tid, TT);
+    // pose and trigonometry are re-read here (volatile: no common sub-expression with phase 0) instead of living in twelve
+    // registers across phase 3
+    {
+        const volatile float* vp = q.pos + n * 3;
+        const double ex_ = (double)vp[0], ey_ = (double)vp[1], ez_ = (double)vp[2];
+        Trig tr2;
+        if (q.trig) {
+            const volatile float* t6 = q.trig + n * 6;
+            tr2 = {t6[0], t6[1], t6[2], t6[3], t6[4], t6[5]};
+        } else {
+            const volatile float* ve = q.euler + n * 3;
+            const float r_ = -ve[0], p_ = -ve[1], y_ = -ve[2];
+            tr2 = {sinf(r_), cosf(r_), sinf(p_), cosf(p_), sinf(y_), cosf(y_)};
+        }
+        epilogue(q, n, p0, np, tr2, ex_, ey_, ez_, dx2, dy2, dz2, sm.res, sm.far, tid, TT);
+    }
 }
 
 }  // namespace
@@ -847,7 +849,7 @@ int launch_heightmap_shadow(const rvb_terrain* t, const float* pos, const float*
                             const double* pattern, int64_t P, int64_t N, uint16_t* dist, int32_t* hit_slot,
                             int32_t* hit_tri, uint16_t* pt, uint16_t* sources, float* obs, int64_t obs_ld,
                             const int32_t* col_a, const int32_t* col_b, float cos_steep, cudaStream_t st) {
-    RVB_REQUIRE(t->sb_ids != nullptr && t->sb_pos != nullptr && t->blk_ids != nullptr, "heightmap ray-cast (shadow): layer has no block lists");
+    RVB_REQUIRE(t->sb_ids != nullptr && t->sb_pos != nullptr && t->blk_ids != nullptr && t->s1recs != nullptr, "heightmap ray-cast (shadow): layer has no block lists");
     rc::TiledParams q;
     int rc_ = fill_tiled_params(t, pos, euler, trig, pattern, P, N, dist, hit_slot, hit_tri, pt, sources, obs, obs_ld, col_a,
                                 col_b, q);

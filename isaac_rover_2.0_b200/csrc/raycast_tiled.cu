@@ -383,7 +383,7 @@ int fill_tiled_params(const rvb_terrain* t, const float* pos, const float* euler
     RVB_REQUIRE(t->K <= 16383, "heightmap ray-cast: K > 16383");
     RVB_REQUIRE(t->G0 * t->G1 < ((int64_t)1 << 32), "heightmap ray-cast: more than 2^32 cells");
     memset(&q, 0, sizeof(q));
-    q.index = t->index; q.recs = t->recs;
+    q.index = t->index; q.recs = t->recs; q.s1 = t->s1recs;
     q.blk_off = t->blk_off; q.blk_ids = t->blk_ids; q.blk_slots = t->blk_slots; q.nBy = t->nBy;
     q.sb_off = t->sb_off; q.sb_ids = t->sb_ids; q.sb_pos = t->sb_pos; q.nSBy = t->nSBy;
     q.G0 = (int)t->G0; q.G1 = (int)t->G1; q.K = (int)t->K; q.Ks = (int)t->Ks;

@@ -67,7 +67,7 @@ __global__ void repack_index_kernel(const int32_t* __restrict__ src, int64_t G0,
 
 // a = v[t2], b = v[t1]-a, c = v[t0]-a, n = b x c with fp16 roundings (ray_casting.py:34-40).
 __global__ void build_records_kernel(const int32_t* __restrict__ tri, int64_t T, const __half* __restrict__ vert,
-                                     int64_t V, TriRec* __restrict__ recs, int* bad) {
+                                     int64_t V, TriRec* __restrict__ recs, S1Rec* __restrict__ s1recs, int* bad) {
     int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i >= T) return;
     int32_t i0 = tri[i * 3 + 0], i1 = tri[i * 3 + 1], i2 = tri[i * 3 + 2];
@@ -87,6 +87,26 @@ __global__ void build_records_kernel(const int32_t* __restrict__ tri, int64_t T,
     r.n[0] = n.x; r.n[1] = n.y; r.n[2] = n.z;
     r.pad[0] = r.pad[1] = r.pad[2] = r.pad[3] = __ushort_as_half(0);
     recs[i] = r;
+    // stage-1 record of the shadow kernel: the same fp32 operations, in the same order, as its per-triangle prologue
+    const float ax = __half2float(a.x), ay = __half2float(a.y), az = __half2float(a.z);
+    const float bx = __half2float(b.x), by = __half2float(b.y), bz = __half2float(b.z);
+    const float cx = __half2float(c.x), cy = __half2float(c.y), cz = __half2float(c.z);
+    const float third = 0.33333334f;
+    const float mx = __fmul_rn(__fadd_rn(bx, cx), third), my = __fmul_rn(__fadd_rn(by, cy), third), mz = __fmul_rn(__fadd_rn(bz, cz), third);
+    const float ex = __fsub_rn(bx, cx), ey = __fsub_rn(by, cy), ez = __fsub_rn(bz, cz);
+    const float b2 = fmaf(bx, bx, fmaf(by, by, __fmul_rn(bz, bz))), c2 = fmaf(cx, cx, fmaf(cy, cy, __fmul_rn(cz, cz))),
+                e2 = fmaf(ex, ex, fmaf(ey, ey, __fmul_rn(ez, ez)));
+    const float amax = fmaxf(fmaxf(fabsf(ax), fabsf(ay)), fabsf(az));
+    const float cb = fmaxf(fmaxf(fmaxf(fabsf(bx), fabsf(by)), fabsf(bz)), fmaxf(fmaxf(fabsf(cx), fabsf(cy)), fabsf(cz)));
+    S1Rec s;
+    s.qx = __fadd_rn(ax, mx); s.qy = __fadd_rn(ay, my); s.qz = __fadd_rn(az, mz);
+    s.r = __fadd_rn(__fmul_rn(__fmul_rn(0.6666667f, sqrtf(fmaxf(fmaxf(b2, c2), e2))), 1.00001f), __fmul_rn(1e-6f, amax));
+    s.nx = __fsub_rn(__fmul_rn(by, cz), __fmul_rn(bz, cy));
+    s.ny = __fsub_rn(__fmul_rn(bz, cx), __fmul_rn(bx, cz));
+    s.nz = __fsub_rn(__fmul_rn(bx, cy), __fmul_rn(by, cx));
+    // cb, amax are fp16 values already (|difference of fp16| can need one more bit: round up)
+    s.cb_amax = (uint32_t)__half_as_ushort(__float2half_ru(cb)) | ((uint32_t)__half_as_ushort(__float2half_ru(amax)) << 16);
+    s1recs[i] = s;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -341,13 +361,14 @@ extern "C" int rvb_terrain_create(rvb_terrain** out, const int32_t* map_indices,
     cudaError_t e = cudaGetDevice(&t->device);
     if (e == cudaSuccess) e = cudaMalloc(&t->index, sizeof(int32_t) * G0 * G1 * t->Ks);
     if (e == cudaSuccess) e = cudaMalloc(&t->recs, sizeof(TriRec) * T);
+    if (e == cudaSuccess) e = cudaMalloc(&t->s1recs, sizeof(S1Rec) * T);
     if (e == cudaSuccess) e = cudaMalloc(&bad, sizeof(int));
     if (e == cudaSuccess) e = cudaMemsetAsync(bad, 0, sizeof(int), st);
     if (e == cudaSuccess) {
         repack_index_kernel<<<148 * 8, 256, 0, st>>>(map_indices, G0, G1, K, t->Ks, stride_g0, stride_g1, stride_k, (int32_t)T,
                                                      t->index, bad);
         build_records_kernel<<<(unsigned)ceil_div(T, 256), 256, 0, st>>>(triangles, T, (const __half*)vertices, V,
-                                                                         t->recs, bad);
+                                                                         t->recs, t->s1recs, bad);
         e = cudaGetLastError();
     }
     if (e == cudaSuccess) e = cudaMemcpyAsync(&hbad, bad, sizeof(int), cudaMemcpyDeviceToHost, st);
@@ -359,6 +380,7 @@ extern "C" int rvb_terrain_create(rvb_terrain** out, const int32_t* map_indices,
         if (rc != RVB_OK || e != cudaSuccess) {
             cudaFree(t->index);
             cudaFree(t->recs);
+            cudaFree(t->s1recs);
             cudaFree(t->blk_off);
             cudaFree(t->blk_ids);
             cudaFree(t->blk_slots);
@@ -372,6 +394,7 @@ extern "C" int rvb_terrain_create(rvb_terrain** out, const int32_t* map_indices,
     if (e != cudaSuccess || hbad) {
         cudaFree(t->index);
         cudaFree(t->recs);
+            cudaFree(t->s1recs);
         delete t;
         if (e != cudaSuccess) return rvb_set_error(RVB_ERR_CUDA, "rvb_terrain_create", cudaGetErrorString(e));
         return rvb_set_error(RVB_ERR_INVALID, "rvb_terrain_create",
@@ -386,6 +409,7 @@ extern "C" int rvb_terrain_destroy(rvb_terrain* t) {
     if (!t) return RVB_OK;
     cudaFree(t->index);
     cudaFree(t->recs);
+            cudaFree(t->s1recs);
     cudaFree(t->blk_off);
     cudaFree(t->blk_ids);
     cudaFree(t->blk_slots);
@@ -398,7 +422,7 @@ extern "C" int rvb_terrain_destroy(rvb_terrain* t) {
 
 extern "C" int64_t rvb_terrain_bytes(const rvb_terrain* t) {
     if (!t) return 0;
-    return (int64_t)sizeof(int32_t) * t->G0 * t->G1 * t->Ks + (int64_t)sizeof(TriRec) * t->T +
+    return (int64_t)sizeof(int32_t) * t->G0 * t->G1 * t->Ks + (int64_t)(sizeof(TriRec) + sizeof(S1Rec)) * t->T +
            (t->blk_ids ? (int64_t)(sizeof(uint4) + sizeof(int32_t)) * t->n_ent + (int64_t)sizeof(uint32_t) * ((int64_t)t->nBx * t->nBy + 1) : 0) +
            (t->sb_ids ? (int64_t)(sizeof(int32_t) + sizeof(uint16_t) * RVB_SB * RVB_SB) * t->n_sb_ent + (int64_t)sizeof(uint32_t) * ((int64_t)t->nSBx * t->nSBy + 1) : 0);
 }
