@@ -214,6 +214,26 @@ int rvb_height_lookup(const float* heightmap, int64_t H0, int64_t H1, const floa
                       float hscale, float vscale, float shift_x, float shift_y, float* out, int sem, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Device-side reset path: RoverTask.pre_physics_step's work for the envs whose reset_buf is set
+ * (rover.py:356-361) in ONE launch and without the reference's host synchronisations (reset_buf.nonzero() + len(),
+ * rover.py:356-357; the `while reset_buf_len > 0` goal loop, :547-549):
+ *   reset_idx book-keeping (rover.py:451-452): progress[n] = 0, reset_out[n] = 0 (both optional; reset_out may alias reset_in);
+ *   generate_goals (rover.py:544-564): a goal on the circle of `radius` around initial_pos[n], re-drawn (at most max_attempts
+ *     times) until min_s(|goal - stone_s| - radius_s) > thr (rover.py:533-542, direct distance formula);
+ *   set_targets (rover.py:582-583): target[n,2] = heightmap value at the goal (rvb_height_lookup arithmetic).
+ * The reference draws torch.rand numbers in resetting-env order, which no device-side scheme can reproduce; here the k-th
+ * draw of env g at call `epoch` is Philox4x32-10(counter = (g lo, g hi, k, epoch lo), key = (seed lo, seed hi ^ epoch hi)),
+ * u = (x0 >> 8) * 2^-24, so results depend on (seed, epoch, global env id) only -- not on sharding.  env_offset = global id of
+ * local env 0.  The reference's re-draw of env 0 on every retry (rover.py:540) is not reproduced.
+ * counters i32 [3] optional, overwritten: envs reset, goals drawn, envs that exhausted max_attempts.
+ * ---------------------------------------------------------------------------------------------- */
+int rvb_reset_targets(const int64_t* reset_in, int64_t N, int64_t env_offset, uint64_t seed, uint64_t epoch,
+                      const float* initial_pos, float radius, const float* stones, int64_t S, float thr,
+                      int32_t max_attempts, const float* heightmap, int64_t H0, int64_t H1, float hscale, float vscale,
+                      float shift_x, float shift_y, float* target, int64_t* progress, int64_t* reset_out,
+                      int32_t* counters, int sem, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Offline index builder (utils/rover_utils.py:52-118 _get_knn_triangles): for cell (i,j) at fp16
  * coordinates (cell_x[i], cell_y[j]) -- torch.arange(0, G*res, res, dtype=float16), rover_utils.py:77-78 --
  * the K triangles with the smallest fp16 centroid distance; ties ordered by triangle id (torch.topk leaves

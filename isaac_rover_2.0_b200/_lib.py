@@ -61,6 +61,8 @@ _SIGNATURES = {
     "rvb_spawn_validate": (C.c_int, [p, i64, p, i64, i32, p, p]),
     "rvb_height_lookup": (C.c_int, [p, i64, i64, p, i64, i64, f32, f32, f32, f32, p, C.c_int, p]),
     "rvb_build_knn_index": (C.c_int, [p, i64, p, i64, p, p, i64, i64, i64, p, p]),
+    "rvb_reset_targets": (C.c_int, [p, i64, i64, C.c_uint64, C.c_uint64, p, f32, p, i64, f32, i32, p, i64, i64, f32, f32, f32, f32,
+                                    p, p, p, p, C.c_int, p]),
 }
 
 EXPORTS = tuple(_SIGNATURES)
@@ -74,7 +76,7 @@ def lib_path():
 KERNELS_PER_CALL = {"rvb_terrain_create": 2, "rvb_heightmap_raycast": 4, "rvb_cast_rays": 2, "rvb_ray_distance": 1,
                     "rvb_rock_collision": 1, "rvb_check_collision": 1, "rvb_quat_to_euler": 1, "rvb_ackermann": 1,
                     "rvb_history_push": 1, "rvb_obs_proprio": 1, "rvb_obs_gather": 1, "rvb_reward_reset": 2, "rvb_env_step": 8,
-    "rvb_stone_validate": 1, "rvb_spawn_validate": 1, "rvb_height_lookup": 1, "rvb_build_knn_index": 6}
+    "rvb_stone_validate": 1, "rvb_spawn_validate": 1, "rvb_height_lookup": 1, "rvb_build_knn_index": 6, "rvb_reset_targets": 1}
 launch_count = 0
 
 

@@ -130,3 +130,99 @@ extern "C" int rvb_height_lookup(const float* heightmap, int64_t H0, int64_t H1,
     RVB_LAUNCH_CHECK();
     return RVB_OK;
 }
+
+// ------------------------------------------------------------------------------------------------------------
+// Device-side reset path: what RoverTask.pre_physics_step does for the envs whose reset_buf is set
+// (rover.py:356-361) without the two host synchronisations of the reference (reset_buf.nonzero() + len(), and the
+// `while reset_buf_len > 0` goal loop, rover.py:356-357,547-549):
+//   reset_idx book-keeping (rover.py:451-452): reset_buf = 0, progress_buf = 0;
+//   generate_goals / random_goals / check_goal_collision (rover.py:533-564): a goal on the circle of `radius` around the
+//     env's initial position, re-drawn until its nearest stone edge is farther than `thr` -- per env, so the loop needs no
+//     global count; the reference's quirk of re-drawing env 0 on every retry (rover.py:540) is not reproduced;
+//   set_targets (rover.py:566-584): target z from the heightmap grid (get_pos_height arithmetic).
+// Random numbers: Philox4x32-10, counter = (global env id lo, hi, attempt, epoch lo), key = (seed lo, seed hi ^ epoch hi);
+// u = (x0 >> 8) * 2^-24, alpha = fl32(2 pi) * u -- a pure function of (seed, epoch, env, attempt): results do not depend on
+// how the envs are sharded over GPUs.  oracle/reset_oracle.py restates it in numpy.
+// One warp per env (lanes stride over the stones, shuffle min); warps of envs that do not reset exit at once.
+// ------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1,
+                                              uint32_t& o0, uint32_t& o1, uint32_t& o2, uint32_t& o3) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        c0 = hi1 ^ c1 ^ k0; c1 = lo1; c2 = hi0 ^ c3 ^ k1; c3 = lo0;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    o0 = c0; o1 = c1; o2 = c2; o3 = c3;
+}
+
+__global__ void reset_targets_kernel(const int64_t* __restrict__ reset_in, int64_t N, int64_t env_offset, uint64_t seed, uint64_t epoch,
+                                     const float* __restrict__ initial_pos, float radius, const float* __restrict__ stones, int S,
+                                     float thr, int max_attempts, const float* __restrict__ hm, int H0, int H1, float hscale,
+                                     float inv_hscale, float vscale, float shx, float shy, float* __restrict__ target,
+                                     int64_t* __restrict__ progress, int64_t* __restrict__ reset_out, int32_t* __restrict__ counters,
+                                     int sem) {
+    const int lane = threadIdx.x & 31;
+    const int64_t n = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    if (n >= N) return;
+    if (reset_in[n] == 0) return;
+    const uint64_t gid = (uint64_t)(env_offset + n);
+    const float ix = initial_pos[n * 3], iy = initial_pos[n * 3 + 1];
+    float x = ix, y = iy;
+    int attempt = 0;
+    bool ok = false;
+    while (attempt < max_attempts) {
+        uint32_t r0, r1, r2, r3;
+        philox4x32_10((uint32_t)gid, (uint32_t)(gid >> 32), (uint32_t)attempt, (uint32_t)epoch, (uint32_t)seed,
+                      (uint32_t)(seed >> 32) ^ (uint32_t)(epoch >> 32), r0, r1, r2, r3);
+        const float u = F::mul((float)(r0 >> 8), 5.9604644775390625e-08f);           // [0, 1), 24 bits like torch.rand
+        const float alpha = F::mul(6.2831854820251465f, u);                           // 2 * math.pi * rand (rover.py:557)
+        x = F::add(F::add(F::mul(radius, cosf(alpha)), 0.0f), ix);                    // rover.py:561-563
+        y = F::add(F::add(F::mul(radius, sinf(alpha)), 0.0f), iy);
+        ++attempt;
+        const float v = warp_nearest(x, y, stones, S, false, lane);
+        if (!(v <= thr)) {                                                            // rover.py:538 (NaN counts as valid there too)
+            ok = true;
+            break;
+        }
+    }
+    if (lane == 0) {
+        target[n * 3] = x;
+        target[n * 3 + 1] = y;
+        float uu = F::sub(x, shx), vv = F::sub(y, shy);
+        if (sem == RVB_SEM_TORCH_CPU) { uu = __fdiv_rn(uu, hscale); vv = __fdiv_rn(vv, hscale); }
+        else { uu = F::mul(uu, inv_hscale); vv = F::mul(vv, inv_hscale); }
+        const float hi = (float)(H0 - 1);
+        const int i = (int)rintf(fminf(fmaxf(uu, 0.f), hi));
+        const int j = min((int)rintf(fminf(fmaxf(vv, 0.f), hi)), H1 - 1);
+        target[n * 3 + 2] = F::mul(hm[(int64_t)i * H1 + j], vscale);
+        if (progress) progress[n] = 0;
+        if (reset_out) reset_out[n] = 0;
+        if (counters) {
+            atomicAdd(counters + 0, 1);                 // envs reset
+            atomicAdd(counters + 1, attempt);           // goals drawn
+            if (!ok) atomicAdd(counters + 2, 1);        // envs that ran out of attempts (goal left at the last draw)
+        }
+    }
+}
+
+extern "C" int rvb_reset_targets(const int64_t* reset_in, int64_t N, int64_t env_offset, uint64_t seed, uint64_t epoch,
+                                 const float* initial_pos, float radius, const float* stones, int64_t S, float thr,
+                                 int32_t max_attempts, const float* heightmap, int64_t H0, int64_t H1, float hscale, float vscale,
+                                 float shift_x, float shift_y, float* target, int64_t* progress, int64_t* reset_out,
+                                 int32_t* counters, int sem, void* stream) {
+    if (N <= 0) return RVB_OK;
+    RVB_REQUIRE(reset_in && initial_pos && stones && heightmap && target, "rvb_reset_targets: null pointer");
+    RVB_REQUIRE(S > 0 && S < (1 << 30) && max_attempts > 0, "rvb_reset_targets: bad S or max_attempts");
+    RVB_REQUIRE(H0 > 0 && H1 > 0 && H0 < (1 << 30) && H1 < (1 << 30) && hscale > 0.f, "rvb_reset_targets: bad heightmap shape or scale");
+    RVB_REQUIRE(env_offset >= 0, "rvb_reset_targets: negative env_offset");
+    cudaStream_t st = as_stream(stream);
+    if (counters) RVB_CUDA(cudaMemsetAsync(counters, 0, 3 * sizeof(int32_t), st));
+    reset_targets_kernel<<<(unsigned)ceil_div(N * 32, 256), 256, 0, st>>>(reset_in, N, env_offset, seed, epoch, initial_pos, radius, stones,
+                                                                         (int)S, thr, max_attempts, heightmap, (int)H0, (int)H1, hscale,
+                                                                         1.0f / hscale, vscale, shift_x, shift_y, target, progress,
+                                                                         reset_out, counters, sem);
+    RVB_LAUNCH_CHECK();
+    return RVB_OK;
+}

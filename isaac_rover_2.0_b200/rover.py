@@ -122,6 +122,9 @@ class RoverTask():
                         motion_contraint_penalty=torch.zeros(num_envs, device=device),
                         goal_angle_penalty=torch.zeros(num_envs, device=device))
         self._count = torch.zeros(1, device=device, dtype=torch.int32)
+        self.reset_seed = 42                                        # cfg/config.yaml:11
+        self.env_offset = 0                                         # global id of local env 0 (env shards, dist.env_shard)
+        self.reset_counters = torch.zeros(3, device=device, dtype=torch.int32)      # envs reset, goals drawn, envs out of attempts
         self._reset_next = None
         self._fused = None
         self.joint_position_targets = None
@@ -247,6 +250,33 @@ class RoverTask():
             self.reset_idx(reset_env_ids)
             self.set_targets(reset_env_ids)
         self.apply_actions(actions)
+
+    def pre_physics_step_device(self, actions, max_attempts=64) -> None:
+        """pre_physics_step (rover.py:338-414) with the reset path on the device: no reset_buf.nonzero(), no host-side goal
+        loop -- one launch (rvb_reset_targets) resets the book-keeping of the envs whose reset_buf is set, draws their goals
+        (Philox, keyed by (reset_seed, global_step, global env id)) until they clear the stones and looks their height up.
+        Pose resets belong to the simulator: `self._rover.reset_idx_masked(reset_mask, initial_pos)` is called when the view
+        provides it (the mask is a snapshot of reset_buf taken before it is cleared)."""
+        self.global_step += 1
+        self.rover_loc, quat = self._rover.get_world_poses()
+        self.rover_rot = tensor_quat_to_eul(quat)
+        if hasattr(self._rover, "reset_idx_masked"):
+            self._rover.reset_idx_masked(self.reset_buf.clone(), self.initial_pos)
+        self.reset_targets_device(max_attempts=max_attempts)
+        self.apply_actions(actions)
+
+    def reset_targets_device(self, radius=8.0, thr=1.0, max_attempts=64, epoch=None):
+        """reset_idx book-keeping + set_targets (rover.py:451-452, 566-584) for every env with reset_buf != 0, on the device."""
+        hm = self.heightmap
+        sh = self.shift.flatten().cpu()
+        with torch.cuda.device(torch.device(self._device)):
+            _lib.check(self._lib.rvb_reset_targets(
+                _lib.ptr(self.reset_buf), self.num_envs, int(self.env_offset), int(self.reset_seed),
+                int(self.global_step if epoch is None else epoch), _lib.ptr(self.initial_pos), float(radius), _lib.ptr(self.stone_info),
+                self.stone_info.shape[0], float(thr), int(max_attempts), _lib.ptr(hm), hm.shape[0], hm.shape[1],
+                float(self.horizontal_scale), float(self.vertical_scale), float(sh[0]), float(sh[1]), _lib.ptr(self.target_positions),
+                _lib.ptr(self.progress_buf), _lib.ptr(self.reset_buf), _lib.ptr(self.reset_counters), self.sem, self._stream()))
+        return self.reset_counters
 
     def apply_actions(self, actions):
         """History push + Ackermann + joint-target mapping (rover.py:366-414)."""
