@@ -30,6 +30,28 @@ PEAKS_FILE = os.path.join(ROOT, "MEASURED_PEAKS.json")
 FALLBACK_HBM_GBS = 6650.0                 # /opt/skills/guides/B200_PROFILING.md fallback
 
 
+_JSON_FD = None
+
+
+def claim_stdout():
+    """Everything that libraries print to stdout while the benchmark runs (NCCL's "NCCL version ..." banner, for one) goes to
+    stderr; the ONE JSON line is written to the real stdout by emit()."""
+    global _JSON_FD
+    if _JSON_FD is None:
+        sys.stdout.flush()
+        _JSON_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
+
+
 def hbm_peak():
     try:
         return float(json.load(open(PEAKS_FILE))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
@@ -165,7 +187,7 @@ def run_reference(args, rank):
             "cpu_baseline": {"value": v, "unit": "env-steps/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": v, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line))
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------------ B200 arm
@@ -195,9 +217,14 @@ def run_b200(args, rank, world, local):
         view.pos, view.quat, view.joints = s["pos"], s["quat"], s["joints"]
         return s["actions"]
 
+    reducer = R.dist.StatsReducer()
+
     def step(i):
         task.hot_step(set_state(i), fused=not args.unfused)
-        R.dist.reduce_stats(task.stats)
+        if args.sync_reduce:
+            R.dist.reduce_stats(task.stats)
+        else:
+            reducer.submit(task.stats)          # asynchronous all-reduce of the 16 sums (off the critical path)
 
     task.Camera.variant = args.variant
     for i in range(args.warmup):
@@ -212,8 +239,11 @@ def run_b200(args, rank, world, local):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
     e0.record()
+    last = None
     for i in range(args.steps):
-        step(args.warmup + i)
+        last = step(args.warmup + i)
+    if not args.sync_reduce:
+        reducer.result((reducer.i - 1) % reducer.depth)       # the timed region ends when the last reduction has landed
     e1.record()
     torch.cuda.synchronize()
     R.dist.barrier()
@@ -229,29 +259,42 @@ def run_b200(args, rank, world, local):
     lib.rvb_timing_enable(0)
     ray_s = R.dist.max_over_ranks(sum(ray_ms) / len(ray_ms) * 1e-3, dev)
     # ---- end to end through the host-buffer API (H2D + hot path + D2H every step)
-    pipe = R.HostPipeline(task)
     hstates = [{k: v.pin_memory() for k, v in s.items() if k in ("pos", "quat", "joints", "actions")} for s in states]
-    for i in range(max(args.warmup, 3)):
-        h = hstates[i % n_sets]
-        pipe.step(h["pos"], h["quat"], h["joints"], h["actions"])
-    torch.cuda.synchronize()
-    R.dist.barrier()
-    # every step: inputs copied from pinned host memory, results (obs, rew, reset) read back and touched on the host;
-    # two slots, so the read-back of step i overlaps the kernels of step i+1
-    t0 = time.perf_counter()
-    prev, checksum = None, 0.0
-    for i in range(args.steps):
-        h = hstates[i % n_sets]
-        k = pipe.submit(h["pos"], h["quat"], h["joints"], h["actions"])
-        R.dist.reduce_stats(task.stats)
-        if prev is not None:
-            obs_h, rew_h, reset_h = pipe.result(prev)
-            checksum += float(rew_h[0]) + float(obs_h[-1, -1]) + int(reset_h[0])
-        prev = k
-    obs_h, rew_h, reset_h = pipe.result(prev)
-    checksum += float(rew_h[0]) + float(obs_h[-1, -1]) + int(reset_h[0])
-    torch.cuda.synchronize()
-    dt_e2e = R.dist.max_over_ranks(time.perf_counter() - t0, dev)
+
+    def run_e2e(packed):
+        """every step: inputs copied from pinned host memory, results (obs, rew, reset) read back and touched on the host;
+        two slots, so the read-back of step i overlaps the kernels of step i+1"""
+        pipe = R.HostPipeline(task, packed_obs=packed)
+        for i in range(max(args.warmup, 3)):
+            h = hstates[i % n_sets]
+            pipe.step(h["pos"], h["quat"], h["joints"], h["actions"])
+        torch.cuda.synchronize()
+        R.dist.barrier()
+        t0 = time.perf_counter()
+        prev, checksum = None, 0.0
+
+        def touch(res):
+            rew_h, reset_h = res[-2], res[-1]
+            return float(rew_h[0]) + float(res[-3][-1, -1]) + int(reset_h[0])
+        for i in range(args.steps):
+            h = hstates[i % n_sets]
+            k = pipe.submit(h["pos"], h["quat"], h["joints"], h["actions"])
+            if args.sync_reduce:
+                R.dist.reduce_stats(task.stats)
+            else:
+                reducer.submit(task.stats)
+            if prev is not None:
+                checksum += touch(pipe.result(prev))
+            prev = k
+        checksum += touch(pipe.result(prev))
+        if not args.sync_reduce:
+            reducer.result((reducer.i - 1) % reducer.depth)
+        torch.cuda.synchronize()
+        dt_ = R.dist.max_over_ranks(time.perf_counter() - t0, dev)
+        task.obs16_buf = None
+        return dt_, pipe.h2d_bytes, pipe.d2h_bytes, checksum
+    dt_e2e, h2d_b, d2h_b, checksum = run_e2e(False)
+    dt_e2e_p, h2d_bp, d2h_bp, checksum_p = run_e2e(True)
     clk = clocks.stop() if clocks else None
     if rank != 0:
         return
@@ -275,7 +318,8 @@ def run_b200(args, rank, world, local):
                        "envs_per_gpu": N, "total_envs": total_envs, "rays_per_env": P_RAYS, "K": w.K, "index_cells": w.G * w.G,
                        "l2": "inputs larger than L2: %d pose sets cycled, %.1f GB of index rows touched per step, index %.1f GB"
                              % (n_sets, N * 785 * w.K * 4 / 1e9, w.G * w.G * w.K * 4 / 1e9),
-                       "parallelism": "env shards x%d, terrain replicated, 1 all-reduce of 16 f64 per step" % world,
+                       "parallelism": "env shards x%d, terrain replicated, 1 all-reduce of 16 f64 per step (%s)"
+                                      % (world, "compute stream" if args.sync_reduce else "asynchronous, NCCL stream"),
                        "raycast_variant": args.variant, "fused_step": not args.unfused, "index_build_s": round(t_index, 3)},
             "rays_per_s": value * P_RAYS,
             "raycast_ms": ray_s * 1e3,
@@ -284,9 +328,14 @@ def run_b200(args, rank, world, local):
                          "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": ALGO_BYTES_PER_ENV_STEP * N,
                          "kernel": "heightmap ray-cast (Camera.get_depths)"},
-            "e2e": {"value": total_envs * args.steps / dt_e2e, "unit": "env-steps/s", "h2d_bytes_per_step": pipe.h2d_bytes * world,
-                    "d2h_bytes_per_step": pipe.d2h_bytes * world, "ms_per_step": dt_e2e / args.steps * 1e3,
-                    "api": "HostPipeline.submit/result (2 slots: read-back of step i overlaps step i+1)", "checksum": checksum},
+            "e2e": {"value": total_envs * args.steps / dt_e2e, "unit": "env-steps/s", "h2d_bytes_per_step": h2d_b * world,
+                    "d2h_bytes_per_step": d2h_b * world, "ms_per_step": dt_e2e / args.steps * 1e3,
+                    "api": "HostPipeline.submit/result (2 slots: read-back of step i overlaps step i+1); obs read back as the "
+                           "reference's f32 [N,1750]", "checksum": checksum},
+            "e2e_packed_obs": {"value": total_envs * args.steps / dt_e2e_p, "unit": "env-steps/s", "h2d_bytes_per_step": h2d_bp * world,
+                               "d2h_bytes_per_step": d2h_bp * world, "ms_per_step": dt_e2e_p / args.steps * 1e3,
+                               "api": "HostPipeline(packed_obs=True): heightmap columns read back as the fp16 values they are "
+                                      "(lossless), proprioceptive columns f32", "checksum": checksum_p},
             "gpu_launches": launches,
             "clocks": clk}
     if world == 1 and not args.no_cpu:
@@ -295,7 +344,7 @@ def run_b200(args, rank, world, local):
         line["cpu_baseline"] = {"value": n / t, "unit": "env-steps/s", "cores": torch.get_num_threads(), "kind": "port",
                                 "sample": "%d envs (x1634 rays x K=200) per step, 1 warm-up + 2 timed steps of the oracle port of the "
                                           "reference's torch path on a 24 m terrain of the same mesh density" % n}
-    print(json.dumps(line))
+    emit(line)
 
 
 def main():
@@ -313,9 +362,11 @@ def main():
     ap.add_argument("--cpu-envs", type=int, default=16)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--unfused", action="store_true", help="one library call per reference call instead of rvb_env_step")
+    ap.add_argument("--sync-reduce", action="store_true", help="all-reduce the statistics on the compute stream every step")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 1 if args.impl == "reference" else 3)
     rank = int(os.environ.get("RANK", "0"))
+    claim_stdout()
     if args.impl == "reference":
         run_reference(args, rank)
         return

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define RVB_ABI_VERSION 1
+#define RVB_ABI_VERSION 2
 
 typedef enum rvb_status {
     RVB_OK = 0,
@@ -186,6 +186,10 @@ typedef struct rvb_step_io {
     float* rew; int64_t* reset;
     float* ex_pos_reward; int64_t* ex_collision; float* ex_uprightness; float* ex_heading; float* ex_motion; float* ex_goal_angle;
     double* stats; double* stats_scratch;
+    /* optional packed observation (ABI 2): obs_h16 f16 [N, obs_h16_ld >= sparse+dense] receives the heightmap columns
+     * (obs column c -> obs_h16 column c - 4) as the fp16 values they are by construction (fp16(dist / 2), rover.py:324-325);
+     * obs[:, 4:] is then NOT written (obs[:, 0:4] still is).  Halves the bytes a host-side consumer has to read back. */
+    uint16_t* obs_h16; int64_t obs_h16_ld;
 } rvb_step_io;
 int rvb_env_step(const rvb_terrain* terrain, const rvb_terrain* rocks, const rvb_reward_params* p, const rvb_step_io* io,
                  const double* pattern, int64_t P, const int32_t* col_a, const int32_t* col_b, int64_t N, int64_t H,

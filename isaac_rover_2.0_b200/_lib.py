@@ -33,7 +33,8 @@ class StepIO(C.Structure):
     _fields_ = [(n, p) for n in ("pos", "quat", "joints", "actions", "target", "lin_hist", "ang_hist", "progress", "euler", "heading",
                                  "steer", "vel", "pos_targets", "vel_targets", "obs")] + [("obs_ld", i64)] + \
                [(n, p) for n in ("dist", "wheel_dist", "body_dist", "rock_collision", "rew", "reset", "ex_pos_reward", "ex_collision",
-                                 "ex_uprightness", "ex_heading", "ex_motion", "ex_goal_angle", "stats", "stats_scratch")]
+                                 "ex_uprightness", "ex_heading", "ex_motion", "ex_goal_angle", "stats", "stats_scratch", "obs_h16")] + \
+               [("obs_h16_ld", i64)]
 
 
 _SIGNATURES = {
@@ -115,7 +116,7 @@ def load():
         fn.restype = res
         fn.argtypes = args
         setattr(lib, name, _Counted(fn, KERNELS_PER_CALL[name]) if name in KERNELS_PER_CALL else fn)
-    if lib.rvb_abi_version() != 1:
+    if lib.rvb_abi_version() != 2:
         raise RuntimeError("librover_b200.so ABI version mismatch")
     _lib = lib
     return lib

@@ -30,6 +30,9 @@ struct TiledParams {
     __half* sources;
     float* obs;
     int64_t obs_ld;
+    __half* obs16;            // optional packed observation: obs16[n * obs16_ld + (column - obs16_col0)] = fp16(dist / 2)
+    int64_t obs16_ld;
+    int obs16_col0;
     const int32_t* col_a;
     const int32_t* col_b;
     // shadow kernel (raycast_shadow.cu): superblock candidate lists + the list of (env, tile) work items it hands back
@@ -215,7 +218,24 @@ __device__ __forceinline__ void epilogue(const TiledParams& q, int64_t n, int p0
             if (ca >= 0) q.obs[n * q.obs_ld + ca] = v;
             if (cb >= 0) q.obs[n * q.obs_ld + cb] = v;
         }
+        if (q.obs16) {                                                                        // the same value, kept in fp16
+            const __half v = h_mul(h_from_bits(kb), __float2half_rn(0.5f));
+            const int ca = q.col_a[p0 + p], cb = q.col_b[p0 + p];
+            if (ca >= 0) q.obs16[n * q.obs16_ld + (ca - q.obs16_col0)] = v;
+            if (cb >= 0) q.obs16[n * q.obs16_ld + (cb - q.obs16_col0)] = v;
+        }
     }
 }
 
 }  // namespace rc
+
+// Packed fp16 observation output of the NEXT heightmap ray-cast launched by this thread (set by rvb_env_step, consumed and
+// cleared by fill_tiled_params); keeps rvb_heightmap_raycast's signature as it is.
+struct RvbObs16 {
+    uint16_t* p;
+    int64_t ld;
+    int col0;
+    const int32_t* col_a;
+    const int32_t* col_b;
+};
+extern thread_local RvbObs16 g_rvb_obs16;

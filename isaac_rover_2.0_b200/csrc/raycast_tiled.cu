@@ -375,6 +375,8 @@ static int configure_tiled() {
     return RVB_OK;
 }
 
+thread_local RvbObs16 g_rvb_obs16 = {nullptr, 0, 0, nullptr, nullptr};
+
 int fill_tiled_params(const rvb_terrain* t, const float* pos, const float* euler, const float* trig, const double* pattern,
                       int64_t P, int64_t N, uint16_t* dist, int32_t* hit_slot, int32_t* hit_tri, uint16_t* pt,
                       uint16_t* sources, float* obs, int64_t obs_ld, const int32_t* col_a, const int32_t* col_b,
@@ -394,6 +396,11 @@ int fill_tiled_params(const rvb_terrain* t, const float* pos, const float* euler
     q.tile_size = (int)ceil_div(P, q.tiles);
     q.dist = (__half*)dist; q.hit_slot = hit_slot; q.hit_tri = hit_tri; q.pt = (__half*)pt; q.sources = (__half*)sources;
     q.obs = obs; q.obs_ld = obs_ld; q.col_a = col_a; q.col_b = col_b;
+    if (g_rvb_obs16.p) {
+        q.obs16 = (__half*)g_rvb_obs16.p; q.obs16_ld = g_rvb_obs16.ld; q.obs16_col0 = g_rvb_obs16.col0;
+        q.col_a = g_rvb_obs16.col_a; q.col_b = g_rvb_obs16.col_b;
+        g_rvb_obs16.p = nullptr;
+    }
     RVB_REQUIRE(N * q.tiles < ((int64_t)1 << 31), "heightmap ray-cast: too many (env, tile) blocks for one launch");
     return RVB_OK;
 }

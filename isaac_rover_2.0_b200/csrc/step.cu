@@ -8,6 +8,7 @@
 // The per-call entry points of rover_b200.h stay the reference-shaped API; this one removes ~25 Python/ctypes round trips
 // per step (the host side was the bottleneck once the ray-cast dropped below 1.5 ms).
 #include "task_dev.cuh"
+#include "raycast_common.cuh"
 
 int launch_heightmap_shadow(const rvb_terrain* t, const float* pos, const float* euler, const float* trig,
                             const double* pattern, int64_t P, int64_t N, uint16_t* dist, int32_t* hit_slot,
@@ -71,6 +72,7 @@ extern "C" int rvb_env_step(const rvb_terrain* terrain, const rvb_terrain* rocks
                     io.obs && io.dist && io.rew && io.reset && io.progress, "rvb_env_step: null pointer in rvb_step_io");
     RVB_REQUIRE(((uintptr_t)io.quat & 15) == 0, "rvb_env_step: quat must be 16-byte aligned");
     RVB_REQUIRE(H >= 2 && H <= 64 && io.obs_ld >= 4, "rvb_env_step: bad history length or obs_ld");
+    RVB_REQUIRE(!io.obs_h16 || io.obs_h16_ld > 0, "rvb_env_step: obs_h16 needs obs_h16_ld");
     RVB_REQUIRE(p->curriculum_level < 2 || (rocks && io.wheel_dist && io.body_dist && io.rock_collision),
                 "rvb_env_step: curriculum_level >= 2 needs the rock layer and its outputs");
     cudaStream_t st = as_stream(stream);
@@ -107,8 +109,12 @@ extern "C" int rvb_env_step(const rvb_terrain* terrain, const rvb_terrain* rocks
         g_timing.used += 2;
         RVB_CUDA(cudaEventRecord(t0, st));
     }
+    // packed observation requested: the heightmap columns go to obs_h16 (fp16, what they are by construction) and the f32
+    // columns 4.. of obs are left alone
+    if (io.obs_h16) g_rvb_obs16 = {io.obs_h16, io.obs_h16_ld, 4, col_a, col_b};
     int rc = rvb_heightmap_raycast(terrain, io.pos, io.euler, nullptr, pattern, P, N, io.dist, nullptr, nullptr, nullptr, nullptr,
-                                   io.obs, io.obs_ld, col_a, col_b, 0, st);
+                                   io.obs_h16 ? nullptr : io.obs, io.obs_ld, col_a, col_b, 0, st);
+    g_rvb_obs16.p = nullptr;
     if (rc != RVB_OK) return rc;
     if (t1) RVB_CUDA(cudaEventRecord(t1, st));
     if (with_rocks) RVB_CUDA(cudaStreamWaitEvent(st, g_side.join, 0));

@@ -39,6 +39,35 @@ def reduce_stats(stats, async_op=False):
     return None
 
 
+class StatsReducer:
+    """The per-step statistics all-reduce taken off the critical path: the step's 16 sums are copied into one of `depth`
+    buffers and all-reduced asynchronously (NCCL's own stream), so the next step's kernels do not wait for the slowest rank
+    of this one.  submit() returns a slot; result(slot) makes the current stream wait for that reduction and returns the
+    reduced vector.  Single process: the copy alone."""
+
+    def __init__(self, depth=2):
+        self.depth, self.bufs, self.works, self.i = depth, [None] * depth, [None] * depth, 0
+
+    def submit(self, stats):
+        k = self.i % self.depth
+        self.i += 1
+        if self.works[k] is not None:
+            self.works[k].wait()
+            self.works[k] = None
+        if self.bufs[k] is None:
+            self.bufs[k] = torch.empty_like(stats)
+        self.bufs[k].copy_(stats)
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            self.works[k] = dist.all_reduce(self.bufs[k], op=dist.ReduceOp.SUM, async_op=True)
+        return k
+
+    def result(self, k):
+        if self.works[k] is not None:
+            self.works[k].wait()
+            self.works[k] = None
+        return self.bufs[k]
+
+
 def max_over_ranks(value, device):
     """max of a python float over ranks (timing)."""
     if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:

@@ -8,14 +8,20 @@ stream into the other slot's device buffers while step i still computes (measure
 start together with the previous step's read-back and wait behind it, +0.2 ms per step).  `step()` = submit + result (no overlap).
 bench.py's `e2e` number times submit/result in a loop where every step's inputs are copied in and every step's results are
 read on the host.
+
+`packed_obs=True`: the heightmap observation columns are produced and read back as the fp16 values they are by construction
+(obs = fp16(dist / 2) widened to f32, rover.py:324-325), i.e. lossless at half the bytes: result() then returns
+(obs_proprio f32 [N,4], obs_heightmap f16 [N,1746], rew, reset); `obs_f32(slot)` widens them on the host when a caller wants
+the reference's [N,1750] f32 layout.  With 8 GPUs reading 28.7 MB each per step the host link is the bottleneck; this halves it.
 """
 import torch
 
 
 class HostPipeline:
-    def __init__(self, task, depth=2):
+    def __init__(self, task, depth=2, packed_obs=False):
         self.task = task
         self.depth = depth
+        self.packed_obs = packed_obs
         N, dev = task.num_envs, torch.device(task._device)
         self.dev = dev
         pin = dict(pin_memory=True)
@@ -28,6 +34,12 @@ class HostPipeline:
         self.d_obs = [torch.zeros((N, task.num_observations), dtype=torch.float32, device=dev) for _ in range(depth)]
         self.d_rew = [torch.zeros((N,), dtype=torch.float32, device=dev) for _ in range(depth)]
         self.d_reset = [torch.zeros((N,), dtype=torch.int64, device=dev) for _ in range(depth)]
+        if packed_obs:
+            n_hm = task.num_observations - 4
+            self.d_obs16 = [torch.zeros((N, n_hm), dtype=torch.float16, device=dev) for _ in range(depth)]
+            self.d_prop = [torch.zeros((N, 4), dtype=torch.float32, device=dev) for _ in range(depth)]
+            self.h_obs16 = mk((N, n_hm), torch.float16)
+            self.h_prop = mk((N, 4), torch.float32)
         self.copy_stream = torch.cuda.Stream(dev)
         self.up_stream = torch.cuda.Stream(dev)
         self.uploaded = [torch.cuda.Event() for _ in range(depth)]
@@ -37,7 +49,8 @@ class HostPipeline:
         view = task._rover
         view.pos, view.quat, view.joints = self.d_pos[0], self.d_quat[0], self.d_joints[0]
         self.h2d_bytes = sum(t[0].numel() * t[0].element_size() for t in (self.h_pos, self.h_quat, self.h_joints, self.h_actions))
-        self.d2h_bytes = sum(t[0].numel() * t[0].element_size() for t in (self.h_obs, self.h_rew, self.h_reset))
+        outs = (self.h_obs16, self.h_prop, self.h_rew, self.h_reset) if packed_obs else (self.h_obs, self.h_rew, self.h_reset)
+        self.d2h_bytes = sum(t[0].numel() * t[0].element_size() for t in outs)
 
     def submit(self, pos, quat, joints, actions):
         """pos/quat/joints/actions: host tensors (any memory).  Enqueues the step and returns its slot."""
@@ -59,11 +72,18 @@ class HostPipeline:
         view = t._rover
         view.pos, view.quat, view.joints = self.d_pos[k], self.d_quat[k], self.d_joints[k]
         t.obs_buf, t.rew_buf, t.reset_buf = self.d_obs[k], self.d_rew[k], self.d_reset[k]
+        t.obs16_buf = self.d_obs16[k] if self.packed_obs else None
         t.hot_step(self.d_actions[k])
+        if self.packed_obs:
+            self.d_prop[k].copy_(self.d_obs[k][:, :4])          # 64 KB, contiguous for the read-back
         self.computed[k].record(cur)
         self.copy_stream.wait_event(self.computed[k])
         with torch.cuda.stream(self.copy_stream):
-            self.h_obs[k].copy_(self.d_obs[k], non_blocking=True)
+            if self.packed_obs:
+                self.h_obs16[k].copy_(self.d_obs16[k], non_blocking=True)
+                self.h_prop[k].copy_(self.d_prop[k], non_blocking=True)
+            else:
+                self.h_obs[k].copy_(self.d_obs[k], non_blocking=True)
             self.h_rew[k].copy_(self.d_rew[k], non_blocking=True)
             self.h_reset[k].copy_(self.d_reset[k], non_blocking=True)
             ev = torch.cuda.Event()
@@ -74,7 +94,16 @@ class HostPipeline:
 
     def result(self, k):
         self.done[k].synchronize()
+        if self.packed_obs:
+            return self.h_prop[k], self.h_obs16[k], self.h_rew[k], self.h_reset[k]
         return self.h_obs[k], self.h_rew[k], self.h_reset[k]
+
+    def obs_f32(self, k):
+        """The reference's [N, 4+sparse+dense] f32 observation of slot k, assembled on the host (packed mode)."""
+        self.done[k].synchronize()
+        if not self.packed_obs:
+            return self.h_obs[k]
+        return torch.cat((self.h_prop[k], self.h_obs16[k].float()), 1)
 
     def step(self, pos, quat, joints, actions):
         """Synchronous convenience: returns pinned host (obs, rew, reset) of this step."""

@@ -122,6 +122,8 @@ class RoverTask():
                         motion_contraint_penalty=torch.zeros(num_envs, device=device),
                         goal_angle_penalty=torch.zeros(num_envs, device=device))
         self._count = torch.zeros(1, device=device, dtype=torch.int32)
+        # optional packed observation of the fused step: f16 [N, sparse+dense]; when set, obs_buf[:, 4:] is not written
+        self.obs16_buf = None
         self.reset_seed = 42                                        # cfg/config.yaml:11
         self.env_offset = 0                                         # global id of local env 0 (env shards, dist.env_shard)
         self.reset_counters = torch.zeros(3, device=device, dtype=torch.int32)      # envs reset, goals drawn, envs out of attempts
@@ -182,7 +184,8 @@ class RoverTask():
                                                   self.rock_collison if want_rocks else None, self.rew_buf, self.reset_buf,
                                                   e["pos_reward"], e["collision_penalty"], e["uprightness_penalty"],
                                                   e["heading_contraint_penalty"], e["motion_contraint_penalty"],
-                                                  e["goal_angle_penalty"], self.stats, self._stats_scratch)])
+                                                  e["goal_angle_penalty"], self.stats, self._stats_scratch, self.obs16_buf)],
+                         0 if self.obs16_buf is None else self.obs16_buf.stride(0))
         prm = self._params()
         cam = self.Camera
         with torch.cuda.device(dev):

@@ -30,10 +30,16 @@ def _worker(rank, world, port, total_envs, q):
     ids = torch.arange(lo, hi, dtype=torch.float64)
     stats = torch.zeros(16, dtype=torch.float64)
     stats[0], stats[1], stats[8] = hi - lo, ids.sum(), (ids % 3 == 0).sum()
+    # the asynchronous reducer: three steps through two slots, the source vector changes between submissions
+    red = R.dist.StatsReducer(depth=2)
+    slots = []
+    for step in range(3):
+        slots.append(red.submit(stats * (step + 1)))
+    async_out = [red.result(slots[-1]).tolist(), red.result(slots[-2]).tolist()]
     R.dist.reduce_stats(stats)
     t = R.dist.max_over_ranks(1.0 + rank, torch.device("cpu"))
     R.dist.barrier()
-    q.put((rank, lo, hi, stats.tolist(), t))
+    q.put((rank, lo, hi, stats.tolist(), t, async_out))
     dist.destroy_process_group()
 
 
@@ -60,8 +66,10 @@ def test_two_rank_stats_reduction_gloo():
         p.join(timeout=60)
         assert p.exitcode == 0
     ids = torch.arange(total, dtype=torch.float64)
-    for rank, lo, hi, stats, t in out:
+    for rank, lo, hi, stats, t, async_out in out:
         assert stats[0] == total and stats[1] == ids.sum().item() and stats[8] == (ids % 3 == 0).sum().item()
+        assert async_out[0][0] == 3 * total and async_out[0][1] == 3 * ids.sum().item()        # step 3 (slot reused)
+        assert async_out[1][0] == 2 * total and async_out[1][1] == 2 * ids.sum().item()        # step 2
         assert t == 2.0                                        # max over ranks of (1 + rank)
     assert out[0][1] == 0 and out[0][2] == out[1][1] and out[1][2] == total
 
@@ -73,3 +81,5 @@ def test_single_process_helpers_are_noops():
     assert R.dist.reduce_stats(s) is None and torch.equal(s, torch.arange(16, dtype=torch.float64))
     assert R.dist.max_over_ranks(3.5, torch.device("cpu")) == 3.5
     R.dist.barrier()
+    red = R.dist.StatsReducer()
+    assert torch.equal(red.result(red.submit(s)), s)

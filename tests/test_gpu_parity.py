@@ -520,3 +520,28 @@ def test_fused_step_equals_call_sequence(R, world20):
         got = pipe.result(k)
         for a, b in zip(got, want):
             assert torch.equal(a, b)
+
+
+def test_packed_observation_is_lossless(R, world20):
+    """rvb_step_io.obs_h16 / HostPipeline(packed_obs=True): the heightmap columns as fp16 equal the f32 columns bit for bit
+    once widened, the proprioceptive columns are the same f32 values, rew / reset are unchanged."""
+    w = world20
+    N = 200
+    st = R.synth.make_env_state(w, N, seed=33)
+    t_ref = R.synth.make_task(w, st, device="cuda:0", level=2)
+    t_pk = R.synth.make_task(w, st, device="cuda:0", level=2)
+    pipe_ref = R.HostPipeline(t_ref)
+    pipe_pk = R.HostPipeline(t_pk, packed_obs=True)
+    g = torch.Generator().manual_seed(2)
+    hs = {k: v.clone() for k, v in st.items()}
+    for step in range(3):
+        act = torch.rand(N, 2, generator=g) * 2 - 1
+        hs["pos"][:, 1] += 0.02
+        obs, rew, reset = pipe_ref.step(hs["pos"], hs["quat"], hs["joints"], act)
+        k = pipe_pk.submit(hs["pos"], hs["quat"], hs["joints"], act)
+        prop, hm16, rew2, reset2 = pipe_pk.result(k)
+        assert hm16.dtype == torch.float16 and hm16.shape == (N, 1746) and prop.shape == (N, 4)
+        assert torch.equal(prop, obs[:, :4]) and torch.equal(hm16.float(), obs[:, 4:])
+        assert torch.equal(rew, rew2) and torch.equal(reset, reset2)
+        assert torch.equal(pipe_pk.obs_f32(k), obs)
+    assert pipe_pk.d2h_bytes < 0.51 * pipe_ref.d2h_bytes
