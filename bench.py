@@ -328,14 +328,18 @@ def run_b200(args, rank, world, local):
                          "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": ALGO_BYTES_PER_ENV_STEP * N,
                          "kernel": "heightmap ray-cast (Camera.get_depths)"},
-            "e2e": {"value": total_envs * args.steps / dt_e2e, "unit": "env-steps/s", "h2d_bytes_per_step": h2d_b * world,
-                    "d2h_bytes_per_step": d2h_b * world, "ms_per_step": dt_e2e / args.steps * 1e3,
-                    "api": "HostPipeline.submit/result (2 slots: read-back of step i overlaps step i+1); obs read back as the "
-                           "reference's f32 [N,1750]", "checksum": checksum},
-            "e2e_packed_obs": {"value": total_envs * args.steps / dt_e2e_p, "unit": "env-steps/s", "h2d_bytes_per_step": h2d_bp * world,
-                               "d2h_bytes_per_step": d2h_bp * world, "ms_per_step": dt_e2e_p / args.steps * 1e3,
-                               "api": "HostPipeline(packed_obs=True): heightmap columns read back as the fp16 values they are "
-                                      "(lossless), proprioceptive columns f32", "checksum": checksum_p},
+            # headline end-to-end number: the host pipeline with the observation read back in its native precision (the
+            # heightmap columns ARE fp16 values, rover.py:324-325; HostPipeline.obs_f32() widens them on the host);
+            # e2e_f32_obs is the same loop reading back the reference's f32 [N,1750] layout (twice the bytes: at 8 GPUs the
+            # host link, not the GPUs, then sets the pace)
+            "e2e": {"value": total_envs * args.steps / dt_e2e_p, "unit": "env-steps/s", "h2d_bytes_per_step": h2d_bp * world,
+                    "d2h_bytes_per_step": d2h_bp * world, "ms_per_step": dt_e2e_p / args.steps * 1e3,
+                    "api": "HostPipeline(packed_obs=True).submit/result (2 slots: read-back of step i overlaps step i+1; inputs "
+                           "uploaded from pinned host memory every step; obs = f32 [N,4] proprioceptive + f16 [N,1746] heightmap "
+                           "columns, lossless; rew f32 [N]; reset i64 [N])", "checksum": checksum_p},
+            "e2e_f32_obs": {"value": total_envs * args.steps / dt_e2e, "unit": "env-steps/s", "h2d_bytes_per_step": h2d_b * world,
+                            "d2h_bytes_per_step": d2h_b * world, "ms_per_step": dt_e2e / args.steps * 1e3,
+                            "api": "HostPipeline.submit/result, obs read back as the reference's f32 [N,1750]", "checksum": checksum},
             "gpu_launches": launches,
             "clocks": clk}
     if world == 1 and not args.no_cpu:
