@@ -51,6 +51,7 @@ struct TiledParams {
     // pre-sorted steep envs (cast by the tiled kernel on a second stream, concurrently); both written by hm_classify_kernel
     const int32_t* order;     // [N] or NULL
     int presorted;            // steep envs are already on a work list: the shadow kernel just skips them
+    int min_sh;               // bins are 2^sh x 2^sh cells, sh >= min_sh (0 = one cell; tuning hook)
     unsigned long long* dbg;  // optional [16] work counters of the shadow kernel (RVB_SHADOW_DBG=1)
 };
 

@@ -327,7 +327,7 @@ __global__ void __launch_bounds__(TT, RTC <= RT_SMALL ? 4 : 3) hm_shadow_kernel(
     __syncthreads();
     // bins: 2^sh x 2^sh cells, the finest that lets the tile's bounding box fit the histogram (sh = 0 for a rover on its wheels);
     // 2^sh divides the superblock side (24 cells), so bins never straddle superblocks
-    int sh = 0;
+    int sh = q.min_sh;
     while (sh < 3 && (int64_t)((s_box[2] >> sh) - (s_box[0] >> sh) + 1) * ((s_box[3] >> sh) - (s_box[1] >> sh) + 1) > BIN_CAP) ++sh;
     const int bx0 = s_box[0] >> sh, by0 = s_box[1] >> sh;          // (bx0, by0, BW, BH: bounding box of the tile's rays in BINS)
     const int BW = (s_box[2] >> sh) - bx0 + 1, BH = (s_box[3] >> sh) - by0 + 1;
@@ -868,6 +868,7 @@ int launch_heightmap_shadow(const rvb_terrain* t, const float* pos, const float*
     q.cos_steep = cos_steep;
     q.order = order;
     q.presorted = 1;
+    if (const char* ms = getenv("RVB_SHADOW_SH")) q.min_sh = atoi(ms);      // tuning hook: coarsest bins to start from
     struct Side {
         int dev = -1;
         cudaStream_t s = nullptr;

@@ -545,3 +545,41 @@ def test_packed_observation_is_lossless(R, world20):
         assert torch.equal(rew, rew2) and torch.equal(reset, reset2)
         assert torch.equal(pipe_pk.obs_f32(k), obs)
     assert pipe_pk.d2h_bytes < 0.51 * pipe_ref.d2h_bytes
+
+
+def test_c3_size_step_is_shard_invariant(R, world200):
+    """BASELINE.json configs[2] size (65,536 envs, big_rock_layer + stones on): the production ray-cast equals the tiled
+    kernel bit for bit, and the whole fused env step gives identical obs / rew / reset / collision flags whether the envs run
+    as one shard or as two (what `bench.py --gpus N` relies on: envs are independent, terrain replicated); the per-shard
+    statistics add up to the single-shard ones."""
+    w = world200
+    if w.rock_indices is None:
+        w.rock_indices = R.build_knn_index(w.rock_triangles, w.rock_vertices, w.G, w.res, w.K, device="cuda:0")
+    N = 65536
+    st = R.synth.make_env_state(w, N, seed=77)
+    whole = R.synth.make_task(w, st, device="cuda:0", level=2, num_envs_total=N)
+    obs, rew, reset, _ = whole.hot_step(st["actions"].cuda())
+    torch.cuda.synchronize()
+    # ray-cast: shadow kernel vs tiled kernel at full size
+    eul = R.tensor_quat_to_eul(st["quat"].cuda())
+    cam = whole.Camera
+    cam.variant = 3
+    d3, _, _ = cam.get_depths(st["pos"].cuda(), eul, want_pt=False)
+    cam.variant = 0
+    d0, _, _ = cam.get_depths(st["pos"].cuda(), eul, want_pt=False)
+    assert_bits_equal(d0, d3, "65,536 envs: shadow vs tiled")
+    assert torch.equal(obs[:, 4:], (d0 * 0.5).float()[:, torch.cat((cam.heightmap.coarse_idx, cam.heightmap.fine_idx))])
+    stats = torch.zeros_like(whole.stats)
+    h = N // 2
+    for lo, hi in ((0, h), (h, N)):
+        sub = {k: v[lo:hi].contiguous() for k, v in st.items()}
+        part = R.synth.make_task(w, sub, device="cuda:0", level=2, num_envs_total=N)
+        o, r, z, _ = part.hot_step(sub["actions"].cuda())
+        torch.cuda.synchronize()
+        assert torch.equal(o, obs[lo:hi]) and torch.equal(r, rew[lo:hi]) and torch.equal(z, reset[lo:hi])
+        assert torch.equal(part.rock_collison, whole.rock_collison[lo:hi])
+        stats += part.stats
+        del part
+    assert stats[0] == N and torch.equal(stats[[0, 3, 8, 9, 10, 11, 12, 13]], whole.stats[[0, 3, 8, 9, 10, 11, 12, 13]])      # counts: exact
+    assert torch.allclose(stats, whole.stats, rtol=1e-12)                                                                 # f64 sums
+    assert 0 < int(whole.rock_collison.sum()) < N and 0 < int(reset.sum()) < N
