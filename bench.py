@@ -168,6 +168,22 @@ def time_cpu_oracle(n_envs, steps, warmup):
     return sum(ts) / len(ts)
 
 
+def time_gpu_eager_oracle(n_envs, dev, steps=3, warmup=1):
+    """The reference's eager-torch op sequence (oracle port) on the GPU itself -- how the reference is actually deployed
+    (it hard-wires 'cuda:0', rover.py:90).  Reported beside the CPU baseline; same 24 m sample world, n_envs envs."""
+    O, assets, st = cpu_sample_assets(n_envs)
+    assets = {k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in assets.items()}
+    st = {k: v.to(dev) for k, v in st.items()}
+    for _ in range(warmup):
+        O.full_step(assets, st, env_chunk=min(n_envs, 128))
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        O.full_step(assets, st, env_chunk=min(n_envs, 128))
+    torch.cuda.synchronize()
+    return (time.perf_counter() - t0) / steps
+
+
 def run_reference(args, rank):
     if rank != 0:
         return
@@ -348,6 +364,15 @@ def run_b200(args, rank, world, local):
         line["cpu_baseline"] = {"value": n / t, "unit": "env-steps/s", "cores": torch.get_num_threads(), "kind": "port",
                                 "sample": "%d envs (x1634 rays x K=200) per step, 1 warm-up + 2 timed steps of the oracle port of the "
                                           "reference's torch path on a 24 m terrain of the same mesh density" % n}
+        try:
+            ng = 256
+            tg = time_gpu_eager_oracle(ng, dev)
+            line["torch_eager_gpu_baseline"] = {"value": ng / tg, "unit": "env-steps/s", "kind": "port",
+                                                "sample": "%d envs per step, 1 warm-up + 3 timed steps of the same oracle port run as eager "
+                                                          "torch ops on this GPU (the reference's own deployment: ~700 ATen launches per "
+                                                          "step, fp16 temporaries in HBM)" % ng}
+        except Exception as e:          # a baseline, never a reason to lose the bench line
+            line["torch_eager_gpu_baseline"] = {"unavailable": str(e)[:200]}
     emit(line)
 
 
