@@ -24,7 +24,7 @@
 // with tlo/thi the outward-rounded fp16 thresholds of the packed pre-filter of raycast_tiled.cu (a superset of the
 // literal test).  |g| is bounded self-consistently from the disc of stage 1.  Triangles for which no bound holds
 // (|det*| within rounding of 0, fp16 overflow possible, NaN) are tested against every ray of the superblock.
-// tools/shadow_proto.py re-states stages 1-2 in numpy and checks them against a brute-force fp16 evaluation;
+// tests/shadow_proto.py re-states stages 1-2 in numpy and checks them against a brute-force fp16 evaluation;
 // tests/test_shadow_bound_cpu.py runs it.  Envs this kernel cannot group (rays spread over more than 8192 bins or
 // 64 superblocks) or whose rays are nearly parallel to the ground (cos < cos_steep: the prisms become long slivers)
 // are handed to the tiled kernel through a work list.
@@ -123,7 +123,7 @@ __device__ __forceinline__ TriF tri_f(const uint4& q0, const uint2& q1) {
     return t;
 }
 
-// Stage 1 (tools/shadow_proto.py: stage1).  Returns false if no source inside the rectangle can pass; gball >= |s - a|
+// Stage 1 (tests/shadow_proto.py: stage1).  Returns false if no source inside the rectangle can pass; gball >= |s - a|
 // for every passing source (+inf: no bound, the caller must test every ray of the item).
 __device__ __forceinline__ bool stage1(const uint4& s0, const uint4& s1, const EnvC& e, float rlox, float rhix, float rloy, float rhiy, float& gball) {
     // S1Rec (common.cuh): centroid, radius, b x c, magnitudes -- computed once per layer by build_records_kernel (terrain.cu)
@@ -155,7 +155,7 @@ __device__ __forceinline__ bool stage1(const uint4& s0, const uint4& s1, const E
     return !out;
 }
 
-// Stage 2 (tools/shadow_proto.py: stage2): xy box of the sources that can pass; full = no bound.
+// Stage 2 (tests/shadow_proto.py: stage2): xy box of the sources that can pass; full = no bound.
 __device__ __forceinline__ void stage2(const TriF& t, const uint2& q1, const EnvC& e, H3 d16, float gball, float& x0, float& x1,
                                        float& y0, float& y1, bool& full) {
     const __half n0 = h_from_bits(q1.x >> 16), n1 = h_from_bits(q1.y & 0xffff), n2 = h_from_bits(q1.y >> 16);
@@ -344,7 +344,7 @@ __global__ void __launch_bounds__(TT, RTC <= RT_SMALL ? 4 : 3) hm_shadow_kernel(
             a_s = fmaxf(a_s, s_red[w][4]); z0 = fminf(z0, s_red[w][5]); z1 = fmaxf(z1, s_red[w][6]); pm = fmaxf(pm, s_red[w][7]);
         }
         if (tid == 0) {
-            // source plane: s = t + x c1 + y c2 + z c3 (columns of camera.py:197-199), nu = c1 x c2 (tools/shadow_proto.py: EnvConsts)
+            // source plane: s = t + x c1 + y c2 + z c3 (columns of camera.py:197-199), nu = c1 x c2 (tests/shadow_proto.py: EnvConsts)
             const double sx = tr.sx, cx = tr.cx, sy = tr.sy, cy = tr.cy, sz = tr.sz, cz = tr.cz;
             const double c1x = cz * cy, c1y = -sz * cy, c1z = sy;
             const double c2x = sz * cx + cz * sy * sx, c2y = cz * cx - sz * sy * sx, c2z = -cy * sx;

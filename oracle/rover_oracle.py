@@ -8,7 +8,7 @@ matmul path above 25 rows); torch (2.11.0 here; the reference pins no version, s
 is therefore the third-party dependency whose semantics define the answer, and this oracle
 calls the same ops in the same order.  Every function cites the reference lines it follows.
 
-Pinned: `tests/test_oracle_vs_reference.py` runs this file against the unmodified reference
+Pinned: `tests/test_oracle_cpu.py` runs this file against the unmodified reference
 imported from /root/reference (bit-exact on CPU) and `tests/golden/*.pt` were produced by the
 reference itself (`tests/golden/make_golden.py`).
 

@@ -6,7 +6,7 @@ re-states that box computation in numpy fp32 (same formulas, same constants) and
 fp16 evaluation of the pre-filter on synthetic worlds: no passing (ray, triangle) pair may lie outside the box.
 It also reports how tight the box is (rays per box vs. passing rays).
 
-Run:  python tools/shadow_proto.py [--envs 12] [--length 200]
+Run:  python tests/shadow_proto.py [--envs 12] [--length 200]
 """
 import argparse
 import math

@@ -1,5 +1,5 @@
 """The culling stages of the production ray-cast kernel (csrc/raycast_shadow.cu) must be CONSERVATIVE: no (ray, triangle)
-pair that passes the packed-fp16 pre-filter of ray_casting.py:34-59 may be dropped.  tools/shadow_proto.py re-states
+pair that passes the packed-fp16 pre-filter of ray_casting.py:34-59 may be dropped.  tests/shadow_proto.py re-states
 stages 1-2 (same formulas and constants, numpy fp32) and checks them against a brute-force fp16 evaluation."""
 import os
 import subprocess
@@ -15,7 +15,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     ["--envs", "3", "--length", "40", "--nv", "142", "--seed", "2", "--wild", "0.34"],
 ])
 def test_shadow_bounds_are_conservative(args):
-    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "shadow_proto.py")] + args, capture_output=True, text=True,
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "shadow_proto.py")] + args, capture_output=True, text=True,
                        timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "violations 0\n" in r.stdout and "'s1_viol': 0.0" in r.stdout and "'gball_viol': 0.0" in r.stdout, r.stdout[-2000:]
