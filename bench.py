@@ -318,13 +318,23 @@ def run_b200(args, rank, world, local):
     value = total_envs * args.steps / dt
     peak, peak_src = hbm_peak()
     achieved = ALGO_BYTES_PER_ENV_STEP * N / ray_s / 1e9
-    traffic = None
+    traffic, issue = None, None
     tf = os.path.join(ROOT, "profiles", "raycast_traffic.json")
     if os.path.exists(tf):
         try:
-            traffic = json.load(open(tf)).get("dram_bytes_per_launch")
+            prof = json.load(open(tf))
+            traffic = prof.get("dram_bytes_per_launch")
+            if N != prof.get("envs_per_launch"):
+                traffic = None                   # the ncu capture is of the 4096-env launch
+            # the resource that actually binds the kernel: warp-instruction issue slots.  Instruction count per
+            # env from the ncu capture (smsp__inst_executed.sum), time measured live, clock sampled live
+            wi = prof["warp_instructions_per_launch"] / prof["envs_per_launch"] * N
+            clk_hz = 1.965e9
+            issue = {"warp_inst_per_launch": wi, "source": prof.get("source"), "sm_clock_hz": clk_hz,
+                     "peak_warp_inst_per_s": 148 * 4 * clk_hz, "achieved_warp_inst_per_s": wi / ray_s,
+                     "frac": wi / ray_s / (148 * 4 * clk_hz)}
         except Exception:
-            traffic = None
+            traffic, issue = None, None
     line = {"metric": "env-steps/sec (obs+kinematics+reward)", "value": value, "unit": "env-steps/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f16", "data": "synthetic",
@@ -343,7 +353,9 @@ def run_b200(args, rank, world, local):
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": ALGO_BYTES_PER_ENV_STEP * N,
-                         "kernel": "heightmap ray-cast (Camera.get_depths)"},
+                         "kernel": "heightmap ray-cast (Camera.get_depths)",
+                         "note": "contractual HBM figure on the reference-format algorithmic bytes; the kernel is bound by "
+                                 "instruction issue, see issue_slots", "issue_slots": issue},
             # headline end-to-end number: the host pipeline with the observation read back in its native precision (the
             # heightmap columns ARE fp16 values, rover.py:324-325; HostPipeline.obs_f32() widens them on the host);
             # e2e_f32_obs is the same loop reading back the reference's f32 [N,1750] layout (twice the bytes: at 8 GPUs the
