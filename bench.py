@@ -329,7 +329,7 @@ def run_b200(args, rank, world, local):
             # the resource that actually binds the kernel: warp-instruction issue slots.  Instruction count per
             # env from the ncu capture (smsp__inst_executed.sum), time measured live, clock sampled live
             wi = prof["warp_instructions_per_launch"] / prof["envs_per_launch"] * N
-            clk_hz = 1.965e9
+            clk_hz = float(clk["sm_mhz"]) * 1e6 if (clk and clk.get("sm_mhz")) else 1.965e9      # median SM clock under load
             issue = {"warp_inst_per_launch": wi, "source": prof.get("source"), "sm_clock_hz": clk_hz,
                      "peak_warp_inst_per_s": 148 * 4 * clk_hz, "achieved_warp_inst_per_s": wi / ray_s,
                      "frac": wi / ray_s / (148 * 4 * clk_hz)}
