@@ -583,3 +583,46 @@ def test_c3_size_step_is_shard_invariant(R, world200):
     assert stats[0] == N and torch.equal(stats[[0, 3, 8, 9, 10, 11, 12, 13]], whole.stats[[0, 3, 8, 9, 10, 11, 12, 13]])      # counts: exact
     assert torch.allclose(stats, whole.stats, rtol=1e-12)                                                                 # f64 sums
     assert 0 < int(whole.rock_collison.sum()) < N and 0 < int(reset.sum()) < N
+
+
+@pytest.mark.parametrize("K,seed", [(200, 0), (96, 1), (255, 2)])
+def test_triangle_soup_all_variants_agree(R, K, seed):
+    """A mesh that is NOT a heightfield (the reference accepts any map.ply): random triangles in several overlapping layers,
+    vertical walls, zero-area and collinear triangles, 10 m sheets and millimetre slivers, some far outside the map.  The
+    production kernel's conservative culling must fall back to 'no bound' wherever its error model gives none: distances,
+    hit slots, hit triangles and intersection points stay bit-identical to the per-pair kernel that evaluates every
+    (ray, candidate) pair literally."""
+    g = torch.Generator().manual_seed(100 + seed)
+    L, G, T = 20.0, 200, 24000
+    c = torch.rand(T, 3, generator=g) * torch.tensor([L, L, 1.5])
+    size = torch.exp(torch.rand(T, 1, generator=g) * 6.0 - 5.0)                     # 7 mm .. 2.7 m
+    e1 = (torch.rand(T, 3, generator=g) - 0.5) * size
+    e2 = (torch.rand(T, 3, generator=g) - 0.5) * size
+    kind = torch.randint(0, 10, (T,), generator=g)
+    e1[kind == 0, 2] = 0.0; e2[kind == 0, 2] = 0.0                                  # horizontal sheets
+    e2[kind == 1] = e1[kind == 1] * 2.0                                             # collinear (zero area)
+    e2[kind == 2] = 0.0                                                             # repeated vertex
+    e1[kind == 3, :2] = 0.0                                                         # vertical edge -> wall
+    big = kind == 4
+    e1[big] *= 10.0; e2[big] *= 10.0                                                # sheets of many metres
+    c[kind == 5, :2] += 60.0                                                        # far outside the map
+    v = torch.stack((c, c + e1, c + e2), 1).reshape(-1, 3).to(torch.float16)
+    tri = torch.arange(3 * T, dtype=torch.int32).reshape(T, 3)
+    idx = R.build_knn_index(tri, v, G, 0.1, K, device="cuda:0")
+    cam = R.Camera("cuda:0", torch.tensor([0, 0, 0.0]), assets=(idx, tri, v))
+    N = 192
+    pos = torch.rand(N, 3, generator=g) * torch.tensor([L, L, 2.5]) + torch.tensor([0.0, 0.0, 0.2])
+    rp = (torch.rand(N, 2, generator=g) - 0.5) * 0.6
+    rp[::7] = (torch.rand(rp[::7].shape, generator=g) - 0.5) * 3.0                  # some steep / upside down
+    yaw = (torch.rand(N, generator=g) - 0.5) * 6.28
+    eul = torch.stack((rp[:, 0], rp[:, 1], yaw), 1)
+    out = {}
+    for variant in (1, 0, 3):
+        cam.variant = variant
+        d, pt, s = cam.get_depths(pos.cuda(), eul.cuda(), want_hits=True)
+        out[variant] = (d.clone(), pt.clone(), cam.last_hit_slot.clone(), cam.last_hit_tri.clone())
+    for variant in (0, 3):
+        for i, what in enumerate(("dist", "pt", "slot", "tri")):
+            assert_bits_equal(out[variant][i], out[1][i], "triangle soup K=%d %s variant %d vs 1" % (K, what, variant))
+    hit = (out[1][0] != 11).float().mean().item()
+    assert 0.05 < hit < 1.0, hit
