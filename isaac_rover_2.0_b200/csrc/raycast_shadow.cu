@@ -624,9 +624,12 @@ __global__ void __launch_bounds__(TT, RTC <= RT_SMALL ? 4 : 3) hm_shadow_kernel(
                 float gball = 0.0f;
                 if (id >= 0) keep = stage1(r0, r1, e, it.rlox, it.rhix, it.rloy, it.rhiy, gball);
                 const uint32_t m = __ballot_sync(FULLM, keep);
-                if (keep)
+                if (keep) {
                     q1[(t1 + __popc(m & lt_mask)) & (QCAP - 1)] =
                         make_uint2(ent, ((__float_as_uint(gball) + 0x7fu) & ~0x7fu) | (uint32_t)item);
+                    // stage 2 will want the triangle's record: start bringing it into L2 now
+                    if (q.spec_slot & 2) asm volatile("prefetch.global.L2 [%0];" ::"l"(q.recs + id));
+                }
                 t1 += __popc(m);
                 DBG(0, 1); DBG(1, __popc(m));
             } while (t1 - h1 < 32u);
@@ -799,6 +802,10 @@ __global__ void __launch_bounds__(TT, RTC <= RT_SMALL ? 4 : 3) hm_shadow_kernel(
                     const int bx = cx / RVB_BLK, by = cy / RVB_BLK;
                     const uint32_t pos16 = __ldg(q.sb_pos + (size_t)ent * (SB * SB) + (uint32_t)((bx % SB) * SB + (by % SB)));
                     const uint32_t o0 = __ldg(q.blk_off + (uint32_t)bx * (uint32_t)q.nBy + (uint32_t)by);
+                    // the slot is fetched before the literal test runs (four in five pairs need it): its latency hides behind the
+                    // arithmetic instead of following it
+                    uint32_t slot = 0xffu;
+                    if (q.spec_slot && pos16 != 0xffffu) slot = __ldg(reinterpret_cast<const unsigned char*>(q.blk_slots + o0 + pos16) + sub);
                     H3 a, b, c, nn;
                     unpack_rec(q.recs + tri, a, b, c, nn);
                     const __half k = pair_test(s, d16, a, b, c, nn);
@@ -807,7 +814,7 @@ __global__ void __launch_bounds__(TT, RTC <= RT_SMALL ? 4 : 3) hm_shadow_kernel(
                     if (DBGK && h_bits(k) != RVB_H_MISS) atomicAdd(q.dbg + 8, 1ull);
                     if (h_bits(k) != RVB_H_MISS && pos16 != 0xffffu && (ord > ORD_MISS || ord <= (sm.res[p] >> 16))) {
                         if (DBGK) atomicAdd(q.dbg + 9, 1ull);
-                        const uint32_t slot = __ldg(reinterpret_cast<const unsigned char*>(q.blk_slots + o0 + pos16) + sub);
+                        if (!q.spec_slot) slot = __ldg(reinterpret_cast<const unsigned char*>(q.blk_slots + o0 + pos16) + sub);
                         if (slot != 0xffu) {                // the triangle is in the ray's own cell list
                             const uint32_t key = key0 | (slot << 1);
                             if (ord > ORD_MISS) atomicOr(&sm.far[p >> 5], 1u << (p & 31));      // k > 11: see epilogue
@@ -868,7 +875,10 @@ int launch_heightmap_shadow(const rvb_terrain* t, const float* pos, const float*
     q.cos_steep = cos_steep;
     q.order = order;
     q.presorted = 1;
-    if (const char* ms = getenv("RVB_SHADOW_SH")) q.min_sh = atoi(ms);      // tuning hook: coarsest bins to start from
+    q.min_sh = 1;                                                            // 2x2-cell bins: 2 % faster than single cells (fewer tasks)
+    if (const char* ms = getenv("RVB_SHADOW_SH")) q.min_sh = atoi(ms);      // tuning hook: finest bins to start from
+    q.spec_slot = 3;
+    if (const char* sp = getenv("RVB_SHADOW_SPEC")) q.spec_slot = atoi(sp); // tuning hook
     struct Side {
         int dev = -1;
         cudaStream_t s = nullptr;
