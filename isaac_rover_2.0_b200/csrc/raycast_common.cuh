@@ -53,7 +53,7 @@ struct TiledParams {
     int presorted;            // steep envs are already on a work list: the shadow kernel just skips them
     int min_sh;               // bins are 2^sh x 2^sh cells, sh >= min_sh (0 = one cell; tuning hook)
     int spec_slot;            // stage 3b fetches the slot byte before the literal test (tuning hook)
-    unsigned long long* dbg;  // optional [16] work counters of the shadow kernel (RVB_SHADOW_DBG=1)
+    unsigned long long* dbg;  // optional [24] work counters / cycle counts of the shadow kernel (RVB_SHADOW_DBG=1)
 };
 
 // two candidates of one cell, component-wise packed: .x = candidate j, .y = candidate j+1

@@ -584,6 +584,8 @@ __global__ void __launch_bounds__(TT, RTC <= RT_SMALL ? 4 : 3) hm_shadow_kernel(
     // stage-3a state (per lane): task + bit i set = ray start + i lies in the box
     uint32_t a_ent = 0, a_start = 0, a_mask = 0;
 
+    long long c_start = 0, c_dry = 0;
+    if (DBGK) c_start = clock64();
     while (true) {
         const uint32_t n1 = t1 - h1, n2 = t2 - h2, n3 = t3 - h3, n4 = t4 - h4;
         int action;
@@ -607,6 +609,7 @@ __global__ void __launch_bounds__(TT, RTC <= RT_SMALL ? 4 : 3) hm_shadow_kernel(
             do {
                 if (itemA < 0) {
                     more = false;
+                    if (DBGK) c_dry = clock64();
                     break;
                 }
                 const int32_t id = idA;
@@ -829,6 +832,18 @@ __global__ void __launch_bounds__(TT, RTC <= RT_SMALL ? 4 : 3) hm_shadow_kernel(
         }
         }
     }
+    if (DBGK) {
+        // per warp: cycles until the chunk supply ran dry, cycles of the drain, cycles waited at the barrier below
+        const long long c_done = clock64();
+        __syncthreads();
+        const long long c_all = clock64();
+        if (lane == 0) {
+            atomicAdd(q.dbg + 16, (unsigned long long)(c_dry - c_start));
+            atomicAdd(q.dbg + 17, (unsigned long long)(c_done - c_dry));
+            atomicAdd(q.dbg + 18, (unsigned long long)(c_all - c_done));
+            atomicAdd(q.dbg + 19, 1ull);
+        }
+    }
     __syncthreads();
 
     // ---- phase 4
@@ -917,8 +932,8 @@ int launch_heightmap_shadow(const rvb_terrain* t, const float* pos, const float*
     }
     const bool dbg = getenv("RVB_SHADOW_DBG") != nullptr;
     if (dbg) {
-        cudaMalloc(&q.dbg, 16 * sizeof(unsigned long long));
-        cudaMemset(q.dbg, 0, 16 * sizeof(unsigned long long));
+        cudaMalloc(&q.dbg, 24 * sizeof(unsigned long long));
+        cudaMemset(q.dbg, 0, 24 * sizeof(unsigned long long));
     }
     // RVB_SHADOW_PAD (bytes, <= 48 KB): extra dynamic shared memory, to measure the kernel at a lower occupancy (tuning hook);
     // RVB_SHADOW_BIG: force the 2048-ray instantiation (3 CTAs per SM) where the 1664-ray one (4 CTAs per SM) would run
@@ -934,7 +949,7 @@ int launch_heightmap_shadow(const rvb_terrain* t, const float* pos, const float*
         else hm_shadow_kernel<false, RT_MAX><<<grid, TT, shadow_smem_bytes(RT_MAX) + pad, st>>>(q);
     }
     if (dbg) {
-        unsigned long long h[16];
+        unsigned long long h[24];
         int fb = 0;
         cudaStreamSynchronize(st);
         cudaMemcpy(h, q.dbg, sizeof(h), cudaMemcpyDeviceToHost);
@@ -947,6 +962,9 @@ int launch_heightmap_shadow(const rvb_terrain* t, const float* pos, const float*
                         "pre-filter batches %.1f (passed %.1f), 3b batches %.1f, literal hits %.1f, slot lookups %.1f, dispatches %.1f\n",
                 (long long)nblocks, fb, h[0] / ne, h[1] / ne, h[2] / ne, h[13] / ne, h[3] / ne, h[10] / ne, h[4] / ne, h[5] / ne, h[6] / ne,
                 h[11] / ne, h[14] / ne, h[15] / ne, h[7] / ne, h[8] / ne, h[9] / ne, h[12] / ne);
+        if (h[19])
+            fprintf(stderr, "[shadow dbg] phase 3 per warp (cycles): pulling chunks %.0f, draining the queues %.0f, waiting at the final barrier %.0f\n",
+                    (double)h[16] / h[19], (double)h[17] / h[19], (double)h[18] / h[19]);
     }
     rc_ = RVB_OK;
     if (cudaGetLastError() != cudaSuccess) rc_ = rvb_set_error(RVB_ERR_CUDA, "hm_shadow_kernel", "launch failed");
