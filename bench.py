@@ -348,6 +348,8 @@ def run_b200(args, rank, world, local):
                                       % (world, "compute stream" if args.sync_reduce else "asynchronous, NCCL stream"),
                        "raycast_variant": args.variant, "fused_step": not args.unfused, "index_build_s": round(t_index, 3)},
             "rays_per_s": value * P_RAYS,
+            # (ray, candidate) tests the reference evaluates for the same output: (1634 heightmap + 26 rock rays) x K per env-step
+            "reference_equivalent_pair_tests_per_s": value * (P_RAYS + 26) * w.K,
             "raycast_ms": ray_s * 1e3,
             "raycast_share_of_step": ray_s / (dt / args.steps),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
