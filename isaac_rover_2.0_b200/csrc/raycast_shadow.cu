@@ -5,15 +5,20 @@
 // that can pass `n >= -eps, m >= -eps, n + m <= 1 + eps` -- is a prism parallel to d, and the sources lie on a plane
 // (the pattern has constant z).  The kernel therefore enumerates TRIANGLES, not (ray, candidate) pairs:
 //
+//   classify   (hm_classify_kernel, one thread per env) steep envs go on the tiled kernel's work list, cast concurrently on a
+//              second stream; the others are ordered tilted-first (their CTAs are the slow ones);
 //   phase 1/2  (as raycast_tiled.cu) fp64 body transform -> fp16 sources, cell lookup, counting sort of the tile's rays
-//              by cell (shared memory, column-major bins, so a cell rectangle is a few contiguous ranges);
+//              into column-major bins of 2x2 cells (shared memory; a cell rectangle is a few contiguous ranges);
 //   stage 1    per (superblock, triangle of its list -- the union of the K-lists of 8x8 blocks): a bounding disc of the
-//              prism's cross-section on the source plane against the rectangle of the superblock's rays (~45 instr.);
-//   stage 2    survivors: exact corners of the cross-section -> xy box -> block columns -> ray ranges (tasks);
-//   stage 3a   rays of a task against the box (two packed-fp16 compares per ray);
-//   stage 3b   the (ray, triangle) pairs left (about 2.3 per hit): LITERAL evaluation of ray_casting.py:34-59 with its
-//              three IEEE divisions, membership + slot of the triangle in the ray's own cell list (binary search in the
-//              cell's 3x3 block list), atomicMin on (order-preserving fp16 bits, slot) = torch.min.
+//              prism's cross-section on the source plane against the rectangle of the superblock's rays, from the
+//              triangle's pre-computed 32-byte stage-1 record (centroid, radius, b x c; terrain.cu);
+//   stage 2    survivors: exact corners of the cross-section -> xy box -> bin columns -> ray ranges (tasks);
+//   stage 3a   rays of a task against the box (two packed-fp16 compares per ray), survivors expanded into pairs;
+//   pre-filter the packed-fp16 conservative test of raycast_common.cuh on the pairs, two per lane;
+//   stage 3b   the (ray, triangle) pairs left (about 1.0 per hit): LITERAL evaluation of ray_casting.py:34-59 with its
+//              three IEEE divisions, membership + slot of the triangle in the ray's own cell list (one look-up in the
+//              superblock entry -> block-list position table), atomicMin on (order-preserving fp16 bits, slot) = torch.min.
+// Two instantiations: <= 1664 rays per tile (64 registers, 55 KB shared memory, 4 CTAs per SM) and <= 2048 (3 CTAs per SM).
 //
 // Bit-exactness rests on stage 3b alone; stages 1-3a only have to be CONSERVATIVE (never drop a pair the literal test
 // would accept).  The bound: with g = s - a, the reference's numerators N = fl((g x c) . d), M = fl((b x g) . d) differ
@@ -25,9 +30,9 @@
 // literal test).  |g| is bounded self-consistently from the disc of stage 1.  Triangles for which no bound holds
 // (|det*| within rounding of 0, fp16 overflow possible, NaN) are tested against every ray of the superblock.
 // tests/shadow_proto.py re-states stages 1-2 in numpy and checks them against a brute-force fp16 evaluation;
-// tests/test_shadow_bound_cpu.py runs it.  Envs this kernel cannot group (rays spread over more than 8192 bins or
-// 64 superblocks) or whose rays are nearly parallel to the ground (cos < cos_steep: the prisms become long slivers)
-// are handed to the tiled kernel through a work list.
+// tests/test_shadow_bound_cpu.py runs it.  Tiles this kernel cannot group (rays spread over more than 6144 bins or
+// 64 superblocks, a list longer than the queue encoding, fp16 overflow) are handed to the tiled kernel through a second
+// work list.
 #include <stdlib.h>
 #include <string.h>
 
