@@ -58,3 +58,16 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 text = open(os.path.join(dirpath, f)).read()
                 assert "rover_oracle" not in text and "ref_import" not in text and "/root/reference" not in text, f
+
+
+def test_library_staleness_is_by_content_not_mtime(monkeypatch):
+    """The built library travels to the GPU box in a copy of the tree (mtimes are not preserved) and eight ranks import it at
+    once: staleness must be decided from a hash of the sources, never from timestamps."""
+    import isaac_rover_b200
+    from isaac_rover_b200 import _build
+    assert os.path.exists(_build.LIB) and os.path.exists(_build.HASH_FILE)
+    assert _build.needs_build() is False
+    os.utime(_build.LIB, (1, 1))                                   # an ancient library with matching sources is still current
+    assert _build.needs_build() is False
+    monkeypatch.setattr(_build, "NVCC_FLAGS", _build.NVCC_FLAGS + ["-DSOMETHING"])
+    assert _build.needs_build() is True                            # other flags (or sources) = another hash
