@@ -233,11 +233,21 @@ __global__ void __launch_bounds__(TT, RTC <= RT_SMALL ? 4 : 3) hm_shadow_kernel(
     __shared__ int s_next, s_nitems, s_nchunks, s_bail;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int64_t n = q.order ? (int64_t)__ldg(q.order + blockIdx.x / q.tiles) : (int64_t)(blockIdx.x / q.tiles);
-    const int tile = blockIdx.x % q.tiles;
+    // The envs at the end of the order are cut in two (rays [0, split_at) and [split_at, P), one CTA each): the grid's last wave
+    // then consists of CTAs of half the duration, which shortens the tail where SMs wait for the last CTAs (tiles == 1 only).
+    int64_t opos = blockIdx.x / q.tiles;
+    int tile = blockIdx.x % q.tiles, p0_ = tile * q.tile_size, np_ = min(q.tile_size, q.P - p0_);
+    if (q.split_from >= 0 && (int64_t)blockIdx.x >= q.split_from) {
+        const int64_t k = (int64_t)blockIdx.x - q.split_from;
+        opos = q.split_from + (k >> 1);
+        tile = 0;
+        p0_ = (k & 1) ? q.split_at : 0;
+        np_ = (k & 1) ? q.P - q.split_at : q.split_at;
+    }
+    const int64_t n = q.order ? (int64_t)__ldg(q.order + opos) : opos;
     const int32_t work_id = (int32_t)(n * q.tiles + tile);
-    const int p0 = tile * q.tile_size;
-    const int np = min(q.tile_size, q.P - p0);
+    const int p0 = p0_;
+    const int np = np_;
     const int RT = q.tile_size;
 
     Smem sm;
@@ -882,7 +892,19 @@ int launch_heightmap_shadow(const rvb_terrain* t, const float* pos, const float*
                                 col_b, q);
     if (rc_ != RVB_OK) return rc_;
     RVB_REQUIRE(q.tile_size <= 2048, "heightmap ray-cast (shadow): tile larger than 2048 rays");
-    const int64_t nblocks = N * q.tiles;
+    int64_t nblocks = N * q.tiles;
+    // RVB_SHADOW_SPLIT = number of envs (at the end of the order) cast by two CTAs of half the rays each; default below
+    q.split_from = -1;
+    {
+        int64_t nsplit = N >= 8 * 148 ? 3 * 148 : 0;            // measured at 4096 envs: -2 % (444), -1.2 % (592), -1 % (296)
+        if (const char* ev = getenv("RVB_SHADOW_SPLIT")) nsplit = atoll(ev);
+        if (q.tiles == 1 && q.P >= 64 && nsplit > 0) {
+            if (nsplit > N) nsplit = N;
+            q.split_from = N - nsplit;
+            q.split_at = q.P / 2;
+            nblocks = N + nsplit;
+        }
+    }
     // scratch: [0] steep count, [1] tilted envs placed, [2] other envs placed, [3] handed-back count, then the steep list
     // [nblocks], the hand-back list [nblocks] and the env order [N]
     int* scratch = nullptr;

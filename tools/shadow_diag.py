@@ -63,6 +63,13 @@ for big in ("1", None):
     d, _, _ = cam.get_depths(st["pos"], eul, want_pt=False)
     print("shadow %s instantiation: median %.3f ms, min %.3f ms, equal to variant 3: %s" % ("2048-ray (3 CTAs/SM)" if big else "1664-ray (4 CTAs/SM)", med, mn,
                                                                         bool(torch.equal(d.view(torch.int16), out[3][0].view(torch.int16)))))
+for ns in ("0", "444", "0", "444"):
+    _os.environ["RVB_SHADOW_SPLIT"] = ns
+    cam.variant = 0
+    med, mn = timed(lambda: cam.get_depths(st["pos"], eul, want_pt=False), reps=30)
+    d, _, _ = cam.get_depths(st["pos"], eul, want_pt=False)
+    print("split envs %s: median %.3f ms, min %.3f, equal to variant 3: %s" % (ns, med, mn, bool(torch.equal(d.view(torch.int16), out[3][0].view(torch.int16)))))
+_os.environ.pop("RVB_SHADOW_SPLIT")
 for sp in ("0", "3"):
     _os.environ["RVB_SHADOW_SPEC"] = sp
     cam.variant = 0
