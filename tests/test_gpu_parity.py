@@ -626,3 +626,33 @@ def test_triangle_soup_all_variants_agree(R, K, seed):
             assert_bits_equal(out[variant][i], out[1][i], "triangle soup K=%d %s variant %d vs 1" % (K, what, variant))
     hit = (out[1][0] != 11).float().mean().item()
     assert 0.05 < hit < 1.0, hit
+
+
+def test_drop_in_constructors_load_reference_asset_files(R, world20, tmp_path, monkeypatch):
+    """Camera(device, shift) / Rock_Detection(device, shift) without `assets` load tasks/utils/terrain/{knn_terrain,knn_rocks}/
+    {map_indices,triangles,vertices}.pt relative to the CWD exactly like the reference (camera.py:154-161,
+    rock_detect.py:151-158), and read_stone_info reads the reference's .npy (terrain_utils.py:416-424): results equal the
+    in-memory construction."""
+    import numpy as np
+    w = world20
+    for sub, idx, tri, ver in (("knn_terrain", w.map_indices, w.triangles, w.vertices),
+                               ("knn_rocks", w.rock_indices, w.rock_triangles, w.rock_vertices)):
+        d = tmp_path / "tasks" / "utils" / "terrain" / sub
+        d.mkdir(parents=True)
+        torch.save(idx, d / "map_indices.pt"); torch.save(tri, d / "triangles.pt"); torch.save(ver, d / "vertices.pt")
+    np.save(tmp_path / "stone_info.npy", w.stone_info.numpy())
+    monkeypatch.chdir(tmp_path)
+    shift = torch.tensor([0, 0, 0.0])
+    cam_files, cam_mem = R.Camera("cuda:0", shift), R.Camera("cuda:0", shift, assets=(w.map_indices, w.triangles, w.vertices))
+    rock_files = R.Rock_Detection("cuda:0", shift)
+    rock_mem = R.Rock_Detection("cuda:0", shift, assets=(w.rock_indices, w.rock_triangles, w.rock_vertices))
+    st = {k: v.cuda() for k, v in R.synth.make_env_state(w, 32, seed=3).items()}
+    eul = R.tensor_quat_to_eul(st["quat"])
+    for a, b in zip(cam_files.get_depths(st["pos"], eul), cam_mem.get_depths(st["pos"], eul)):
+        assert_bits_equal(a, b, "Camera from files vs from memory")
+    assert cam_files.get_num_exteroceptive() == 1634 and cam_files.map_indices.shape == (w.G, w.G, w.K)
+    for a, b in zip(rock_files.get_collisions(st["pos"], eul, st["joints"]), rock_mem.get_collisions(st["pos"], eul, st["joints"])):
+        assert_bits_equal(a, b, "Rock_Detection from files vs from memory")
+    s7 = R.read_stone_info(str(tmp_path / "stone_info.npy"))
+    assert s7.shape == (w.stone_info.shape[0], 7) and s7.is_cuda
+    assert torch.equal(s7[:, 6].cpu(), (torch.maximum(w.stone_info[:, 3], w.stone_info[:, 4]) / 4).float())
