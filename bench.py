@@ -184,6 +184,58 @@ def time_gpu_eager_oracle(n_envs, dev, steps=3, warmup=1):
     return (time.perf_counter() - t0) / steps
 
 
+def time_policy_epilogue(R, obs, steps=20, warmup=3):
+    """SURVEY.md 8f-3, reported beside the step (not part of `value`): actor + critic inference on the step's obs_buf through
+    rvb_policy_forward, and the same two networks as eager torch fp32 (cuBLAS) on this GPU for comparison."""
+    import torch.nn.functional as F
+    N = obs.shape[0]
+    net = R.model.NetworkInfo([256, 160, 128], [80, 60], [80, 60], [80, 60], "leakyrelu")
+    info = R.model.ObserverationInfo(4, 634, 1112, 0)
+    actor = R.model.StochasticActorHeightmap(1750, 2, net, info, device=obs.device)
+    critic = R.model.DeterministicHeightmap(1750, 2, net, info, device=obs.device)
+    out_a = torch.empty((N, 2), dtype=torch.float32, device=obs.device)
+    out_c = torch.empty((N, 1), dtype=torch.float32, device=obs.device)
+
+    def ours():
+        actor._forward(obs, out_a)
+        critic._forward(obs, out_c)
+
+    def eager_net(sd, tanh):
+        sd = {k: v.to(obs.device) for k, v in sd.items()}
+
+        def chain(x, prefix, n):
+            for i in range(n):
+                x = F.leaky_relu(F.linear(x, sd["%s.%d.layer.0.weight" % (prefix, i)], sd["%s.%d.layer.0.bias" % (prefix, i)]))
+            return x
+
+        def fwd():
+            x = torch.cat((obs[:, 0:4], chain(obs[:, 4:638], "encoder0.encoder", 2), chain(obs[:, 638:1750], "encoder1.encoder", 2)), dim=1)
+            x = F.linear(chain(x, "network", 3), sd["network.3.weight"], sd["network.3.bias"])
+            return torch.tanh(x) if tanh else x
+        return fwd
+    ea, ec = eager_net(actor.state_dict(), True), eager_net(critic.state_dict(), False)
+
+    def timed(fn):
+        for _ in range(warmup):
+            fn()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / steps
+    ms = timed(ours)
+    ms_eager = timed(lambda: (ea(), ec()))
+    err = max((out_a - ea()).abs().max().item(), (out_c - ec()).abs().max().item())
+    flops = 2 * 2 * N * (634 * 80 + 1112 * 80 + 2 * 80 * 60 + 124 * 256 + 256 * 160 + 160 * 128 + 128 * 2)
+    return {"ms": ms, "envs_per_s": N / ms * 1e3, "fp32_tflops": flops / ms / 1e9, "torch_eager_fp32_ms": ms_eager,
+            "max_abs_diff_vs_torch": err, "launches": 2,
+            "what": "actor + critic (encoders [80,60] x2, mlp [256,160,128], model.py:152-241) on the step's obs_buf f32 [%d,1750]; "
+                    "one fused fp32 kernel per network; not included in `value`" % N}
+
+
 def run_reference(args, rank):
     if rank != 0:
         return
@@ -387,6 +439,11 @@ def run_b200(args, rank, world, local):
                                                           "step, fp16 temporaries in HBM)" % ng}
         except Exception as e:          # a baseline, never a reason to lose the bench line
             line["torch_eager_gpu_baseline"] = {"unavailable": str(e)[:200]}
+    if world == 1:
+        try:
+            line["policy_epilogue"] = time_policy_epilogue(R, task.obs_buf)
+        except Exception as e:          # reported beside the step, never a reason to lose the bench line
+            line["policy_epilogue"] = {"unavailable": str(e)[:200]}
     emit(line)
 
 

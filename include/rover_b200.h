@@ -247,6 +247,39 @@ int rvb_build_knn_index(const int32_t* triangles, int64_t T, const uint16_t* ver
                         const uint16_t* cell_x, const uint16_t* cell_y, int64_t G0, int64_t G1, int64_t K,
                         int32_t* out, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Policy-inference epilogue: the consumer of obs_buf.  Replaces
+ * StochasticActorHeightmap.compute and DeterministicHeightmap.compute (../learning/model.py:152-195,197-241):
+ *   x0 = encoder0(obs[:, p:p+S]); x1 = encoder1(obs[:, p+S:p+S+D]); x = cat(obs[:, 0:p], x0, x1)   (model.py:183-189)
+ *   x = mlp(x); out = head(x) [tanh for the actor, model.py:176]                                   (model.py:190-191)
+ * every hidden layer being Linear + activation (model.py:86-116).  The layer widths are the ones the reference
+ * hard-wires (../train.py:95, ../cfg/trainSKRL/RoverPPOSKRL.yaml:4-9): encoders [80,60], mlp [256,160,128]; other widths
+ * return RVB_ERR_UNSUPPORTED.  p <= 8, S and D are free (the C5 patterns change them), head width 1..4.
+ * rvb_linear = one torch nn.Linear: weight f32 [out_features, in_features] row-major, bias f32 [out_features], both
+ * borrowed DEVICE pointers that may be released when rvb_policy_create returns (it re-packs them into k-major panels
+ * owned by the handle and synchronises `stream`).  enc_sparse / enc_dense point at 2 layers, mlp at 3, head at 1.
+ * fp32 FMA arithmetic like the reference's (TF32 off); accumulation order differs from cuBLAS, parity gate 2e-5 absolute.
+ * rvb_policy_forward: obs f32 [N, obs_ld] (obs_ld >= p+S+D) -> out f32 [N, out_ld] columns 0..head-1; one kernel, reads obs
+ * once, asynchronous on `stream`; the handle is immutable => usable from any stream.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct rvb_policy rvb_policy;
+typedef struct rvb_linear {
+    const float* weight;
+    const float* bias;
+    int32_t in_features, out_features;
+} rvb_linear;
+typedef enum rvb_activation {   /* the keys of Layer.activation_functions, model.py:104-111 */
+    RVB_ACT_LEAKYRELU = 0, RVB_ACT_RELU = 1, RVB_ACT_ELU = 2, RVB_ACT_TANH = 3, RVB_ACT_SIGMOID = 4, RVB_ACT_RELU6 = 5
+} rvb_activation;
+
+int rvb_policy_create(rvb_policy** out, int32_t n_proprio, int32_t n_sparse, int32_t n_dense,
+                      const rvb_linear* enc_sparse, const rvb_linear* enc_dense, const rvb_linear* mlp,
+                      const rvb_linear* head, int32_t activation, int32_t head_tanh, int device, void* stream);
+int rvb_policy_destroy(rvb_policy* policy);
+int64_t rvb_policy_bytes(const rvb_policy* policy);
+int rvb_policy_forward(const rvb_policy* policy, const float* obs, int64_t obs_ld, int64_t N, float* out, int64_t out_ld,
+                       void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -28,6 +28,14 @@ class RewardParams(C.Structure):
                 ("sem", i32), ("reserved", i32)]
 
 
+class Linear(C.Structure):
+    """rvb_linear (include/rover_b200.h): one torch nn.Linear, borrowed device pointers."""
+    _fields_ = [("weight", p), ("bias", p), ("in_features", i32), ("out_features", i32)]
+
+
+ACTIVATIONS = {"leakyrelu": 0, "relu": 1, "elu": 2, "tanh": 3, "sigmoid": 4, "relu6": 5}   # rvb_activation
+
+
 class StepIO(C.Structure):
     """rvb_step_io (include/rover_b200.h)."""
     _fields_ = [(n, p) for n in ("pos", "quat", "joints", "actions", "target", "lin_hist", "ang_hist", "progress", "euler", "heading",
@@ -64,6 +72,11 @@ _SIGNATURES = {
     "rvb_build_knn_index": (C.c_int, [p, i64, p, i64, p, p, i64, i64, i64, p, p]),
     "rvb_reset_targets": (C.c_int, [p, i64, i64, C.c_uint64, C.c_uint64, p, f32, p, i64, f32, i32, p, i64, i64, f32, f32, f32, f32,
                                     p, p, p, p, C.c_int, p]),
+    "rvb_policy_create": (C.c_int, [C.POINTER(p), i32, i32, i32, C.POINTER(Linear), C.POINTER(Linear), C.POINTER(Linear),
+                                    C.POINTER(Linear), i32, i32, C.c_int, p]),
+    "rvb_policy_destroy": (C.c_int, [p]),
+    "rvb_policy_bytes": (i64, [p]),
+    "rvb_policy_forward": (C.c_int, [p, p, i64, i64, p, i64, p]),
 }
 
 EXPORTS = tuple(_SIGNATURES)
@@ -77,7 +90,8 @@ def lib_path():
 KERNELS_PER_CALL = {"rvb_terrain_create": 2, "rvb_heightmap_raycast": 4, "rvb_cast_rays": 2, "rvb_ray_distance": 1,
                     "rvb_rock_collision": 1, "rvb_check_collision": 1, "rvb_quat_to_euler": 1, "rvb_ackermann": 1,
                     "rvb_history_push": 1, "rvb_obs_proprio": 1, "rvb_obs_gather": 1, "rvb_reward_reset": 2, "rvb_env_step": 8,
-    "rvb_stone_validate": 1, "rvb_spawn_validate": 1, "rvb_height_lookup": 1, "rvb_build_knn_index": 6, "rvb_reset_targets": 1}
+    "rvb_stone_validate": 1, "rvb_spawn_validate": 1, "rvb_height_lookup": 1, "rvb_build_knn_index": 6, "rvb_reset_targets": 1,
+                    "rvb_policy_create": 7, "rvb_policy_forward": 1}
 launch_count = 0
 
 
