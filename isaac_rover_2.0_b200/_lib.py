@@ -77,6 +77,7 @@ _SIGNATURES = {
     "rvb_policy_destroy": (C.c_int, [p]),
     "rvb_policy_bytes": (i64, [p]),
     "rvb_policy_forward": (C.c_int, [p, p, i64, i64, p, i64, p]),
+    "rvb_policy_forward_pair": (C.c_int, [p, p, p, i64, i64, p, i64, p, i64, p]),
 }
 
 EXPORTS = tuple(_SIGNATURES)
@@ -91,7 +92,7 @@ KERNELS_PER_CALL = {"rvb_terrain_create": 2, "rvb_heightmap_raycast": 4, "rvb_ca
                     "rvb_rock_collision": 1, "rvb_check_collision": 1, "rvb_quat_to_euler": 1, "rvb_ackermann": 1,
                     "rvb_history_push": 1, "rvb_obs_proprio": 1, "rvb_obs_gather": 1, "rvb_reward_reset": 2, "rvb_env_step": 8,
     "rvb_stone_validate": 1, "rvb_spawn_validate": 1, "rvb_height_lookup": 1, "rvb_build_knn_index": 6, "rvb_reset_targets": 1,
-                    "rvb_policy_create": 7, "rvb_policy_forward": 1}
+                    "rvb_policy_create": 7, "rvb_policy_forward": 1, "rvb_policy_forward_pair": 1}
 launch_count = 0
 
 

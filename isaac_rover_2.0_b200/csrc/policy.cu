@@ -42,15 +42,24 @@ struct PackedLinear {
     int in, out, outp;
 };
 
-struct rvb_policy {
+// What the kernel reads: a copy lives at the start of the handle's device allocation, so one launch can serve two
+// networks (blockIdx.y) without indexing kernel parameters dynamically.
+struct PolicyDev {
     PackedLinear es1, es2, ed1, ed2, m1, m2, m3;
     float* head_w;   // [A][PL_M3]  torch layout
     float* head_b;   // [A]
     int n_proprio, n_sparse, n_dense, n_head;
-    int act, head_tanh, device;
-    float* storage;  // the one allocation everything above points into
-    int64_t storage_floats;
+    int act, head_tanh;
 };
+
+struct rvb_policy : PolicyDev {
+    int device;
+    float* storage;        // the one allocation everything points into: [PolicyDev | panels | head]
+    int64_t storage_floats;
+    const PolicyDev* dev;  // = storage
+};
+#define PL_DESC_FLOATS 128   // room reserved for the descriptor (keeps the panels 512-byte aligned)
+static_assert(sizeof(PolicyDev) <= PL_DESC_FLOATS * sizeof(float), "descriptor does not fit its slot");
 
 __device__ __forceinline__ float pl_act(float v, int kind) {
     switch (kind) {
@@ -91,24 +100,41 @@ __device__ __forceinline__ void pl_dense(const float* __restrict__ act_in, const
 #pragma unroll
         for (int j = 0; j < CN; ++j) acc[i][j] = 0.f;
 
-    for (int k0 = 0; k0 < K; k0 += KC) {
+    // Software pipeline: chunk i+1 travels global -> registers while chunk i is multiplied out of shared memory.
+    constexpr int WV = (KC * (OUTP / 4) + PL_THREADS - 1) / PL_THREADS;
+    float4 wreg[WV];
+    float xreg[PL_TM / 8];
+    auto fetch = [&](int k0) {
         const int kc = min(KC, K - k0);
-        __syncthreads();                                   // previous chunk fully consumed (and act_in fully written)
-        {   // weight panel rows k0 .. k0+kc: contiguous, 16-byte aligned
-            const float4* src = reinterpret_cast<const float4*>(L.wt + (int64_t)k0 * OUTP);
-            float4* dst = reinterpret_cast<float4*>(ws);
-            for (int i = tid; i < kc * (OUTP / 4); i += PL_THREADS) dst[i] = __ldg(src + i);
+        const float4* src = reinterpret_cast<const float4*>(L.wt + (int64_t)k0 * OUTP);   // contiguous rows, 16-byte aligned
+#pragma unroll
+        for (int v = 0; v < WV; ++v) {
+            const int i = tid + v * PL_THREADS;
+            wreg[v] = i < kc * (OUTP / 4) ? __ldg(src + i) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
-        if (GLOBAL_IN) {                                   // obs chunk, transposed: a warp reads 32 consecutive floats of one env
+        if (GLOBAL_IN) {                                   // a warp reads 32 consecutive floats of one env's row
 #pragma unroll
             for (int r = 0; r < PL_TM / 8; ++r) {
                 const int m = mg + 8 * r;
-                float v = 0.f;
-                if (ng < kc && m0 + m < N) v = __ldg(obs + (m0 + m) * obs_ld + col0 + k0 + ng);
-                xs[ng * PL_LDA + m] = v;
+                xreg[r] = (ng < kc && m0 + m < N) ? __ldg(obs + (m0 + m) * obs_ld + col0 + k0 + ng) : 0.f;
             }
         }
+    };
+    fetch(0);
+    for (int k0 = 0; k0 < K; k0 += KC) {
+        const int kc = min(KC, K - k0);
+        __syncthreads();                                   // previous chunk fully consumed (and act_in fully written)
+#pragma unroll
+        for (int v = 0; v < WV; ++v) {
+            const int i = tid + v * PL_THREADS;
+            if (i < kc * (OUTP / 4)) reinterpret_cast<float4*>(ws)[i] = wreg[v];
+        }
+        if (GLOBAL_IN) {                                   // transposed: xs[k][env]
+#pragma unroll
+            for (int r = 0; r < PL_TM / 8; ++r) xs[ng * PL_LDA + mg + 8 * r] = xreg[r];
+        }
         __syncthreads();
+        if (k0 + KC < K) fetch(k0 + KC);
         const float* a_base = GLOBAL_IN ? xs : act_in + (int64_t)k0 * PL_LDA;
 #pragma unroll 4
         for (int kk = 0; kk < kc; ++kk) {
@@ -150,8 +176,13 @@ __device__ __forceinline__ void pl_dense(const float* __restrict__ act_in, const
 #define PL_SMEM_BYTES (PL_SM_FLOATS * 4)
 
 __global__ void __launch_bounds__(PL_THREADS, 2)
-policy_forward_kernel(const rvb_policy P, const float* __restrict__ obs, int64_t obs_ld, int64_t N, float* __restrict__ out,
-                      int64_t out_ld) {
+policy_forward_kernel(const PolicyDev* __restrict__ p0, const PolicyDev* __restrict__ p1, const float* __restrict__ obs,
+                      int64_t obs_ld, int64_t N, float* __restrict__ out0, int64_t out0_ld, float* __restrict__ out1,
+                      int64_t out1_ld) {
+    // blockIdx.y selects the network (actor / critic of one PPO step read the same obs tile, hot in L2)
+    const PolicyDev& P = *(blockIdx.y ? p1 : p0);
+    float* __restrict__ out = blockIdx.y ? out1 : out0;
+    const int64_t out_ld = blockIdx.y ? out1_ld : out0_ld;
     extern __shared__ __align__(16) float sm[];
     float* A = sm + PL_SM_A;
     float* B = sm + PL_SM_B;
@@ -231,12 +262,13 @@ extern "C" int rvb_policy_create(rvb_policy** out, int32_t n_proprio, int32_t n_
         s.dst->in = s.src->in_features; s.dst->out = s.src->out_features; s.dst->outp = pad32(s.src->out_features);
         total += (int64_t)s.dst->in * s.dst->outp + s.dst->outp;
     }
-    total += (int64_t)P->n_head * PL_M3 + 32;
+    total += (int64_t)P->n_head * PL_M3 + 32 + PL_DESC_FLOATS;
     cudaError_t e = cudaMalloc((void**)&P->storage, sizeof(float) * total);
     if (e != cudaSuccess) { delete P; return rvb_set_error(RVB_ERR_NOMEM, "rvb_policy_create: cudaMalloc", cudaGetErrorString(e)); }
     P->storage_floats = total;
     cudaStream_t st = as_stream(stream);
-    float* cur = P->storage;
+    P->dev = reinterpret_cast<const PolicyDev*>(P->storage);
+    float* cur = P->storage + PL_DESC_FLOATS;
     for (auto& s : slots) {
         PackedLinear& L = *s.dst;
         L.wt = cur; cur += (int64_t)L.in * L.outp;       // every panel size is a multiple of 32 floats: 16-byte alignment holds
@@ -248,6 +280,8 @@ extern "C" int rvb_policy_create(rvb_policy** out, int32_t n_proprio, int32_t n_
     P->head_b = cur;
     e = cudaMemcpyAsync(P->head_w, head->weight, sizeof(float) * P->n_head * PL_M3, cudaMemcpyDeviceToDevice, st);
     if (e == cudaSuccess) e = cudaMemcpyAsync(P->head_b, head->bias, sizeof(float) * P->n_head, cudaMemcpyDeviceToDevice, st);
+    if (e == cudaSuccess)       // the descriptor the kernel reads (P outlives the copy: the stream is synchronised below)
+        e = cudaMemcpyAsync(P->storage, static_cast<const PolicyDev*>(P), sizeof(PolicyDev), cudaMemcpyHostToDevice, st);
     if (e == cudaSuccess) e = cudaGetLastError();
     if (e == cudaSuccess) e = cudaFuncSetAttribute(policy_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PL_SMEM_BYTES);
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);   // the caller may free its weight tensors on return
@@ -269,15 +303,37 @@ extern "C" int rvb_policy_destroy(rvb_policy* P) {
 
 extern "C" int64_t rvb_policy_bytes(const rvb_policy* P) { return P ? P->storage_floats * (int64_t)sizeof(float) : 0; }
 
+static int check_forward(const rvb_policy* P, const float* obs, int64_t obs_ld, const float* out, int64_t out_ld) {
+    RVB_REQUIRE(obs && out, "rvb_policy_forward: null pointer");
+    RVB_REQUIRE(obs_ld >= (int64_t)P->n_proprio + P->n_sparse + P->n_dense, "rvb_policy_forward: obs rows are shorter than the network's input");
+    RVB_REQUIRE(out_ld >= P->n_head, "rvb_policy_forward: out rows are shorter than the head");
+    return RVB_OK;
+}
+
 extern "C" int rvb_policy_forward(const rvb_policy* P, const float* obs, int64_t obs_ld, int64_t N, float* out, int64_t out_ld,
                                   void* stream) {
     RVB_REQUIRE(P, "rvb_policy_forward: null handle");
     if (N <= 0) return RVB_OK;
-    RVB_REQUIRE(obs && out, "rvb_policy_forward: null pointer");
-    RVB_REQUIRE(obs_ld >= (int64_t)P->n_proprio + P->n_sparse + P->n_dense, "rvb_policy_forward: obs rows are shorter than the network's input");
-    RVB_REQUIRE(out_ld >= P->n_head, "rvb_policy_forward: out rows are shorter than the head");
+    int rc;
+    if ((rc = check_forward(P, obs, obs_ld, out, out_ld))) return rc;
     RVB_REQUIRE(N <= (int64_t)PL_TM * 0x7fffffff, "rvb_policy_forward: too many envs");
-    policy_forward_kernel<<<(unsigned)ceil_div(N, PL_TM), PL_THREADS, PL_SMEM_BYTES, as_stream(stream)>>>(*P, obs, obs_ld, N, out, out_ld);
+    policy_forward_kernel<<<dim3((unsigned)ceil_div(N, PL_TM), 1), PL_THREADS, PL_SMEM_BYTES, as_stream(stream)>>>(
+        P->dev, nullptr, obs, obs_ld, N, out, out_ld, nullptr, 0);
+    RVB_LAUNCH_CHECK();
+    return RVB_OK;
+}
+
+extern "C" int rvb_policy_forward_pair(const rvb_policy* A, const rvb_policy* B, const float* obs, int64_t obs_ld, int64_t N,
+                                       float* out_a, int64_t out_a_ld, float* out_b, int64_t out_b_ld, void* stream) {
+    RVB_REQUIRE(A && B, "rvb_policy_forward_pair: null handle");
+    if (N <= 0) return RVB_OK;
+    int rc;
+    if ((rc = check_forward(A, obs, obs_ld, out_a, out_a_ld))) return rc;
+    if ((rc = check_forward(B, obs, obs_ld, out_b, out_b_ld))) return rc;
+    RVB_REQUIRE(A->device == B->device, "rvb_policy_forward_pair: the two networks live on different devices");
+    RVB_REQUIRE(N <= (int64_t)PL_TM * 0x7fffffff, "rvb_policy_forward: too many envs");
+    policy_forward_kernel<<<dim3((unsigned)ceil_div(N, PL_TM), 2), PL_THREADS, PL_SMEM_BYTES, as_stream(stream)>>>(
+        A->dev, B->dev, obs, obs_ld, N, out_a, out_a_ld, out_b, out_b_ld);
     RVB_LAUNCH_CHECK();
     return RVB_OK;
 }

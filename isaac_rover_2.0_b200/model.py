@@ -193,6 +193,26 @@ class _HeightmapNet:
         return out
 
 
+def compute_pair(policy, value, states, out_policy=None, out_value=None):
+    """`policy.compute(states)[0]` and `value.compute(states)` in ONE launch (rvb_policy_forward_pair): the two calls a PPO
+    step makes on the same states (skrl's agent.act + value.act on the reference's models_ppo, train.py:98-99)."""
+    _lib.require_cuda(states)
+    for net in (policy, value):
+        if states.dim() != 2 or states.dtype != torch.float32 or states.shape[1] < net.num_observations:
+            raise RuntimeError("states must be float32 [N, >=%d]" % net.num_observations)
+    if states.stride(1) != 1:
+        states = states.contiguous()
+    N = states.shape[0]
+    if out_policy is None:
+        out_policy = torch.empty((N, policy._head_out), dtype=torch.float32, device=states.device)
+    if out_value is None:
+        out_value = torch.empty((N, value._head_out), dtype=torch.float32, device=states.device)
+    _lib.check(policy._lib.rvb_policy_forward_pair(policy._handle, value._handle, _lib.ptr(states), states.stride(0), N,
+                                                   _lib.ptr(out_policy), out_policy.stride(0), _lib.ptr(out_value),
+                                                   out_value.stride(0), _lib.stream_of(states)))
+    return out_policy, out_value
+
+
 class StochasticActorHeightmap(_HeightmapNet):
     """model.py:152-195: `compute()` returns (tanh(mean actions) f32[N, A], log_std_parameter f32[A])."""
 

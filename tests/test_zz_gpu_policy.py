@@ -115,6 +115,19 @@ def test_consumes_the_step_observation(R, PO):
     assert (value.cpu().double() - value64).abs().max().item() < TOL * max(1.0, value64.abs().max().item())
 
 
+def test_pair_launch_equals_single_launches(R):
+    """rvb_policy_forward_pair (actor + critic in one grid) returns the very bits of the two single launches."""
+    torch.manual_seed(21)
+    actor, critic = _models(R)
+    for N in (1, 33, 4096):
+        obs = torch.rand(N, 1750, device="cuda")
+        mean, value = R.model.compute_pair(actor, critic, obs)
+        assert torch.equal(mean, actor.compute(obs)[0]) and torch.equal(value, critic.compute(obs))
+        assert mean.shape == (N, 2) and value.shape == (N, 1)
+    with pytest.raises(RuntimeError):
+        R.model.compute_pair(actor, critic, torch.zeros(3, 1750))
+
+
 def test_argument_validation(R):
     actor, _ = _models(R)
     with pytest.raises(RuntimeError):
@@ -144,3 +157,16 @@ def test_throughput_note(R):
     ms = e0.elapsed_time(e1) / 20
     print("\npolicy_forward 4096 envs: %.4f ms/launch (%.1f M envs/s)" % (ms, 4096 / ms / 1e3))
     assert ms > 0
+    big = torch.rand(65536, 1750, device="cuda")
+    _, critic = _models(R)
+    for _ in range(2):
+        R.model.compute_pair(actor, critic, big)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(5):
+        R.model.compute_pair(actor, critic, big)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 5
+    print("policy_forward_pair 65536 envs: %.4f ms/launch (%.1f M envs/s, %.1f fp32 TFLOP/s)" % (
+        ms, 65536 / ms / 1e3, 2 * 2 * 65536 * 243.3e3 / ms / 1e9))
