@@ -284,6 +284,25 @@ int rvb_policy_forward(const rvb_policy* policy, const float* obs, int64_t obs_l
 int rvb_policy_forward_pair(const rvb_policy* a, const rvb_policy* b, const float* obs, int64_t obs_ld, int64_t N,
                             float* out_a, int64_t out_a_ld, float* out_b, int64_t out_b_ld, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Observation hooks and the teacher-data recorder.
+ * rvb_obs_hooks: the four in-place epilogues of RoverTask.get_observations the reference keeps commented out
+ * (rover.py:326-329), applied in the reference's order on obs f32 [N, obs_ld] columns [0, C):
+ *   columns >= col0:  v += noise_std * z           (rover.py:326, sqrt(0.20) * randn; 0 = off)
+ *   columns >= col0:  v  = dropped ? 0 : v / (1 - dropout_p)      (rover.py:327, F.dropout p=0.1; 0 = off)
+ *   every column:     v -= offset                  (rover.py:328, 0.02)
+ *   zero_mask[c]!=0:  v  = 0                       (rover.py:329, remove_idx + 4 as a u8 [C] column mask; NULL = off)
+ * Draws: Philox4x32-10, counter = (global env id lo, hi, column, epoch lo), key = (seed lo, seed hi ^ epoch hi);
+ * normal by Box-Muller from x0, x1, dropout from x2 -- a function of (seed, epoch, env_offset + n, column) only, so shards
+ * reproduce the unsharded run (torch's own generator stream is not reproduced).
+ * rvb_teacher_record: one row of the teacher data set per env (rover.py:299-300,364,374-375):
+ *   record[n] = [reset_info[n], actions[n,0], actions[n,1], obs[n, 0..C)],  record f32 [N, record_ld >= C+3].
+ * ---------------------------------------------------------------------------------------------- */
+int rvb_obs_hooks(float* obs, int64_t obs_ld, int64_t N, int64_t C, int64_t col0, float noise_std, float dropout_p,
+                  float offset, const uint8_t* zero_mask, uint64_t seed, uint64_t epoch, int64_t env_offset, void* stream);
+int rvb_teacher_record(const float* reset_info, const float* actions, int64_t actions_ld, const float* obs, int64_t obs_ld,
+                       int64_t N, int64_t C, float* record, int64_t record_ld, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -3,7 +3,8 @@
 Mirrors the reference's call signatures; every numeric op runs in hand-written sm_100a
 kernels behind the C ABI of include/rover_b200.h (librover_b200.so, bound with ctypes).  No CPU path.
 """
-from . import _lib, dist, model, synth
+from . import _lib, dist, hooks, model, synth
+from .hooks import ObsHooks, TeacherRecorder
 from ._lib import SEM_TORCH_CPU, SEM_TORCH_CUDA
 from .camera import Camera, cast_rays
 from .heightmap_distribution import Heightmap
@@ -18,4 +19,4 @@ from .terrain_utils import read_stone_info, stone_info_from_array
 
 __all__ = ["Camera", "Heightmap", "Ackermann", "ray_distance", "Rock_Detection", "Memory", "RoverTask",
            "tensor_quat_to_eul", "TerrainLayer", "build_knn_index", "read_stone_info", "stone_info_from_array",
-           "cast_rays", "HostPipeline", "synth", "model", "SEM_TORCH_CPU", "SEM_TORCH_CUDA", "STAT_NAMES"]
+           "cast_rays", "HostPipeline", "synth", "model", "hooks", "ObsHooks", "TeacherRecorder", "SEM_TORCH_CPU", "SEM_TORCH_CUDA", "STAT_NAMES"]

@@ -6,7 +6,7 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "librover_b200.so")
-SOURCES = ["terrain.cu", "raycast.cu", "raycast_tiled.cu", "raycast_shadow.cu", "rock.cu", "task.cu", "step.cu", "stones.cu", "knn.cu", "policy.cu"]
+SOURCES = ["terrain.cu", "raycast.cu", "raycast_tiled.cu", "raycast_shadow.cu", "rock.cu", "task.cu", "step.cu", "stones.cu", "knn.cu", "policy.cu", "hooks.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-fmad=false",                 # bit-exact parity: never contract mul+add
               "-Xcompiler", "-fPIC", "-shared"]

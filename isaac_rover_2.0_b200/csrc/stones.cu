@@ -145,18 +145,6 @@ extern "C" int rvb_height_lookup(const float* heightmap, int64_t H0, int64_t H1,
 // how the envs are sharded over GPUs.  oracle/reset_oracle.py restates it in numpy.
 // One warp per env (lanes stride over the stones, shuffle min); warps of envs that do not reset exit at once.
 // ------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1,
-                                              uint32_t& o0, uint32_t& o1, uint32_t& o2, uint32_t& o3) {
-#pragma unroll
-    for (int r = 0; r < 10; ++r) {
-        const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
-        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
-        c0 = hi1 ^ c1 ^ k0; c1 = lo1; c2 = hi0 ^ c3 ^ k1; c3 = lo0;
-        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
-    }
-    o0 = c0; o1 = c1; o2 = c2; o3 = c3;
-}
-
 __global__ void reset_targets_kernel(const int64_t* __restrict__ reset_in, int64_t N, int64_t env_offset, uint64_t seed, uint64_t epoch,
                                      const float* __restrict__ initial_pos, float radius, const float* __restrict__ stones, int S,
                                      float thr, int max_attempts, const float* __restrict__ hm, int H0, int H1, float hscale,

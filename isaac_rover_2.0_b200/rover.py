@@ -88,7 +88,11 @@ class RoverTask():
         self.curriculum_level = 1                                   # rover.py:104 (raised to 2 at :353)
         self.max_episode_length = 3000                              # rover.py:119
         self.is_evaluation = False
-        self.save_teacher_data = False
+        self.save_teacher_data = False                              # rover.py:151; set a hooks.TeacherRecorder in `teacher_recorder`
+        self.teacher_recorder = None
+        self.reset_info = torch.zeros(num_envs, device=device)      # rover.py:180
+        self._teacher_actions = torch.zeros((num_envs, 2), device=device)
+        self.obs_hooks = None                                       # hooks.ObsHooks: rover.py:326-329 when enabled
         self.target_positions = torch.zeros((num_envs, 3), device=device, dtype=torch.float32)
         self.initial_pos = torch.zeros((num_envs, 3), device=device, dtype=torch.float32)
         self.stone_info = stone_info.to(device).float().contiguous()
@@ -211,6 +215,9 @@ class RoverTask():
     # ------------------------------------------------------------------ get_observations (rover.py:272-336)
     def get_observations(self) -> dict:
         lib = self._lib
+        if self.save_teacher_data and self.teacher_recorder is not None:       # rover.py:298-317: BEFORE obs_buf is refreshed --
+            # the row pairs the actions of this step with the observation they were computed from
+            self.teacher_recorder.record(self.reset_info, self._teacher_actions, self.obs_buf)
         pos, quat = self._rover.get_world_poses()
         self.rover_positions = pos.to(torch.float32).contiguous()
         self.rover_rotation = tensor_quat_to_eul(quat)
@@ -229,6 +236,8 @@ class RoverTask():
             self.rover_positions, self.rover_rotation, self._rover.get_joint_positions(), want_collision=want)
         if want:
             self.rock_collison = self.Rock_detector.last_collision
+        if self.obs_hooks is not None:                              # rover.py:326-329
+            self.obs_hooks.apply(self.obs_buf, epoch=self.global_step, env_offset=self.env_offset)
         return {self._rover_name: {"obs_buf": self.obs_buf}}
 
     def check_collision(self, wheel_dists, body_dists):
@@ -284,6 +293,8 @@ class RoverTask():
     def apply_actions(self, actions):
         """History push + Ackermann + joint-target mapping (rover.py:366-414)."""
         _actions = actions.to(self._device)
+        if self.save_teacher_data:                                  # rover.py:373-375
+            self._teacher_actions = _actions[:, 0:2].to(torch.float32)
         self.linear_velocity.input_state(_actions[:, 0])
         self.angular_velocity.input_state(_actions[:, 1])
         _, _, positions, velocities = Ackermann(_actions[:, 0], _actions[:, 1], self._device, sem=self.sem,
@@ -297,6 +308,9 @@ class RoverTask():
 
     def reset_idx(self, env_ids):
         """Book-keeping half of rover.py:416-453 (pose resets belong to the simulator)."""
+        if self.save_teacher_data:                                  # rover.py:420-422 (sets every env, as the reference does)
+            self.reset_info[:] = 1
+            self.reset_info[env_ids] = 1
         if hasattr(self._rover, "reset_idx"):
             self._rover.reset_idx(env_ids, self.initial_pos)
         self.reset_buf[env_ids] = 0
