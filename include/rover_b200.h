@@ -258,6 +258,7 @@ int rvb_build_knn_index(const int32_t* triangles, int64_t T, const uint16_t* ver
  * rvb_linear = one torch nn.Linear: weight f32 [out_features, in_features] row-major, bias f32 [out_features], both
  * borrowed DEVICE pointers that may be released when rvb_policy_create returns (it re-packs them into k-major panels
  * owned by the handle and synchronises `stream`).  enc_sparse / enc_dense point at 2 layers, mlp at 3, head at 1.
+ * `device` must be the calling thread's current CUDA device (the library never switches devices).
  * fp32 FMA arithmetic like the reference's (TF32 off); accumulation order differs from cuBLAS, parity gate 2e-5 absolute.
  * rvb_policy_forward: obs f32 [N, obs_ld] (obs_ld >= p+S+D) -> out f32 [N, out_ld] columns 0..head-1; one kernel, reads obs
  * once, asynchronous on `stream`; the handle is immutable => usable from any stream.

@@ -164,7 +164,7 @@ class _HeightmapNet:
             _lib.check(self._lib.rvb_policy_create(C.byref(h), self.num_proprioception, self.num_sparse, self.num_dense,
                                                    arr(names[0:ns]), arr(names[ns:ns + nd]), arr(names[ns + nd:ns + nd + nm]),
                                                    arr(names[-1:]), _lib.ACTIVATIONS[self.activation_function],
-                                                   1 if self._head_tanh else 0, self.device.index or 0, st))
+                                                   1 if self._head_tanh else 0, torch.cuda.current_device(), st))
         self._handle = h
 
     def close(self):

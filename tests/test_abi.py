@@ -40,6 +40,21 @@ def test_argument_validation_without_gpu():
     rc = lib.rvb_terrain_create(ctypes.byref(h), None, 10, 10, 8, 1, 1, 1, None, 4, None, 4, 0.1, 0.0, 0.0, 0, None)
     assert rc == -1 and h.value is None
     assert lib.rvb_stats_scratch_len(1000) == 4 * 16
+    # policy epilogue / hooks
+    h = ctypes.c_void_p()
+    rc = lib.rvb_policy_create(ctypes.byref(h), 4, 634, 1112, None, None, None, None, 0, 1, 0, None)
+    assert rc == -1 and h.value is None and b"null pointer" in lib.rvb_last_error()
+    lin = (_lib.Linear * 3)()
+    rc = lib.rvb_policy_create(ctypes.byref(h), 9, 634, 1112, lin, lin, lin, lin, 0, 1, 0, None)      # more than 8 proprioceptive columns
+    assert rc == -1 and h.value is None
+    rc = lib.rvb_policy_create(ctypes.byref(h), 4, 634, 1112, lin, lin, lin, lin, 17, 1, 0, None)     # unknown activation
+    assert rc == -1 and b"activation" in lib.rvb_last_error()
+    assert lib.rvb_policy_forward(None, None, 1750, 4, None, 2, None) == -1
+    assert lib.rvb_policy_forward_pair(None, None, None, 1750, 4, None, 2, None, 1, None) == -1
+    assert lib.rvb_policy_destroy(None) == 0 and lib.rvb_policy_bytes(None) == 0
+    assert lib.rvb_obs_hooks(None, 1750, 4, 1750, 4, 0.0, 0.0, 0.0, None, 1, 1, 0, None) == -1
+    assert lib.rvb_obs_hooks(None, 1750, 0, 1750, 4, 0.0, 0.0, 0.0, None, 1, 1, 0, None) == 0        # nothing to do
+    assert lib.rvb_teacher_record(None, None, 2, None, 1750, 4, 1750, None, 1753, None) == -1
 
 
 def test_no_cpu_fallback():
