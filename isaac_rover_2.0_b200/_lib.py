@@ -124,9 +124,13 @@ def load():
     if not os.path.exists(_build.LIB) or (_build.needs_build() and os.environ.get("ROVER_B200_NO_REBUILD") != "1"):
         try:
             _build.build()
-        except Exception as e:                      # stale-but-present library is still usable
+        except Exception as e:
             if not os.path.exists(_build.LIB):
                 raise RuntimeError("librover_b200.so is missing and could not be built: %s" % e)
+            if "nvcc failed" in str(e):             # the sources do not compile: never run yesterday's kernels in their place
+                raise RuntimeError("librover_b200.so is stale and its sources do not compile: %s" % e)
+            import warnings                         # no compiler on this box: a present library is still usable, but say so
+            warnings.warn("librover_b200.so is older than its sources and could not be rebuilt (%s); using it as is" % e)
     raw = C.CDLL(_build.LIB)
     lib = _Lib()
     for name, (res, args) in _SIGNATURES.items():

@@ -249,9 +249,9 @@ extern "C" int rvb_policy_create(rvb_policy** out, int32_t n_proprio, int32_t n_
     if ((rc = check_linear(&mlp[2], PL_M2, PL_M3, "mlp layer 2"))) return rc;
     if ((rc = check_linear(head, PL_M3, head->out_features, "head"))) return rc;
 
-    int cur = -1;                      // like every other entry point: the caller's current device, never changed here
-    RVB_CUDA(cudaGetDevice(&cur));
-    RVB_REQUIRE(device == cur, "rvb_policy_create: `device` is not the calling thread's current CUDA device");
+    int cur_dev = -1;                  // like every other entry point: the caller's current device, never changed here
+    RVB_CUDA(cudaGetDevice(&cur_dev));
+    RVB_REQUIRE(device == cur_dev, "rvb_policy_create: `device` is not the calling thread's current CUDA device");
     rvb_policy* P = new (std::nothrow) rvb_policy();
     if (!P) return rvb_set_error(RVB_ERR_NOMEM, "rvb_policy_create", "host allocation failed");
     P->n_proprio = n_proprio; P->n_sparse = n_sparse; P->n_dense = n_dense; P->n_head = head->out_features;
