@@ -280,6 +280,10 @@ int rvb_policy_destroy(rvb_policy* policy);
 int64_t rvb_policy_bytes(const rvb_policy* policy);
 int rvb_policy_forward(const rvb_policy* policy, const float* obs, int64_t obs_ld, int64_t N, float* out, int64_t out_ld,
                        void* stream);
+/* Inner-loop variant of the policy kernel, process-wide: 1 = packed FFMA2 (two fp32 FMAs per issue slot; default),
+ * 0 = scalar FFMA.  Both are IEEE fma per element => bit-identical results; exists for A/B measurement.  Returns the previous
+ * value; any other argument only queries. */
+int rvb_policy_variant(int variant);
 /* Two networks on the same observations in ONE launch (grid.y = network): what a PPO step asks for -- policy.compute and
  * value.compute on the same states.  Twice the CTAs for the same obs tile (second read served by L2). */
 int rvb_policy_forward_pair(const rvb_policy* a, const rvb_policy* b, const float* obs, int64_t obs_ld, int64_t N,

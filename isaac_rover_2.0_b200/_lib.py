@@ -78,6 +78,7 @@ _SIGNATURES = {
     "rvb_policy_bytes": (i64, [p]),
     "rvb_policy_forward": (C.c_int, [p, p, i64, i64, p, i64, p]),
     "rvb_policy_forward_pair": (C.c_int, [p, p, p, i64, i64, p, i64, p, i64, p]),
+    "rvb_policy_variant": (C.c_int, [C.c_int]),
     "rvb_obs_hooks": (C.c_int, [p, i64, i64, i64, i64, f32, f32, f32, p, C.c_uint64, C.c_uint64, i64, p]),
     "rvb_teacher_record": (C.c_int, [p, p, i64, p, i64, i64, i64, p, i64, p]),
 }

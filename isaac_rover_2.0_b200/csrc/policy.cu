@@ -73,6 +73,15 @@ __device__ __forceinline__ float pl_act(float v, int kind) {
     }
 }
 
+// Two fp32 FMAs in one issue slot (Blackwell FFMA2: d.xy = a.xy * b + c.xy; ptxas folds the {b, b} pair into the
+// instruction's broadcast operand).  Each half is an IEEE fma, so the result equals two fmaf() calls bit for bit.
+__device__ __forceinline__ void ffma2(float& d0, float& d1, float a0, float a1, float b) {
+    asm("{\n\t.reg .b64 ra, rb, rc;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %4};\n\tmov.b64 rc, {%0, %1};\n\t"
+        "fma.rn.f32x2 rc, ra, rb, rc;\n\tmov.b64 {%0, %1}, rc;\n\t}"
+        : "+f"(d0), "+f"(d1)
+        : "f"(a0), "f"(a1), "f"(b));
+}
+
 // torch [out][in] -> k-major padded panel
 __global__ void pl_pack_kernel(const float* __restrict__ w, const float* __restrict__ b, int in, int out, int outp,
                                float* __restrict__ wt, float* __restrict__ bias) {
@@ -87,7 +96,7 @@ __global__ void pl_pack_kernel(const float* __restrict__ w, const float* __restr
 // One dense layer of the tile.  Input activations: shared memory `act_in` [K][PL_LDA] (GLOBAL_IN = false) or columns
 // [col0, col0 + K) of the tile's observation rows in global memory, staged transposed through `xs` (GLOBAL_IN = true).
 // Output: act(in . Wt + bias) into shared memory `act_out` [n][PL_LDA], rows n < OUT only.
-template <int CN, bool GLOBAL_IN>
+template <int CN, bool GLOBAL_IN, bool F2>
 __device__ __forceinline__ void pl_dense(const float* __restrict__ act_in, const float* __restrict__ obs, int64_t obs_ld, int64_t m0,
                                          int64_t N, int col0, int K, const PackedLinear& L, float* __restrict__ xs,
                                          float* __restrict__ ws, float* __restrict__ act_out, int act_kind) {
@@ -136,18 +145,39 @@ __device__ __forceinline__ void pl_dense(const float* __restrict__ act_in, const
         __syncthreads();
         if (k0 + KC < K) fetch(k0 + KC);
         const float* a_base = GLOBAL_IN ? xs : act_in + (int64_t)k0 * PL_LDA;
+        if (F2) {
+            auto step = [&](int kk) {
+                const float4 a = *reinterpret_cast<const float4*>(a_base + kk * PL_LDA + mg * 4);
+                float w[CN];
+#pragma unroll
+                for (int j = 0; j < CN; ++j) w[j] = ws[kk * OUTP + ng + 32 * j];
+#pragma unroll
+                for (int j = 0; j < CN; ++j) {
+                    ffma2(acc[0][j], acc[1][j], a.x, a.y, w[j]);
+                    ffma2(acc[2][j], acc[3][j], a.z, a.w, w[j]);
+                }
+            };
+            if (kc == KC) {                                // full chunks: no loop overhead
+#pragma unroll
+                for (int kk = 0; kk < KC; ++kk) step(kk);
+            } else {
 #pragma unroll 4
-        for (int kk = 0; kk < kc; ++kk) {
-            const float4 a = *reinterpret_cast<const float4*>(a_base + kk * PL_LDA + mg * 4);
-            float w[CN];
+                for (int kk = 0; kk < kc; ++kk) step(kk);
+            }
+        } else {
+#pragma unroll 4
+            for (int kk = 0; kk < kc; ++kk) {
+                const float4 a = *reinterpret_cast<const float4*>(a_base + kk * PL_LDA + mg * 4);
+                float w[CN];
 #pragma unroll
-            for (int j = 0; j < CN; ++j) w[j] = ws[kk * OUTP + ng + 32 * j];
+                for (int j = 0; j < CN; ++j) w[j] = ws[kk * OUTP + ng + 32 * j];
 #pragma unroll
-            for (int j = 0; j < CN; ++j) {
-                acc[0][j] = fmaf(a.x, w[j], acc[0][j]);
-                acc[1][j] = fmaf(a.y, w[j], acc[1][j]);
-                acc[2][j] = fmaf(a.z, w[j], acc[2][j]);
-                acc[3][j] = fmaf(a.w, w[j], acc[3][j]);
+                for (int j = 0; j < CN; ++j) {
+                    acc[0][j] = fmaf(a.x, w[j], acc[0][j]);
+                    acc[1][j] = fmaf(a.y, w[j], acc[1][j]);
+                    acc[2][j] = fmaf(a.z, w[j], acc[2][j]);
+                    acc[3][j] = fmaf(a.w, w[j], acc[3][j]);
+                }
             }
         }
     }
@@ -175,6 +205,7 @@ __device__ __forceinline__ void pl_dense(const float* __restrict__ act_in, const
 #define PL_SM_FLOATS (PL_SM_WS + PL_WS_FLOATS)
 #define PL_SMEM_BYTES (PL_SM_FLOATS * 4)
 
+template <bool F2>
 __global__ void __launch_bounds__(PL_THREADS, 2)
 policy_forward_kernel(const PolicyDev* __restrict__ p0, const PolicyDev* __restrict__ p1, const float* __restrict__ obs,
                       int64_t obs_ld, int64_t N, float* __restrict__ out0, int64_t out0_ld, float* __restrict__ out1,
@@ -199,15 +230,15 @@ policy_forward_kernel(const PolicyDev* __restrict__ p0, const PolicyDev* __restr
         A[k * PL_LDA + m] = (m0 + m < N) ? __ldg(obs + (m0 + m) * obs_ld + k) : 0.f;
     }
     // sparse encoder (model.py:186) -> concat rows p .. p+59
-    pl_dense<3, true>(nullptr, obs, obs_ld, m0, N, p, P.n_sparse, P.es1, xs, ws, Cb, P.act);
-    pl_dense<2, false>(Cb, nullptr, 0, 0, 0, 0, PL_E1, P.es2, xs, ws, A + p * PL_LDA, P.act);
+    pl_dense<3, true, F2>(nullptr, obs, obs_ld, m0, N, p, P.n_sparse, P.es1, xs, ws, Cb, P.act);
+    pl_dense<2, false, F2>(Cb, nullptr, 0, 0, 0, 0, PL_E1, P.es2, xs, ws, A + p * PL_LDA, P.act);
     // dense encoder (model.py:187) -> concat rows p+60 .. p+119
-    pl_dense<3, true>(nullptr, obs, obs_ld, m0, N, p + P.n_sparse, P.n_dense, P.ed1, xs, ws, Cb, P.act);
-    pl_dense<2, false>(Cb, nullptr, 0, 0, 0, 0, PL_E1, P.ed2, xs, ws, A + (p + PL_E2) * PL_LDA, P.act);
+    pl_dense<3, true, F2>(nullptr, obs, obs_ld, m0, N, p + P.n_sparse, P.n_dense, P.ed1, xs, ws, Cb, P.act);
+    pl_dense<2, false, F2>(Cb, nullptr, 0, 0, 0, 0, PL_E1, P.ed2, xs, ws, A + (p + PL_E2) * PL_LDA, P.act);
     // MLP (model.py:190-191)
-    pl_dense<8, false>(A, nullptr, 0, 0, 0, 0, p + 2 * PL_E2, P.m1, xs, ws, B, P.act);
-    pl_dense<5, false>(B, nullptr, 0, 0, 0, 0, PL_M1, P.m2, xs, ws, Cb, P.act);
-    pl_dense<4, false>(Cb, nullptr, 0, 0, 0, 0, PL_M2, P.m3, xs, ws, A, P.act);
+    pl_dense<8, false, F2>(A, nullptr, 0, 0, 0, 0, p + 2 * PL_E2, P.m1, xs, ws, B, P.act);
+    pl_dense<5, false, F2>(B, nullptr, 0, 0, 0, 0, PL_M1, P.m2, xs, ws, Cb, P.act);
+    pl_dense<4, false, F2>(Cb, nullptr, 0, 0, 0, 0, PL_M2, P.m3, xs, ws, A, P.act);
     __syncthreads();
     // head: Linear(128, A) [+ Tanh] -- warp o computes output o for the tile's 32 envs
     const int m = tid & 31, o = tid >> 5;
@@ -285,7 +316,8 @@ extern "C" int rvb_policy_create(rvb_policy** out, int32_t n_proprio, int32_t n_
     if (e == cudaSuccess)       // the descriptor the kernel reads (P outlives the copy: the stream is synchronised below)
         e = cudaMemcpyAsync(P->storage, static_cast<const PolicyDev*>(P), sizeof(PolicyDev), cudaMemcpyHostToDevice, st);
     if (e == cudaSuccess) e = cudaGetLastError();
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(policy_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PL_SMEM_BYTES);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(policy_forward_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, PL_SMEM_BYTES);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(policy_forward_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, PL_SMEM_BYTES);
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);   // the caller may free its weight tensors on return
     if (e != cudaSuccess) {
         cudaFree(P->storage);
@@ -305,6 +337,14 @@ extern "C" int rvb_policy_destroy(rvb_policy* P) {
 
 extern "C" int64_t rvb_policy_bytes(const rvb_policy* P) { return P ? P->storage_floats * (int64_t)sizeof(float) : 0; }
 
+// 1 = packed FFMA2 inner loop (default), 0 = scalar FFMA.  Bit-identical results; the switch exists for A/B measurement.
+static int g_policy_variant = 1;
+extern "C" int rvb_policy_variant(int v) {
+    const int prev = g_policy_variant;
+    if (v == 0 || v == 1) g_policy_variant = v;
+    return prev;
+}
+
 static int check_forward(const rvb_policy* P, const float* obs, int64_t obs_ld, const float* out, int64_t out_ld) {
     RVB_REQUIRE(obs && out, "rvb_policy_forward: null pointer");
     RVB_REQUIRE(obs_ld >= (int64_t)P->n_proprio + P->n_sparse + P->n_dense, "rvb_policy_forward: obs rows are shorter than the network's input");
@@ -319,7 +359,8 @@ extern "C" int rvb_policy_forward(const rvb_policy* P, const float* obs, int64_t
     int rc;
     if ((rc = check_forward(P, obs, obs_ld, out, out_ld))) return rc;
     RVB_REQUIRE(N <= (int64_t)PL_TM * 0x7fffffff, "rvb_policy_forward: too many envs");
-    policy_forward_kernel<<<dim3((unsigned)ceil_div(N, PL_TM), 1), PL_THREADS, PL_SMEM_BYTES, as_stream(stream)>>>(
+    auto kern = g_policy_variant ? policy_forward_kernel<true> : policy_forward_kernel<false>;
+    kern<<<dim3((unsigned)ceil_div(N, PL_TM), 1), PL_THREADS, PL_SMEM_BYTES, as_stream(stream)>>>(
         P->dev, nullptr, obs, obs_ld, N, out, out_ld, nullptr, 0);
     RVB_LAUNCH_CHECK();
     return RVB_OK;
@@ -334,7 +375,8 @@ extern "C" int rvb_policy_forward_pair(const rvb_policy* A, const rvb_policy* B,
     if ((rc = check_forward(B, obs, obs_ld, out_b, out_b_ld))) return rc;
     RVB_REQUIRE(A->device == B->device, "rvb_policy_forward_pair: the two networks live on different devices");
     RVB_REQUIRE(N <= (int64_t)PL_TM * 0x7fffffff, "rvb_policy_forward: too many envs");
-    policy_forward_kernel<<<dim3((unsigned)ceil_div(N, PL_TM), 2), PL_THREADS, PL_SMEM_BYTES, as_stream(stream)>>>(
+    auto kern = g_policy_variant ? policy_forward_kernel<true> : policy_forward_kernel<false>;
+    kern<<<dim3((unsigned)ceil_div(N, PL_TM), 2), PL_THREADS, PL_SMEM_BYTES, as_stream(stream)>>>(
         A->dev, B->dev, obs, obs_ld, N, out_a, out_a_ld, out_b, out_b_ld);
     RVB_LAUNCH_CHECK();
     return RVB_OK;

@@ -128,6 +128,23 @@ def test_pair_launch_equals_single_launches(R):
         R.model.compute_pair(actor, critic, torch.zeros(3, 1750))
 
 
+def test_ffma2_and_scalar_variants_are_bit_identical(R):
+    """rvb_policy_variant: the packed-FFMA2 inner loop (default) and the scalar FFMA one are both IEEE fma per element."""
+    lib = R._lib.load()
+    torch.manual_seed(8)
+    actor, critic = _models(R)
+    obs = torch.rand(1000, 1750, device="cuda")
+    assert lib.rvb_policy_variant(-1) == 1                            # default: FFMA2
+    try:
+        m1, v1 = R.model.compute_pair(actor, critic, obs)
+        assert lib.rvb_policy_variant(0) == 1
+        m0, v0 = R.model.compute_pair(actor, critic, obs)
+        s0 = actor.compute(obs)[0]
+    finally:
+        lib.rvb_policy_variant(1)
+    assert torch.equal(m0, m1) and torch.equal(v0, v1) and torch.equal(s0, m1)
+
+
 def test_argument_validation(R):
     actor, _ = _models(R)
     with pytest.raises(RuntimeError):
@@ -168,5 +185,19 @@ def test_throughput_note(R):
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / 5
+    lib = R._lib.load()
+    lib.rvb_policy_variant(0)
+    try:
+        for _ in range(2):
+            R.model.compute_pair(actor, critic, big)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(5):
+            R.model.compute_pair(actor, critic, big)
+        e1.record()
+        torch.cuda.synchronize()
+    finally:
+        lib.rvb_policy_variant(1)
+    print("policy_forward_pair 65536 envs, scalar-FFMA variant: %.4f ms/launch" % (e0.elapsed_time(e1) / 5))
     print("policy_forward_pair 65536 envs: %.4f ms/launch (%.1f M envs/s, %.1f fp32 TFLOP/s)" % (
         ms, 65536 / ms / 1e3, 2 * 2 * 65536 * 243.3e3 / ms / 1e9))
