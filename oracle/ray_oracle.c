@@ -1,0 +1,94 @@
+/* TEST INFRASTRUCTURE ONLY -- never linked, loaded or called by the product (only tests/ and __graft_entry__.build() touch it).
+ *
+ * Plain-C restatement of the reference's ray / triangle test, independent of torch:
+ *   ray_distance            utils/camera/ray_casting.py:3-66   (n rays against n triangles, fp16)
+ *   min over the K candidates of a ray, value + first index    utils/camera/camera.py:116-117 (torch.min(dim=2))
+ * Arithmetic model (what ATen does for Half tensors on either device): every elementwise op converts its operands to
+ * fp32, computes, and rounds the result once to fp16; comparisons are exact; F.normalize = v / max(||v||, eps) with the
+ * norm accumulated in fp32 and rounded to fp16, eps = 1e-12 -> 0 in fp16.  _Float16 <-> float conversions of gcc are IEEE
+ * round-to-nearest-even; build with -ffp-contract=off so that no multiply-add is fused.
+ * Pinned by tests/test_c_oracle_cpu.py against the golden vectors the reference itself produced (tests/golden/rover_golden.pt).
+ */
+#include <math.h>
+#include <stdint.h>
+#include <string.h>
+
+typedef _Float16 h16;
+
+static inline h16 from_bits(uint16_t b) { h16 h; memcpy(&h, &b, 2); return h; }
+static inline uint16_t to_bits(h16 h) { uint16_t b; memcpy(&b, &h, 2); return b; }
+static inline h16 hadd(h16 a, h16 b) { return (h16)((float)a + (float)b); }
+static inline h16 hsub(h16 a, h16 b) { return (h16)((float)a - (float)b); }
+static inline h16 hmul(h16 a, h16 b) { return (h16)((float)a * (float)b); }
+static inline h16 hdiv(h16 a, h16 b) { return (h16)((float)a / (float)b); }
+
+typedef struct { h16 x, y, z; } v3;
+
+static inline v3 load3(const uint16_t* p) { v3 v = {from_bits(p[0]), from_bits(p[1]), from_bits(p[2])}; return v; }
+static inline v3 sub3(v3 u, v3 v) { v3 r = {hsub(u.x, v.x), hsub(u.y, v.y), hsub(u.z, v.z)}; return r; }
+/* Tensor.cross (ray_casting.py:40,44,49,54): (u1 v2 - u2 v1, u2 v0 - u0 v2, u0 v1 - u1 v0), every op rounded */
+static inline v3 cross3(v3 u, v3 v) {
+    v3 r = {hsub(hmul(u.y, v.z), hmul(u.z, v.y)), hsub(hmul(u.z, v.x), hmul(u.x, v.z)), hsub(hmul(u.x, v.y), hmul(u.y, v.x))};
+    return r;
+}
+/* x0*d0 + x1*d1 + x2*d2, left to right (ray_casting.py:41) */
+static inline h16 dot3(v3 u, v3 v) { return hadd(hadd(hmul(u.x, v.x), hmul(u.y, v.y)), hmul(u.z, v.z)); }
+
+/* One ray against one triangle.  tri = 3 vertices x 3 coordinates.  Returns k_after_check; pt (3 halves) optional. */
+static h16 ray_triangle(v3 s, v3 dir, const uint16_t* tri, uint16_t* pt) {
+    const h16 zeros = (h16)(0.0f - 0.1f);             /* ray_casting.py:26  torch.zeros(half) - epsilon */
+    const h16 ones = (h16)(1.0f + 0.1f);              /* ray_casting.py:27 */
+    const h16 err = (h16)((float)ones * 10.0f);       /* ray_casting.py:28 */
+    /* ray_casting.py:31  d = -normalize(directions) */
+    const float fx = (float)dir.x, fy = (float)dir.y, fz = (float)dir.z;
+    h16 nrm = (h16)sqrtf(fx * fx + fy * fy + fz * fz);
+    const h16 eps = (h16)1e-12f;
+    h16 den = (nrm != nrm) ? nrm : ((float)nrm > (float)eps ? nrm : eps);     /* clamp_min, NaN propagates */
+    v3 d = {(h16)(-(float)hdiv(dir.x, den)), (h16)(-(float)hdiv(dir.y, den)), (h16)(-(float)hdiv(dir.z, den))};
+    v3 a = load3(tri + 6);                            /* ray_casting.py:34  a = triangles[:,2] */
+    v3 b = sub3(load3(tri + 3), a);                   /* :35 */
+    v3 c = sub3(load3(tri + 0), a);                   /* :36 */
+    v3 g = sub3(s, a);                                /* :37 */
+    v3 bc = cross3(b, c);
+    h16 det = dot3(bc, d);                            /* :40-41 */
+    h16 n = hdiv(dot3(cross3(g, c), d), det);         /* :44-45 */
+    if (det == zeros) n = err;                        /* :46 */
+    h16 m = hdiv(dot3(cross3(b, g), d), det);         /* :49-50 */
+    if (det == ones) m = err;                         /* :51 */
+    h16 k = hdiv(dot3(bc, g), det);                   /* :54-55 */
+    if (det == ones) k = err;                         /* :56 */
+    h16 kk = (n >= zeros && m >= zeros && hadd(n, m) <= ones) ? k : err;      /* :59 */
+    if (pt) {                                         /* :63  pt = sources - d * k */
+        pt[0] = to_bits(hsub(s.x, hmul(d.x, kk)));
+        pt[1] = to_bits(hsub(s.y, hmul(d.y, kk)));
+        pt[2] = to_bits(hsub(s.z, hmul(d.z, kk)));
+    }
+    return kk;
+}
+
+/* ray_distance(sources [n,3], directions [n,3], triangles [n,3,3]) -> k [n], pt [n,3]; all IEEE binary16 bit patterns */
+void rvo_ray_distance(const uint16_t* sources, const uint16_t* directions, const uint16_t* triangles, int64_t n, uint16_t* k,
+                      uint16_t* pt) {
+    for (int64_t i = 0; i < n; ++i)
+        k[i] = to_bits(ray_triangle(load3(sources + 3 * i), load3(directions + 3 * i), triangles + 9 * i, pt ? pt + 3 * i : 0));
+}
+
+/* One env's Camera.get_depths core (camera.py:84-120): ray r against the K candidates ids[r*K..] of its cell through the
+ * reference's indirection vertices[triangles[id]]; torch.min(dim) = smallest value, first index on ties, NaN wins. */
+void rvo_cast_min(const uint16_t* sources, const uint16_t* directions, int64_t n_rays, const int32_t* ids, int64_t K,
+                  const int32_t* triangles, const uint16_t* vertices, uint16_t* dist, int32_t* slot) {
+    for (int64_t r = 0; r < n_rays; ++r) {
+        v3 s = load3(sources + 3 * r), dir = load3(directions + 3 * r);
+        h16 best = 0;
+        int32_t best_j = -1;
+        for (int64_t j = 0; j < K; ++j) {
+            const int32_t* t = triangles + 3 * (int64_t)ids[r * K + j];
+            uint16_t tri[9];
+            for (int v = 0; v < 3; ++v) memcpy(tri + 3 * v, vertices + 3 * (int64_t)t[v], 6);
+            h16 kk = ray_triangle(s, dir, tri, 0);
+            if (best_j < 0 || (best == best && (kk != kk || kk < best))) { best = kk; best_j = (int32_t)j; }
+        }
+        dist[r] = to_bits(best);
+        slot[r] = best_j;
+    }
+}

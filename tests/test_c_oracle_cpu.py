@@ -1,0 +1,103 @@
+"""The plain-C restatement of the reference's ray / triangle test (oracle/ray_oracle.c, gcc, no torch in the arithmetic) against
+the golden vectors the reference itself produced and against the torch-based oracle: two independent statements of the fp16
+arithmetic that every CUDA ray-cast kernel is held to bit for bit."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+import torch
+
+import rover_oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORACLE_DIR = os.path.join(ROOT, "oracle")
+
+
+@pytest.fixture(scope="module")
+def clib():
+    subprocess.run(["make", "-s", "-C", ORACLE_DIR], check=True)
+    lib = C.CDLL(os.path.join(ORACLE_DIR, "libray_oracle.so"))
+    p, i64 = C.c_void_p, C.c_int64
+    lib.rvo_ray_distance.argtypes = [p, p, p, i64, p, p]
+    lib.rvo_ray_distance.restype = None
+    lib.rvo_cast_min.argtypes = [p, p, i64, p, i64, p, p, p, p]
+    lib.rvo_cast_min.restype = None
+    return lib
+
+
+@pytest.fixture(scope="module")
+def golden():
+    return torch.load(os.path.join(ROOT, "tests", "golden", "rover_golden.pt"))
+
+
+def _u16(t):
+    return np.ascontiguousarray(t.to(torch.float16).contiguous().view(torch.int16).numpy().view(np.uint16))
+
+
+def c_ray_distance(lib, src, dirs, tri):
+    s, d, t = _u16(src), _u16(dirs), _u16(tri)
+    n = s.shape[0]
+    k = np.empty(n, np.uint16)
+    pt = np.empty((n, 3), np.uint16)
+    lib.rvo_ray_distance(s.ctypes.data, d.ctypes.data, t.ctypes.data, n, k.ctypes.data, pt.ctypes.data)
+    return k, pt
+
+
+def same_halves(a_u16, b_half):
+    """Bit equality, any NaN equal to any NaN (payloads are not part of the contract)."""
+    b = _u16(b_half).reshape(a_u16.shape)
+    nan_a, nan_b = (a_u16 & 0x7FFF) > 0x7C00, (b & 0x7FFF) > 0x7C00
+    return bool(np.array_equal(nan_a, nan_b) and np.array_equal(a_u16[~nan_a], b[~nan_b]))
+
+
+def test_golden_ray_distance_vectors(clib, golden):
+    for tag in ("rd", "rr"):
+        k, pt = c_ray_distance(clib, golden["in_%s_src" % tag], golden["in_%s_dir" % tag], golden["in_%s_tri" % tag])
+        assert same_halves(k, golden["ref_%s_k" % tag]) and same_halves(pt, golden["ref_%s_pt" % tag]), tag
+    k, _ = c_ray_distance(clib, golden["in_rd_src"], golden["in_rd_dir"], golden["in_rd_tri"])
+    assert [float(x) for x in k[:5].view(np.float16)] == [1.0, -1.0, 11.0, 11.0, 11.0]
+
+
+def test_random_pairs_equal_torch_oracle(clib):
+    g = torch.Generator().manual_seed(7)
+    n = 200_000
+    tri = (torch.rand(n, 3, 3, generator=g) * 4 - 2).half()
+    src = (torch.rand(n, 3, generator=g) * 4 - 2).half()
+    dirs = (torch.rand(n, 3, generator=g) * 2 - 1).half()
+    # degenerate cases: zero direction, zero-area triangle, ray in the triangle's plane, huge values (fp16 overflow -> inf / nan)
+    dirs[:100] = 0
+    tri[100:200, 1] = tri[100:200, 0]
+    dirs[200:300, 2] = 0
+    tri[200:300, :, 2] = 0
+    src[300:400] *= 300
+    tri[400:500] *= 300
+    k_ref, pt_ref = O.ray_distance(src, dirs, tri)
+    k, pt = c_ray_distance(clib, src, dirs, tri)
+    assert same_halves(k, k_ref) and same_halves(pt, pt_ref)
+    hits = (k_ref.float() < 11.0).float().mean().item()
+    assert 0.01 < hits < 0.9                                      # the sample exercises both outcomes
+
+
+def test_golden_get_depths_through_c(clib, golden):
+    """camera.py:84-120 for the first envs of the golden world: K-list gather, ray_distance per pair, torch.min(dim) value + index."""
+    w = golden["world"]
+    n_env = 2
+    pos, euler = golden["in_pos"][:n_env], golden["ref_euler"][:n_env]
+    src, d = O.depth_transform(pos, euler, golden["ref_pattern"])
+    idx = O.permute_index(w["map_indices"].to(torch.int32))
+    G, K = idx.shape[0], idx.shape[2]
+    cx, cy = O.cell_lookup(src[:, :, 0:2], torch.zeros(2), 0.1, G)
+    tri = np.ascontiguousarray(w["triangles"].to(torch.int32).numpy())
+    ver = _u16(w["vertices"])
+    for e in range(n_env):
+        ids = np.ascontiguousarray(idx[cx[e], cy[e]].numpy().astype(np.int32))          # [P,K]
+        P = ids.shape[0]
+        s = _u16(src[e])
+        dd = _u16(d[e].unsqueeze(0).expand(P, 3))
+        dist, slot = np.empty(P, np.uint16), np.empty(P, np.int32)
+        clib.rvo_cast_min(s.ctypes.data, dd.ctypes.data, P, ids.ctypes.data, K, tri.ctypes.data, ver.ctypes.data,
+                          dist.ctypes.data, slot.ctypes.data)
+        assert same_halves(dist, golden["ref_dist"][e])
+        assert np.array_equal(slot, golden["oracle_slot"][e].numpy().astype(np.int32))
