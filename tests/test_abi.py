@@ -73,6 +73,9 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 text = open(os.path.join(dirpath, f)).read()
                 assert "rover_oracle" not in text and "ref_import" not in text and "/root/reference" not in text, f
+                assert "libray_oracle" not in text, f
+                if f.endswith(".py"):                      # no import of anything under oracle/ (comments may cite it)
+                    assert not re.search(r"^\s*(import|from)\s+\S*oracle", text, flags=re.M), f
 
 
 def test_library_staleness_is_by_content_not_mtime(monkeypatch):
