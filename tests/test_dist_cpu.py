@@ -83,3 +83,46 @@ def test_single_process_helpers_are_noops():
     R.dist.barrier()
     red = R.dist.StatsReducer()
     assert torch.equal(red.result(red.submit(s)), s)
+
+
+def _hooks_worker(rank, world, port, total_envs, q):
+    sys.path[:0] = [ROOT, os.path.join(ROOT, "oracle")]
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    import numpy as np
+    import hooks_oracle as HO
+    import reset_oracle as RO
+    import isaac_rover_b200 as R
+    r, w, _ = R.dist.init_from_env(backend="gloo")
+    lo, hi = R.dist.env_shard(total_envs, r, w)
+    base = np.full((hi - lo, 40), 0.25, np.float32)
+    # what each rank's device kernels compute for its env block: env-indexed Philox draws with env_offset = first global env id
+    hooked = HO.obs_hooks(base, 4, 0.45, 0.1, 0.02, None, seed=42, epoch=7, env_offset=lo)
+    goal_u = RO.uniform(42, 7, np.arange(lo, hi), 0)
+    parts = [None] * w
+    dist.all_gather_object(parts, (lo, hooked, goal_u))
+    dist.barrier()
+    if r == 0:
+        q.put(parts)
+    dist.destroy_process_group()
+
+
+def test_two_rank_env_indexed_draws_equal_unsharded_gloo():
+    """'results are independent of W when env-indexed Philox counters are used' -- the observation hooks (8f-4) and the
+    goal draws (8f-2) of two env shards, gathered, equal the unsharded run bit for bit."""
+    sys.path[:0] = [ROOT, os.path.join(ROOT, "oracle")]
+    import numpy as np
+    import hooks_oracle as HO
+    import reset_oracle as RO
+    total, world, port = 77, 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_hooks_worker, args=(r, world, port, total, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    parts = sorted(q.get(timeout=120), key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    full = HO.obs_hooks(np.full((total, 40), 0.25, np.float32), 4, 0.45, 0.1, 0.02, None, seed=42, epoch=7)
+    assert np.array_equal(np.concatenate([h for _, h, _ in parts]), full)
+    assert np.array_equal(np.concatenate([u for _, _, u in parts]), RO.uniform(42, 7, np.arange(total), 0))
