@@ -3,6 +3,8 @@
  * Plain-C restatement of the reference's ray / triangle test, independent of torch:
  *   ray_distance            utils/camera/ray_casting.py:3-66   (n rays against n triangles, fp16)
  *   min over the K candidates of a ray, value + first index    utils/camera/camera.py:116-117 (torch.min(dim=2))
+ *   Camera._depth_transform + _height_lookup for one env         utils/camera/camera.py:165-264 (given sin/cos of the negated
+ *                                                                euler angles, so that no libm enters the comparison)
  * Arithmetic model (what ATen does for Half tensors on either device): every elementwise op converts its operands to
  * fp32, computes, and rounds the result once to fp16; comparisons are exact; F.normalize = v / max(||v||, eps) with the
  * norm accumulated in fp32 and rounded to fp16, eps = 1e-12 -> 0 in fp16.  _Float16 <-> float conversions of gcc are IEEE
@@ -91,4 +93,57 @@ void rvo_cast_min(const uint16_t* sources, const uint16_t* directions, int64_t n
         dist[r] = to_bits(best);
         slot[r] = best_j;
     }
+}
+
+/* Camera.get_depths for ONE env (camera.py:60-145), torch-CPU semantics, given trig = (sx, cx, sy, cy, sz, cz) =
+ * sin/cos of the NEGATED roll, pitch, yaw in fp32 (camera.py:184-189).
+ *   _depth_transform (camera.py:165-212): pattern f64 [P,3] (+ the extra point (0,0,-1), :179-181); fp32 inputs promote to
+ *   fp64 (f64 [1,P] x f32 [N,1] -> f64); x' = tx + sz*(y*cx + z*sx) + cz*(x*cy - sy*(z*cx - y*sx)) etc. (:197-199);
+ *   direction = transformed extra point - translation (:202-207); cast to fp16 through fp32 (:212).
+ *   _height_lookup (camera.py:233-264): cell = round_half_even(clamp((xy16 - shift) / res, 0, G-1)) in fp32 (f16 - f32 -> f32),
+ *   candidates = map_indices[:, cx, cy] of the [K,G,G] asset (the reference indexes its permuted [G,G,K] view, :157-158).
+ *   then ray_distance per (ray, candidate) and torch.min over K (:110-117). */
+void rvo_get_depths_env(const float* pos, const float* trig, const double* pattern, int64_t P, const int32_t* map_kgg, int64_t G,
+                        int64_t K, const int32_t* triangles, const uint16_t* vertices, float shift_x, float shift_y, float res,
+                        uint16_t* sources, uint16_t* dist, int32_t* slot) {
+    const double sx = trig[0], cx = trig[1], sy = trig[2], cy = trig[3], sz = trig[4], cz = trig[5];
+    const double tx = pos[0], ty = pos[1], tz = pos[2];
+    double out[3];
+#define RVO_XFORM(x, y, z)                                                  \
+    do {                                                                    \
+        const double A_ = (y) * cx + (z) * sx, C_ = (z) * cx - (y) * sx;    \
+        const double B_ = (x) * cy - sy * C_;                               \
+        out[0] = (tx + sz * A_) + cz * B_;                                  \
+        out[1] = (ty + cz * A_) - sz * B_;                                  \
+        out[2] = (tz + (x) * sy) + cy * C_;                                 \
+    } while (0)
+    RVO_XFORM(0.0, 0.0, -1.0);
+    uint16_t dir[3];
+    for (int i = 0; i < 3; ++i) dir[i] = to_bits((h16)(float)(out[i] - (double)pos[i]));
+    const v3 d = load3(dir);
+    for (int64_t r = 0; r < P; ++r) {
+        RVO_XFORM(pattern[3 * r], pattern[3 * r + 1], pattern[3 * r + 2]);
+        uint16_t* s16 = sources + 3 * r;
+        for (int i = 0; i < 3; ++i) s16[i] = to_bits((h16)(float)out[i]);
+        int64_t cell[2];
+        const float shift[2] = {shift_x, shift_y};
+        for (int i = 0; i < 2; ++i) {
+            float v = ((float)from_bits(s16[i]) - shift[i]) / res;
+            v = fminf(fmaxf(v, 0.0f), (float)(G - 1));
+            cell[i] = (int64_t)rintf(v);                   /* round half to even (default rounding mode) */
+        }
+        const v3 s = load3(s16);
+        h16 best = 0;
+        int32_t best_j = -1;
+        for (int64_t j = 0; j < K; ++j) {
+            const int32_t* t = triangles + 3 * (int64_t)map_kgg[(j * G + cell[0]) * G + cell[1]];
+            uint16_t tri[9];
+            for (int v = 0; v < 3; ++v) memcpy(tri + 3 * v, vertices + 3 * (int64_t)t[v], 6);
+            h16 kk = ray_triangle(s, d, tri, 0);
+            if (best_j < 0 || (best == best && (kk != kk || kk < best))) { best = kk; best_j = (int32_t)j; }
+        }
+        dist[r] = to_bits(best);
+        slot[r] = best_j;
+    }
+#undef RVO_XFORM
 }

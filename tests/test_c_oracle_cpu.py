@@ -24,6 +24,8 @@ def clib():
     lib.rvo_ray_distance.restype = None
     lib.rvo_cast_min.argtypes = [p, p, i64, p, i64, p, p, p, p]
     lib.rvo_cast_min.restype = None
+    lib.rvo_get_depths_env.argtypes = [p, p, p, i64, p, i64, i64, p, p, C.c_float, C.c_float, C.c_float, p, p, p]
+    lib.rvo_get_depths_env.restype = None
     return lib
 
 
@@ -101,3 +103,25 @@ def test_golden_get_depths_through_c(clib, golden):
                           dist.ctypes.data, slot.ctypes.data)
         assert same_halves(dist, golden["ref_dist"][e])
         assert np.array_equal(slot, golden["oracle_slot"][e].numpy().astype(np.int32))
+
+
+def test_golden_get_depths_whole_chain_in_c(clib, golden):
+    """Camera.get_depths end to end in C for every env of the golden world (pose transform in fp64, fp16 cast, cell lookup, K-list
+    gather, ray_distance, min): sources, distances and hit slots equal the reference's outputs bit for bit.  The sin/cos values
+    are the reference run's own (golden["trig"]), so no libm enters the comparison."""
+    w = golden["world"]
+    pat = np.ascontiguousarray(golden["ref_pattern"].numpy().astype(np.float64))
+    P = pat.shape[0]
+    m = np.ascontiguousarray(w["map_indices"].to(torch.int32).numpy())
+    K, G = m.shape[0], m.shape[1]
+    tri = np.ascontiguousarray(w["triangles"].to(torch.int32).numpy())
+    ver = _u16(w["vertices"])
+    for e in range(golden["in_pos"].shape[0]):
+        pos = np.ascontiguousarray(golden["in_pos"][e].numpy().astype(np.float32))
+        trig = np.ascontiguousarray(golden["trig"][e].numpy().astype(np.float32))
+        src, dist, slot = np.empty((P, 3), np.uint16), np.empty(P, np.uint16), np.empty(P, np.int32)
+        clib.rvo_get_depths_env(pos.ctypes.data, trig.ctypes.data, pat.ctypes.data, P, m.ctypes.data, G, K, tri.ctypes.data,
+                                ver.ctypes.data, 0.0, 0.0, 0.1, src.ctypes.data, dist.ctypes.data, slot.ctypes.data)
+        assert same_halves(src, golden["ref_sources"][e]), e
+        assert same_halves(dist, golden["ref_dist"][e]), e
+        assert np.array_equal(slot, golden["oracle_slot"][e].numpy().astype(np.int32)), e
