@@ -26,6 +26,10 @@ def clib():
     lib.rvo_cast_min.restype = None
     lib.rvo_get_depths_env.argtypes = [p, p, p, i64, p, i64, i64, p, p, C.c_float, C.c_float, C.c_float, p, p, p]
     lib.rvo_get_depths_env.restype = None
+    lib.rvo_ackermann.argtypes = [p, p, i64, p, p]
+    lib.rvo_ackermann.restype = None
+    lib.rvo_joint_targets.argtypes = [p, p, i64, p, p]
+    lib.rvo_joint_targets.restype = None
     return lib
 
 
@@ -125,3 +129,30 @@ def test_golden_get_depths_whole_chain_in_c(clib, golden):
         assert same_halves(src, golden["ref_sources"][e]), e
         assert same_halves(dist, golden["ref_dist"][e]), e
         assert np.array_equal(slot, golden["oracle_slot"][e].numpy().astype(np.int32)), e
+
+
+def _c_ackermann(lib, lin, ang):
+    l, a = np.ascontiguousarray(lin.numpy().astype(np.float32)), np.ascontiguousarray(ang.numpy().astype(np.float32))
+    n = l.shape[0]
+    steer, vel = np.empty((n, 6), np.float32), np.empty((n, 6), np.float32)
+    lib.rvo_ackermann(l.ctypes.data, a.ctypes.data, n, steer.ctypes.data, vel.ctypes.data)
+    return steer, vel
+
+
+def test_golden_ackermann_in_c(clib, golden):
+    """kinematics.py:14-67 in C: wheel velocities bit for bit (IEEE arithmetic only), steering angles to an ulp of atan2."""
+    for lin, ang, ref_s, ref_v in ((golden["in_ka_lin"], golden["in_ka_ang"], golden["ref_ka_steer"], golden["ref_ka_vel"]),
+                                   (golden["in_actions"][:, 0], golden["in_actions"][:, 1], golden["ref_steer"], golden["ref_vel"])):
+        steer, vel = _c_ackermann(clib, lin, ang)
+        rv = ref_v.numpy()
+        assert np.array_equal(np.isnan(vel), np.isnan(rv)) and np.array_equal(vel[~np.isnan(rv)], rv[~np.isnan(rv)])
+        assert np.allclose(steer, ref_s.numpy(), rtol=0, atol=2.4e-7, equal_nan=True)
+    # every branch is in the sample: turn on the spot, straight (ang = 0 -> P = inf), reverse, |P| just above / below the bound
+    lin, ang = golden["in_ka_lin"], golden["in_ka_ang"]
+    P = torch.copysign(lin / ang, -ang)
+    assert (P.abs() <= 0.45).any() and torch.isinf(P).any() and (lin < 0).any() and ((lin == 0) & (ang != 0)).any()
+    steer, vel = _c_ackermann(clib, lin, ang)
+    pos, vt = np.empty((len(lin), 4), np.float32), np.empty((len(lin), 6), np.float32)
+    clib.rvo_joint_targets(steer.ctypes.data, vel.ctypes.data, len(lin), pos.ctypes.data, vt.ctypes.data)
+    p_ref, v_ref = O.joint_targets(torch.from_numpy(steer), torch.from_numpy(vel))
+    assert np.array_equal(pos, p_ref.numpy()) and np.array_equal(vt, v_ref.numpy(), equal_nan=True)
