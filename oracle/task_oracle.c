@@ -45,3 +45,43 @@ void rvo_joint_targets(const float* steer, const float* vel, int64_t n, float* p
         for (int j = 0; j < 6; ++j) velocities[6 * i + j] = vel[6 * i + VI_[j]];
     }
 }
+
+/* RoverTask.calculate_metrics (rover.py:460-531) and is_done (rover.py:610-647), fp32 with torch's promotion rules (a Python
+ * float meeting a float32 tensor is rounded to float32 first; int64 tensors times a Python float give float32).  Reward scales:
+ * cfg/task/Rover.yaml:37-46.  Pure IEEE arithmetic (+ sqrt) => bit for bit.
+ * extras [n,5] = pos_reward, heading_contraint_penalty, motion_contraint_penalty, goal_angle_penalty, uprightness_penalty. */
+void rvo_reward_reset(const float* pos, const float* target, const float* heading, const float* lin, const float* lin_prev,
+                      const float* ang, const float* ang_prev, const float* joints, int64_t joints_ld, const int64_t* progress,
+                      const int64_t* rock_collision, const float* rover_rot, int level, int64_t max_len, int64_t n, float* rew,
+                      int64_t* reset, float* extras) {
+    const float heading_scale = 0.05f, motion_scale = -0.01f, goal_scale = 0.3f, boogie_scale = 0.5f, pos_scale = 1.0f;
+    const float k33 = (float)(0.33 * 0.33), near = (float)0.18, tilt = (float)(0.78 * 1.5);
+    for (int64_t i = 0; i < n; ++i) {
+        const float dx = target[3 * i] - pos[3 * i], dy = target[3 * i + 1] - pos[3 * i + 1];
+        const float td = sqrtf(dx * dx + dy * dy);                                         /* :482 */
+        const float heading_pen = (lin[i] < 0.0f ? -1.0f : 0.0f) * heading_scale;          /* :486 */
+        const float* j = joints + joints_ld * i;
+        const float boogie = ((fabsf(j[0]) + fabsf(j[1])) + fabsf(j[2])) * boogie_scale;   /* :492 */
+        const float hd = heading[i];
+        const float goal_pen = fabsf(hd) > 2.0f ? -fabsf((hd * 0.3f) * goal_scale) : 0.0f; /* :495 */
+        const float dl = fabsf(lin[i] * 3.0f - 3.0f * lin_prev[i]);                        /* :498 */
+        const float da = fabsf(ang[i] * 3.0f - 3.0f * ang_prev[i]);
+        const float p1 = dl > 0.05f ? dl * dl : 0.0f, p2 = da > 0.05f ? da * da : 0.0f;    /* :499-500 */
+        const float motion = (p1 * p1) * motion_scale + (p2 * p2) * motion_scale;          /* :501-502 */
+        float pos_rew = (1.0f / (1.0f + ((k33 * td) * td))) * pos_scale;                   /* :505 */
+        if (td <= near) pos_rew = 1.03f * (float)(max_len - progress[i]);                  /* :506 */
+        float r = ((pos_rew + heading_pen) + motion) + goal_pen;                           /* :512 */
+        const int hit = level >= 2 && rock_collision && rock_collision[i] == 1;
+        if (hit) r = r - 300.0f;                                                           /* :519 */
+        rew[i] = r / 3000.0f;                                                              /* :522 */
+        float* e = extras + 5 * i;
+        e[0] = pos_rew; e[1] = heading_pen; e[2] = motion; e[3] = goal_pen; e[4] = boogie;
+        int64_t done = progress[i] >= max_len;                                             /* :614 */
+        if (fabsf(rover_rot[3 * i]) >= tilt) done = 1;                                     /* :615 */
+        if (fabsf(rover_rot[3 * i + 1]) >= tilt) done = 1;                                 /* :616 */
+        if (td >= 11.0f) done = 1;                                                         /* :617 */
+        if (td <= near) done = 1;                                                          /* :618 */
+        if (hit) done = 1;                                                                 /* :619 */
+        reset[i] = done;
+    }
+}

@@ -30,6 +30,8 @@ def clib():
     lib.rvo_ackermann.restype = None
     lib.rvo_joint_targets.argtypes = [p, p, i64, p, p]
     lib.rvo_joint_targets.restype = None
+    lib.rvo_reward_reset.argtypes = [p] * 8 + [i64, p, p, p, C.c_int, i64, i64, p, p, p]
+    lib.rvo_reward_reset.restype = None
     return lib
 
 
@@ -156,3 +158,31 @@ def test_golden_ackermann_in_c(clib, golden):
     clib.rvo_joint_targets(steer.ctypes.data, vel.ctypes.data, len(lin), pos.ctypes.data, vt.ctypes.data)
     p_ref, v_ref = O.joint_targets(torch.from_numpy(steer), torch.from_numpy(vel))
     assert np.array_equal(pos, p_ref.numpy()) and np.array_equal(vt, v_ref.numpy(), equal_nan=True)
+
+
+def test_golden_reward_and_reset_in_c(clib, golden):
+    """calculate_metrics + is_done (rover.py:460-531,610-647) in C, both curriculum levels: rewards, reward terms and reset masks
+    bit for bit against the reference's outputs."""
+    g = golden
+    f = lambda t: np.ascontiguousarray(t.numpy().astype(np.float32))
+    pos, target, heading = f(g["in_pos"]), f(g["in_target"]), f(g["ref_heading"])
+    lin, ang = f(g["in_actions"][:, 0]), f(g["in_actions"][:, 1])
+    lin_p, ang_p = f(g["in_prev_actions"][:, 0]), f(g["in_prev_actions"][:, 1])
+    joints, eul = f(g["in_joints"]), f(g["ref_euler"])
+    progress = np.ascontiguousarray(g["in_progress"].numpy().astype(np.int64))
+    coll = np.ascontiguousarray(g["ref_rock_collision"].numpy().astype(np.int64))
+    n = pos.shape[0]
+    for level, ref_rew, ref_reset in ((2, g["ref_rew"], g["ref_reset"]), (1, g["ref_rew_level1"], g["ref_reset_level1"])):
+        rew, reset, ex = np.empty(n, np.float32), np.empty(n, np.int64), np.empty((n, 5), np.float32)
+        clib.rvo_reward_reset(pos.ctypes.data, target.ctypes.data, heading.ctypes.data, lin.ctypes.data, lin_p.ctypes.data,
+                              ang.ctypes.data, ang_p.ctypes.data, joints.ctypes.data, joints.shape[1], progress.ctypes.data,
+                              coll.ctypes.data if level >= 2 else None, eul.ctypes.data, level, 3000, n, rew.ctypes.data,
+                              reset.ctypes.data, ex.ctypes.data)
+        assert np.array_equal(rew, ref_rew.numpy()), level
+        assert np.array_equal(reset, ref_reset.numpy()), level
+        if level == 2:
+            e = g["ref_extras"]
+            for col, key in enumerate(("pos_reward", "heading_contraint_penalty", "motion_contraint_penalty", "goal_angle_penalty",
+                                       "uprightness_penalty")):
+                assert np.array_equal(ex[:, col], e[key].numpy().astype(np.float32)), key
+    assert g["ref_reset"].sum() > 0 and (g["ref_reset"] == 0).sum() > 0
