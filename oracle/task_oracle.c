@@ -85,3 +85,55 @@ void rvo_reward_reset(const float* pos, const float* target, const float* headin
         reset[i] = done;
     }
 }
+
+/* tensor_quat_to_eul (tasks/utils/math/tensor_quat_to_euler.py:6-31), wxyz -> roll, pitch, yaw in fp32.  atan2 / asin are libm's
+ * here and Sleef's in torch: equal to an ulp, not bit for bit.  torch.pi of the reference = 3.1415927410125732 (:4). */
+void rvo_quat_to_euler(const float* q, int64_t n, float* e) {
+    const float pi = 3.1415927410125732f;
+    for (int64_t i = 0; i < n; ++i) {
+        const float w = q[4 * i], x = q[4 * i + 1], y = q[4 * i + 2], z = q[4 * i + 3];
+        e[3 * i] = atan2f(2.0f * (w * x + y * z), 1.0f - (2.0f * (x * x + y * y)));           /* :17-19 */
+        const float sinp = 2.0f * (w * y - z * x);                                            /* :22 */
+        const float t = sinp - 1.0f;
+        const float sgn = (t > 0.0f) - (t < 0.0f);                                            /* torch.sign; NaN -> 0 here, NaN >= 0 false there: both take asin */
+        e[3 * i + 1] = (t == t && sgn >= 0.0f) ? copysignf((1.0f * pi) / 2.0f, sinp) : asinf(sinp);   /* :23-24 */
+        e[3 * i + 2] = atan2f(2.0f * (w * z + x * y), 1.0f - (2.0f * (y * y + z * z)));       /* :27-29 */
+    }
+}
+
+/* The four proprioceptive observation columns and heading_diff (rover.py:279-283,320-323). */
+void rvo_obs_proprio(const float* pos, const float* euler, const float* target, const float* lin_now, const float* ang_now,
+                     int64_t n, float* obs4, float* heading) {
+    for (int64_t i = 0; i < n; ++i) {
+        const float yaw = euler[3 * i + 2];
+        const float dx = cosf(yaw), dy = sinf(yaw);                                           /* :279-280 */
+        const float tx = target[3 * i] - pos[3 * i], ty = target[3 * i + 1] - pos[3 * i + 1]; /* :281 */
+        const float h = -atan2f(tx * dy - ty * dx, tx * dx + ty * dy);                        /* :283 */
+        heading[i] = h;
+        obs4[4 * i] = sqrtf(tx * tx + ty * ty) / 9.0f;                                        /* :320 */
+        obs4[4 * i + 1] = h / (float)3.141592653589793;                                       /* :321 math.pi */
+        obs4[4 * i + 2] = lin_now[i];                                                         /* :322 */
+        obs4[4 * i + 3] = ang_now[i];                                                         /* :323 */
+    }
+}
+
+/* obs_buf[:, 4:] (rover.py:324-325): sparse / 2 and dense / 2 are fp16 divisions (one rounding), stored as fp32.
+ * dist = fp16 bits [P] of one env; idx = the pattern's coarse then fine index vectors (heightmap_distribution.py:107-133). */
+void rvo_obs_heightmap(const uint16_t* dist, const int64_t* idx, int64_t n_idx, float* out) {
+    for (int64_t i = 0; i < n_idx; ++i) {
+        _Float16 h;
+        __builtin_memcpy(&h, dist + idx[i], 2);
+        out[i] = (float)(_Float16)((float)h / 2.0f);
+    }
+}
+
+/* get_pos_height (rover.py:588-608): idx = round_half_even(clamp((xy - shift) / hscale, 0, H - 1)); heightmap[ix, iy] * vscale */
+void rvo_pos_height(const float* heightmap, int64_t H0, int64_t H1, const float* xy, int64_t xy_ld, int64_t n, float hscale,
+                    float vscale, float shift_x, float shift_y, float* out) {
+    for (int64_t i = 0; i < n; ++i) {
+        float u = (xy[xy_ld * i] - shift_x) / hscale, v = (xy[xy_ld * i + 1] - shift_y) / hscale;
+        u = fminf(fmaxf(u, 0.0f), (float)(H0 - 1));                                           /* the reference clamps both to size()[0] - 1 */
+        v = fminf(fmaxf(v, 0.0f), (float)(H0 - 1));
+        out[i] = heightmap[(int64_t)rintf(u) * H1 + (int64_t)rintf(v)] * vscale;
+    }
+}

@@ -32,6 +32,12 @@ def clib():
     lib.rvo_joint_targets.restype = None
     lib.rvo_reward_reset.argtypes = [p] * 8 + [i64, p, p, p, C.c_int, i64, i64, p, p, p]
     lib.rvo_reward_reset.restype = None
+    lib.rvo_quat_to_euler.argtypes = [p, i64, p]
+    lib.rvo_obs_proprio.argtypes = [p, p, p, p, p, i64, p, p]
+    lib.rvo_obs_heightmap.argtypes = [p, p, i64, p]
+    lib.rvo_pos_height.argtypes = [p, i64, i64, p, i64, i64, C.c_float, C.c_float, C.c_float, C.c_float, p]
+    for fn in (lib.rvo_quat_to_euler, lib.rvo_obs_proprio, lib.rvo_obs_heightmap, lib.rvo_pos_height):
+        fn.restype = None
     return lib
 
 
@@ -186,3 +192,39 @@ def test_golden_reward_and_reset_in_c(clib, golden):
                                        "uprightness_penalty")):
                 assert np.array_equal(ex[:, col], e[key].numpy().astype(np.float32)), key
     assert g["ref_reset"].sum() > 0 and (g["ref_reset"] == 0).sum() > 0
+
+
+def test_golden_observation_in_c(clib, golden):
+    """get_observations (rover.py:272-336) in C: quat -> euler and the proprioceptive columns to an ulp of libm's atan2 / asin /
+    sin / cos, the 1746 heightmap columns (fp16 halving of the ray distances, gathered by the pattern's index vectors) bit for bit."""
+    g = golden
+    f = lambda t: np.ascontiguousarray(t.numpy().astype(np.float32))
+    n = g["in_quat"].shape[0]
+    q, e = f(g["in_quat"]), np.empty((n, 3), np.float32)
+    clib.rvo_quat_to_euler(q.ctypes.data, n, e.ctypes.data)
+    assert np.allclose(e, g["ref_euler"].numpy(), rtol=0, atol=5e-7)
+    pos, target, eul = f(g["in_pos"]), f(g["in_target"]), f(g["ref_euler"])
+    lin, ang = f(g["in_actions"][:, 0]), f(g["in_actions"][:, 1])
+    obs4, heading = np.empty((n, 4), np.float32), np.empty(n, np.float32)
+    clib.rvo_obs_proprio(pos.ctypes.data, eul.ctypes.data, target.ctypes.data, lin.ctypes.data, ang.ctypes.data, n,
+                         obs4.ctypes.data, heading.ctypes.data)
+    assert np.allclose(heading, g["ref_heading"].numpy(), rtol=0, atol=5e-7)
+    assert np.allclose(obs4, g["ref_obs"][:, :4].numpy(), rtol=1e-6, atol=2e-7)
+    assert np.array_equal(obs4[:, 2:], g["ref_obs"][:, 2:4].numpy())
+    idx = np.ascontiguousarray(torch.cat((g["ref_coarse_idx"], g["ref_fine_idx"])).numpy().astype(np.int64))
+    assert idx.shape[0] == 634 + 1112                                   # teacher_loader.py:47-48
+    for env in range(n):
+        d = _u16(g["ref_dist"][env])
+        out = np.empty(idx.shape[0], np.float32)
+        clib.rvo_obs_heightmap(d.ctypes.data, idx.ctypes.data, idx.shape[0], out.ctypes.data)
+        assert np.array_equal(out, g["ref_obs"][env, 4:].numpy()), env
+
+
+def test_golden_pos_height_in_c(clib, golden):
+    g = golden
+    hm = np.ascontiguousarray(g["world"]["heightmap"].numpy().astype(np.float32))
+    xy = np.ascontiguousarray(g["ref_spawn_pos"][:, 0:2].numpy().astype(np.float32))
+    out = np.empty(xy.shape[0], np.float32)
+    clib.rvo_pos_height(hm.ctypes.data, hm.shape[0], hm.shape[1], xy.ctypes.data, 2, xy.shape[0], float(g["world"]["hm_res"]), 1.0,
+                        0.0, 0.0, out.ctypes.data)
+    assert np.array_equal(out, g["ref_spawn_height"].numpy())
