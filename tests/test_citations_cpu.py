@@ -26,7 +26,7 @@ def _sources():
     out = [os.path.join(ROOT, "include", "rover_b200.h"), os.path.join(ROOT, "DESIGN.md"), os.path.join(ROOT, "INTEGRATION.md")]
     for sub in ("isaac_rover_2.0_b200", os.path.join("isaac_rover_2.0_b200", "csrc"), "oracle"):
         d = os.path.join(ROOT, sub)
-        out += [os.path.join(d, f) for f in sorted(os.listdir(d)) if f.endswith((".py", ".cu", ".cuh"))]
+        out += [os.path.join(d, f) for f in sorted(os.listdir(d)) if f.endswith((".py", ".cu", ".cuh", ".c"))]
     return out
 
 
