@@ -147,3 +147,45 @@ void rvo_get_depths_env(const float* pos, const float* trig, const double* patte
     }
 #undef RVO_XFORM
 }
+
+/* Rock_Detection.get_collisions' cast (rock_detect.py:65-115) for ONE env given its 26 rays (24 wheel + 2 body; sources and
+ * directions fp16 [R,3]): per ray the cell lookup of rock_detect.py:373-401 (same arithmetic as camera.py:233-264), the K-list of
+ * that cell, ray_distance per candidate and torch.min over K. */
+void rvo_cast_rays_env(const uint16_t* sources, const uint16_t* directions, int64_t R, const int32_t* map_kgg, int64_t G, int64_t K,
+                       const int32_t* triangles, const uint16_t* vertices, float shift_x, float shift_y, float res, uint16_t* dist,
+                       int32_t* slot) {
+    const float shift[2] = {shift_x, shift_y};
+    for (int64_t r = 0; r < R; ++r) {
+        const uint16_t* s16 = sources + 3 * r;
+        int64_t cell[2];
+        for (int i = 0; i < 2; ++i) {
+            float v = ((float)from_bits(s16[i]) - shift[i]) / res;
+            v = fminf(fmaxf(v, 0.0f), (float)(G - 1));
+            cell[i] = (int64_t)rintf(v);
+        }
+        const v3 s = load3(s16), d = load3(directions + 3 * r);
+        h16 best = 0;
+        int32_t best_j = -1;
+        for (int64_t j = 0; j < K; ++j) {
+            const int32_t* t = triangles + 3 * (int64_t)map_kgg[(j * G + cell[0]) * G + cell[1]];
+            uint16_t tri[9];
+            for (int v = 0; v < 3; ++v) memcpy(tri + 3 * v, vertices + 3 * (int64_t)t[v], 6);
+            h16 kk = ray_triangle(s, d, tri, 0);
+            if (best_j < 0 || (best == best && (kk != kk || kk < best))) { best = kk; best_j = (int32_t)j; }
+        }
+        dist[r] = to_bits(best);
+        slot[r] = best_j;
+    }
+}
+
+/* RoverTask.check_collision (rover.py:663-668), torch-CPU semantics: min over the 24 wheel / 2 body distances (NaN wins), then
+ * |min| < 0.8 resp. 0.45 with the Python scalar rounded to fp16 first (the comparison runs in the tensor's dtype on the CPU). */
+int64_t rvo_check_collision(const uint16_t* wheel, int64_t n_wheel, const uint16_t* body, int64_t n_body) {
+    h16 w = from_bits(wheel[0]), b = from_bits(body[0]);
+    for (int64_t i = 1; i < n_wheel; ++i) { h16 v = from_bits(wheel[i]); if (w == w && (v != v || v < w)) w = v; }
+    for (int64_t i = 1; i < n_body; ++i) { h16 v = from_bits(body[i]); if (b == b && (v != v || v < b)) b = v; }
+    const h16 aw = (h16)fabsf((float)w), ab = (h16)fabsf((float)b);
+    int64_t col = aw < (h16)0.8f ? 1 : 0;
+    if (ab < (h16)0.45f) col = 1;
+    return col;
+}

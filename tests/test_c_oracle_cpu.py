@@ -26,6 +26,10 @@ def clib():
     lib.rvo_cast_min.restype = None
     lib.rvo_get_depths_env.argtypes = [p, p, p, i64, p, i64, i64, p, p, C.c_float, C.c_float, C.c_float, p, p, p]
     lib.rvo_get_depths_env.restype = None
+    lib.rvo_cast_rays_env.argtypes = [p, p, i64, p, i64, i64, p, p, C.c_float, C.c_float, C.c_float, p, p]
+    lib.rvo_cast_rays_env.restype = None
+    lib.rvo_check_collision.argtypes = [p, i64, p, i64]
+    lib.rvo_check_collision.restype = i64
     lib.rvo_ackermann.argtypes = [p, p, i64, p, p]
     lib.rvo_ackermann.restype = None
     lib.rvo_joint_targets.argtypes = [p, p, i64, p, p]
@@ -228,3 +232,26 @@ def test_golden_pos_height_in_c(clib, golden):
     clib.rvo_pos_height(hm.ctypes.data, hm.shape[0], hm.shape[1], xy.ctypes.data, 2, xy.shape[0], float(g["world"]["hm_res"]), 1.0,
                         0.0, 0.0, out.ctypes.data)
     assert np.array_equal(out, g["ref_spawn_height"].numpy())
+
+
+def test_golden_rock_cast_and_collision_in_c(clib, golden):
+    """Rock_Detection.get_collisions' cast (rock_detect.py:65-115) + check_collision (rover.py:663-668) in C, fed with the 26 rays per
+    env the reference produced: wheel / body distances and collision flags bit for bit."""
+    g, w = golden, golden["world"]
+    m = np.ascontiguousarray(w["rock_indices"].to(torch.int32).numpy())
+    K, G = m.shape[0], m.shape[1]
+    tri = np.ascontiguousarray(w["rock_triangles"].to(torch.int32).numpy())
+    ver = _u16(w["rock_vertices"])
+    ref = torch.cat((g["ref_wheel"], g["ref_body"]), 1)
+    flags = []
+    for e in range(ref.shape[0]):
+        s, d = _u16(g["ref_rock_sources"][e]), _u16(g["ref_rock_dirs"][e])
+        R = s.shape[0]
+        dist, slot = np.empty(R, np.uint16), np.empty(R, np.int32)
+        clib.rvo_cast_rays_env(s.ctypes.data, d.ctypes.data, R, m.ctypes.data, G, K, tri.ctypes.data, ver.ctypes.data, 0.0, 0.0, 0.1,
+                               dist.ctypes.data, slot.ctypes.data)
+        assert R == 26 and same_halves(dist, ref[e]), e
+        wd, bd = np.ascontiguousarray(dist[:24]), np.ascontiguousarray(dist[24:])
+        flags.append(clib.rvo_check_collision(wd.ctypes.data, 24, bd.ctypes.data, 2))
+    assert flags == g["ref_rock_collision"].tolist()
+    assert 0 < sum(flags) < len(flags)
