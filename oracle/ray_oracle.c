@@ -189,3 +189,66 @@ int64_t rvo_check_collision(const uint16_t* wheel, int64_t n_wheel, const uint16
     if (ab < (h16)0.45f) col = 1;
     return col;
 }
+
+/* Rock_Detection._get_wheel_rays + _get_body_rays (rock_detect.py:160-371) for ONE env, fp32 -> fp16.
+ * trig = sin/cos of the negated body euler angles (given, as in rvo_get_depths_env); the sin/cos of the joint angles are
+ * libm's here (Sleef's in torch): the rays equal the reference's to an fp32 ulp before the fp16 cast, i.e. bit for bit for
+ * almost all of them.  joints = the 13 DOF positions in the order of rock_detect.py:174-188.
+ * Output: 24 wheel rays (6 wheels x 4 points, :193-198,317) then 2 body rays (:326,338-340): sources, dirs fp16 [26,3]. */
+static void body_xform_f(float x, float y, float z, const float* t6, float tx, float ty, float tz, float* o) {
+    const float sx = t6[0], cx = t6[1], sy = t6[2], cy = t6[3], sz = t6[4], cz = t6[5];
+    const float A = y * cx + z * sx, C = z * cx - y * sx, B = x * cy - sy * C;       /* :305-307 / :356-358 */
+    o[0] = (tx + sz * A) + cz * B;
+    o[1] = (ty + cz * A) - sz * B;
+    o[2] = (tz + x * sy) + cy * C;
+}
+
+void rvo_rock_rays_env(const float* pos, const float* trig, const float* joints, uint16_t* sources, uint16_t* dirs) {
+    static const float RAYS[5][3] = {{(float)(0.215 / 2), (float)(0.130 / 2), 0.1f}, {(float)(0.215 / 2), (float)(-0.130 / 2), 0.1f},
+                                     {(float)(-0.215 / 2), (float)(0.130 / 2), 0.1f}, {(float)(-0.215 / 2), (float)(-0.130 / 2), 0.1f},
+                                     {0.0f, 0.0f, -1.0f}};                                        /* :193-197 */
+    static const float POS0[6][3] = {{0.286f, 0.385f, -0.197f}, {0.286f, -0.385f, -0.197f}, {-0.146f, 0.447f, -0.197f},
+                                     {-0.146f, -0.447f, -0.197f}, {-0.440f, 0.385f, -0.197f}, {-0.440f, -0.385f, -0.197f}};   /* :201-206 */
+    static const float POS1[6][3] = {{0.153f, 0.0f, 0.03f}, {0.153f, 0.0f, 0.03f}, {0.153f, 0.0f, 0.03f}, {0.153f, -0.0f, 0.03f},
+                                     {0.0f, 0.0f, 0.03f}, {0.0f, 0.0f, 0.03f}};                  /* :210-215 */
+    const float* j = joints;
+    const float steer[6] = {j[4], j[6], 0.0f, 0.0f, -j[7], j[8]};                                 /* :248 */
+    const float susy[6] = {-j[0], j[1], -j[0], j[1], 0.0f, 0.0f};                                 /* :263 */
+    const float susx[6] = {0.0f, 0.0f, 0.0f, 0.0f, -j[2], -j[2]};                                 /* :264 */
+    for (int w = 0; w < 6; ++w) {
+        const float ss = sinf(-steer[w]), cs = cosf(-steer[w]);
+        const float sux = sinf(susx[w]), cux = cosf(susx[w]), suy = sinf(susy[w]), cuy = cosf(susy[w]);
+        float dir[3] = {0, 0, 0};
+        float pts[4][3];
+        for (int p = 4; p >= 0; --p) {                       /* entry 4 = the direction: zero translation at every stage */
+            const int isdir = (p == 4);
+            const float x = RAYS[p][0], y = RAYS[p][1], z = RAYS[p][2];
+            const float t0x = isdir ? 0.0f : POS0[w][0], t0y = isdir ? 0.0f : POS0[w][1], t0z = isdir ? 0.0f : POS0[w][2];
+            const float t1x = isdir ? 0.0f : POS1[w][0], t1y = isdir ? 0.0f : POS1[w][1], t1z = isdir ? 0.0f : POS1[w][2];
+            const float x1 = (t0x + x * cs) + y * ss;                                             /* :256-258 */
+            const float y1 = (t0y + y * cs) - x * ss;
+            const float z1 = t0z + z;
+            const float Cq = z1 * cux - y1 * sux;
+            const float x2 = (t1x + x1 * cuy) - suy * Cq;                                         /* :275-277 */
+            const float y2 = (t1y + y1 * cux) + z1 * sux;
+            const float z2 = (t1z + x1 * suy) + cuy * Cq;
+            float o[3];
+            body_xform_f(x2, y2, z2, trig, isdir ? 0.0f : pos[0], isdir ? 0.0f : pos[1], isdir ? 0.0f : pos[2], o);
+            if (isdir) { dir[0] = o[0]; dir[1] = o[1]; dir[2] = o[2]; }
+            else { pts[p][0] = o[0]; pts[p][1] = o[1]; pts[p][2] = o[2]; }
+        }
+        for (int p = 0; p < 4; ++p)
+            for (int i = 0; i < 3; ++i) {
+                sources[3 * (4 * w + p) + i] = to_bits((h16)pts[p][i]);                           /* :317 */
+                dirs[3 * (4 * w + p) + i] = to_bits((h16)dir[i]);                                 /* :314 */
+            }
+    }
+    static const float BODY[3][3] = {{0.340f, 0.0f, -0.01f}, {-0.485f, 0.0f, -0.01f}, {0.0f, 1.0f, 0.0f}};   /* :326,338 */
+    float o[3][3];
+    for (int p = 0; p < 3; ++p) body_xform_f(BODY[p][0], BODY[p][1], BODY[p][2], trig, pos[0], pos[1], pos[2], o[p]);
+    for (int p = 0; p < 2; ++p)
+        for (int i = 0; i < 3; ++i) {
+            sources[3 * (24 + p) + i] = to_bits((h16)o[p][i]);
+            dirs[3 * (24 + p) + i] = to_bits((h16)(o[2][i] - pos[i]));                            /* :340 */
+        }
+}

@@ -28,6 +28,8 @@ def clib():
     lib.rvo_get_depths_env.restype = None
     lib.rvo_cast_rays_env.argtypes = [p, p, i64, p, i64, i64, p, p, C.c_float, C.c_float, C.c_float, p, p]
     lib.rvo_cast_rays_env.restype = None
+    lib.rvo_rock_rays_env.argtypes = [p, p, p, p, p]
+    lib.rvo_rock_rays_env.restype = None
     lib.rvo_check_collision.argtypes = [p, i64, p, i64]
     lib.rvo_check_collision.restype = i64
     lib.rvo_ackermann.argtypes = [p, p, i64, p, p]
@@ -255,3 +257,23 @@ def test_golden_rock_cast_and_collision_in_c(clib, golden):
         flags.append(clib.rvo_check_collision(wd.ctypes.data, 24, bd.ctypes.data, 2))
     assert flags == g["ref_rock_collision"].tolist()
     assert 0 < sum(flags) < len(flags)
+
+
+def test_golden_rock_rays_in_c(clib, golden):
+    """_get_wheel_rays / _get_body_rays (rock_detect.py:160-371) in C.  The joint-angle sin / cos are libm's (Sleef's in torch), so
+    the fp32 values may differ in the last ulp before the fp16 cast: every ray within one fp16 ulp, almost all bit-identical."""
+    g = golden
+    n = g["in_pos"].shape[0]
+    same = total = 0
+    for e in range(n):
+        pos = np.ascontiguousarray(g["in_pos"][e].numpy().astype(np.float32))
+        trig = np.ascontiguousarray(g["trig"][e].numpy().astype(np.float32))
+        joints = np.ascontiguousarray(g["in_joints"][e].numpy().astype(np.float32))
+        src, dirs = np.empty((26, 3), np.uint16), np.empty((26, 3), np.uint16)
+        clib.rvo_rock_rays_env(pos.ctypes.data, trig.ctypes.data, joints.ctypes.data, src.ctypes.data, dirs.ctypes.data)
+        rs, rd = g["ref_rock_sources"][e], g["ref_rock_dirs"][e]
+        assert np.abs(src.view(np.float16).astype(np.float32) - rs.float().numpy()).max() <= 2e-3
+        assert np.abs(dirs.view(np.float16).astype(np.float32) - rd.float().numpy()).max() <= 1e-3
+        same += int((src == _u16(rs)).sum() + (dirs == _u16(rd)).sum())
+        total += src.size + dirs.size
+    assert same / total > 0.98, same / total
