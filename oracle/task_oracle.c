@@ -137,3 +137,43 @@ void rvo_pos_height(const float* heightmap, int64_t H0, int64_t H1, const float*
         out[i] = heightmap[(int64_t)rintf(u) * H1 + (int64_t)rintf(v)] * vscale;
     }
 }
+
+/* Stones (terrain_utils.py:416-424, rover.py:533-542,649-661).
+ * read_stone_info: column 6 = max(col 3, col 4) / 4 in the file's dtype (f64), then the whole row cast to f32.
+ * nearest stone edge = min_s(||xy - stone_s.xy|| - radius_s): the direct formula torch.cdist uses up to 25 rows (bit for bit);
+ * above that torch switches to its matmul formulation (|a|^2 + |b|^2 - 2ab), which agrees to ~1e-4 only.
+ * check_goal_collision: invalid iff nearest <= 1.0 (rover.py:539); avoid_pos_rock_collision: x += 0.05 while nearest <= 1.4
+ * for any env, until nothing changes (rover.py:655-660). */
+void rvo_read_stone_info(const double* stone6, int64_t S, float* stone7) {
+    for (int64_t s = 0; s < S; ++s) {
+        const double* r = stone6 + 6 * s;
+        for (int c = 0; c < 6; ++c) stone7[7 * s + c] = (float)r[c];
+        stone7[7 * s + 6] = (float)((r[3] > r[4] ? r[3] : r[4]) / 4);
+    }
+}
+
+void rvo_nearest_stone_edge(const float* xy, int64_t xy_ld, int64_t n, const float* stone7, int64_t S, float* nearest) {
+    for (int64_t i = 0; i < n; ++i) {
+        float best = INFINITY;
+        for (int64_t s = 0; s < S; ++s) {
+            const float dx = xy[xy_ld * i] - stone7[7 * s], dy = xy[xy_ld * i + 1] - stone7[7 * s + 1];
+            const float d = sqrtf(dx * dx + dy * dy) - stone7[7 * s + 6];
+            if (d < best) best = d;
+        }
+        nearest[i] = best;
+    }
+}
+
+/* pos f32 [n,3] in place; returns the number of sweeps */
+int64_t rvo_avoid_pos_rock_collision(float* pos, int64_t n, const float* stone7, int64_t S, int64_t max_iter) {
+    for (int64_t it = 1; it <= max_iter; ++it) {
+        int changed = 0;
+        for (int64_t i = 0; i < n; ++i) {
+            float near;
+            rvo_nearest_stone_edge(pos + 3 * i, 3, 1, stone7, S, &near);
+            if (near <= 1.4f) { pos[3 * i] = pos[3 * i] + 0.05f; changed = 1; }
+        }
+        if (!changed) return it;
+    }
+    return -1;
+}

@@ -38,6 +38,12 @@ def clib():
     lib.rvo_joint_targets.restype = None
     lib.rvo_reward_reset.argtypes = [p] * 8 + [i64, p, p, p, C.c_int, i64, i64, p, p, p]
     lib.rvo_reward_reset.restype = None
+    lib.rvo_read_stone_info.argtypes = [p, i64, p]
+    lib.rvo_read_stone_info.restype = None
+    lib.rvo_nearest_stone_edge.argtypes = [p, i64, i64, p, i64, p]
+    lib.rvo_nearest_stone_edge.restype = None
+    lib.rvo_avoid_pos_rock_collision.argtypes = [p, i64, p, i64, i64]
+    lib.rvo_avoid_pos_rock_collision.restype = i64
     lib.rvo_quat_to_euler.argtypes = [p, i64, p]
     lib.rvo_obs_proprio.argtypes = [p, p, p, p, p, i64, p, p]
     lib.rvo_obs_heightmap.argtypes = [p, p, i64, p]
@@ -277,3 +283,29 @@ def test_golden_rock_rays_in_c(clib, golden):
         same += int((src == _u16(rs)).sum() + (dirs == _u16(rd)).sum())
         total += src.size + dirs.size
     assert same / total > 0.98, same / total
+
+
+def test_golden_stones_in_c(clib, golden):
+    """read_stone_info, check_goal_collision's distance, avoid_pos_rock_collision (terrain_utils.py:416-424, rover.py:533-542,649-661)."""
+    g = golden
+    s6 = np.ascontiguousarray(g["world"]["stone_info6"].numpy().astype(np.float64))
+    S = s6.shape[0]
+    s7 = np.empty((S, 7), np.float32)
+    clib.rvo_read_stone_info(s6.ctypes.data, S, s7.ctypes.data)
+    assert np.array_equal(s7, g["ref_stone7"].numpy())
+    xy = np.ascontiguousarray(g["in_target"][:, 0:2].numpy().astype(np.float32))
+    near = np.empty(xy.shape[0], np.float32)
+    clib.rvo_nearest_stone_edge(xy.ctypes.data, 2, xy.shape[0], s7.ctypes.data, S, near.ctypes.data)
+    assert xy.shape[0] <= 25 and np.array_equal(near, g["ref_goal_nearest"].numpy())          # cdist's direct path: bit for bit
+    assert int((near <= 1.0).sum()) == g["ref_goal_count"]
+    many = np.ascontiguousarray(g["in_spawn_pos"].numpy().astype(np.float32))
+    near = np.empty(many.shape[0], np.float32)
+    clib.rvo_nearest_stone_edge(many.ctypes.data, 3, many.shape[0], s7.ctypes.data, S, near.ctypes.data)
+    assert many.shape[0] > 25 and np.allclose(near, g["ref_many_nearest"].numpy(), rtol=0, atol=2e-4)   # cdist's matmul path
+    moved = many.copy()
+    sweeps = clib.rvo_avoid_pos_rock_collision(moved.ctypes.data, moved.shape[0], s7.ctypes.data, S, 100000)
+    assert sweeps > 1
+    ref = g["ref_spawn_pos"].numpy()
+    assert np.array_equal(moved[:, 1:], ref[:, 1:])                        # only x moves
+    # the fixed point is reached in steps of 0.05: equal unless a matmul-path rounding flipped one `<= 1.4` decision
+    assert np.abs(moved[:, 0] - ref[:, 0]).max() <= 0.05 + 1e-6 and (moved[:, 0] == ref[:, 0]).mean() >= 0.95
