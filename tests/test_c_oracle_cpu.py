@@ -38,6 +38,8 @@ def clib():
     lib.rvo_joint_targets.restype = None
     lib.rvo_reward_reset.argtypes = [p] * 8 + [i64, p, p, p, C.c_int, i64, i64, p, p, p]
     lib.rvo_reward_reset.restype = None
+    lib.rvo_heightmap_pattern.argtypes = [p, i64, p, p, p, p]
+    lib.rvo_heightmap_pattern.restype = i64
     lib.rvo_read_stone_info.argtypes = [p, i64, p]
     lib.rvo_read_stone_info.restype = None
     lib.rvo_nearest_stone_edge.argtypes = [p, i64, i64, p, i64, p]
@@ -309,3 +311,15 @@ def test_golden_stones_in_c(clib, golden):
     assert np.array_equal(moved[:, 1:], ref[:, 1:])                        # only x moves
     # the fixed point is reached in steps of 0.05: equal unless a matmul-path rounding flipped one `<= 1.4` decision
     assert np.abs(moved[:, 0] - ref[:, 0]).max() <= 0.05 + 1e-6 and (moved[:, 0] == ref[:, 0]).mean() >= 0.95
+
+
+def test_golden_pattern_in_c(clib, golden):
+    """Heightmap (heightmap_distribution.py:11-204) in C: the 1634 points and both index vectors equal the reference's bit for bit."""
+    cap = 4096
+    pts = np.empty((cap, 3), np.float64)
+    ci, fi = np.empty(cap, np.int64), np.empty(cap, np.int64)
+    nc, nf = C.c_int64(), C.c_int64()
+    n = clib.rvo_heightmap_pattern(pts.ctypes.data, cap, ci.ctypes.data, C.addressof(nc), fi.ctypes.data, C.addressof(nf))
+    assert (n, nc.value, nf.value) == (1634, 634, 1112)                 # teacher_loader.py:47-48
+    assert np.array_equal(pts[:n], golden["ref_pattern"].numpy())
+    assert np.array_equal(ci[:nc.value], golden["ref_coarse_idx"].numpy()) and np.array_equal(fi[:nf.value], golden["ref_fine_idx"].numpy())
