@@ -323,3 +323,66 @@ def test_golden_pattern_in_c(clib, golden):
     assert (n, nc.value, nf.value) == (1634, 634, 1112)                 # teacher_loader.py:47-48
     assert np.array_equal(pts[:n], golden["ref_pattern"].numpy())
     assert np.array_equal(ci[:nc.value], golden["ref_coarse_idx"].numpy()) and np.array_equal(fi[:nf.value], golden["ref_fine_idx"].numpy())
+
+
+def test_c_and_torch_oracles_agree_on_random_task_inputs(clib):
+    """The two independent restatements (C and torch) on 20 000 random envs -- far more branch combinations than the 8 golden envs:
+    Ackermann (incl. 0/0, x/0, tiny angular rates), reward terms and reset masks for both curriculum levels, height lookups."""
+    g = torch.Generator().manual_seed(123)
+    n = 20_000
+    rnd = lambda *shape: torch.rand(*shape, generator=g)
+    lin, ang = rnd(n) * 2 - 1, rnd(n) * 2 - 1
+    lin[:200], ang[200:400] = 0.0, 0.0
+    ang[400:600] = (rnd(200) - 0.5) * 1e-6
+    lin[600:700], ang[600:700] = 0.0, 0.0
+    steer_t, vel_t = O.ackermann(lin, ang)
+    steer, vel = _c_ackermann(clib, lin, ang)
+    # torch-CPU's float32 sqrt is not correctly rounded (e.g. sqrt(4.087024211883545) -> 2.0216388702 where IEEE / sqrtf / CUDA give
+    # 2.0216391087, the nearer float): the wheel distance, hence the velocity, is one ulp off for ~0.3 % of the inputs
+    vt = vel_t.numpy()
+    assert np.allclose(vel, vt, rtol=2.5e-7, atol=0, equal_nan=True)
+    assert (vel != vt)[~np.isnan(vt)].mean() < 0.01
+    assert np.allclose(steer, steer_t.numpy(), rtol=0, atol=2.4e-7, equal_nan=True)
+
+    f = lambda t: np.ascontiguousarray(t.numpy().astype(np.float32))
+    pos = torch.cat((rnd(n, 2) * 40, rnd(n, 1)), 1)
+    target = pos.clone()
+    ang_t, rad = rnd(n) * 6.2831853, torch.where(rnd(n) < 0.1, rnd(n) * 0.3, rnd(n) * 13)      # near-goal and too-far cases
+    target[:, 0] += rad * torch.cos(ang_t)
+    target[:, 1] += rad * torch.sin(ang_t)
+    heading = rnd(n) * 6.4 - 3.2
+    lin_p, ang_p = rnd(n) * 2 - 1, rnd(n) * 2 - 1
+    same = rnd(n) < 0.2
+    lin_p, ang_p = torch.where(same, lin, lin_p), torch.where(same, ang + 0.01, ang_p)           # |delta| around the 0.05 threshold
+    joints = rnd(n, 13) * 0.6 - 0.3
+    progress = torch.randint(0, 3002, (n,), generator=g)
+    coll = (rnd(n) < 0.2).long()
+    rot = torch.where(rnd(n, 3) < 0.05, rnd(n, 3) * 2.6 - 1.3, rnd(n, 3) * 0.4 - 0.2)
+    for level in (1, 2):
+        rew_t, ex_t = O.metrics(pos, target, heading, lin, lin_p, ang, ang_p, joints, progress, coll if level >= 2 else None, level)
+        reset_t = O.is_done(pos, target, rot, progress, coll if level >= 2 else None, level)
+        rew, reset, ex = np.empty(n, np.float32), np.empty(n, np.int64), np.empty((n, 5), np.float32)
+        a = [f(pos), f(target), f(heading), f(lin), f(lin_p), f(ang), f(ang_p), f(joints)]
+        pr, co, ro = np.ascontiguousarray(progress.numpy()), np.ascontiguousarray(coll.numpy()), f(rot)
+        clib.rvo_reward_reset(*[x.ctypes.data for x in a], 13, pr.ctypes.data, co.ctypes.data if level >= 2 else None, ro.ctypes.data,
+                              level, 3000, n, rew.ctypes.data, reset.ctypes.data, ex.ctypes.data)
+        # the target distance goes through the same sqrt: position reward / total reward to an ulp, everything else bit for bit
+        assert np.allclose(rew, rew_t.numpy(), rtol=1e-6, atol=1e-10), level
+        assert (rew != rew_t.numpy()).mean() < 0.02
+        assert (reset != reset_t.numpy()).sum() <= 1, level                  # a distance within an ulp of 0.18 / 11 could flip
+        for col, key in enumerate(("pos_reward", "heading_contraint_penalty", "motion_contraint_penalty", "goal_angle_penalty",
+                                   "uprightness_penalty")):
+            ref = ex_t[key].numpy().astype(np.float32)
+            if key == "pos_reward":
+                assert np.allclose(ex[:, col], ref, rtol=1e-6, atol=0), (level, key)
+            else:
+                assert np.array_equal(ex[:, col], ref), (level, key)
+        assert 0.05 < reset_t.float().mean() < 0.95
+
+    hm = rnd(300, 300)
+    xy = rnd(n, 2) * 9 - 1                                                    # includes points off both edges of the 7.5 m grid
+    h_t = O.pos_height(hm, xy, 0.025, 1, torch.tensor([0.0, 0.0]))
+    out = np.empty(n, np.float32)
+    hmn, xyn = f(hm), f(xy)
+    clib.rvo_pos_height(hmn.ctypes.data, 300, 300, xyn.ctypes.data, 2, n, 0.025, 1.0, 0.0, 0.0, out.ctypes.data)
+    assert np.array_equal(out, h_t.numpy())
