@@ -386,3 +386,44 @@ def test_c_and_torch_oracles_agree_on_random_task_inputs(clib):
     hmn, xyn = f(hm), f(xy)
     clib.rvo_pos_height(hmn.ctypes.data, 300, 300, xyn.ctypes.data, 2, n, 0.025, 1.0, 0.0, 0.0, out.ctypes.data)
     assert np.array_equal(out, h_t.numpy())
+
+
+def test_c_get_depths_equals_torch_oracle_on_a_fresh_world(clib):
+    """Camera.get_depths in C against the torch oracle on a fresh synthetic world with 24 envs (1 % wildly tilted, border poses):
+    sources, distances and hit slots bit for bit; same for the rock cast of the oracle's wheel / body rays."""
+    import isaac_rover_b200  # noqa: F401  (CPU-side synthetic world helpers only)
+    from isaac_rover_b200 import synth
+    world = synth.make_world(length=10.0, nv=36, K=48, n_stones=6, seed=77)
+    st = synth.make_env_state(world, 24, seed=9, margin=1.0)
+    eul = O.quat_to_euler(st["quat"])
+    eul[0, 0], eul[1, 1], eul[2, 0] = 1.25, -1.2, 3.0                        # steep, steep, upside down
+    pat, _, _ = O.heightmap_pattern()
+    ref = O.get_depths(st["pos"], eul, pat, world.map_indices, world.triangles, world.vertices, torch.zeros(3))
+    trig = torch.cat(O._neg_trig(eul), 1)
+    patn = np.ascontiguousarray(pat.numpy())
+    P = patn.shape[0]
+    m = np.ascontiguousarray(world.map_indices.to(torch.int32).numpy())
+    K, G = m.shape[0], m.shape[1]
+    tri = np.ascontiguousarray(world.triangles.to(torch.int32).numpy())
+    ver = _u16(world.vertices)
+    for e in range(st["pos"].shape[0]):
+        pos = np.ascontiguousarray(st["pos"][e].numpy().astype(np.float32))
+        tg = np.ascontiguousarray(trig[e].numpy().astype(np.float32))
+        src, dist, slot = np.empty((P, 3), np.uint16), np.empty(P, np.uint16), np.empty(P, np.int32)
+        clib.rvo_get_depths_env(pos.ctypes.data, tg.ctypes.data, patn.ctypes.data, P, m.ctypes.data, G, K, tri.ctypes.data,
+                                ver.ctypes.data, 0.0, 0.0, 0.1, src.ctypes.data, dist.ctypes.data, slot.ctypes.data)
+        assert same_halves(src, ref["sources"][e]) and same_halves(dist, ref["dist"][e]), e
+        assert np.array_equal(slot, ref["slot"][e].numpy().astype(np.int32)), e
+    hits = (ref["dist"].float() < 11.0).float().mean().item()
+    assert 0.3 < hits < 1.0
+    rk = O.get_collisions(st["pos"], eul, st["joints"], world.rock_indices, world.rock_triangles, world.rock_vertices, torch.zeros(3))
+    rm = np.ascontiguousarray(world.rock_indices.to(torch.int32).numpy())
+    rtri = np.ascontiguousarray(world.rock_triangles.to(torch.int32).numpy())
+    rver = _u16(world.rock_vertices)
+    want = torch.cat((rk["wheel"], rk["body"]), 1)
+    for e in range(st["pos"].shape[0]):
+        s, d = _u16(rk["sources"][e]), _u16(rk["dirs"][e])
+        dist, slot = np.empty(26, np.uint16), np.empty(26, np.int32)
+        clib.rvo_cast_rays_env(s.ctypes.data, d.ctypes.data, 26, rm.ctypes.data, rm.shape[1], rm.shape[0], rtri.ctypes.data,
+                               rver.ctypes.data, 0.0, 0.0, 0.1, dist.ctypes.data, slot.ctypes.data)
+        assert same_halves(dist, want[e]), e
