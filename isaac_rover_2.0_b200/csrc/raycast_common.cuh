@@ -53,6 +53,7 @@ struct TiledParams {
     int presorted;            // steep envs are already on a work list: the shadow kernel just skips them
     int min_sh;               // bins are 2^sh x 2^sh cells, sh >= min_sh (0 = one cell; tuning hook)
     int spec_slot;            // stage 3b fetches the slot byte before the literal test (tuning hook)
+    int task_rays;            // shadow kernel: rays per task of stage 3L (<= 16; tuning hook)
     int64_t split_from;       // shadow kernel: order positions >= split_from are cast by two CTAs (half the rays each); -1 = none
     int split_at;             // first ray of the second half
     unsigned long long* dbg;  // optional [24] work counters / cycle counts of the shadow kernel (RVB_SHADOW_DBG=1)

@@ -13,14 +13,15 @@
 //              prism's cross-section on the source plane against the rectangle of the superblock's rays, from the
 //              triangle's pre-computed 32-byte stage-1 record (centroid, radius, b x c; terrain.cu);
 //   stage 2    survivors: exact corners of the cross-section -> xy box -> bin columns -> ray ranges (tasks);
-//   stage 3a   rays of a task against the box (two packed-fp16 compares per ray), survivors expanded into pairs;
-//   pre-filter the packed-fp16 conservative test of raycast_common.cuh on the pairs, two per lane;
-//   stage 3b   the (ray, triangle) pairs left (about 1.0 per hit): LITERAL evaluation of ray_casting.py:34-59 with its
+//   stage 3L   rays of a task (one triangle, <= 16 consecutive sorted rays; one task per lane) against the prism ITSELF: the
+//              exact linear forms N* = (s - a) . (c x d), M* = (s - a) . (d x b) in fp32 (three packed FFMA2 per ray) against
+//              the thresholds stage 2 derived for the triangle -- the same three half-planes whose corners make the box;
+//   stage 3b   the (ray, triangle) pairs left (about 1.2 per hit): LITERAL evaluation of ray_casting.py:34-59 with its
 //              three IEEE divisions, membership + slot of the triangle in the ray's own cell list (one look-up in the
 //              superblock entry -> block-list position table), atomicMin on (order-preserving fp16 bits, slot) = torch.min.
 // Two instantiations: <= 1664 rays per tile (64 registers, 55 KB shared memory, 4 CTAs per SM) and <= 2048 (3 CTAs per SM).
 //
-// Bit-exactness rests on stage 3b alone; stages 1-3a only have to be CONSERVATIVE (never drop a pair the literal test
+// Bit-exactness rests on stage 3b alone; stages 1-3L only have to be CONSERVATIVE (never drop a pair the literal test
 // would accept).  The bound: with g = s - a, the reference's numerators N = fl((g x c) . d), M = fl((b x g) . d) differ
 // from the exact N* = n det*, M* = m det* (det* = (b x c) . d, s = a + n b + m c + t d) by at most
 //     E = GAMMA * |g|_2 * sum_i aw_i + ALPHA,   aw_i = |c_j||d_k| + |c_k||d_j|,   GAMMA = 2^-8 >= (1 + 2^-11)^6 - 1
@@ -58,8 +59,8 @@ constexpr int ITEM_CAP = 64;       // superblocks per tile (7 bits travel in the
 constexpr int CHUNK = 32;          // list entries per pulled work chunk (one stage-1 batch)
 constexpr int CHUNK_CAP = 1024;    // chunks per tile (u8 chunk -> item table)
 constexpr int QCAP = 64;           // per-warp queues q1, q2 (each drained below 32 after every push of <= 32)
-constexpr int QCAP3 = 128;         // q3 (drained in batches of 64), q4 (receives up to 64 per batch)
-constexpr int TASK_RAYS = 16;
+constexpr int QCAP3 = 128;         // q4 (stage 3L pushes while it holds < 32 entries, stage 3b drains in batches of 32)
+constexpr int TASK_RAYS = 16;      // upper bound of the tuning hook q.task_rays
 constexpr int REL_BITS = 15;        // queue entries name a triangle as item << 15 | position in the item's list
 constexpr int RT_SMALL = 1664;      // ray capacity of the 4-CTAs-per-SM instantiation (the reference pattern has 1634 rays)
 
@@ -69,6 +70,7 @@ constexpr float EPS0 = 0.1057f;
 constexpr float L_CAP = 64.0f;
 constexpr float OVF = 16000.0f;
 constexpr float SQ3 = 1.7320509f;
+constexpr float LIN_SLACK = 1.0005f;            // stage 3L: fp32 evaluation of N*, M* (error <= 2^-13 of E_N, E_M) + threshold sums
 
 struct Item {
     uint32_t list_off, list_len;
@@ -93,15 +95,14 @@ struct Smem {
     uint32_t* cum;       // [ITEM_CAP + 1]  chunks before item i
     unsigned char* chunk_item;   // [CHUNK_CAP]
     uint2* q1;           // [NW][QCAP]  stage-1 survivors: (superblock-list entry, gball bits | item)
-    uint4* q2;           // [NW][QCAP]  tasks: (item << 15 | list position, ray start | count << 16, box lo half2, box hi half2)
-    uint32_t* q3;        // [NW][QCAP3]  pairs inside the box: ray position | (item << 15 | list position) << 11
-    uint32_t* q4;        // [NW][QCAP3]  pairs that passed the packed fp16 pre-filter
+    uint4* q2;           // [NW][QCAP]  tasks: (item << 15 | list position, ray start | count << 16, T1 | T2 << 16, T3 | sign << 15)
+    uint32_t* q4;        // [NW][QCAP3]  pairs inside the prism: ray position | (item << 15 | list position) << 11
     uint32_t* far;       // [RT / 32]
 };
 
 __host__ __device__ inline size_t shadow_smem_bytes(int RT) {       // RT = ray capacity of the instantiation
     return (size_t)RT * 8 + (size_t)((RT + 3) & ~3) * 4 + (size_t)(BIN_CAP / 2 + 4) * 4 + (size_t)ITEM_CAP * 32 +
-           (size_t)(ITEM_CAP + 4) * 4 + (size_t)CHUNK_CAP + (size_t)NW * (QCAP * (8 + 16) + QCAP3 * (4 + 4)) + (size_t)(((RT + 31) / 32 + 3) & ~3) * 4;
+           (size_t)(ITEM_CAP + 4) * 4 + (size_t)CHUNK_CAP + (size_t)NW * (QCAP * (8 + 16) + QCAP3 * 4) + (size_t)(((RT + 31) / 32 + 3) & ~3) * 4;
 }
 
 __device__ __forceinline__ float rcp_up(float x) { return __fdividef(1.0f, x) * 1.000001f; }
@@ -126,6 +127,14 @@ __device__ __forceinline__ TriF tri_f(const uint4& q0, const uint2& q1) {
     t.bx = hf(q0.y >> 16); t.by = hf(q0.z & 0xffff); t.bz = hf(q0.z >> 16);
     t.cx = hf(q0.w & 0xffff); t.cy = hf(q0.w >> 16); t.cz = hf(q1.x & 0xffff);
     return t;
+}
+
+// Two fp32 FMAs in one issue slot (sm_100 FFMA2): d.xy = a.xy * b + d.xy, b broadcast.
+__device__ __forceinline__ void ffma2(float& d0, float& d1, float a0, float a1, float b) {
+    asm("{\n\t.reg .b64 ra, rb, rc;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %4};\n\tmov.b64 rc, {%0, %1};\n\t"
+        "fma.rn.f32x2 rc, ra, rb, rc;\n\tmov.b64 {%0, %1}, rc;\n\t}"
+        : "+f"(d0), "+f"(d1)
+        : "f"(a0), "f"(a1), "f"(b));
 }
 
 // Stage 1 (tests/shadow_proto.py: stage1).  Returns false if no source inside the rectangle can pass; gball >= |s - a|
@@ -160,9 +169,14 @@ __device__ __forceinline__ bool stage1(const uint4& s0, const uint4& s1, const E
     return !out;
 }
 
-// Stage 2 (tests/shadow_proto.py: stage2): xy box of the sources that can pass; full = no bound.
+// positive fp32 (or +inf) -> its upper 16 bits, rounded up
+__device__ __forceinline__ uint32_t bf16_up(float x) { return (__float_as_uint(x) + 0xFFFFu) >> 16; }
+
+// Stage 2 (tests/shadow_proto.py: stage2): xy box of the sources that can pass; full = no bound.  T12 / T3s: the thresholds of
+// the three half-planes N' >= -T1, M' >= -T2, N' + M' <= T3 that bound the prism (un-normalised: N' = sgn N*, ...), 16 bits each,
+// rounded up, with the sign of the literal det in bit 15 of T3s -- what stage 3L tests every ray of the triangle's tasks against.
 __device__ __forceinline__ void stage2(const TriF& t, const uint2& q1, const EnvC& e, H3 d16, float gball, float& x0, float& x1,
-                                       float& y0, float& y1, bool& full) {
+                                       float& y0, float& y1, bool& full, uint32_t& T12, uint32_t& T3s) {
     const __half n0 = h_from_bits(q1.x >> 16), n1 = h_from_bits(q1.y & 0xffff), n2 = h_from_bits(q1.y >> 16);
     const __half det_h = h_add(h_add(h_mul(n0, d16.x), h_mul(n1, d16.y)), h_mul(n2, d16.z));           // ray_casting.py:41
     const __half da = __habs(det_h);
@@ -177,7 +191,8 @@ __device__ __forceinline__ void stage2(const TriF& t, const uint2& q1, const Env
     const float rdet = __fdividef(1.0f, fabsf(dets)) * 1.001f;
     const float EN = fmaf(GAMMA * gball, saw, ALPHA), EM = fmaf(GAMMA * gball, sawp, ALPHA);
     const float l1 = (tlo + EN) * rdet, l2 = (tlo + EM) * rdet;
-    const float l3 = (fmaf(thi, 1.0009766f, 5.9604645e-08f) + EN + EM) * rdet;
+    const float t3 = fmaf(thi, 1.0009766f, 5.9604645e-08f) + EN + EM;
+    const float l3 = t3 * rdet;
     const bool sign_ok = (__float_as_uint(dets) >> 31) == (uint32_t)(h_bits(det_h) >> 15);
     const bool good = sign_ok && (fmaxf(fmaxf(l1, l2), l3) <= L_CAP) && (l1 == l1) && (l2 == l2) && (l3 == l3);
     x0 = y0 = __int_as_float(0x7f800000);
@@ -198,6 +213,8 @@ __device__ __forceinline__ void stage2(const TriF& t, const uint2& q1, const Env
     const float sl = fmaf(ext, 7.6293945e-06f, 9.5367432e-07f);       // 2 * 2^-18 (ext is max |x| + |y| of one corner), 2^-20
     x0 -= sl; x1 += sl; y0 -= sl; y1 += sl;
     full = !good || !(x0 <= x1) || !(y0 <= y1);
+    T12 = full ? 0x7F807F80u : (bf16_up((tlo + EN) * LIN_SLACK) | (bf16_up((tlo + EM) * LIN_SLACK) << 16));
+    T3s = full ? 0x7F80u : (bf16_up(t3 * LIN_SLACK) | ((uint32_t)(h_bits(det_h) >> 15) << 15));
 }
 
 __device__ __forceinline__ bool is_steep(const H3& d16, float cos_steep) { return !(fabsf(__half2float(d16.z)) >= cos_steep); }
@@ -260,8 +277,7 @@ __global__ void __launch_bounds__(TT, RTC <= RT_SMALL ? 4 : 3) hm_shadow_kernel(
     sm.chunk_item = reinterpret_cast<unsigned char*>(sm.cum + ITEM_CAP + 4);
     sm.q1 = reinterpret_cast<uint2*>(sm.chunk_item + CHUNK_CAP);
     sm.q2 = reinterpret_cast<uint4*>(sm.q1 + NW * QCAP);
-    sm.q3 = reinterpret_cast<uint32_t*>(sm.q2 + NW * QCAP);
-    sm.q4 = sm.q3 + NW * QCAP3;
+    sm.q4 = reinterpret_cast<uint32_t*>(sm.q2 + NW * QCAP);
     sm.far = reinterpret_cast<uint32_t*>(sm.q4 + NW * QCAP3);
 
     // ---- phase 0
@@ -557,18 +573,17 @@ __global__ void __launch_bounds__(TT, RTC <= RT_SMALL ? 4 : 3) hm_shadow_kernel(
     }
     __syncthreads();
 
-    // ---- phase 3: warps pull (superblock, 32 list entries); stage 1 -> q1 -> stage 2 -> q2 -> stage 3a -> q3 -> stage 3b.
+    // ---- phase 3: warps pull (superblock, 32 list entries); stage 1 -> q1 -> stage 2 -> q2 -> stage 3L -> q4 -> stage 3b.
     // One dispatcher loop per warp; every stage's code exists once (the kernel must stay inside the instruction cache).
     const EnvC& e = s_env;            // read from shared memory where used (stages 1 and 2), not held in registers
     const int nchunks = s_nchunks;
     uint2* q1 = sm.q1 + warp * QCAP;
     uint4* q2 = sm.q2 + warp * QCAP;
-    uint32_t* q3 = sm.q3 + warp * QCAP3;
     uint32_t* q4 = sm.q4 + warp * QCAP3;
-    uint32_t h1 = 0, t1 = 0, h2 = 0, t2 = 0, h3 = 0, t3 = 0, h4 = 0, t4 = 0;          // warp-uniform
+    uint32_t h1 = 0, t1 = 0, h2 = 0, t2 = 0, h4 = 0, t4 = 0;          // warp-uniform
     const uint32_t lt_mask = (1u << lane) - 1u;
     const uint32_t FULLM = 0xffffffffu;
-    enum { A1 = 0, A2_START, A2_EMIT, A3A_START, A3A_RUN, A3P, A3B };
+    enum { A1 = 0, A2_START, A2_EMIT, A3L_START, A3L_RUN, A3B };
 #define DBG(i, v) do { if (DBGK) { const unsigned long long v_ = (unsigned long long)(v); if (lane == 0) atomicAdd(q.dbg + (i), v_); } } while (0)
 
     // stage-1 pipeline: the ids of chunk k+1 are in flight while chunk k is tested (its stage-1 records are loaded on the spot:
@@ -592,29 +607,28 @@ __global__ void __launch_bounds__(TT, RTC <= RT_SMALL ? 4 : 3) hm_shadow_kernel(
     };
     pull(idA, entA, itemA);
     pull(idB, entB, itemB);
-    bool more = true, in2 = false, in3a = false;
+    bool more = true, in2 = false, in3 = false;
     // stage-2 emission state (per lane)
-    uint32_t e_ent = 0, e_lo16 = 0, e_hi16 = 0, e_cur = 0, e_end = 0;
+    uint32_t e_ent = 0, e_T12 = 0, e_T3s = 0, e_cur = 0, e_end = 0;
     int e_col = 1, e_cx1 = 0, e_rlo = 0, e_rhi = 0;
-    // stage-3a state (per lane): task + bit i set = ray start + i lies in the box
+    // stage-3L state (per lane): task + bit i set = ray start + i lies inside the prism
     uint32_t a_ent = 0, a_start = 0, a_mask = 0;
+    const int task_rays = q.task_rays;
 
     long long c_start = 0, c_dry = 0;
     if (DBGK) c_start = clock64();
     while (true) {
-        const uint32_t n1 = t1 - h1, n2 = t2 - h2, n3 = t3 - h3, n4 = t4 - h4;
+        const uint32_t n1 = t1 - h1, n2 = t2 - h2, n4 = t4 - h4;
         int action;
         uint32_t cnt = 32u;
         if (n4 >= 32u) action = A3B;
-        else if (n3 >= 64u) { action = A3P; cnt = 64u; }
-        else if (in3a) action = A3A_RUN;
-        else if (n2 >= 32u) action = A3A_START;
+        else if (in3) action = A3L_RUN;
+        else if (n2 >= 32u) action = A3L_START;
         else if (in2) action = A2_EMIT;
         else if (n1 >= 32u) action = A2_START;
         else if (more) action = A1;
         else if (n1) { action = A2_START; cnt = n1; }
-        else if (n2) { action = A3A_START; cnt = n2; }
-        else if (n3) { action = A3P; cnt = n3; }
+        else if (n2) { action = A3L_START; cnt = n2; }
         else if (n4) { action = A3B; cnt = n4; }
         else break;
         __syncwarp();
@@ -667,18 +681,13 @@ __global__ void __launch_bounds__(TT, RTC <= RT_SMALL ? 4 : 3) hm_shadow_kernel(
                 const uint2 r1 = __ldg(reinterpret_cast<const uint2*>(q.recs + tri) + 2);
                 float x0, x1, y0, y1;
                 bool full;
-                stage2(tri_f(r0, r1), r1, e, d16, gball, x0, x1, y0, y1, full);
+                stage2(tri_f(r0, r1), r1, e, d16, gball, x0, x1, y0, y1, full, e_T12, e_T3s);
                 int bxl = (int)(it.bx & 0xffffu), bxh = (int)(it.bx >> 16), byl = (int)(it.by & 0xffffu), byh = (int)(it.by >> 16);
                 if (!full) {
                     bxl = max(bxl, cell_coord_f(x0, q.shift_x, q.res, q.inv_res, q.G0 - 1, q.sem) >> sh);
                     bxh = min(bxh, cell_coord_f(x1, q.shift_x, q.res, q.inv_res, q.G0 - 1, q.sem) >> sh);
                     byl = max(byl, min(cell_coord_f(y0, q.shift_y, q.res, q.inv_res, q.G0 - 1, q.sem), q.G1 - 1) >> sh);
                     byh = min(byh, min(cell_coord_f(y1, q.shift_y, q.res, q.inv_res, q.G0 - 1, q.sem), q.G1 - 1) >> sh);
-                    e_lo16 = (uint32_t)h_bits(__float2half_ru(x0)) | ((uint32_t)h_bits(__float2half_ru(y0)) << 16);
-                    e_hi16 = (uint32_t)h_bits(__float2half_rd(x1)) | ((uint32_t)h_bits(__float2half_rd(y1)) << 16);
-                } else {
-                    e_lo16 = 0xFC00FC00u;
-                    e_hi16 = 0x7C007C00u;
                 }
                 if (bxl <= bxh && byl <= byh) {
                     e_col = bxl; e_cx1 = bxh;
@@ -687,7 +696,7 @@ __global__ void __launch_bounds__(TT, RTC <= RT_SMALL ? 4 : 3) hm_shadow_kernel(
             }
             h1 += cnt;
             in2 = true;
-            DBG(2, cnt); DBG(13, __popc(__ballot_sync(FULLM, e_lo16 == 0xFC00FC00u && (uint32_t)lane < cnt)));
+            DBG(2, cnt); DBG(13, __popc(__ballot_sync(FULLM, e_T12 == 0x7F807F80u && (uint32_t)lane < cnt)));
         }
         // fall through: nothing of higher priority became ready
         case A2_EMIT: {
@@ -706,8 +715,8 @@ __global__ void __launch_bounds__(TT, RTC <= RT_SMALL ? 4 : 3) hm_shadow_kernel(
                     break;
                 }
                 if (have) {
-                    const uint32_t c = min(e_end - e_cur, (uint32_t)TASK_RAYS);
-                    q2[(t2 + __popc(m & lt_mask)) & (QCAP - 1)] = make_uint4(e_ent, e_cur | (c << 16), e_lo16, e_hi16);
+                    const uint32_t c = min(e_end - e_cur, (uint32_t)task_rays);
+                    q2[(t2 + __popc(m & lt_mask)) & (QCAP - 1)] = make_uint4(e_ent, e_cur | (c << 16), e_T12, e_T3s);
                     e_cur += c;
                 }
                 t2 += __popc(m);
@@ -716,34 +725,53 @@ __global__ void __launch_bounds__(TT, RTC <= RT_SMALL ? 4 : 3) hm_shadow_kernel(
             }
             break;
         }
-        case A3A_START: {
-            // one task per lane: its rays against the box -> bit mask (no warp-level work inside the loop)
+        case A3L_START: {
+            // One task per lane: every ray of the task against the three half-planes of the triangle's prism, N' = g . (c x d'),
+            // M' = g . (d' x b) with g = s - a and d' = sgn(det) d -- exact linear forms evaluated in fp32 (FFMA2: N' and M' in one
+            // issue slot) -> bit mask of the rays inside.  No warp-level work inside the loop.
             a_mask = 0u;
             if ((uint32_t)lane < cnt) {
                 const uint4 tk = q2[(h2 + lane) & (QCAP - 1)];
                 a_ent = tk.x;
                 a_start = tk.y & 0xffffu;
                 const int c = (int)(tk.y >> 16);
-                const __half2 lo = *reinterpret_cast<const __half2*>(&tk.z), hi = *reinterpret_cast<const __half2*>(&tk.w);
+                const uint32_t ent = sm.items[a_ent >> REL_BITS].list_off + (a_ent & ((1u << REL_BITS) - 1u));
+                const int32_t tri = __ldg(q.sb_ids + ent);
+                const uint4 r0 = __ldg(reinterpret_cast<const uint4*>(q.recs + tri));
+                const uint32_t r1 = __ldg(reinterpret_cast<const uint32_t*>(q.recs + tri) + 4);
+                const float sg = (tk.w & 0x8000u) ? -1.0f : 1.0f;
+                const float dx = sg * e.dx, dy = sg * e.dy, dz = sg * e.dz;
+                const float ax = hf(r0.x & 0xffff), ay = hf(r0.x >> 16), az = hf(r0.y & 0xffff);
+                const float bx = hf(r0.y >> 16), by = hf(r0.z & 0xffff), bz = hf(r0.z >> 16);
+                const float cx = hf(r0.w & 0xffff), cy = hf(r0.w >> 16), cz = hf(r1 & 0xffff);
+                const float w1x = cy * dz - cz * dy, w1y = cz * dx - cx * dz, w1z = cx * dy - cy * dx;          // c x d'
+                const float w2x = dy * bz - dz * by, w2y = dz * bx - dx * bz, w2z = dx * by - dy * bx;          // d' x b
+                const float T1 = -__uint_as_float(tk.z << 16), T2 = -__uint_as_float(tk.z & 0xffff0000u);
+                const float T3 = __uint_as_float((tk.w & 0x7fffu) << 16);
                 for (int i = 0; i < c; ++i) {
-                    const uint32_t w0 = sm.rays[a_start + i].x;
-                    const bool in = __hbge2(*reinterpret_cast<const __half2*>(&w0), lo) && __hble2(*reinterpret_cast<const __half2*>(&w0), hi);
+                    const uint2 ray = sm.rays[a_start + i];
+                    const float gx = hf(ray.x & 0xffff) - ax, gy = hf(ray.x >> 16) - ay, gz = hf(ray.y & 0xffff) - az;
+                    float Nn = 0.f, Mn = 0.f;
+                    ffma2(Nn, Mn, w1x, w2x, gx);
+                    ffma2(Nn, Mn, w1y, w2y, gy);
+                    ffma2(Nn, Mn, w1z, w2z, gz);
+                    const bool in = (Nn >= T1) && (Mn >= T2) && (Nn + Mn <= T3);
                     a_mask |= (in ? 1u : 0u) << i;
                 }
             }
             h2 += cnt;
-            in3a = __any_sync(FULLM, a_mask != 0u);
+            in3 = __any_sync(FULLM, a_mask != 0u);
             if (DBGK) {
                 const int c = (uint32_t)lane < cnt ? (int)(q2[(h2 - cnt + lane) & (QCAP - 1)].y >> 16) : 0;
                 const int cm = __reduce_max_sync(FULLM, c), cs = __reduce_add_sync(FULLM, c), ib = __reduce_add_sync(FULLM, __popc(a_mask));
                 DBG(4, cm); DBG(5, cs); DBG(6, ib);
             }
-            if (!in3a) break;
+            if (!in3) break;
         }
         // fall through
-        case A3A_RUN: {
+        case A3L_RUN: {
             // expand the masks into (ray, entry) pairs: a warp scan gives every lane the queue position of its first pair, so the
-            // lanes write their pairs without any warp-level work inside the loop; runs until q3 holds a batch or the masks are empty
+            // lanes write their pairs without any warp-level work inside the loop; runs until q4 is full or the masks are empty
             while (true) {
                 const uint32_t c = (uint32_t)__popc(a_mask);
                 uint32_t inc = c;
@@ -754,54 +782,22 @@ __global__ void __launch_bounds__(TT, RTC <= RT_SMALL ? 4 : 3) hm_shadow_kernel(
                 }
                 const uint32_t total = __shfl_sync(FULLM, inc, 31);
                 if (!total) {
-                    in3a = false;
+                    in3 = false;
                     break;
                 }
-                const uint32_t room = (uint32_t)QCAP3 - (t3 - h3);        // >= 64: this stage only runs while q3 holds < 64 pairs
-                uint32_t at = inc - c;                                    // queue position of this lane's next pair, relative to t3
+                const uint32_t room = (uint32_t)QCAP3 - (t4 - h4);        // > 96: this stage only runs while q4 holds < 32 pairs
+                uint32_t at = inc - c;                                    // queue position of this lane's next pair, relative to t4
                 const uint32_t code = a_ent << 11;
                 while (a_mask != 0u && at < room) {
                     const uint32_t bit = (uint32_t)__ffs((int)a_mask) - 1u;
                     a_mask &= a_mask - 1u;
-                    q3[(t3 + at) & (QCAP3 - 1)] = (a_start + bit) | code;
+                    q4[(t4 + at) & (QCAP3 - 1)] = (a_start + bit) | code;
                     ++at;
                 }
-                t3 += min(total, room);
+                t4 += min(total, room);
                 DBG(11, 1);
-                if (t3 - h3 >= 64u) break;
+                if (t4 - h4 >= 32u) break;
             }
-            break;
-        }
-        case A3P: {
-            // packed fp16 pre-filter (raycast_common.cuh: prefilter2, conservative) on up to 64 pairs, two per lane
-            const bool v0 = (uint32_t)(2 * lane) < cnt, v1 = (uint32_t)(2 * lane + 1) < cnt;
-            uint2 pq = make_uint2(0, 0);                // pairs A, B; h3 stays even until the last batch
-            if (v0) pq = *reinterpret_cast<const uint2*>(q3 + ((h3 + 2 * lane) & (QCAP3 - 1)));
-            if (!v1) pq.y = pq.x;
-            bool passA = false, passB = false;
-            if (v0) {
-                const uint2 ra = sm.rays[pq.x & 0x7ffu], rb = sm.rays[pq.y & 0x7ffu];
-                const uint32_t ea = sm.items[pq.x >> (11 + REL_BITS)].list_off + ((pq.x >> 11) & ((1u << REL_BITS) - 1u));
-                const uint32_t eb = sm.items[pq.y >> (11 + REL_BITS)].list_off + ((pq.y >> 11) & ((1u << REL_BITS) - 1u));
-                const int32_t ta = __ldg(q.sb_ids + ea), tb = __ldg(q.sb_ids + eb);
-                const uint4* pa = reinterpret_cast<const uint4*>(q.recs + ta);
-                const uint4* pb = reinterpret_cast<const uint4*>(q.recs + tb);
-                const uint4 a0 = __ldg(pa), b0 = __ldg(pb);
-                const uint2 a1 = __ldg(reinterpret_cast<const uint2*>(pa + 1)), b1 = __ldg(reinterpret_cast<const uint2*>(pb + 1));
-                const Tri2 t = pack_tri2(a0, a1, b0, b1);
-                const Cand2 cd = make_cand2(t, dx2, dy2, dz2, v0, v1);
-                const uint32_t f = prefilter2(u2h(__byte_perm(ra.x, rb.x, 0x5410)), u2h(__byte_perm(ra.x, rb.x, 0x7632)),
-                                              u2h(__byte_perm(ra.y, rb.y, 0x5410)), dx2, dy2, dz2, t, cd);
-                passA = (f & 0xffffu) != 0u;
-                passB = (f >> 16) != 0u;
-            }
-            h3 += cnt;
-            const uint32_t m0 = __ballot_sync(FULLM, passA), m1 = __ballot_sync(FULLM, passB);
-            if (passA) q4[(t4 + __popc(m0 & lt_mask)) & (QCAP3 - 1)] = pq.x;
-            t4 += __popc(m0);
-            if (passB) q4[(t4 + __popc(m1 & lt_mask)) & (QCAP3 - 1)] = pq.y;
-            t4 += __popc(m1);
-            DBG(14, 1); DBG(15, __popc(m0) + __popc(m1));
             break;
         }
         case A3B: {
@@ -920,6 +916,8 @@ int launch_heightmap_shadow(const rvb_terrain* t, const float* pos, const float*
     q.min_sh = 1;                                                            // 2x2-cell bins: 2 % faster than single cells (fewer tasks)
     if (const char* ms = getenv("RVB_SHADOW_SH")) q.min_sh = atoi(ms);      // tuning hook: finest bins to start from
     q.spec_slot = 3;
+    q.task_rays = TASK_RAYS;
+    if (const char* tr = getenv("RVB_SHADOW_TASK_RAYS")) q.task_rays = min(max(atoi(tr), 1), TASK_RAYS);   // tuning hook
     if (const char* sp = getenv("RVB_SHADOW_SPEC")) q.spec_slot = atoi(sp); // tuning hook
     struct Side {
         int dev = -1;
@@ -985,10 +983,10 @@ int launch_heightmap_shadow(const rvb_terrain* t, const float* pos, const float*
         q.dbg = nullptr;
         const double ne = (double)(nblocks - fb);
         fprintf(stderr, "[shadow dbg] tiles %lld, handed back %d; per tile: chunks %.1f, stage-1 keeps %.1f, stage-2 triangles %.1f (no bound: %.2f), "
-                        "tasks %.1f (emit iterations %.1f), box loop iterations %.1f, rays box-tested %.1f, in box %.1f (expand iterations %.1f), "
-                        "pre-filter batches %.1f (passed %.1f), 3b batches %.1f, literal hits %.1f, slot lookups %.1f, dispatches %.1f\n",
+                        "tasks %.1f (emit iterations %.1f), prism loop iterations %.1f, rays tested %.1f, inside the prism %.1f, "
+                        "3b batches %.1f, literal hits %.1f, slot lookups %.1f, dispatches %.1f\n",
                 (long long)nblocks, fb, h[0] / ne, h[1] / ne, h[2] / ne, h[13] / ne, h[3] / ne, h[10] / ne, h[4] / ne, h[5] / ne, h[6] / ne,
-                h[11] / ne, h[14] / ne, h[15] / ne, h[7] / ne, h[8] / ne, h[9] / ne, h[12] / ne);
+                h[7] / ne, h[8] / ne, h[9] / ne, h[12] / ne);
         if (h[19])
             fprintf(stderr, "[shadow dbg] phase 3 per warp (cycles): pulling chunks %.0f, draining the queues %.0f, waiting at the final barrier %.0f\n",
                     (double)h[16] / h[19], (double)h[17] / h[19], (double)h[18] / h[19]);

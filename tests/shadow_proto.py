@@ -200,7 +200,39 @@ def stage2(a16, b16, c16, n16, ec, gball):
                 ys.append(P[:, 1] + t * d[1])
         xs, ys = np.stack(xs, 1), np.stack(ys, 1)
         sl = (np.abs(xs).max(1) + np.abs(ys).max(1)) * F32(2.0 ** -18) + F32(2.0 ** -20)
-    return xs.min(1) - sl, xs.max(1) + sl, ys.min(1) - sl, ys.max(1) + sl, ~good
+    # thresholds of the per-ray linear test (stage 3L of the kernel): the prism itself, un-normalised
+    with np.errstate(invalid="ignore", over="ignore"):
+        T1 = bf16_up((tlo + EN) * LIN_SLACK)
+        T2 = bf16_up((tlo + EM) * LIN_SLACK)
+        T3 = bf16_up((thi * F32(1.0 + 2.0 ** -10) + F32(2.0 ** -24) + EN + EM) * LIN_SLACK)
+    return xs.min(1) - sl, xs.max(1) + sl, ys.min(1) - sl, ys.max(1) + sl, ~good, (T1, T2, T3, sgn)
+
+
+LIN_SLACK = F32(1.0005)       # fp32 evaluation of N*, M* (error <= 2^-13 EN) + the threshold sums
+
+
+def bf16_up(x):
+    """positive fp32 -> the next value with 16 significant bits kept (how the kernel packs the thresholds into a task)."""
+    u = np.asarray(x, dtype=F32).view(np.uint32).astype(np.uint64)
+    u = ((u + 0xFFFF) & 0xFFFF0000).astype(np.uint32)
+    return u.view(F32)
+
+
+def lin_test(s16, a16, b16, c16, ec, T, full):
+    """Stage 3L: per (ray, triangle) the exact linear forms N* = ((s-a) x c).d, M* = (b x (s-a)).d in fp32 against the
+    thresholds of stage 2.  -> bool [P,T] (True = may pass the pre-filter; `full` triangles pass every ray)."""
+    T1, T2, T3, sgn = T
+    a, b, c = a16.astype(F32), b16.astype(F32), c16.astype(F32)
+    ds = ec.d[None, :] * sgn[:, None]                                   # +-d
+    w1 = np.stack((c[:, 1] * ds[:, 2] - c[:, 2] * ds[:, 1], c[:, 2] * ds[:, 0] - c[:, 0] * ds[:, 2], c[:, 0] * ds[:, 1] - c[:, 1] * ds[:, 0]), 1)
+    w2 = np.stack((ds[:, 1] * b[:, 2] - ds[:, 2] * b[:, 1], ds[:, 2] * b[:, 0] - ds[:, 0] * b[:, 2], ds[:, 0] * b[:, 1] - ds[:, 1] * b[:, 0]), 1)
+    s = s16.astype(F32)
+    g = [s[:, None, i] - a[None, :, i] for i in range(3)]
+    Nn = (g[0] * w1[None, :, 0] + g[1] * w1[None, :, 1]) + g[2] * w1[None, :, 2]
+    Mn = (g[0] * w2[None, :, 0] + g[1] * w2[None, :, 1]) + g[2] * w2[None, :, 2]
+    with np.errstate(invalid="ignore"):
+        ok = (Nn >= -T1[None]) & (Mn >= -T2[None]) & (Nn + Mn <= T3[None])
+    return ok | full[None, :]
 
 
 def main():
@@ -265,8 +297,13 @@ def main():
         gtrue = np.sqrt(((s.astype(F32)[:, None, :] - a[sel].astype(F32)[None]) ** 2).sum(2))
         gviol = (ps & (gtrue > gb[None, :]) & ~ill[None, :]).sum()
         stats["gball_viol"] = stats.get("gball_viol", 0) + int(gviol) + int(ps[:, rej].any())
-        x0, x1, y0, y1, full = stage2(a[sel], b[sel], c[sel], n[sel], ec, gb)
+        x0, x1, y0, y1, full, T = stage2(a[sel], b[sel], c[sel], n[sel], ec, gb)
         full = full | ill
+        lin = lin_test(s, a[sel], b[sel], c[sel], ec, T, full)
+        stats["lin_viol"] = stats.get("lin_viol", 0) + int((ps & ~lin).sum())
+        stats["lin_pass"] = stats.get("lin_pass", 0) + int((lin & ~rej[None, :] & ~full[None, :]).sum())
+        stats["pre_pass_bounded"] = stats.get("pre_pass_bounded", 0) + int((ps & ~full[None, :]).sum())
+        stats["pre_pass"] = stats.get("pre_pass", 0) + int(ps.sum())
         stats["s2_in"] = stats.get("s2_in", 0) + int((~rej).sum())
         inbox = ((sx[:, None] >= x0[None, :]) & (sx[:, None] <= x1[None, :]) & (sy[:, None] >= y0[None, :]) &
                  (sy[:, None] <= y1[None, :])) | full[None, :]
@@ -294,7 +331,7 @@ def main():
     print("TOTAL pass %d, box tests %d (%.2fx), triangles %d, full-range %d, violations %d" % (
         tot_pass, tot_box, tot_box / max(tot_pass, 1), tot_tri, tot_full, tot_viol))
     print({k: v / N for k, v in stats.items()})
-    return 0 if tot_viol == 0 else 1
+    return 0 if (tot_viol == 0 and stats.get("lin_viol", 0) == 0) else 1
 
 
 if __name__ == "__main__":

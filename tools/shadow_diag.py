@@ -84,6 +84,13 @@ for msh in ("1", "0", "1", "0"):
     d, _, _ = cam.get_depths(st["pos"], eul, want_pt=False)
     print("min bin shift %s: median %.3f ms, min %.3f, equal to variant 3: %s" % (msh, med, mn, bool(torch.equal(d.view(torch.int16), out[3][0].view(torch.int16)))))
 _os.environ.pop("RVB_SHADOW_SH")
+for trn in ("8", "12", "16", "8", "16"):
+    _os.environ["RVB_SHADOW_TASK_RAYS"] = trn
+    cam.variant = 0
+    med, mn = timed(lambda: cam.get_depths(st["pos"], eul, want_pt=False), reps=30)
+    d, _, _ = cam.get_depths(st["pos"], eul, want_pt=False)
+    print("rays per task %s: median %.3f ms, min %.3f, equal to variant 3: %s" % (trn, med, mn, bool(torch.equal(d.view(torch.int16), out[3][0].view(torch.int16)))))
+_os.environ.pop("RVB_SHADOW_TASK_RAYS")
 for cs in ("0.7", "0.9"):
     _os.environ["RVB_COS_STEEP"] = cs
     cam.variant = 0
