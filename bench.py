@@ -2,13 +2,15 @@
 """Benchmark of the rover hot path (BASELINE.json metric: env-steps/s and heightmap rays/s).
 
   python bench.py --gpus N --steps K --warmup W            # this repo (hand-written sm_100a kernels)
-  python bench.py --impl reference --gpus N --steps K ...  # the reference's torch-CPU algorithm (oracle port)
+  python bench.py --impl reference --gpus N --steps K ...  # the UNMODIFIED reference's torch code on the host cores
 
-Workload (BASELINE.json configs[1]): 4,096 envs per GPU, full dense+sparse heightmap (1634 rays/env, K=200
-candidates/ray) on a synthetic 200 x 200 m, ~1M-triangle terrain (708^2 heightfield), big_rock_layer
-collision, Ackermann kinematics, reward/reset terms.  One "step" = one pass of the hot path over all envs
-(RoverTask.hot_step), PhysX excluded.  Multi-GPU: envs sharded by index (weak scaling), terrain replicated,
-one NCCL all-reduce of the 16-entry statistics vector per step.
+Workload (BASELINE.json configs[3], one rank's share = configs[2] plus the device-side reset path): 131,072 envs per GPU
+(`--envs`; 65,536 when the GPU has less than 60 GB free; `--envs 4096` = configs[1]), full dense+sparse heightmap (1634
+rays/env, K=200 candidates/ray) on a synthetic 200 x 200 m, ~1M-triangle terrain (708^2 heightfield), big_rock_layer
+collision, stone_info goal validation for the envs that reset, Ackermann kinematics, reward/reset terms.  One "step" = one
+pass of the hot path over all envs: the reset half of pre_physics_step on the device (rover.py:356-361) + its action half +
+post_physics_step (RoverTask.hot_step(device_reset=True)), PhysX excluded.  Multi-GPU: envs sharded by index (weak scaling),
+terrain replicated, one NCCL all-reduce of the 16-entry statistics vector per step.
 Prints ONE JSON line (rank 0).
 """
 import argparse
@@ -28,6 +30,8 @@ P_RAYS = 1634
 ALGO_BYTES_PER_ENV_STEP = 665196          # index rows 785*K*4 + unique triangles + inputs + outputs
 PEAKS_FILE = os.path.join(ROOT, "MEASURED_PEAKS.json")
 FALLBACK_HBM_GBS = 6650.0                 # /opt/skills/guides/B200_PROFILING.md fallback
+METRIC = "env-steps/sec (obs+kinematics+reward)"
+C4_ENVS_PER_GPU = 131072                  # BASELINE.json configs[3]: 1,048,576 envs over 8 GPUs
 
 
 _JSON_FD = None
@@ -59,10 +63,25 @@ def hbm_peak():
         return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
 
 
+def workload_config(envs_per_gpu, world_size, K=200, length=200.0, nv=708):
+    """The `config` object of BOTH arms (this repo's and `--impl reference`): the workload, nothing measured."""
+    ntri = 2 * (nv - 1) * (nv - 1)
+    cfg_name = {4096: "configs[1]", 65536: "configs[2]", C4_ENVS_PER_GPU: "configs[3] (1,048,576 envs / 8 GPUs), one rank's share = configs[2] at twice the envs"}
+    return {"workload": "%d envs/GPU, 1634 rays/env, K=%d, %gx%g m %d-triangle synthetic terrain + big_rock_layer collision + "
+                        "stone_info goal validation of resetting envs + Ackermann + reward/reset; BASELINE.json %s"
+                        % (envs_per_gpu, K, length, length, ntri, cfg_name.get(envs_per_gpu, "(custom size)")),
+            "envs_per_gpu": envs_per_gpu, "total_envs": envs_per_gpu * world_size, "rays_per_env": P_RAYS, "K": K,
+            "index_cells": int(round(length / 0.1)) ** 2,
+            "l2": "inputs larger than L2: 3 pose sets cycled, %.1f GB of index rows touched per step, index %.1f GB"
+                  % (envs_per_gpu * 785 * K * 4 / 1e9, int(round(length / 0.1)) ** 2 * K * 4 / 1e9),
+            "parallelism": "env shards x%d, terrain replicated, 1 all-reduce of 16 f64 per step" % world_size}
+
+
 class ClockSampler:
     """SM clock + throttle reasons sampled every 10 ms during the timed regions: NVML in a background thread of this
     process (what `nvidia-smi --query-gpu=clocks.sm,clocks_event_reasons.*` reads, without spawning a poller process
-    that contends with the benchmark for the driver); falls back to an `nvidia-smi -lms 50` child if NVML is missing."""
+    that contends with the benchmark for the driver); falls back to an `nvidia-smi -lms 50` child if NVML is missing.
+    Constructed on EVERY rank, before the barrier that precedes the timed region (NVML initialisation takes milliseconds)."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
@@ -82,17 +101,19 @@ class ClockSampler:
             bits = {"hw_slowdown": nv.nvmlClocksEventReasonHwSlowdown, "hw_thermal_slowdown": nv.nvmlClocksEventReasonHwThermalSlowdown,
                     "sw_thermal_slowdown": nv.nvmlClocksEventReasonSwThermalSlowdown, "sw_power_cap": nv.nvmlClocksEventReasonSwPowerCap}
             self.stop_flag = threading.Event()
+            self.active = threading.Event()
 
             def poll():
                 while not self.stop_flag.is_set():
-                    try:
-                        self.sm.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
-                        r = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
-                        for name, b in bits.items():
-                            if r & b:
-                                self.reasons.add(name)
-                    except Exception:
-                        pass
+                    if self.active.is_set():
+                        try:
+                            self.sm.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+                            r = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+                            for name, b in bits.items():
+                                if r & b:
+                                    self.reasons.add(name)
+                        except Exception:
+                            pass
                     self.stop_flag.wait(0.01)
             self.thread = threading.Thread(target=poll, daemon=True)
             self.thread.start()
@@ -104,6 +125,10 @@ class ClockSampler:
                                           "-lms", "50"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except Exception:
             self.proc = None
+
+    def start(self):
+        if self.thread is not None:
+            self.active.set()
 
     def stop(self):
         if self.thread is not None:
@@ -137,51 +162,110 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons), "source": "nvidia-smi -lms 50"}
 
 
-# ------------------------------------------------------------------------------------------------ CPU reference arm
-def cpu_sample_assets(n_envs, seed=42):
-    """A 24 m crop-sized terrain with the SAME mesh density (0.2825 m vertex spacing), K=200, res 0.1 m as the
-    200 m benchmark terrain; index by CPU brute force (rover_utils.py:52-118 semantics).  Per-env CPU cost does
-    not depend on the map extent, so env-steps/s measured here is the CPU figure for the full workload."""
-    import isaac_rover_b200  # noqa: F401  (synthetic generator only; no kernels on this path)
+# ------------------------------------------------------------------------------------------------ reference arm
+def reference_world(args):
+    """The benchmark's world with the index tensors in the reference's asset format ([K,G,G] int32 on the host).  The index of
+    the 200 m world (4 M cells x 1 M triangles) cannot be built by CPU brute force in any reasonable time, so the synthetic asset
+    is produced with the GPU index builder when a GPU is present (input synthesis, like the terrain itself -- nothing of the
+    timed path); without a GPU the world is a 24 m crop of the same mesh density (the reference's per-env cost does not depend
+    on the map extent)."""
+    import isaac_rover_b200 as R
     from isaac_rover_b200 import synth
+    if torch.cuda.is_available():
+        w = synth.make_world(length=args.length, nv=args.nv, K=args.K, n_stones=args.stones, seed=42, build_index=None)
+        w.map_indices = R.build_knn_index(w.triangles, w.vertices, w.G, w.res, w.K, device="cuda:0").cpu()
+        w.rock_indices = R.build_knn_index(w.rock_triangles, w.rock_vertices, w.G, w.res, w.K, device="cuda:0").cpu()
+        torch.cuda.empty_cache()
+        return w, "%gx%g m world, %d triangles (the benchmark's)" % (args.length, args.length, w.triangles.shape[0])
+    w = synth.make_world(length=24.0, nv=86, K=args.K, n_stones=30, seed=42, build_index="cpu")
+    return w, "24 m crop of the benchmark's mesh density (no GPU here to synthesise the 200 m index)"
+
+
+def time_reference(args, device, n_envs, steps, warmup):
+    """-> (seconds per step, kind, description).  kind = "reference": the unmodified reference's classes (oracle/ref_harness.py,
+    from baseline/_ref or /root/reference); "port": the oracle restatement, only if no reference tree is present."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
-    import rover_oracle as O
-    w = synth.make_world(length=24.0, nv=86, K=200, n_stones=30, seed=seed, build_index="cpu")
-    pat, ci, fi = O.heightmap_pattern()
-    assets = dict(pattern=pat, coarse_idx=ci, fine_idx=fi, map_indices=w.map_indices, triangles=w.triangles,
-                  vertices=w.vertices, rock_indices=w.rock_indices, rock_triangles=w.rock_triangles,
-                  rock_vertices=w.rock_vertices, shift=torch.tensor([0, 0, 0.0]))
-    st = synth.make_env_state(w, n_envs, seed=seed, margin=6.0)
-    return O, assets, st
+    from isaac_rover_b200 import synth
+    w, wdesc = reference_world(args)
+    st = synth.make_env_state(w, n_envs, seed=100, margin=6.0)
+    st = {k: v.to(device) for k, v in st.items()}
+    import ref_harness
+    root = ref_harness.reference_root()
+    cuda = device != "cpu"
 
+    def sync():
+        if cuda:
+            torch.cuda.synchronize()
+    if root is not None:
+        ns = ref_harness.load("cpu" if not cuda else "cuda")
+        fake = ref_harness.make_fake_task(ns, w, st, level=2, device=device)
+        w.map_indices = w.rock_indices = None
 
-def time_cpu_oracle(n_envs, steps, warmup):
-    torch.set_num_threads(os.cpu_count())
-    O, assets, st = cpu_sample_assets(n_envs)
+        def step():
+            ref_harness.reference_step(ns, fake, st)
+        kind, what = "reference", "unmodified reference classes from %s" % os.path.relpath(root, ROOT)
+    else:
+        import rover_oracle as O
+        pat, ci, fi = O.heightmap_pattern()
+        assets = dict(pattern=pat, coarse_idx=ci, fi=fi, fine_idx=fi, map_indices=w.map_indices, triangles=w.triangles,
+                      vertices=w.vertices, rock_indices=w.rock_indices, rock_triangles=w.rock_triangles,
+                      rock_vertices=w.rock_vertices, shift=torch.tensor([0, 0, 0.0]))
+        assets = {k: (v.to(device) if torch.is_tensor(v) else v) for k, v in assets.items()}
+
+        def step():
+            O.full_step(assets, st, env_chunk=min(n_envs, 128))
+        kind, what = "port", "oracle restatement (no reference tree on this box)"
     for _ in range(warmup):
-        O.full_step(assets, st)
+        step()
+    sync()
     ts = []
     for _ in range(steps):
         t0 = time.perf_counter()
-        O.full_step(assets, st)
+        step()
+        sync()
         ts.append(time.perf_counter() - t0)
-    return sum(ts) / len(ts)
+    return statistics.median(ts), kind, "%s; %s; %d envs x %d rays x K=%d per step, %d warm-up + %d timed steps (median)" % (
+        what, wdesc, n_envs, P_RAYS, args.K, warmup, steps)
 
 
-def time_gpu_eager_oracle(n_envs, dev, steps=3, warmup=1):
-    """The reference's eager-torch op sequence (oracle port) on the GPU itself -- how the reference is actually deployed
-    (it hard-wires 'cuda:0', rover.py:90).  Reported beside the CPU baseline; same 24 m sample world, n_envs envs."""
-    O, assets, st = cpu_sample_assets(n_envs)
-    assets = {k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in assets.items()}
-    st = {k: v.to(dev) for k, v in st.items()}
-    for _ in range(warmup):
-        O.full_step(assets, st, env_chunk=min(n_envs, 128))
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    for _ in range(steps):
-        O.full_step(assets, st, env_chunk=min(n_envs, 128))
-    torch.cuda.synchronize()
-    return (time.perf_counter() - t0) / steps
+def run_reference(args, rank, world):
+    """`--impl reference`: BASELINE.json configs[0] -- the reference's torch path on the host cores (all of them), 64 envs per
+    step on the benchmark's world.  Rank 0 only."""
+    if rank != 0:
+        return
+    device = args.ref_device
+    n = args.ref_envs
+    if device == "cpu":
+        torch.set_num_threads(os.cpu_count())
+        budget = 30                                    # keep the whole run within a few minutes (~5 s per 64-env step)
+        if args.steps + args.warmup > budget:
+            n = max(8, n * budget // (args.steps + args.warmup))
+    t, kind, sample = time_reference(args, device, n, args.steps, args.warmup)
+    v = n / t
+    cores = torch.get_num_threads() if device == "cpu" else 0
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "env-steps/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f16", "data": "synthetic",
+            "config": workload_config(args.envs or C4_ENVS_PER_GPU, world, args.K, args.length, args.nv),
+            "rays_per_s": v * P_RAYS, "device": device, "sample_envs": n,
+            "cpu_baseline": {"value": v, "unit": "env-steps/s", "cores": cores, "kind": kind, "sample": sample},
+            "e2e": {"value": v, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    emit(line)
+
+
+def reference_subprocess(device, envs, steps, warmup, timeout=420):
+    """The reference arm in a child process (its CPU recipe re-points torch defaults that this process must not see)."""
+    cmd = [sys.executable, os.path.abspath(__file__), "--impl", "reference", "--ref-device", device, "--ref-envs", str(envs),
+           "--steps", str(steps), "--warmup", str(warmup)]
+    env = dict(os.environ)
+    for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK", "MASTER_ADDR", "MASTER_PORT"):
+        env.pop(k, None)
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, env=env)
+    for ln in reversed(r.stdout.strip().splitlines()):
+        if ln.startswith("{"):
+            return json.loads(ln)
+    raise RuntimeError("reference arm failed: " + (r.stderr or r.stdout)[-300:])
 
 
 def time_policy_epilogue(R, obs, steps=20, warmup=3):
@@ -236,29 +320,7 @@ def time_policy_epilogue(R, obs, steps=20, warmup=3):
     return {"ms": ms, "envs_per_s": N / ms * 1e3, "fp32_tflops": flops / ms / 1e9, "torch_eager_fp32_ms": ms_eager,
             "max_abs_diff_vs_torch": err, "launches": 1, "actor_alone_ms": ms_single,
             "what": "actor + critic (encoders [80,60] x2, mlp [256,160,128], model.py:152-241) on the step's obs_buf f32 [%d,1750]; "
-                    "one fused fp32 launch for both networks (rvb_policy_forward_pair); not included in `value`" % N}
-
-
-def run_reference(args, rank):
-    if rank != 0:
-        return
-    n = args.cpu_envs
-    t = time_cpu_oracle(n, args.steps, args.warmup)
-    v = n / t
-    cores = torch.get_num_threads()
-    sample = ("%d envs x %d rays x K=200 per step on a 24 m terrain of the benchmark's mesh density; the reference is Python "
-              "(cannot travel to the GPU box), so its torch-CPU algorithm is run through the oracle restatement "
-              "(oracle/rover_oracle.py, pinned bit-exact to the reference)" % (n, P_RAYS))
-    line = {"impl": "reference", "metric": "env-steps/sec (obs+kinematics+reward)", "value": v, "unit": "env-steps/s",
-            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f16", "data": "synthetic",
-            "config": {"workload": "4096 envs/GPU, 1634 rays/env, K=200, 200x200 m ~1M-triangle synthetic terrain (configs[1])",
-                       "sample_envs": n},
-            "rays_per_s": v * P_RAYS,
-            "cpu_baseline": {"value": v, "unit": "env-steps/s", "cores": cores, "kind": "port", "sample": sample},
-            "e2e": {"value": v, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "gpu_launches": 0}
-    emit(line)
+                    "one fused launch for both networks (rvb_policy_forward_pair); not included in `value`" % N}
 
 
 # ------------------------------------------------------------------------------------------------ B200 arm
@@ -270,6 +332,9 @@ def run_b200(args, rank, world, local):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     N = args.envs
+    if not N:
+        free_b, _ = torch.cuda.mem_get_info(dev)
+        N = C4_ENVS_PER_GPU if free_b > 60e9 else 65536
     w = synth.make_world(length=args.length, nv=args.nv, K=args.K, n_stones=args.stones, seed=42, build_index=None)
     t0 = time.perf_counter()
     w.map_indices = R.build_knn_index(w.triangles, w.vertices, w.G, w.res, w.K, device=dev)
@@ -279,7 +344,9 @@ def run_b200(args, rank, world, local):
     n_sets = 3
     states = [synth.make_env_state(w, N, seed=100 + s, env_offset=rank * N) for s in range(n_sets)]
     task = synth.make_task(w, states[0], device=str(dev), level=2, num_envs_total=N * world)
+    task.env_offset = rank * N
     w.map_indices = w.rock_indices = None          # the layers own K-contiguous copies
+    torch.cuda.empty_cache()
     dstates = [{k: v.to(dev) for k, v in s.items()} for s in states]
     view = task._rover
 
@@ -288,31 +355,34 @@ def run_b200(args, rank, world, local):
         view.pos, view.quat, view.joints = s["pos"], s["quat"], s["joints"]
         return s["actions"]
 
-    reducer = R.dist.StatsReducer()
+    reducer = R.dist.StatsReducer(depth=4)
+    device_reset = not args.no_reset
 
     def step(i):
-        task.hot_step(set_state(i), fused=not args.unfused)
+        task.hot_step(set_state(i), fused=not args.unfused, device_reset=device_reset)
         if args.sync_reduce:
             R.dist.reduce_stats(task.stats)
         else:
             reducer.submit(task.stats)          # asynchronous all-reduce of the 16 sums (off the critical path)
 
     task.Camera.variant = args.variant
+    clocks = ClockSampler(local)                # every rank, BEFORE the barrier (pynvml import + nvmlInit take milliseconds)
+    lib = R._lib.load()
     for i in range(args.warmup):
         step(i)
     torch.cuda.synchronize()
-    R.dist.barrier()
-    clocks = ClockSampler(local) if rank == 0 else None
+    task.reset_counters.zero_()
     task.Camera.timing = []
-    lib = R._lib.load()
     lib.rvb_timing_enable(1)
     launches0 = R._lib.launch_count
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if rank == 0:
+        clocks.start()
+    R.dist.barrier()
     torch.cuda.synchronize()
     e0.record()
-    last = None
     for i in range(args.steps):
-        last = step(args.warmup + i)
+        step(args.warmup + i)
     if not args.sync_reduce:
         reducer.result((reducer.i - 1) % reducer.depth)       # the timed region ends when the last reduction has landed
     e1.record()
@@ -320,6 +390,7 @@ def run_b200(args, rank, world, local):
     R.dist.barrier()
     launches = R._lib.launch_count - launches0
     dt = R.dist.max_over_ranks(e0.elapsed_time(e1) * 1e-3, dev)
+    reset_counts = task.reset_counters.cpu().tolist()
     ray_ms = [a.elapsed_time(b) for a, b in task.Camera.timing]
     task.Camera.timing = None
     if not ray_ms:          # fused step: the library timed the ray-cast itself (CUDA events on the launching stream)
@@ -335,7 +406,7 @@ def run_b200(args, rank, world, local):
     def run_e2e(packed):
         """every step: inputs copied from pinned host memory, results (obs, rew, reset) read back and touched on the host;
         two slots, so the read-back of step i overlaps the kernels of step i+1"""
-        pipe = R.HostPipeline(task, packed_obs=packed)
+        pipe = R.HostPipeline(task, packed_obs=packed, device_reset=device_reset)
         for i in range(max(args.warmup, 3)):
             h = hstates[i % n_sets]
             pipe.step(h["pos"], h["quat"], h["joints"], h["actions"])
@@ -363,10 +434,12 @@ def run_b200(args, rank, world, local):
         torch.cuda.synchronize()
         dt_ = R.dist.max_over_ranks(time.perf_counter() - t0, dev)
         task.obs16_buf = None
-        return dt_, pipe.h2d_bytes, pipe.d2h_bytes, checksum
+        h2d, d2h = pipe.h2d_bytes, pipe.d2h_bytes
+        pipe.close()
+        return dt_, h2d, d2h, checksum
     dt_e2e, h2d_b, d2h_b, checksum = run_e2e(False)
     dt_e2e_p, h2d_bp, d2h_bp, checksum_p = run_e2e(True)
-    clk = clocks.stop() if clocks else None
+    clk = clocks.stop()
     if rank != 0:
         return
     total_envs = N * world
@@ -378,30 +451,34 @@ def run_b200(args, rank, world, local):
     if os.path.exists(tf):
         try:
             prof = json.load(open(tf))
-            traffic = prof.get("dram_bytes_per_launch")
-            if N != prof.get("envs_per_launch"):
-                traffic = None                   # the ncu capture is of the 4096-env launch
+            # the capture is only quoted for the build it was taken from: raycast_traffic.json carries the source hash
+            same_build = prof.get("source_hash") == R._build.raycast_hash()
+            traffic = prof.get("dram_bytes_per_launch") if same_build else None
+            if traffic is not None:
+                traffic = traffic / prof["envs_per_launch"] * N          # per launch of THIS run (traffic scales with the envs)
             # the resource that actually binds the kernel: warp-instruction issue slots.  Instruction count per
             # env from the ncu capture (smsp__inst_executed.sum), time measured live, clock sampled live
-            wi = prof["warp_instructions_per_launch"] / prof["envs_per_launch"] * N
-            clk_hz = float(clk["sm_mhz"]) * 1e6 if (clk and clk.get("sm_mhz")) else 1.965e9      # median SM clock under load
-            issue = {"warp_inst_per_launch": wi, "source": prof.get("source"), "sm_clock_hz": clk_hz,
-                     "peak_warp_inst_per_s": 148 * 4 * clk_hz, "achieved_warp_inst_per_s": wi / ray_s,
-                     "frac": wi / ray_s / (148 * 4 * clk_hz)}
+            if same_build:
+                wi = prof["warp_instructions_per_launch"] / prof["envs_per_launch"] * N
+                clk_hz = float(clk["sm_mhz"]) * 1e6 if (clk and clk.get("sm_mhz")) else 1.965e9      # median SM clock under load
+                issue = {"warp_inst_per_launch": wi, "source": prof.get("source"), "sm_clock_hz": clk_hz,
+                         "peak_warp_inst_per_s": 148 * 4 * clk_hz, "achieved_warp_inst_per_s": wi / ray_s,
+                         "frac": wi / ray_s / (148 * 4 * clk_hz)}
+            else:
+                issue = {"unavailable": "profiles/raycast_traffic.json was captured from another build of the kernels"}
         except Exception:
             traffic, issue = None, None
-    line = {"metric": "env-steps/sec (obs+kinematics+reward)", "value": value, "unit": "env-steps/s", "n_gpus": world,
+    cfg = workload_config(N, world, w.K, w.length, args.nv)
+    line = {"metric": METRIC, "value": value, "unit": "env-steps/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f16", "data": "synthetic",
-            "config": {"workload": "%d envs/GPU, 1634 rays/env, K=%d, %gx%g m %d-triangle synthetic terrain + big_rock_layer "
-                                   "(%d triangles), %d stones (configs[1])" % (N, w.K, w.length, w.length, w.triangles.shape[0],
-                                                                               w.rock_triangles.shape[0], w.stone_info.shape[0]),
-                       "envs_per_gpu": N, "total_envs": total_envs, "rays_per_env": P_RAYS, "K": w.K, "index_cells": w.G * w.G,
-                       "l2": "inputs larger than L2: %d pose sets cycled, %.1f GB of index rows touched per step, index %.1f GB"
-                             % (n_sets, N * 785 * w.K * 4 / 1e9, w.G * w.G * w.K * 4 / 1e9),
-                       "parallelism": "env shards x%d, terrain replicated, 1 all-reduce of 16 f64 per step (%s)"
-                                      % (world, "compute stream" if args.sync_reduce else "asynchronous, NCCL stream"),
-                       "raycast_variant": args.variant, "fused_step": not args.unfused, "index_build_s": round(t_index, 3)},
+            "config": cfg,
+            "setup": {"raycast_variant": args.variant, "fused_step": not args.unfused, "index_build_s": round(t_index, 3),
+                      "rock_triangles": int(w.rock_triangles.shape[0]), "stones": int(w.stone_info.shape[0]),
+                      "stats_reduction": "compute stream" if args.sync_reduce else "asynchronous, NCCL stream",
+                      "device_reset_in_step": device_reset,
+                      "resets_per_step": reset_counts[0] / max(args.steps, 1), "goals_drawn_per_step": reset_counts[1] / max(args.steps, 1),
+                      "reset_rate": reset_counts[0] / max(args.steps, 1) / N},
             "rays_per_s": value * P_RAYS,
             # (ray, candidate) tests the reference evaluates for the same output: (1634 heightmap + 26 rock rays) x K per env-step
             "reference_equivalent_pair_tests_per_s": value * (P_RAYS + 26) * w.K,
@@ -413,35 +490,35 @@ def run_b200(args, rank, world, local):
                          "kernel": "heightmap ray-cast (Camera.get_depths)",
                          "note": "contractual HBM figure on the reference-format algorithmic bytes; the kernel is bound by "
                                  "instruction issue, see issue_slots", "issue_slots": issue},
-            # headline end-to-end number: the host pipeline with the observation read back in its native precision (the
-            # heightmap columns ARE fp16 values, rover.py:324-325; HostPipeline.obs_f32() widens them on the host);
-            # e2e_f32_obs is the same loop reading back the reference's f32 [N,1750] layout (twice the bytes: at 8 GPUs the
-            # host link, not the GPUs, then sets the pace)
-            "e2e": {"value": total_envs * args.steps / dt_e2e_p, "unit": "env-steps/s", "h2d_bytes_per_step": h2d_bp * world,
-                    "d2h_bytes_per_step": d2h_bp * world, "ms_per_step": dt_e2e_p / args.steps * 1e3,
-                    "api": "HostPipeline(packed_obs=True).submit/result (2 slots: read-back of step i overlaps step i+1; inputs "
-                           "uploaded from pinned host memory every step; obs = f32 [N,4] proprioceptive + f16 [N,1746] heightmap "
-                           "columns, lossless; rew f32 [N]; reset i64 [N])", "checksum": checksum_p},
-            "e2e_f32_obs": {"value": total_envs * args.steps / dt_e2e, "unit": "env-steps/s", "h2d_bytes_per_step": h2d_b * world,
-                            "d2h_bytes_per_step": d2h_b * world, "ms_per_step": dt_e2e / args.steps * 1e3,
-                            "api": "HostPipeline.submit/result, obs read back as the reference's f32 [N,1750]", "checksum": checksum},
+            # headline end-to-end number: the host pipeline returning the reference's output type, obs_buf f32 [N,1750]
+            # (rover.py:320-325); e2e_packed_obs is the same loop with the heightmap columns read back as the fp16 values they
+            # are (half the bytes; HostPipeline.obs_f32() widens them on the host)
+            "e2e": {"value": total_envs * args.steps / dt_e2e, "unit": "env-steps/s", "h2d_bytes_per_step": h2d_b * world,
+                    "d2h_bytes_per_step": d2h_b * world, "ms_per_step": dt_e2e / args.steps * 1e3,
+                    "api": "HostPipeline.submit/result (2 slots: read-back of step i overlaps step i+1; inputs uploaded from "
+                           "pinned host memory every step; obs f32 [N,1750], rew f32 [N], reset i64 [N] read back)",
+                    "checksum": checksum},
+            "e2e_packed_obs": {"value": total_envs * args.steps / dt_e2e_p, "unit": "env-steps/s", "h2d_bytes_per_step": h2d_bp * world,
+                               "d2h_bytes_per_step": d2h_bp * world, "ms_per_step": dt_e2e_p / args.steps * 1e3,
+                               "api": "HostPipeline(packed_obs=True): obs = f32 [N,4] proprioceptive + f16 [N,1746] heightmap "
+                                      "columns, lossless", "checksum": checksum_p},
             "gpu_launches": launches,
             "clocks": clk}
     if world == 1 and not args.no_cpu:
-        n = args.cpu_envs
-        t = time_cpu_oracle(n, 2, 1)
-        line["cpu_baseline"] = {"value": n / t, "unit": "env-steps/s", "cores": torch.get_num_threads(), "kind": "port",
-                                "sample": "%d envs (x1634 rays x K=200) per step, 1 warm-up + 2 timed steps of the oracle port of the "
-                                          "reference's torch path on a 24 m terrain of the same mesh density" % n}
+        del dstates, hstates
+        torch.cuda.empty_cache()
         try:
-            ng = 256
-            tg = time_gpu_eager_oracle(ng, dev)
-            line["torch_eager_gpu_baseline"] = {"value": ng / tg, "unit": "env-steps/s", "kind": "port",
-                                                "sample": "%d envs per step, 1 warm-up + 3 timed steps of the same oracle port run as eager "
-                                                          "torch ops on this GPU (the reference's own deployment: ~700 ATen launches per "
-                                                          "step, fp16 temporaries in HBM)" % ng}
+            ref = reference_subprocess("cpu", args.ref_envs, 2, 1)
+            line["cpu_baseline"] = ref["cpu_baseline"]
         except Exception as e:          # a baseline, never a reason to lose the bench line
-            line["torch_eager_gpu_baseline"] = {"unavailable": str(e)[:200]}
+            line["cpu_baseline"] = {"unavailable": str(e)[:300]}
+        try:
+            ref = reference_subprocess("cuda:0", 512, 3, 1)
+            line["torch_eager_gpu_baseline"] = {"value": ref["value"], "unit": "env-steps/s", "kind": ref["cpu_baseline"]["kind"],
+                                                "sample": ref["cpu_baseline"]["sample"] + " -- the reference's own deployment: "
+                                                "eager torch on cuda:0 (rover.py:90), N = 512 (its default)"}
+        except Exception as e:
+            line["torch_eager_gpu_baseline"] = {"unavailable": str(e)[:300]}
     if world == 1:
         try:
             line["policy_epilogue"] = time_policy_epilogue(R, task.obs_buf)
@@ -453,25 +530,28 @@ def run_b200(args, rank, world, local):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=100)
-    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--envs", type=int, default=4096, help="envs per GPU")
+    ap.add_argument("--envs", type=int, default=0, help="envs per GPU (default 131072 = BASELINE.json configs[3]'s share; 4096 = configs[1])")
     ap.add_argument("--length", type=float, default=200.0)
     ap.add_argument("--nv", type=int, default=708)
     ap.add_argument("--K", type=int, default=200)
     ap.add_argument("--stones", type=int, default=2000)
     ap.add_argument("--variant", type=int, default=0)
-    ap.add_argument("--cpu-envs", type=int, default=16)
+    ap.add_argument("--ref-envs", type=int, default=64, help="envs per step of the reference arm (BASELINE.json configs[0]: 64)")
+    ap.add_argument("--ref-device", default="cpu", help="reference arm: cpu (the baseline) or cuda:0 (its own eager deployment)")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-reset", action="store_true", help="leave the device-side reset path out of the step")
     ap.add_argument("--unfused", action="store_true", help="one library call per reference call instead of rvb_env_step")
     ap.add_argument("--sync-reduce", action="store_true", help="all-reduce the statistics on the compute stream every step")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 1 if args.impl == "reference" else 3)
     rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
     claim_stdout()
     if args.impl == "reference":
-        run_reference(args, rank)
+        run_reference(args, rank, world)
         return
     import isaac_rover_b200 as R
     rank, world, local = R.dist.init_from_env()

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define RVB_ABI_VERSION 2
+#define RVB_ABI_VERSION 3
 
 typedef enum rvb_status {
     RVB_OK = 0,
@@ -88,6 +88,16 @@ int rvb_heightmap_raycast(const rvb_terrain* t, const float* pos, const float* e
                           float* obs, int64_t obs_ld, const int32_t* col_a, const int32_t* col_b,
                           int variant, void* stream);
 
+/* The same with an optional PACKED observation output: the heightmap observation columns are fp16 values by construction
+ * (rover.py:324-325 stores fp16(dist / 2) into the f32 obs_buf), so a consumer that wants half the bytes passes
+ *   obs_h16 u16(f16) [N, obs_h16_ld]:  obs_h16[n*obs_h16_ld + (col - obs_h16_col0)] = fp16(dist/2)  for col in col_a/col_b >= 0
+ * (obs may then be NULL).  Not available with variant 1.  rvb_env_step uses this entry point for rvb_step_io.obs_h16. */
+int rvb_heightmap_raycast2(const rvb_terrain* t, const float* pos, const float* euler, const float* trig,
+                           const double* pattern, int64_t P, int64_t N,
+                           uint16_t* dist, int32_t* hit_slot, int32_t* hit_tri, uint16_t* pt, uint16_t* sources,
+                           float* obs, int64_t obs_ld, uint16_t* obs_h16, int64_t obs_h16_ld, int obs_h16_col0,
+                           const int32_t* col_a, const int32_t* col_b, int variant, void* stream);
+
 /* Cast pre-computed fp16 rays (sources/directions [R,3], directions NOT normalised, as handed to
  * ray_distance by camera.py:110) against a layer: _height_lookup + gather + ray_distance + min over K. */
 int rvb_cast_rays(const rvb_terrain* t, const uint16_t* sources, const uint16_t* directions, int64_t R,
@@ -108,6 +118,14 @@ int rvb_ray_distance(const uint16_t* sources, const uint16_t* directions, const 
  * ---------------------------------------------------------------------------------------------- */
 int rvb_rock_collision(const rvb_terrain* rocks, const float* pos, const float* euler, const float* trig,
                        const float* joints, int64_t N,
+                       uint16_t* wheel_dist, uint16_t* body_dist, int32_t* hit_tri, int64_t* collision,
+                       uint16_t* rays_out, int variant, void* stream);
+/* The same with the joint trigonometry supplied by the caller: joint_trig f32 [N,18] = (sin j_i, cos j_i) for the DOFs
+ * i = 0..8 the wheel chain uses (rock_detect.py:248-291), NULL = sinf/cosf on the device.  Like `trig` for the body rotation:
+ * libm results differ in the last ulp between torch-CPU, torch-CUDA and CUDA's sinf, and parity tests that demand bit-identical
+ * rays inject the oracle's values. */
+int rvb_rock_collision2(const rvb_terrain* rocks, const float* pos, const float* euler, const float* trig,
+                       const float* joints, const float* joint_trig, int64_t N,
                        uint16_t* wheel_dist, uint16_t* body_dist, int32_t* hit_tri, int64_t* collision,
                        uint16_t* rays_out, int variant, void* stream);
 /* check_collision alone (rover.py:663-668) on caller-provided distances. */

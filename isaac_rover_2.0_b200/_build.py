@@ -37,6 +37,18 @@ def source_hash():
     return h.hexdigest()
 
 
+def raycast_hash():
+    """sha256 over the sources of the heightmap ray-cast kernels alone: what profiles/raycast_traffic.json (an ncu capture of
+    that kernel) is tied to -- bench.py quotes the capture only for the build it was taken from."""
+    import hashlib
+    h = hashlib.sha256(" ".join(NVCC_FLAGS).encode())
+    for f in ("common.cuh", "raycast_common.cuh", "raycast_shadow.cu", "raycast_tiled.cu"):
+        h.update(f.encode())
+        with open(os.path.join(CSRC, f), "rb") as fh:
+            h.update(fh.read())
+    return h.hexdigest()
+
+
 def needs_build():
     if not os.path.exists(LIB):
         return True

@@ -26,6 +26,35 @@ int rvb_set_error(int code, const char* what, const char* detail);
 // per env step (the host pipeline) then pays a driver re-allocation of several ms inside the next call.
 cudaError_t rvb_scratch_alloc(void** p, size_t bytes, cudaStream_t st);
 
+// Side stream + fork / join events of the calling thread for the current device (slot 0: rock layer beside the heightmap in
+// rvb_env_step; slot 1: steep envs beside the shadow kernel), created once per (thread, device, slot) and kept.
+struct RvbSide {
+    cudaStream_t s;
+    cudaEvent_t fork, join;
+};
+cudaError_t rvb_side_stream(int slot, RvbSide** out);
+
+// Runs on EVERY exit path of a launcher that forked work onto a side stream and / or holds stream-ordered scratch: the caller's
+// stream waits for the side stream's join event (once it has been recorded) and the scratch goes back to the pool.
+struct RvbJoinGuard {
+    cudaStream_t st;
+    cudaEvent_t join = nullptr;      // set after cudaEventRecord(join, side)
+    void* scratch = nullptr;
+    explicit RvbJoinGuard(cudaStream_t s) : st(s) {}
+    ~RvbJoinGuard() {
+        if (join) cudaStreamWaitEvent(st, join, 0);
+        if (scratch) cudaFreeAsync(scratch, st);
+    }
+};
+
+// Optional packed fp16 observation output of a heightmap ray-cast (rvb_heightmap_raycast2, rvb_step_io.obs_h16):
+// obs16[n * ld + (column - col0)] = fp16(dist / 2) for the columns col_a / col_b name.
+struct RvbObs16 {
+    uint16_t* p;
+    int64_t ld;
+    int col0;
+};
+
 // ---------------------------------------------------------------- terrain handle
 // One pre-resolved record per triangle, 32 B = one L2 sector, two 16-byte loads.
 // halves: a.xyz | b.xyz | c.xyz | n.xyz (n = b x c) | 4 x pad      (ray_casting.py:34-40)

@@ -349,6 +349,9 @@ static int check_forward(const rvb_policy* P, const float* obs, int64_t obs_ld, 
     RVB_REQUIRE(obs && out, "rvb_policy_forward: null pointer");
     RVB_REQUIRE(obs_ld >= (int64_t)P->n_proprio + P->n_sparse + P->n_dense, "rvb_policy_forward: obs rows are shorter than the network's input");
     RVB_REQUIRE(out_ld >= P->n_head, "rvb_policy_forward: out rows are shorter than the head");
+    int cur_dev = -1;
+    RVB_CUDA(cudaGetDevice(&cur_dev));
+    RVB_REQUIRE(P->device == cur_dev, "rvb_policy_forward: the network lives on another device than the calling thread's current one");
     return RVB_OK;
 }
 

@@ -11,11 +11,11 @@
 int launch_heightmap_tiled(const rvb_terrain* t, const float* pos, const float* euler, const float* trig,
                            const double* pattern, int64_t P, int64_t N, uint16_t* dist, int32_t* hit_slot,
                            int32_t* hit_tri, uint16_t* pt, uint16_t* sources, float* obs, int64_t obs_ld,
-                           const int32_t* col_a, const int32_t* col_b, bool per_cell, cudaStream_t st);
+                           const int32_t* col_a, const int32_t* col_b, bool per_cell, const RvbObs16* o16, cudaStream_t st);
 int launch_heightmap_shadow(const rvb_terrain* t, const float* pos, const float* euler, const float* trig,
                            const double* pattern, int64_t P, int64_t N, uint16_t* dist, int32_t* hit_slot,
                            int32_t* hit_tri, uint16_t* pt, uint16_t* sources, float* obs, int64_t obs_ld,
-                           const int32_t* col_a, const int32_t* col_b, float cos_steep, cudaStream_t st);
+                           const int32_t* col_a, const int32_t* col_b, float cos_steep, const RvbObs16* o16, cudaStream_t st);
 // envs whose ray direction has |d_z| below this are ray-cast by the tiled kernel (their prisms are long slivers)
 #define RVB_COS_STEEP 0.8f
 
@@ -146,22 +146,34 @@ extern "C" int rvb_heightmap_raycast(const rvb_terrain* t, const float* pos, con
                                      const double* pattern, int64_t P, int64_t N, uint16_t* dist, int32_t* hit_slot,
                                      int32_t* hit_tri, uint16_t* pt, uint16_t* sources, float* obs, int64_t obs_ld,
                                      const int32_t* col_a, const int32_t* col_b, int variant, void* stream) {
+    return rvb_heightmap_raycast2(t, pos, euler, trig, pattern, P, N, dist, hit_slot, hit_tri, pt, sources, obs, obs_ld, nullptr, 0,
+                                  0, col_a, col_b, variant, stream);
+}
+
+extern "C" int rvb_heightmap_raycast2(const rvb_terrain* t, const float* pos, const float* euler, const float* trig,
+                                      const double* pattern, int64_t P, int64_t N, uint16_t* dist, int32_t* hit_slot,
+                                      int32_t* hit_tri, uint16_t* pt, uint16_t* sources, float* obs, int64_t obs_ld,
+                                      uint16_t* obs_h16, int64_t obs_h16_ld, int obs_h16_col0, const int32_t* col_a,
+                                      const int32_t* col_b, int variant, void* stream) {
     RVB_REQUIRE(N >= 0 && P > 0 && P <= 65535, "rvb_heightmap_raycast: need N >= 0, 0 < P <= 65535");
     if (N == 0) return RVB_OK;
     RVB_REQUIRE(t && pos && euler && pattern && dist, "rvb_heightmap_raycast: null pointer");
     RVB_REQUIRE(!obs || (col_a && col_b && obs_ld > 0), "rvb_heightmap_raycast: obs needs col_a, col_b, obs_ld");
+    RVB_REQUIRE(!obs_h16 || (col_a && col_b && obs_h16_ld > 0 && obs_h16_col0 >= 0), "rvb_heightmap_raycast2: obs_h16 needs col_a, col_b, obs_h16_ld");
     RVB_REQUIRE(variant >= 0 && variant <= 3, "rvb_heightmap_raycast: variant must be 0, 1, 2 or 3");
-    if (N == 0) return RVB_OK;
+    RVB_REQUIRE(!obs_h16 || variant != 1, "rvb_heightmap_raycast2: the per-pair cross-check kernel (variant 1) has no packed output");
+    const RvbObs16 o16v = {obs_h16, obs_h16_ld, obs_h16_col0};
+    const RvbObs16* o16 = obs_h16 ? &o16v : nullptr;
     cudaStream_t st = as_stream(stream);
     if (variant == 0 && t->sb_ids != nullptr) {
         float cos_steep = RVB_COS_STEEP;
         if (const char* ev = getenv("RVB_COS_STEEP")) cos_steep = (float)atof(ev);      // tuning hook; results do not depend on it
         return launch_heightmap_shadow(t, pos, euler, trig, pattern, P, N, dist, hit_slot, hit_tri, pt, sources, obs,
-                                       obs_ld, col_a, col_b, cos_steep, st);
+                                       obs_ld, col_a, col_b, cos_steep, o16, st);
     }
     if (variant != 1)
         return launch_heightmap_tiled(t, pos, euler, trig, pattern, P, N, dist, hit_slot, hit_tri, pt, sources, obs,
-                                      obs_ld, col_a, col_b, variant == 2, st);
+                                      obs_ld, col_a, col_b, variant == 2, o16, st);
     RVB_REQUIRE(N <= 65535, "rvb_heightmap_raycast: variant 1 handles at most 65535 envs per call");
     __half* src16 = (__half*)sources;
     __half* scratch = nullptr;

@@ -234,13 +234,3 @@ __device__ __forceinline__ void epilogue(const TiledParams& q, int64_t n, int p0
 
 }  // namespace rc
 
-// Packed fp16 observation output of the NEXT heightmap ray-cast launched by this thread (set by rvb_env_step, consumed and
-// cleared by fill_tiled_params); keeps rvb_heightmap_raycast's signature as it is.
-struct RvbObs16 {
-    uint16_t* p;
-    int64_t ld;
-    int col0;
-    const int32_t* col_a;
-    const int32_t* col_b;
-};
-extern thread_local RvbObs16 g_rvb_obs16;

@@ -42,7 +42,7 @@
 int fill_tiled_params(const rvb_terrain* t, const float* pos, const float* euler, const float* trig, const double* pattern,
                       int64_t P, int64_t N, uint16_t* dist, int32_t* hit_slot, int32_t* hit_tri, uint16_t* pt,
                       uint16_t* sources, float* obs, int64_t obs_ld, const int32_t* col_a, const int32_t* col_b,
-                      rc::TiledParams& q);
+                      const RvbObs16* o16, rc::TiledParams& q);
 int launch_tiled(const rc::TiledParams& q, bool blocks, int64_t grid, cudaStream_t st);
 
 namespace {
@@ -796,6 +796,10 @@ __global__ void __launch_bounds__(TT, RTC <= RT_SMALL ? 4 : 3) hm_shadow_kernel(
                 }
                 t4 += min(total, room);
                 DBG(11, 1);
+                if (total <= room) {            // every mask is empty now
+                    in3 = false;
+                    break;
+                }
                 if (t4 - h4 >= 32u) break;
             }
             break;
@@ -881,11 +885,11 @@ __global__ void __launch_bounds__(TT, RTC <= RT_SMALL ? 4 : 3) hm_shadow_kernel(
 int launch_heightmap_shadow(const rvb_terrain* t, const float* pos, const float* euler, const float* trig,
                             const double* pattern, int64_t P, int64_t N, uint16_t* dist, int32_t* hit_slot,
                             int32_t* hit_tri, uint16_t* pt, uint16_t* sources, float* obs, int64_t obs_ld,
-                            const int32_t* col_a, const int32_t* col_b, float cos_steep, cudaStream_t st) {
+                            const int32_t* col_a, const int32_t* col_b, float cos_steep, const RvbObs16* o16, cudaStream_t st) {
     RVB_REQUIRE(t->sb_ids != nullptr && t->sb_pos != nullptr && t->blk_ids != nullptr && t->s1recs != nullptr, "heightmap ray-cast (shadow): layer has no block lists");
     rc::TiledParams q;
     int rc_ = fill_tiled_params(t, pos, euler, trig, pattern, P, N, dist, hit_slot, hit_tri, pt, sources, obs, obs_ld, col_a,
-                                col_b, q);
+                                col_b, o16, q);
     if (rc_ != RVB_OK) return rc_;
     RVB_REQUIRE(q.tile_size <= 2048, "heightmap ray-cast (shadow): tile larger than 2048 rays");
     int64_t nblocks = N * q.tiles;
@@ -904,7 +908,9 @@ int launch_heightmap_shadow(const rvb_terrain* t, const float* pos, const float*
     // scratch: [0] steep count, [1] tilted envs placed, [2] other envs placed, [3] handed-back count, then the steep list
     // [nblocks], the hand-back list [nblocks] and the env order [N]
     int* scratch = nullptr;
+    RvbJoinGuard guard(st);
     RVB_CUDA(rvb_scratch_alloc((void**)&scratch, sizeof(int) * (size_t)(4 + 2 * nblocks + N), st));
+    guard.scratch = scratch;
     RVB_CUDA(cudaMemsetAsync(scratch, 0, sizeof(int) * 4, st));
     int32_t* steep_list = scratch + 4;
     q.fb_count = scratch + 3;
@@ -919,21 +925,12 @@ int launch_heightmap_shadow(const rvb_terrain* t, const float* pos, const float*
     q.task_rays = TASK_RAYS;
     if (const char* tr = getenv("RVB_SHADOW_TASK_RAYS")) q.task_rays = min(max(atoi(tr), 1), TASK_RAYS);   // tuning hook
     if (const char* sp = getenv("RVB_SHADOW_SPEC")) q.spec_slot = atoi(sp); // tuning hook
-    struct Side {
-        int dev = -1;
-        cudaStream_t s = nullptr;
-        cudaEvent_t fork = nullptr, join = nullptr;
-    };
-    static thread_local Side side;
+    RvbSide* side_p = nullptr;
+    RVB_CUDA(rvb_side_stream(1, &side_p));
+    RvbSide& side = *side_p;
     static thread_local int configured_device = -1;
     int dev = 0;
     RVB_CUDA(cudaGetDevice(&dev));
-    if (side.dev != dev) {
-        RVB_CUDA(cudaStreamCreateWithFlags(&side.s, cudaStreamNonBlocking));
-        RVB_CUDA(cudaEventCreateWithFlags(&side.fork, cudaEventDisableTiming));
-        RVB_CUDA(cudaEventCreateWithFlags(&side.join, cudaEventDisableTiming));
-        side.dev = dev;
-    }
     hm_classify_kernel<<<(unsigned)ceil_div(N, 256), 256, 0, st>>>(q, N, order, scratch, steep_list);
     // steep envs: the tiled kernel on the second stream, concurrently with the shadow kernel
     const int64_t tgrid = nblocks < 148 * 3 ? nblocks : 148 * 3;
@@ -947,6 +944,7 @@ int launch_heightmap_shadow(const rvb_terrain* t, const float* pos, const float*
         const int rcs = launch_tiled(qs, true, tgrid, side.s);
         if (rcs != RVB_OK) return rcs;
         RVB_CUDA(cudaEventRecord(side.join, side.s));
+        guard.join = side.join;
     }
     if (configured_device != dev) {
         RVB_CUDA(cudaFuncSetAttribute(hm_shadow_kernel<false, RT_MAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shadow_smem_bytes(RT_MAX) + 48 * 1024));
@@ -1000,7 +998,5 @@ int launch_heightmap_shadow(const rvb_terrain* t, const float* pos, const float*
         q.work_slices = 8;
         rc_ = launch_tiled(q, true, tgrid, st);
     }
-    cudaStreamWaitEvent(st, side.join, 0);
-    cudaFreeAsync(scratch, st);
-    return rc_;
+    return rc_;          // guard: st waits for the steep list's kernel, scratch goes back to the pool
 }

@@ -375,12 +375,10 @@ static int configure_tiled() {
     return RVB_OK;
 }
 
-thread_local RvbObs16 g_rvb_obs16 = {nullptr, 0, 0, nullptr, nullptr};
-
 int fill_tiled_params(const rvb_terrain* t, const float* pos, const float* euler, const float* trig, const double* pattern,
                       int64_t P, int64_t N, uint16_t* dist, int32_t* hit_slot, int32_t* hit_tri, uint16_t* pt,
                       uint16_t* sources, float* obs, int64_t obs_ld, const int32_t* col_a, const int32_t* col_b,
-                      rc::TiledParams& q) {
+                      const RvbObs16* o16, rc::TiledParams& q) {
     RVB_REQUIRE(t->G0 <= 32767 && t->G1 <= 65535, "heightmap ray-cast: grid larger than 32767 x 65535 cells");
     RVB_REQUIRE(t->K <= 16383, "heightmap ray-cast: K > 16383");
     RVB_REQUIRE(t->G0 * t->G1 < ((int64_t)1 << 32), "heightmap ray-cast: more than 2^32 cells");
@@ -396,10 +394,8 @@ int fill_tiled_params(const rvb_terrain* t, const float* pos, const float* euler
     q.tile_size = (int)ceil_div(P, q.tiles);
     q.dist = (__half*)dist; q.hit_slot = hit_slot; q.hit_tri = hit_tri; q.pt = (__half*)pt; q.sources = (__half*)sources;
     q.obs = obs; q.obs_ld = obs_ld; q.col_a = col_a; q.col_b = col_b;
-    if (g_rvb_obs16.p) {
-        q.obs16 = (__half*)g_rvb_obs16.p; q.obs16_ld = g_rvb_obs16.ld; q.obs16_col0 = g_rvb_obs16.col0;
-        q.col_a = g_rvb_obs16.col_a; q.col_b = g_rvb_obs16.col_b;
-        g_rvb_obs16.p = nullptr;
+    if (o16 && o16->p) {
+        q.obs16 = (__half*)o16->p; q.obs16_ld = o16->ld; q.obs16_col0 = o16->col0;
     }
     RVB_REQUIRE(N * q.tiles < ((int64_t)1 << 31), "heightmap ray-cast: too many (env, tile) blocks for one launch");
     return RVB_OK;
@@ -419,10 +415,10 @@ int launch_tiled(const rc::TiledParams& q, bool blocks, int64_t grid, cudaStream
 int launch_heightmap_tiled(const rvb_terrain* t, const float* pos, const float* euler, const float* trig,
                            const double* pattern, int64_t P, int64_t N, uint16_t* dist, int32_t* hit_slot,
                            int32_t* hit_tri, uint16_t* pt, uint16_t* sources, float* obs, int64_t obs_ld,
-                           const int32_t* col_a, const int32_t* col_b, bool per_cell, cudaStream_t st) {
+                           const int32_t* col_a, const int32_t* col_b, bool per_cell, const RvbObs16* o16, cudaStream_t st) {
     rc::TiledParams q;
     const int rc_ = fill_tiled_params(t, pos, euler, trig, pattern, P, N, dist, hit_slot, hit_tri, pt, sources, obs, obs_ld,
-                                      col_a, col_b, q);
+                                      col_a, col_b, o16, q);
     if (rc_ != RVB_OK) return rc_;
     return launch_tiled(q, t->blk_ids != nullptr && !per_cell, N * q.tiles, st);
 }

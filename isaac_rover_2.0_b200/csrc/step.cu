@@ -10,11 +10,6 @@
 #include "task_dev.cuh"
 #include "raycast_common.cuh"
 
-int launch_heightmap_shadow(const rvb_terrain* t, const float* pos, const float* euler, const float* trig,
-                            const double* pattern, int64_t P, int64_t N, uint16_t* dist, int32_t* hit_slot,
-                            int32_t* hit_tri, uint16_t* pt, uint16_t* sources, float* obs, int64_t obs_ld,
-                            const int32_t* col_a, const int32_t* col_b, float cos_steep, cudaStream_t st);
-
 __global__ void step_pre_kernel(rvb_step_io io, int64_t N, int H, int sem) {
     const int64_t n = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (n >= N) return;
@@ -53,12 +48,6 @@ struct Timing {
 };
 thread_local Timing g_timing;
 
-struct SideStream {
-    int dev = -1;
-    cudaStream_t side = nullptr;
-    cudaEvent_t fork = nullptr, join = nullptr;
-};
-thread_local SideStream g_side;
 }  // namespace
 
 extern "C" int rvb_env_step(const rvb_terrain* terrain, const rvb_terrain* rocks, const rvb_reward_params* p,
@@ -79,21 +68,17 @@ extern "C" int rvb_env_step(const rvb_terrain* terrain, const rvb_terrain* rocks
     step_pre_kernel<<<(unsigned)ceil_div(N, 256), 256, 0, st>>>(io, N, (int)H, p->sem);
     RVB_LAUNCH_CHECK();
     const bool with_rocks = rocks && io.wheel_dist && io.body_dist;
+    RvbJoinGuard guard(st);          // on every exit path below: st waits for the rock layer's kernel
     if (with_rocks) {
-        int dev = 0;
-        RVB_CUDA(cudaGetDevice(&dev));
-        if (g_side.dev != dev) {
-            RVB_CUDA(cudaStreamCreateWithFlags(&g_side.side, cudaStreamNonBlocking));
-            RVB_CUDA(cudaEventCreateWithFlags(&g_side.fork, cudaEventDisableTiming));
-            RVB_CUDA(cudaEventCreateWithFlags(&g_side.join, cudaEventDisableTiming));
-            g_side.dev = dev;
-        }
-        RVB_CUDA(cudaEventRecord(g_side.fork, st));
-        RVB_CUDA(cudaStreamWaitEvent(g_side.side, g_side.fork, 0));
+        RvbSide* side = nullptr;
+        RVB_CUDA(rvb_side_stream(0, &side));
+        RVB_CUDA(cudaEventRecord(side->fork, st));
+        RVB_CUDA(cudaStreamWaitEvent(side->s, side->fork, 0));
         const int rc = rvb_rock_collision(rocks, io.pos, io.euler, nullptr, io.joints, N, io.wheel_dist, io.body_dist, nullptr,
-                                          io.rock_collision, nullptr, 0, g_side.side);
+                                          io.rock_collision, nullptr, 0, side->s);
         if (rc != RVB_OK) return rc;
-        RVB_CUDA(cudaEventRecord(g_side.join, g_side.side));
+        RVB_CUDA(cudaEventRecord(side->join, side->s));
+        guard.join = side->join;
     }
     cudaEvent_t t0 = nullptr, t1 = nullptr;
     if (g_timing.on) {
@@ -111,13 +96,14 @@ extern "C" int rvb_env_step(const rvb_terrain* terrain, const rvb_terrain* rocks
     }
     // packed observation requested: the heightmap columns go to obs_h16 (fp16, what they are by construction) and the f32
     // columns 4.. of obs are left alone
-    if (io.obs_h16) g_rvb_obs16 = {io.obs_h16, io.obs_h16_ld, 4, col_a, col_b};
-    int rc = rvb_heightmap_raycast(terrain, io.pos, io.euler, nullptr, pattern, P, N, io.dist, nullptr, nullptr, nullptr, nullptr,
-                                   io.obs_h16 ? nullptr : io.obs, io.obs_ld, col_a, col_b, 0, st);
-    g_rvb_obs16.p = nullptr;
+    int rc = rvb_heightmap_raycast2(terrain, io.pos, io.euler, nullptr, pattern, P, N, io.dist, nullptr, nullptr, nullptr, nullptr,
+                                    io.obs_h16 ? nullptr : io.obs, io.obs_ld, io.obs_h16, io.obs_h16_ld, 4, col_a, col_b, 0, st);
     if (rc != RVB_OK) return rc;
     if (t1) RVB_CUDA(cudaEventRecord(t1, st));
-    if (with_rocks) RVB_CUDA(cudaStreamWaitEvent(st, g_side.join, 0));
+    if (guard.join) {
+        RVB_CUDA(cudaStreamWaitEvent(st, guard.join, 0));
+        guard.join = nullptr;
+    }
     // hist[:, 0] = this step's action, hist[:, 1] = the previous one (rover.py:498-501); rover_rot = euler (no physics in between)
     return launch_reward_reset(p, io.pos, io.target, io.heading, io.euler, io.lin_hist, io.lin_hist + 1, io.ang_hist, io.ang_hist + 1, H,
                             io.joints, io.progress, p->curriculum_level >= 2 ? io.rock_collision : nullptr, N, io.rew, io.reset,

@@ -145,11 +145,11 @@ extern "C" int rvb_height_lookup(const float* heightmap, int64_t H0, int64_t H1,
 // how the envs are sharded over GPUs.  oracle/reset_oracle.py restates it in numpy.
 // One warp per env (lanes stride over the stones, shuffle min); warps of envs that do not reset exit at once.
 // ------------------------------------------------------------------------------------------------------------
-__global__ void reset_targets_kernel(const int64_t* __restrict__ reset_in, int64_t N, int64_t env_offset, uint64_t seed, uint64_t epoch,
+__global__ void reset_targets_kernel(const int64_t* reset_in, int64_t N, int64_t env_offset, uint64_t seed, uint64_t epoch,
                                      const float* __restrict__ initial_pos, float radius, const float* __restrict__ stones, int S,
                                      float thr, int max_attempts, const float* __restrict__ hm, int H0, int H1, float hscale,
                                      float inv_hscale, float vscale, float shx, float shy, float* __restrict__ target,
-                                     int64_t* __restrict__ progress, int64_t* __restrict__ reset_out, int32_t* __restrict__ counters,
+                                     int64_t* __restrict__ progress, int64_t* reset_out, int32_t* __restrict__ counters,
                                      int sem) {
     const int lane = threadIdx.x & 31;
     const int64_t n = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;

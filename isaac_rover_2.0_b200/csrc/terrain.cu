@@ -42,6 +42,24 @@ cudaError_t rvb_scratch_alloc(void** p, size_t bytes, cudaStream_t st) {
     }
     return cudaMallocFromPoolAsync(p, bytes, pool, st);
 }
+cudaError_t rvb_side_stream(int slot, RvbSide** out) {
+    static thread_local RvbSide table[64][2] = {};
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev < 0 || dev >= 64 || slot < 0 || slot > 1) return cudaErrorInvalidValue;
+    RvbSide& sd = table[dev][slot];
+    if (!sd.s) {
+        cudaStream_t s = nullptr;
+        cudaEvent_t f = nullptr, j = nullptr;
+        if ((e = cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking)) != cudaSuccess) return e;
+        if ((e = cudaEventCreateWithFlags(&f, cudaEventDisableTiming)) != cudaSuccess) { cudaStreamDestroy(s); return e; }
+        if ((e = cudaEventCreateWithFlags(&j, cudaEventDisableTiming)) != cudaSuccess) { cudaStreamDestroy(s); cudaEventDestroy(f); return e; }
+        sd.s = s; sd.fork = f; sd.join = j;
+    }
+    *out = &sd;
+    return cudaSuccess;
+}
 extern "C" int rvb_abi_version(void) { return RVB_ABI_VERSION; }
 
 // [G0,G1,K] strided view -> contiguous.  One thread per output element; consecutive threads walk K, so

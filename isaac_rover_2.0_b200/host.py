@@ -18,10 +18,15 @@ import torch
 
 
 class HostPipeline:
-    def __init__(self, task, depth=2, packed_obs=False):
+    def __init__(self, task, depth=2, packed_obs=False, device_reset=False):
         self.task = task
         self.depth = depth
         self.packed_obs = packed_obs
+        # device_reset: every step starts with the reset half of pre_physics_step on the device (RoverTask.hot_step); the mask it
+        # consumes is the PREVIOUS step's reset_buf, which lives in the previous slot's buffer (read only: it may be in flight to
+        # the host)
+        self.device_reset = device_reset
+        self._prev_reset = None
         N, dev = task.num_envs, torch.device(task._device)
         self.dev = dev
         pin = dict(pin_memory=True)
@@ -73,7 +78,8 @@ class HostPipeline:
         view.pos, view.quat, view.joints = self.d_pos[k], self.d_quat[k], self.d_joints[k]
         t.obs_buf, t.rew_buf, t.reset_buf = self.d_obs[k], self.d_rew[k], self.d_reset[k]
         t.obs16_buf = self.d_obs16[k] if self.packed_obs else None
-        t.hot_step(self.d_actions[k])
+        t.hot_step(self.d_actions[k], device_reset=self.device_reset and self._prev_reset is not None, reset_mask=self._prev_reset)
+        self._prev_reset = self.d_reset[k]
         if self.packed_obs:
             self.d_prop[k].copy_(self.d_obs[k][:, :4])          # 64 KB, contiguous for the read-back
         self.computed[k].record(cur)
@@ -104,6 +110,16 @@ class HostPipeline:
         if not self.packed_obs:
             return self.h_obs[k]
         return torch.cat((self.h_prop[k], self.h_obs16[k].float()), 1)
+
+    def close(self):
+        """Wait for the copies in flight and drop the buffers (pinned host memory is returned to torch's caching allocator)."""
+        for ev in self.done:
+            if ev is not None:
+                ev.synchronize()
+        for name in ("h_obs", "h_obs16", "h_prop", "d_obs", "d_obs16", "d_prop", "h_rew", "h_reset", "d_rew", "d_reset"):
+            if hasattr(self, name):
+                setattr(self, name, None)
+        self._prev_reset = None
 
     def step(self, pos, quat, joints, actions):
         """Synchronous convenience: returns pinned host (obs, rew, reset) of this step."""

@@ -188,8 +188,11 @@ class _HeightmapNet:
         N = states.shape[0]
         if out is None:
             out = torch.empty((N, self._head_out), dtype=torch.float32, device=states.device)
-        _lib.check(self._lib.rvb_policy_forward(self._handle, _lib.ptr(states), states.stride(0), N, _lib.ptr(out), out.stride(0),
-                                                _lib.stream_of(states)))
+        if self.device.index is not None and states.device.index != self.device.index:
+            raise RuntimeError("states live on %s, the network on %s" % (states.device, self.device))
+        with torch.cuda.device(states.device):
+            _lib.check(self._lib.rvb_policy_forward(self._handle, _lib.ptr(states), states.stride(0), N, _lib.ptr(out), out.stride(0),
+                                                    _lib.stream_of(states)))
         return out
 
 
@@ -200,6 +203,8 @@ def compute_pair(policy, value, states, out_policy=None, out_value=None):
     for net in (policy, value):
         if states.dim() != 2 or states.dtype != torch.float32 or states.shape[1] < net.num_observations:
             raise RuntimeError("states must be float32 [N, >=%d]" % net.num_observations)
+        if net.device.index is not None and states.device.index != net.device.index:
+            raise RuntimeError("states live on %s, the network on %s" % (states.device, net.device))
     if states.stride(1) != 1:
         states = states.contiguous()
     N = states.shape[0]
@@ -207,9 +212,10 @@ def compute_pair(policy, value, states, out_policy=None, out_value=None):
         out_policy = torch.empty((N, policy._head_out), dtype=torch.float32, device=states.device)
     if out_value is None:
         out_value = torch.empty((N, value._head_out), dtype=torch.float32, device=states.device)
-    _lib.check(policy._lib.rvb_policy_forward_pair(policy._handle, value._handle, _lib.ptr(states), states.stride(0), N,
-                                                   _lib.ptr(out_policy), out_policy.stride(0), _lib.ptr(out_value),
-                                                   out_value.stride(0), _lib.stream_of(states)))
+    with torch.cuda.device(states.device):
+        _lib.check(policy._lib.rvb_policy_forward_pair(policy._handle, value._handle, _lib.ptr(states), states.stride(0), N,
+                                                       _lib.ptr(out_policy), out_policy.stride(0), _lib.ptr(out_value),
+                                                       out_value.stride(0), _lib.stream_of(states)))
     return out_policy, out_value
 
 

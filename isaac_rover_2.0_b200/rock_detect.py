@@ -29,7 +29,7 @@ class Rock_Detection():
         self.last_rays = None
 
     def get_collisions(self, positions, rotations, joint_states, trig=None, want_hits=False, want_collision=False,
-                       want_rays=False):
+                       want_rays=False, joint_trig=None):
         _lib.require_cuda(positions, rotations, joint_states)
         lib = _lib.load()
         pos = positions.to(torch.float32).contiguous()
@@ -45,9 +45,13 @@ class Rock_Detection():
         rays = torch.empty((N, 26, 6), dtype=torch.float16, device=dev) if want_rays else None
         if trig is not None:
             trig = trig.to(torch.float32).contiguous()
+        if joint_trig is not None:          # f32 [N,18]: sin, cos of joints 0..8 (tests: the oracle's values, for bit-identical rays)
+            joint_trig = joint_trig.to(torch.float32).contiguous()
+            if tuple(joint_trig.shape) != (N, 18):
+                raise ValueError("joint_trig must be [N,18]")
         with torch.cuda.device(dev):
-            _lib.check(lib.rvb_rock_collision(self.layer.handle, _lib.ptr(pos), _lib.ptr(rot), _lib.ptr(trig), _lib.ptr(jnt), N,
-                                              _lib.ptr(wheel), _lib.ptr(body), _lib.ptr(tri), _lib.ptr(col), _lib.ptr(rays), 0,
-                                              _lib.stream_of(pos)))
+            _lib.check(lib.rvb_rock_collision2(self.layer.handle, _lib.ptr(pos), _lib.ptr(rot), _lib.ptr(trig), _lib.ptr(jnt),
+                                               _lib.ptr(joint_trig), N, _lib.ptr(wheel), _lib.ptr(body), _lib.ptr(tri), _lib.ptr(col),
+                                               _lib.ptr(rays), 0, _lib.stream_of(pos)))
         self.last_hit_tri, self.last_collision, self.last_rays = tri, col, rays
         return wheel, body

@@ -107,6 +107,7 @@ class RoverTask():
         self.rew_buf = torch.zeros(num_envs, device=device, dtype=torch.float)
         self.reset_buf = torch.ones(num_envs, device=device, dtype=torch.long)
         self.progress_buf = torch.zeros(num_envs, device=device, dtype=torch.long)
+        self.states_buf = torch.zeros((num_envs, 0), device=device, dtype=torch.float)
         self.extras = {}
         self.rover_positions = None
         self.rover_rotation = None
@@ -128,6 +129,10 @@ class RoverTask():
         self._count = torch.zeros(1, device=device, dtype=torch.int32)
         # optional packed observation of the fused step: f16 [N, sparse+dense]; when set, obs_buf[:, 4:] is not written
         self.obs16_buf = None
+        # parity-test hooks (unfused path only): f32 [N,6] sin/cos of -roll,-pitch,-yaw and f32 [N,18] sin/cos of joints 0..8
+        # to use instead of the device's sinf/cosf, so that tests can demand bit-identical rays (libm differs in the last ulp)
+        self.parity_trig = None
+        self.parity_joint_trig = None
         self.reset_seed = 42                                        # cfg/config.yaml:11
         self.env_offset = 0                                         # global id of local env 0 (env shards, dist.env_shard)
         self.reset_counters = torch.zeros(3, device=device, dtype=torch.int32)      # envs reset, goals drawn, envs out of attempts
@@ -140,20 +145,73 @@ class RoverTask():
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream(torch.device(self._device)).cuda_stream)
 
+    # ------------------------------------------------------------------ drop-in constructor (rover.py:81-87)
+    @classmethod
+    def from_reference(cls, name, sim_config, env, offset=None, rover_view=None, stone_info=None, heightmap=None,
+                       terrain_assets=None, rock_assets=None, **kw):
+        """The reference's constructor signature `RoverTask(name, sim_config, env, offset)` (rover.py:81-87): numEnvs and the
+        reward scales are read from `sim_config.task_config` the way rover.py:113,158 read them, the terrain / rock assets
+        are loaded from the reference's relative paths (camera.py:154-161) unless given, `env` is kept for the
+        `is_playing()` guard of post_physics_step (rl_task.py:250).  What Isaac Sim creates in set_up_scene -- the rover view,
+        stone_info (rover.py:144) and the height grid (rover.py:210) -- is passed by keyword or attached afterwards
+        (`task._rover = RoverView(...)`, `task.stone_info = ...`, `task.heightmap = ...`)."""
+        cfg = getattr(sim_config, "task_config", None) or {}
+        env_cfg = cfg.get("env", {}) if hasattr(cfg, "get") else {}
+        n = int(env_cfg.get("numEnvs", kw.pop("num_envs", 1)))
+        rewards = dict(DEFAULT_REWARDS)
+        for k in DEFAULT_REWARDS:
+            if k in (cfg.get("rewards", {}) if hasattr(cfg, "get") else {}):
+                rewards[k] = cfg["rewards"][k]
+        if stone_info is None:
+            stone_info = torch.zeros((1, 7), dtype=torch.float32)
+            stone_info[0, :2] = 1e9                         # one stone infinitely far away: every goal / spawn point is valid
+        task = cls(rover_view, n, terrain_assets, rock_assets, stone_info, heightmap, rewards=rewards, **kw)
+        task._name, task._sim_config, task._env, task._offset = name, sim_config, env, offset
+        task._cfg = getattr(sim_config, "config", None)
+        task._task_cfg = cfg
+        return task
+
     # ------------------------------------------------------------------ RLTask.post_physics_step (rl_task.py:239-259)
+    def get_states(self):
+        """rl_task.py:210-216 (asymmetric-critic states buffer; the rover task has num_states = 0)."""
+        return self.states_buf
+
+    def get_extras(self):
+        """rl_task.py:218-223: the rover task fills `extras` in calculate_metrics."""
+        return self.extras
+
+    def _is_playing(self):
+        env = getattr(self, "_env", None)
+        world = getattr(env, "_world", None)
+        return True if world is None else bool(world.is_playing())
+
     def post_physics_step(self):
         self.progress_buf[:] += 1
-        self.get_observations()
-        self.calculate_metrics()
-        self.is_done()
+        if self._is_playing():                                      # rl_task.py:250
+            self.get_observations()
+            self.get_states()
+            self.calculate_metrics()
+            self.is_done()
+            self.get_extras()
         return self.obs_buf, self.rew_buf, self.reset_buf, self.extras
 
-    def hot_step(self, actions, fused=True):
+    def hot_step(self, actions, fused=True, device_reset=False, reset_mask=None):
         """One env-step of the hot path with PhysX excluded: the action half of pre_physics_step (history,
         Ackermann, joint targets; rover.py:343,366-414) followed by post_physics_step (rl_task.py:239-259).
-        Reset poses / goal re-sampling (rover.py:356-361) are the caller's (simulator-side) business.
-        fused=True enqueues the whole step with ONE library call (rvb_env_step); fused=False makes the reference's
-        sequence of calls (same results, ~25 host round trips)."""
+        device_reset=True runs the reset half of pre_physics_step first (rover.py:356-361: book-keeping, goal
+        re-sampling against stone_info, target heights) for every env whose reset_buf is set, on the device
+        (rvb_reset_targets; pose resets stay with the simulator: `_rover.reset_idx_masked(mask, initial_pos)` when the
+        view offers it).  fused=True enqueues the rest of the step with ONE library call (rvb_env_step); fused=False makes
+        the reference's sequence of calls (same results, ~25 host round trips).  The observation hooks and the teacher
+        recorder (rover.py:298-317,326-329) run on both paths.  reset_mask: the mask to consume instead of reset_buf (i64 [N],
+        read only -- used by HostPipeline, whose reset_buf rotates between slots)."""
+        self.global_step += 1                                       # rover.py:341
+        if device_reset:
+            mask = self.reset_buf if reset_mask is None else reset_mask
+            self._mark_reset_info(mask)
+            if hasattr(self._rover, "reset_idx_masked"):
+                self._rover.reset_idx_masked(mask.clone(), self.initial_pos)
+            self.reset_targets_device(reset_mask=reset_mask)
         if fused:
             return self._hot_step_fused(actions)
         _, quat = self._rover.get_world_poses()
@@ -171,6 +229,13 @@ class RoverTask():
         joints = joints if (joints.dtype == f32 and joints.is_contiguous()) else joints.to(f32).contiguous()
         act = actions if (actions.dtype == f32 and actions.is_contiguous() and actions.device == dev) else actions.to(dev, f32).contiguous()
         _lib.require_cuda(pos, quat, joints, act)
+        if self.obs_hooks is not None and self.obs16_buf is not None:
+            raise RuntimeError("hot_step: observation hooks work on obs_buf (f32); they cannot be combined with the packed "
+                               "fp16 observation output (obs16_buf)")
+        if self.save_teacher_data:                                  # rover.py:373-375, then :298-317 BEFORE obs_buf is refreshed
+            self._teacher_actions = act[:, 0:2]
+            if self.teacher_recorder is not None:
+                self.teacher_recorder.record(self.reset_info, self._teacher_actions, self.obs_buf)
         if self._fused is None:
             P = self.num_exteroceptive
             self._fused = dict(
@@ -199,6 +264,8 @@ class RoverTask():
                                               self._stream()))
         if not want_rocks:
             _lib.launch_count -= 1
+        if self.obs_hooks is not None:                              # rover.py:326-329
+            self.obs_hooks.apply(self.obs_buf, epoch=self.global_step, env_offset=self.env_offset)
         self.rover_positions, self.rover_rotation, self.rover_rot = pos, fb["euler"], fb["euler"]
         self.rock_wheel_dist, self.rock_body_dist = (fb["wheel"], fb["body"]) if want_rocks else (None, None)
         self.joint_position_targets, self.joint_velocity_targets = fb["pos_t"], fb["vel_t"]
@@ -229,11 +296,12 @@ class RoverTask():
                                            self.num_envs, _lib.ptr(self.obs_buf), self.obs_buf.stride(0),
                                            _lib.ptr(self.heading_diff), self.sem, self._stream()))
         # heightmap: ray-cast with the sparse/dense gather + /2 fused into obs_buf[:, 4:] (rover.py:286-288,324-325)
-        self.Camera.get_depths(self.rover_positions, self.rover_rotation, obs=self.obs_buf, want_pt=False)
+        self.Camera.get_depths(self.rover_positions, self.rover_rotation, obs=self.obs_buf, want_pt=False, trig=self.parity_trig)
         # rock collision (rover.py:291-293)
         want = self.curriculum_level >= 2
         self.rock_wheel_dist, self.rock_body_dist = self.Rock_detector.get_collisions(
-            self.rover_positions, self.rover_rotation, self._rover.get_joint_positions(), want_collision=want)
+            self.rover_positions, self.rover_rotation, self._rover.get_joint_positions(), want_collision=want,
+            trig=self.parity_trig, joint_trig=self.parity_joint_trig)
         if want:
             self.rock_collison = self.Rock_detector.last_collision
         if self.obs_hooks is not None:                              # rover.py:326-329
@@ -272,22 +340,31 @@ class RoverTask():
         self.global_step += 1
         self.rover_loc, quat = self._rover.get_world_poses()
         self.rover_rot = tensor_quat_to_eul(quat)
+        self._mark_reset_info()
         if hasattr(self._rover, "reset_idx_masked"):
             self._rover.reset_idx_masked(self.reset_buf.clone(), self.initial_pos)
         self.reset_targets_device(max_attempts=max_attempts)
         self.apply_actions(actions)
 
-    def reset_targets_device(self, radius=8.0, thr=1.0, max_attempts=64, epoch=None):
-        """reset_idx book-keeping + set_targets (rover.py:451-452, 566-584) for every env with reset_buf != 0, on the device."""
+    def _mark_reset_info(self, mask=None):
+        """rover.py:420-422 without the host-side nonzero(): when any env resets, the reference sets reset_info of EVERY env."""
+        if self.save_teacher_data:
+            any_reset = ((self.reset_buf if mask is None else mask) != 0).any().to(self.reset_info.dtype)
+            torch.maximum(self.reset_info, any_reset.expand_as(self.reset_info), out=self.reset_info)
+
+    def reset_targets_device(self, radius=8.0, thr=1.0, max_attempts=64, epoch=None, reset_mask=None):
+        """reset_idx book-keeping + set_targets (rover.py:451-452, 566-584) for every env with reset_buf != 0, on the device.
+        reset_mask: consume this mask instead (left untouched; reset_buf is then not cleared)."""
         hm = self.heightmap
         sh = self.shift.flatten().cpu()
         with torch.cuda.device(torch.device(self._device)):
             _lib.check(self._lib.rvb_reset_targets(
-                _lib.ptr(self.reset_buf), self.num_envs, int(self.env_offset), int(self.reset_seed),
+                _lib.ptr(self.reset_buf if reset_mask is None else reset_mask), self.num_envs, int(self.env_offset), int(self.reset_seed),
                 int(self.global_step if epoch is None else epoch), _lib.ptr(self.initial_pos), float(radius), _lib.ptr(self.stone_info),
                 self.stone_info.shape[0], float(thr), int(max_attempts), _lib.ptr(hm), hm.shape[0], hm.shape[1],
                 float(self.horizontal_scale), float(self.vertical_scale), float(sh[0]), float(sh[1]), _lib.ptr(self.target_positions),
-                _lib.ptr(self.progress_buf), _lib.ptr(self.reset_buf), _lib.ptr(self.reset_counters), self.sem, self._stream()))
+                _lib.ptr(self.progress_buf), _lib.ptr(self.reset_buf if reset_mask is None else None), _lib.ptr(self.reset_counters),
+                self.sem, self._stream()))
         return self.reset_counters
 
     def apply_actions(self, actions):

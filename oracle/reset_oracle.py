@@ -46,12 +46,15 @@ def uniform(seed, epoch, gid, attempt):
     return ((r0 >> np.uint32(8)).astype(np.float32) * np.float32(2.0 ** -24)).astype(np.float32)
 
 
-def goal_from_uniform(u, initial_xy, radius):
-    """random_goals (rover.py:554-564) in f32: alpha = 2 pi u; target = radius * (cos, sin) + 0 + initial."""
+def goal_from_uniform(u, initial_xy, radius, cos_sin=None):
+    """random_goals (rover.py:554-564) in f32: alpha = 2 pi u; target = radius * (cos, sin) + 0 + initial.
+    cos_sin: optional f32 array -> (cos, sin) f32 arrays; default numpy's (tests pass the CUDA math library's, whose last ulp
+    differs from numpy's, to demand bit-identical goals from the kernel)."""
     f = np.float32
     alpha = (f(2 * math.pi) * u).astype(f)
-    x = ((f(radius) * np.cos(alpha).astype(f)).astype(f) + f(0)) + initial_xy[:, 0].astype(f)
-    y = ((f(radius) * np.sin(alpha).astype(f)).astype(f) + f(0)) + initial_xy[:, 1].astype(f)
+    c, s_ = cos_sin(alpha) if cos_sin is not None else (np.cos(alpha), np.sin(alpha))
+    x = ((f(radius) * np.asarray(c).astype(f)).astype(f) + f(0)) + initial_xy[:, 0].astype(f)
+    y = ((f(radius) * np.asarray(s_).astype(f)).astype(f) + f(0)) + initial_xy[:, 1].astype(f)
     return x.astype(f), y.astype(f)
 
 
@@ -78,7 +81,7 @@ def height(hm, x, y, hscale, vscale, shift, cuda_semantics=True):
 
 
 def reset_targets(reset, env_offset, seed, epoch, initial_pos, radius, stones, thr, max_attempts, hm, hscale, vscale, shift,
-                  target, progress, cuda_semantics=True):
+                  target, progress, cuda_semantics=True, cos_sin=None):
     """-> (target, progress, reset_out, counters[3], attempts per env)"""
     reset = np.asarray(reset)
     target, progress = target.copy(), progress.copy()
@@ -90,7 +93,7 @@ def reset_targets(reset, env_offset, seed, epoch, initial_pos, radius, stones, t
     x = np.zeros(0, np.float32)
     while todo.size and k < max_attempts:
         u = uniform(seed, epoch, todo + env_offset, k)
-        x, y = goal_from_uniform(u, initial_pos[todo], radius)
+        x, y = goal_from_uniform(u, initial_pos[todo], radius, cos_sin)
         target[todo, 0], target[todo, 1] = x, y
         attempts[todo] = k + 1
         bad = nearest_edge(x, y, stones) <= np.float32(thr)

@@ -24,7 +24,7 @@ def test_header_symbols_exported():
     for n in names:
         assert hasattr(raw, n), "missing export " + n
     assert set(names) == set(_lib.EXPORTS), set(names) ^ set(_lib.EXPORTS)
-    assert lib.rvb_abi_version() == 2
+    assert lib.rvb_abi_version() == 3
 
 
 def test_argument_validation_without_gpu():

@@ -152,3 +152,14 @@ def test_product_pattern_matches_reference():
     pts, ci, fi = build_pattern()
     assert torch.equal(torch.from_numpy(pts), hm.distribution)
     assert torch.equal(torch.from_numpy(ci), hm.coarse_idx) and torch.equal(torch.from_numpy(fi), hm.fine_idx)
+
+
+def test_golden_spawn_direct_path():
+    """cdist's direct path (<= 25 rows on both sides): the oracle reproduces the reference's spawn loop and nearest stone edge bit
+    for bit on the vectors tests/golden/make_spawn_golden.py took from the reference."""
+    sg = torch.load(os.path.join(HERE, "golden", "spawn_direct_golden.pt"))
+    assert len(sg["cases"]) == 4
+    for case in sg["cases"]:
+        assert case["in_pos"].shape[0] <= 25 and case["stone7"].shape[0] <= 25
+        assert torch.equal(O.avoid_pos_rock_collision(case["in_pos"].clone(), case["stone7"]), case["ref_pos"])
+        assert torch.equal(O.nearest_stone_edge(case["in_pos"][:, 0:2], case["stone7"]), case["ref_nearest"])

@@ -110,3 +110,38 @@ def test_rovertask_applies_hooks_and_records(R):
     expect = plain - 0.02
     expect[:, 4:7] = 0
     assert torch.equal(task.obs_buf, expect)
+
+
+def test_fused_and_unfused_hot_step_with_hooks_agree_over_steps(R):
+    """hot_step(fused=True) and hot_step(fused=False) with noise / dropout hooks and the teacher recorder switched on: the same
+    observations, the same recorder rows, a NEW Philox epoch every step (global_step advances on both paths), and the device-side
+    reset path sets reset_info like rover.py:420-422."""
+    dev = "cuda:0"
+    w = R.synth.make_world(length=12.0, nv=44, K=64, n_stones=8, seed=3, build_index=None)
+    w.map_indices = R.build_knn_index(w.triangles, w.vertices, w.G, w.res, w.K, device=dev).cpu()
+    kr = min(w.K, w.rock_triangles.shape[0])
+    w.rock_indices = R.build_knn_index(w.rock_triangles, w.rock_vertices, w.G, w.res, kr, device=dev).cpu()
+    st = R.synth.make_env_state(w, 24, seed=5, margin=3.0)
+    runs = []
+    for fused in (True, False):
+        task = R.synth.make_task(w, st, device=dev, level=2)
+        task.obs_hooks = R.ObsHooks(1750, noise_std=0.1, dropout_p=0.05, offset=0.02, remove_idx=[3, 9])
+        task.save_teacher_data = True
+        task.teacher_recorder = R.TeacherRecorder(24, 1750, 634, 1112, steps=8, save=False)
+        obs_steps = []
+        for k in range(3):
+            act = (st["actions"] * (1.0 - 0.25 * k)).to(dev)
+            obs, rew, reset, _ = task.hot_step(act, fused=fused, device_reset=(k == 2))
+            obs_steps.append((obs.clone(), rew.clone(), reset.clone()))
+        assert task.global_step == 3
+        runs.append((obs_steps, task.teacher_recorder.teacher_dataset[:3].clone(), task.reset_info.clone()))
+    (fa, ra, ia), (fb, rb, ib) = runs
+    for (oa, wa, sa), (ob, wb, sb) in zip(fa, fb):
+        assert torch.equal(oa, ob) and torch.equal(sa, sb)
+        assert (wa - wb).abs().max().item() <= 1e-6
+    assert torch.equal(ra, rb) and torch.equal(ia, ib)
+    assert bool((ia == 1).all())                                   # some env resets in the synthetic state -> every env flagged
+    # the noise pattern changes from step to step (a frozen epoch would repeat it): heightmap columns of step 0 and step 1 come
+    # from the same poses, so their difference is pure noise / dropout
+    d01 = (fa[0][0][:, 4:] - fa[1][0][:, 4:]).abs()
+    assert float((d01 > 0).float().mean()) > 0.5

@@ -24,8 +24,8 @@ def find(s):
 
 marks = [('phase 0-1 (transform, cells)', find('// ---- phase 0')), ('phase 2 (sort)', find('// ---- phase 2')), ('items', find('// ---- superblock items')),
          ('phase 3 set-up', find('// ---- phase 3')), ('dispatcher', find('const uint32_t n1 = t1 - h1')), ('A1 (stage 1 loop)', find('case A1: {')),
-         ('A2_START (stage 2)', find('case A2_START: {')), ('A2_EMIT (tasks)', find('case A2_EMIT: {')), ('A3A_START (box test)', find('case A3A_START: {')),
-         ('A3A_RUN (expand)', find('case A3A_RUN: {')), ('A3P (pre-filter)', find('case A3P: {')), ('A3B (literal)', find('case A3B: {')),
+         ('A2_START (stage 2)', find('case A2_START: {')), ('A2_EMIT (tasks)', find('case A2_EMIT: {')), ('A3L_START (prism test)', find('case A3L_START: {')),
+         ('A3L_RUN (expand)', find('case A3L_RUN: {')), ('A3B (literal)', find('case A3B: {')),
          ('phase 4 (epilogue call)', find('// ---- phase 4')), ('host', find('}  // namespace'))]
 s1a, s1b = find('__device__ __forceinline__ bool stage1('), find('__device__ __forceinline__ void stage2(')
 s2b = find('__device__ __forceinline__ bool is_steep(')
