@@ -133,6 +133,7 @@ class RoverTask():
         # to use instead of the device's sinf/cosf, so that tests can demand bit-identical rays (libm differs in the last ulp)
         self.parity_trig = None
         self.parity_joint_trig = None
+        self._shift_host = None
         self.reset_seed = 42                                        # cfg/config.yaml:11
         self.env_offset = 0                                         # global id of local env 0 (env shards, dist.env_shard)
         self.reset_counters = torch.zeros(3, device=device, dtype=torch.int32)      # envs reset, goals drawn, envs out of attempts
@@ -356,7 +357,9 @@ class RoverTask():
         """reset_idx book-keeping + set_targets (rover.py:451-452, 566-584) for every env with reset_buf != 0, on the device.
         reset_mask: consume this mask instead (left untouched; reset_buf is then not cleared)."""
         hm = self.heightmap
-        sh = self.shift.flatten().cpu()
+        if self._shift_host is None:          # read once: a .cpu() per step would synchronise the stream
+            self._shift_host = [float(v) for v in self.shift.flatten().cpu()]
+        sh = self._shift_host
         with torch.cuda.device(torch.device(self._device)):
             _lib.check(self._lib.rvb_reset_targets(
                 _lib.ptr(self.reset_buf if reset_mask is None else reset_mask), self.num_envs, int(self.env_offset), int(self.reset_seed),

@@ -36,17 +36,19 @@ def load(device="cpu"):
 
 
 @contextlib.contextmanager
-def reference_assets(world, directory=None):
-    """Write the world in the reference's asset layout (camera.py:154-161, rock_detect.py:151-158) and chdir there."""
+def reference_assets(world, directory=None, device="cpu"):
+    """Write the world in the reference's asset layout (camera.py:154-161, rock_detect.py:151-158) and chdir there.  The
+    reference never moves the loaded tensors: its asset files were saved from tensors on its device, so they are written from
+    `device` here (torch.load restores them there)."""
     old = os.getcwd()
     with tempfile.TemporaryDirectory(dir=directory) as tmp:
         for sub, idx, tri, ver in (("knn_terrain", world.map_indices, world.triangles, world.vertices),
                                    ("knn_rocks", world.rock_indices, world.rock_triangles, world.rock_vertices)):
             d = os.path.join(tmp, "tasks/utils/terrain", sub)
             os.makedirs(d)
-            torch.save(idx, os.path.join(d, "map_indices.pt"))
-            torch.save(tri, os.path.join(d, "triangles.pt"))
-            torch.save(ver, os.path.join(d, "vertices.pt"))
+            torch.save(idx.to(device), os.path.join(d, "map_indices.pt"))
+            torch.save(tri.to(device), os.path.join(d, "triangles.pt"))
+            torch.save(ver.to(device), os.path.join(d, "vertices.pt"))
         os.chdir(tmp)
         try:
             yield tmp
@@ -58,7 +60,7 @@ def make_fake_task(ns, world, st, level=2, device="cpu"):
     """A SimpleNamespace standing in for `self` of RoverTask; `st` tensors must live on `device`."""
     N = st["pos"].shape[0]
     shift = torch.tensor([0, 0, 0.0], device=device)
-    with reference_assets(world):
+    with reference_assets(world, device=device):
         cam = ns.Camera(device, shift)
         rock = ns.Rock_Detection(device, shift)
     rover = types.SimpleNamespace(name="rover_view", count=N,

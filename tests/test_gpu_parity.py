@@ -238,7 +238,11 @@ def test_golden_stones_and_heights(R, golden):
         moved = task.avoid_pos_rock_collision(case["in_pos"].cuda().clone())
         assert torch.equal(moved.cpu(), case["ref_pos"]), "spawn validation, direct cdist path"
         near, flag, _ = task.nearest_stone_edge(case["in_pos"].cuda()[:, 0:2], 1.0)
-        assert torch.equal(near.cpu(), case["ref_nearest"]) and torch.equal(flag.cpu(), (case["ref_nearest"] <= 1.0).long())
+        # the golden distances come from torch-CPU, whose vectorised float32 sqrt is not correctly rounded:
+        # one ulp of slack on the distance, none on the validity flag (no golden distance sits within 1e-6 of the threshold)
+        assert (case["ref_nearest"] - 1.0).abs().min().item() > 1e-6
+        assert torch.allclose(near.cpu(), case["ref_nearest"], rtol=2.4e-7, atol=1e-7)
+        assert torch.equal(flag.cpu(), (case["ref_nearest"] <= 1.0).long())
     task.stone_info = golden["ref_stone7"].cuda()
     # cdist's MATMUL path (> 25 rows; GEMM summation order unspecified, so a position can take one 0.05 m step more or less):
     # rows that differ must still satisfy the loop's invariants
