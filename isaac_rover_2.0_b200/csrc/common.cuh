@@ -73,6 +73,17 @@ struct __align__(16) S1Rec {
 };
 static_assert(sizeof(S1Rec) == 32, "S1Rec must be one 32-byte sector");
 
+// Bounds of the stage-1 inputs of 32 consecutive superblock-list entries (window w = entries [32 w, 32 w + 32) of sb_ids, whatever
+// lists they belong to): the shadow kernel tests a whole window against a superblock item's ray rectangle before it enumerates
+// the window's triangles (raycast_shadow.cu: chunk_cull; numpy statement + proof by comparison with stage 1: tests/shadow_proto.py).
+struct __align__(16) ChunkRec {
+    float x0, x1, y0, y1, z0, z1;      // centroid box (x0 = NaN: the window holds a non-finite record -- never culled)
+    float rmax, cbmax, amax;            // max of S1Rec.r, cb, amax
+    float nxlo, nxhi, nylo, nyhi, nzlo, nzhi;      // component ranges of b x c
+    float pad;
+};
+static_assert(sizeof(ChunkRec) == 64, "ChunkRec");
+
 struct rvb_terrain {
     int32_t* index;    // [G0,G1,Ks] device; row stride Ks = K rounded up to even (8-byte aligned id pairs), pad ids = 0
     TriRec* recs;      // [T], device
@@ -99,6 +110,7 @@ struct rvb_terrain {
     int32_t* sb_ids;     // [n_sb_ent]
     uint16_t* sb_pos;    // [n_sb_ent][RVB_SB*RVB_SB]  position of the triangle in the list of block (i % SB, j % SB); 0xFFFF = absent
     int64_t n_sb_ent;
+    ChunkRec* sb_chunk;  // [ceil(n_sb_ent / 32)]
 };
 #define RVB_BLK 3
 #define RVB_SB 8

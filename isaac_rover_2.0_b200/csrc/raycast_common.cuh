@@ -39,6 +39,7 @@ struct TiledParams {
     const uint32_t* sb_off;
     const int32_t* sb_ids;
     const uint16_t* sb_pos;
+    const ChunkRec* sb_chunk;   // bounds per window of 32 list entries (chunk culling); NULL = none
     int nSBy;
     float cos_steep;          // envs whose ray direction is flatter than this go to the fall-back list
     int* fb_count;            // [1]

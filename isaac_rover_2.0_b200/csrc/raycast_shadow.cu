@@ -93,7 +93,8 @@ struct Smem {
     uint32_t* bins;      // [BIN_CAP / 2 + 2]  u16 counters, then exclusive offsets (column-major bins)
     Item* items;         // [ITEM_CAP]
     uint32_t* cum;       // [ITEM_CAP + 1]  chunks before item i
-    unsigned char* chunk_item;   // [CHUNK_CAP]
+    unsigned char* chunk_item;   // [CHUNK_CAP]  item of the k-th chunk that survived the window cull
+    unsigned short* chunk_win;   // [CHUNK_CAP]  its window, relative to the first window of the item's list
     uint2* q1;           // [NW][QCAP]  stage-1 survivors: (superblock-list entry, gball bits | item)
     uint4* q2;           // [NW][QCAP]  tasks: (item << 15 | list position, ray start | count << 16, T1 | T2 << 16, T3 | sign << 15)
     uint32_t* q4;        // [NW][QCAP3]  pairs inside the prism: ray position | (item << 15 | list position) << 11
@@ -102,7 +103,7 @@ struct Smem {
 
 __host__ __device__ inline size_t shadow_smem_bytes(int RT) {       // RT = ray capacity of the instantiation
     return (size_t)RT * 8 + (size_t)((RT + 3) & ~3) * 4 + (size_t)(BIN_CAP / 2 + 4) * 4 + (size_t)ITEM_CAP * 32 +
-           (size_t)(ITEM_CAP + 4) * 4 + (size_t)CHUNK_CAP + (size_t)NW * (QCAP * (8 + 16) + QCAP3 * 4) + (size_t)(((RT + 31) / 32 + 3) & ~3) * 4;
+           (size_t)(ITEM_CAP + 4) * 4 + (size_t)CHUNK_CAP * 3 + (size_t)NW * (QCAP * (8 + 16) + QCAP3 * 4) + (size_t)(((RT + 31) / 32 + 3) & ~3) * 4;
 }
 
 __device__ __forceinline__ float rcp_up(float x) { return __fdividef(1.0f, x) * 1.000001f; }
@@ -167,6 +168,40 @@ __device__ __forceinline__ bool stage1(const uint4& s0, const uint4& s1, const E
     const float Rs = R * 1.00001f + 1e-5f * (fabsf(qx) + fabsf(qy));
     const bool out = (qx + Rs < rlox) || (qx - Rs > rhix) || (qy + Rs < rloy) || (qy - Rs > rhiy);
     return !out;
+}
+
+// Window cull (tests/shadow_proto.py: chunk_cull): true = stage 1 would reject EVERY triangle whose record went into `c` for this
+// rectangle, so the window's 32 list entries need not be enumerated.  Stage 1's formulas on the window's worst-case inputs
+// (every quantity is monotone in them); any NaN makes a comparison false and the window is kept.
+__device__ __forceinline__ bool chunk_cull(const ChunkRec& c, const EnvC& e, float rlox, float rhix, float rloy, float rhiy) {
+    const float lo = fminf(c.nxlo * e.dx, c.nxhi * e.dx) + fminf(c.nylo * e.dy, c.nyhi * e.dy) + fminf(c.nzlo * e.dz, c.nzhi * e.dz);
+    const float hi = fmaxf(c.nxlo * e.dx, c.nxhi * e.dx) + fmaxf(c.nylo * e.dy, c.nyhi * e.dy) + fmaxf(c.nzlo * e.dz, c.nzhi * e.dz);
+    float adet = fmaxf(lo, -hi);                                 // |n . d| >= adet for every triangle of the window
+    adet = adet * 0.99999f - 1e-7f * (fabsf(lo) + fabsf(hi));
+    if (!(adet > 0.0f) || !(c.x0 == c.x0)) return false;
+    const float e_det = GAMMA * 6.1f * c.cbmax * c.cbmax + ALPHA;
+    const float rdet = rcp_up(adet) * 1.0001f;
+    const float eps0 = EPS0 + 1.3f * (e_det + 4.0f * ALPHA) * rdet;
+    const float rho = GAMMA * 2.01f * c.cbmax * rdet;
+    const float hl = fminf(e.nux * c.x0, e.nux * c.x1) + fminf(e.nuy * c.y0, e.nuy * c.y1) + fminf(e.nuz * c.z0, e.nuz * c.z1);
+    const float hh = fmaxf(e.nux * c.x0, e.nux * c.x1) + fmaxf(e.nuy * c.y0, e.nuy * c.y1) + fmaxf(e.nuz * c.z0, e.nuz * c.z1);
+    const float slh = 1e-6f * (fabsf(hl) + fabsf(hh)) + 1e-7f;
+    const float ta = (e.hmid - (hl - slh)) * e.inv_nd, tb = (e.hmid - (hh + slh)) * e.inv_nd;
+    const float tlo = fminf(ta, tb), thi = fmaxf(ta, tb);
+    const float atc = fmaxf(fabsf(tlo), fabsf(thi)) * e.dn;
+    const float kr = e.kappa * c.rmax;
+    const float Bn = SQ3 * (kr * (1.0f + 3.0f * eps0) + e.lam + atc + c.rmax);
+    const float den = 1.0f - 10.4f * kr * rho;
+    if (!(den > 0.5f)) return false;
+    const float gsum = Bn * rcp_up(den) * 1.0001f;
+    const float eps = eps0 + 2.0f * rho * gsum;
+    const bool fine = (adet > 4.0f * e_det) && (eps <= 16.0f) && ((e.smax + c.amax) * fmaxf(c.cbmax, 1.0f) <= OVF);
+    if (!fine) return false;
+    const float R = (kr * (1.0f + 3.0f * eps) + e.lam) * 1.0001f;
+    const float qxl = c.x0 + fminf(tlo * e.dx, thi * e.dx), qxh = c.x1 + fmaxf(tlo * e.dx, thi * e.dx);
+    const float qyl = c.y0 + fminf(tlo * e.dy, thi * e.dy), qyh = c.y1 + fmaxf(tlo * e.dy, thi * e.dy);
+    const float Rs = R * 1.00001f + 1.1e-5f * (fmaxf(fabsf(qxl), fabsf(qxh)) + fmaxf(fabsf(qyl), fabsf(qyh))) + 1e-5f;
+    return (qxh + Rs < rlox) || (qxl - Rs > rhix) || (qyh + Rs < rloy) || (qyl - Rs > rhiy);
 }
 
 // positive fp32 (or +inf) -> its upper 16 bits, rounded up
@@ -275,7 +310,8 @@ __global__ void __launch_bounds__(TT, RTC <= RT_SMALL ? 4 : 3) hm_shadow_kernel(
     sm.items = reinterpret_cast<Item*>(sm.bins + BIN_CAP / 2 + 4);
     sm.cum = reinterpret_cast<uint32_t*>(sm.items + ITEM_CAP);
     sm.chunk_item = reinterpret_cast<unsigned char*>(sm.cum + ITEM_CAP + 4);
-    sm.q1 = reinterpret_cast<uint2*>(sm.chunk_item + CHUNK_CAP);
+    sm.chunk_win = reinterpret_cast<unsigned short*>(sm.chunk_item + CHUNK_CAP);
+    sm.q1 = reinterpret_cast<uint2*>(sm.chunk_win + CHUNK_CAP);
     sm.q2 = reinterpret_cast<uint4*>(sm.q1 + NW * QCAP);
     sm.q4 = reinterpret_cast<uint32_t*>(sm.q2 + NW * QCAP);
     sm.far = reinterpret_cast<uint32_t*>(sm.q4 + NW * QCAP3);
@@ -538,14 +574,15 @@ __global__ void __launch_bounds__(TT, RTC <= RT_SMALL ? 4 : 3) hm_shadow_kernel(
     }
     __syncthreads();
     {
-        // chunks before each item (warp 0: 4 items per lane), then the chunk -> item table
+        // chunks = windows of 32 list entries ALIGNED in sb_ids (window w = entries [32 w, 32 w + 32): the lists' ends share windows
+        // with their neighbours); windows before each item (warp 0: 4 items per lane), then the chunk -> item table
         const int ni = s_nitems;
         if (warp == 0) {
             uint32_t c[4], tot = 0;
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 const int i = lane * 4 + j;
-                c[j] = i < ni ? (sm.items[i].list_len + CHUNK - 1) / CHUNK : 0u;
+                c[j] = i < ni ? ((sm.items[i].list_off & (CHUNK - 1)) + sm.items[i].list_len + CHUNK - 1) / CHUNK : 0u;
                 tot += c[j];
             }
             uint32_t inc = tot;
@@ -568,8 +605,50 @@ __global__ void __launch_bounds__(TT, RTC <= RT_SMALL ? 4 : 3) hm_shadow_kernel(
             if (tid == 0) q.fb_list[atomicAdd(q.fb_count, 1)] = work_id;
             return;
         }
+        unsigned char* all_item = reinterpret_cast<unsigned char*>(sm.q1);          // [CHUNK_CAP], the queues are idle here
         for (int i = tid; i < ni; i += TT)
-            for (uint32_t c = sm.cum[i]; c < sm.cum[i + 1]; ++c) sm.chunk_item[c] = (unsigned char)i;
+            for (uint32_t c = sm.cum[i]; c < sm.cum[i + 1]; ++c) all_item[c] = (unsigned char)i;
+        if (tid == 0) s_next = 0;
+        __syncthreads();
+        // window cull: a window none of whose triangles stage 1 could keep for the item's ray rectangle is dropped here, 32
+        // entries at a time (one thread per window); the survivors are compacted into the chunk table the warps pull from
+        const int total = s_nchunks;
+        const bool cull_on = q.sb_chunk != nullptr && (q.spec_slot & 4);
+        for (int g0 = 0; g0 < total; g0 += TT) {
+            const int g = g0 + tid;
+            bool keep = false;
+            int item = 0, rel = 0;
+            if (g < total) {
+                item = all_item[g];
+                rel = g - (int)sm.cum[item];
+                keep = true;
+                if (cull_on) {
+                    const Item& it = sm.items[item];
+                    const uint4* rp = reinterpret_cast<const uint4*>(q.sb_chunk + (it.list_off >> 5) + rel);
+                    union { uint4 u[4]; ChunkRec c; } rec;
+                    rec.u[0] = __ldg(rp); rec.u[1] = __ldg(rp + 1); rec.u[2] = __ldg(rp + 2); rec.u[3] = __ldg(rp + 3);
+                    keep = !chunk_cull(rec.c, s_env, it.rlox, it.rhix, it.rloy, it.rhiy);
+                }
+            }
+            const uint32_t m = __ballot_sync(0xffffffffu, keep);
+            int base = 0;
+            if (lane == 0 && m) base = atomicAdd(&s_next, __popc(m));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (keep) {
+                const int at = base + __popc(m & ((1u << lane) - 1u));
+                sm.chunk_item[at] = (unsigned char)item;
+                sm.chunk_win[at] = (unsigned short)rel;
+            }
+        }
+        __syncthreads();
+        if (tid == 0) {
+            if (DBGK) {
+                atomicAdd(q.dbg + 20, (unsigned long long)total);
+                atomicAdd(q.dbg + 21, (unsigned long long)s_next);
+            }
+            s_nchunks = s_next;
+            s_next = 0;
+        }
     }
     __syncthreads();
 
@@ -600,9 +679,8 @@ __global__ void __launch_bounds__(TT, RTC <= RT_SMALL ? 4 : 3) hm_shadow_kernel(
         if (g < nchunks) {
             item = sm.chunk_item[g];
             const Item& it = sm.items[item];
-            const uint32_t cbeg = ((uint32_t)g - sm.cum[item]) * CHUNK;
-            ent = it.list_off + cbeg + lane;
-            if (cbeg + lane < it.list_len) id = __ldg(q.sb_ids + ent);
+            ent = (((it.list_off >> 5) + (uint32_t)sm.chunk_win[g]) << 5) + lane;
+            if (ent >= it.list_off && ent - it.list_off < it.list_len) id = __ldg(q.sb_ids + ent);
         }
     };
     pull(idA, entA, itemA);
@@ -921,7 +999,7 @@ int launch_heightmap_shadow(const rvb_terrain* t, const float* pos, const float*
     q.presorted = 1;
     q.min_sh = 1;                                                            // 2x2-cell bins: 2 % faster than single cells (fewer tasks)
     if (const char* ms = getenv("RVB_SHADOW_SH")) q.min_sh = atoi(ms);      // tuning hook: finest bins to start from
-    q.spec_slot = 3;
+    q.spec_slot = 7;          // bit 0: slot byte fetched ahead of the literal test, bit 1: L2 prefetch of the records, bit 2: window cull
     q.task_rays = TASK_RAYS;
     if (const char* tr = getenv("RVB_SHADOW_TASK_RAYS")) q.task_rays = min(max(atoi(tr), 1), TASK_RAYS);   // tuning hook
     if (const char* sp = getenv("RVB_SHADOW_SPEC")) q.spec_slot = atoi(sp); // tuning hook
@@ -985,6 +1063,7 @@ int launch_heightmap_shadow(const rvb_terrain* t, const float* pos, const float*
                         "3b batches %.1f, literal hits %.1f, slot lookups %.1f, dispatches %.1f\n",
                 (long long)nblocks, fb, h[0] / ne, h[1] / ne, h[2] / ne, h[13] / ne, h[3] / ne, h[10] / ne, h[4] / ne, h[5] / ne, h[6] / ne,
                 h[7] / ne, h[8] / ne, h[9] / ne, h[12] / ne);
+        fprintf(stderr, "[shadow dbg] windows of 32 list entries per tile: %.1f, kept by the window cull: %.1f\n", h[20] / ne, h[21] / ne);
         if (h[19])
             fprintf(stderr, "[shadow dbg] phase 3 per warp (cycles): pulling chunks %.0f, draining the queues %.0f, waiting at the final barrier %.0f\n",
                     (double)h[16] / h[19], (double)h[17] / h[19], (double)h[18] / h[19]);

@@ -270,6 +270,48 @@ __global__ void sb_pos_kernel(const uint32_t* __restrict__ sb_off, const int32_t
     }
 }
 
+// one warp per window of 32 superblock-list entries: bounds of their stage-1 records
+__global__ void sb_chunk_kernel(const int32_t* __restrict__ sb_ids, int64_t n, const S1Rec* __restrict__ s1, ChunkRec* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const int64_t w = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    if (w * 32 >= n) return;
+    const int64_t ent = w * 32 + lane;
+    const float inf = __int_as_float(0x7f800000);
+    float lo[3] = {inf, inf, inf}, hi[3] = {-inf, -inf, -inf}, nlo[3] = {inf, inf, inf}, nhi[3] = {-inf, -inf, -inf};
+    float rmax = 0.f, cbmax = 0.f, amax = 0.f;
+    bool bad = false;
+    if (ent < n) {
+        const S1Rec r = s1[sb_ids[ent]];
+        const float cb = __half2float(__ushort_as_half((unsigned short)(r.cb_amax & 0xffffu)));
+        const float am = __half2float(__ushort_as_half((unsigned short)(r.cb_amax >> 16)));
+        lo[0] = hi[0] = r.qx; lo[1] = hi[1] = r.qy; lo[2] = hi[2] = r.qz;
+        nlo[0] = nhi[0] = r.nx; nlo[1] = nhi[1] = r.ny; nlo[2] = nhi[2] = r.nz;
+        rmax = r.r; cbmax = cb; amax = am;
+        const float sum = r.qx + r.qy + r.qz + r.r + r.nx + r.ny + r.nz + cb + am;
+        bad = !(fabsf(sum) <= 3.0e38f);          // NaN or inf anywhere
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            lo[i] = fminf(lo[i], __shfl_xor_sync(0xffffffffu, lo[i], o)); hi[i] = fmaxf(hi[i], __shfl_xor_sync(0xffffffffu, hi[i], o));
+            nlo[i] = fminf(nlo[i], __shfl_xor_sync(0xffffffffu, nlo[i], o)); nhi[i] = fmaxf(nhi[i], __shfl_xor_sync(0xffffffffu, nhi[i], o));
+        }
+        rmax = fmaxf(rmax, __shfl_xor_sync(0xffffffffu, rmax, o));
+        cbmax = fmaxf(cbmax, __shfl_xor_sync(0xffffffffu, cbmax, o));
+        amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+    }
+    bad = __any_sync(0xffffffffu, bad);
+    if (lane == 0) {
+        ChunkRec c;
+        c.x0 = bad ? __int_as_float(0x7fc00000) : lo[0]; c.x1 = hi[0]; c.y0 = lo[1]; c.y1 = hi[1]; c.z0 = lo[2]; c.z1 = hi[2];
+        c.rmax = rmax; c.cbmax = cbmax; c.amax = amax;
+        c.nxlo = nlo[0]; c.nxhi = nhi[0]; c.nylo = nlo[1]; c.nyhi = nhi[1]; c.nzlo = nlo[2]; c.nzhi = nhi[2];
+        c.pad = 0.f;
+        out[w] = c;
+    }
+}
+
 static int build_superblock_lists(rvb_terrain* t, cudaStream_t st) {
     t->nSBx = (int32_t)ceil_div(t->nBx, RVB_SB);
     t->nSBy = (int32_t)ceil_div(t->nBy, RVB_SB);
@@ -311,6 +353,12 @@ static int build_superblock_lists(rvb_terrain* t, cudaStream_t st) {
             if (e == cudaSuccess) e = cudaMalloc(&t->sb_pos, sizeof(uint16_t) * RVB_SB * RVB_SB * (size_t)(n_u > 0 ? n_u : 1));
             if (e == cudaSuccess) {
                 sb_pos_kernel<<<(unsigned)nsb, 256, 0, st>>>(t->sb_off, t->sb_ids, t->blk_off, t->blk_ids, t->nBx, t->nBy, t->nSBy, t->sb_pos);
+                e = cudaGetLastError();
+            }
+            const int64_t nwin = ceil_div(n_u > 0 ? n_u : 1, 32);
+            if (e == cudaSuccess) e = cudaMalloc(&t->sb_chunk, sizeof(ChunkRec) * (size_t)nwin);
+            if (e == cudaSuccess) {
+                sb_chunk_kernel<<<(unsigned)ceil_div(nwin * 32, 256), 256, 0, st>>>(t->sb_ids, n_u, t->s1recs, t->sb_chunk);
                 e = cudaGetLastError();
             }
             if (e == cudaSuccess) e = cudaStreamSynchronize(st);
@@ -405,6 +453,7 @@ extern "C" int rvb_terrain_create(rvb_terrain** out, const int32_t* map_indices,
             cudaFree(t->sb_off);
             cudaFree(t->sb_ids);
             cudaFree(t->sb_pos);
+            cudaFree(t->sb_chunk);
             delete t;
             return rc != RVB_OK ? rc : rvb_set_error(RVB_ERR_CUDA, "rvb_terrain_create (block lists)", cudaGetErrorString(e));
         }
@@ -434,6 +483,7 @@ extern "C" int rvb_terrain_destroy(rvb_terrain* t) {
     cudaFree(t->sb_off);
     cudaFree(t->sb_ids);
     cudaFree(t->sb_pos);
+    cudaFree(t->sb_chunk);
     delete t;
     return RVB_OK;
 }
@@ -442,5 +492,6 @@ extern "C" int64_t rvb_terrain_bytes(const rvb_terrain* t) {
     if (!t) return 0;
     return (int64_t)sizeof(int32_t) * t->G0 * t->G1 * t->Ks + (int64_t)(sizeof(TriRec) + sizeof(S1Rec)) * t->T +
            (t->blk_ids ? (int64_t)(sizeof(uint4) + sizeof(int32_t)) * t->n_ent + (int64_t)sizeof(uint32_t) * ((int64_t)t->nBx * t->nBy + 1) : 0) +
-           (t->sb_ids ? (int64_t)(sizeof(int32_t) + sizeof(uint16_t) * RVB_SB * RVB_SB) * t->n_sb_ent + (int64_t)sizeof(uint32_t) * ((int64_t)t->nSBx * t->nSBy + 1) : 0);
+           (t->sb_ids ? (int64_t)(sizeof(int32_t) + sizeof(uint16_t) * RVB_SB * RVB_SB) * t->n_sb_ent + (int64_t)sizeof(uint32_t) * ((int64_t)t->nSBx * t->nSBy + 1) +
+                         (int64_t)sizeof(ChunkRec) * ceil_div(t->n_sb_ent > 0 ? t->n_sb_ent : 1, 32) : 0);
 }

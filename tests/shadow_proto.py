@@ -163,6 +163,62 @@ def stage1(a16, b16, c16, ec, rlo, rhi):
     return out & ~ill, ill, gball
 
 
+def chunk_records(a16, b16, c16, win=32):
+    """Per window of `win` consecutive list entries: bounds of the stage-1 inputs (terrain.cu: sb_chunk_kernel)."""
+    a, b, c = a16.astype(F32), b16.astype(F32), c16.astype(F32)
+    ctr = a + (b + c) * F32(1.0 / 3.0)
+    bc = b - c
+    e2 = np.maximum(np.maximum((b * b).sum(1), (c * c).sum(1)), (bc * bc).sum(1))
+    r = F32(2.0 / 3.0) * np.sqrt(e2) * F32(1.0 + 1e-5) + F32(1e-6) * np.abs(a).max(1)
+    nx = np.stack((b[:, 1] * c[:, 2] - b[:, 2] * c[:, 1], b[:, 2] * c[:, 0] - b[:, 0] * c[:, 2], b[:, 0] * c[:, 1] - b[:, 1] * c[:, 0]), 1)
+    cb = np.maximum(np.abs(b).max(1), np.abs(c).max(1))
+    amax = np.abs(a).max(1)
+    recs = []
+    for w0 in range(0, a.shape[0], win):
+        sl = slice(w0, w0 + win)
+        recs.append(dict(lo=ctr[sl].min(0), hi=ctr[sl].max(0), rmax=r[sl].max(), cbmax=cb[sl].max(), amax=amax[sl].max(),
+                         nlo=nx[sl].min(0), nhi=nx[sl].max(0), sl=sl))
+    return recs
+
+
+def chunk_cull(rec, ec, rlo, rhi):
+    """True = NO triangle of the window can be kept by stage 1 for this rectangle (csrc/raycast_shadow.cu: chunk_cull)."""
+    d, nu = ec.d, ec.nu
+    with np.errstate(invalid="ignore", divide="ignore", over="ignore"):
+        lo = sum(min(rec["nlo"][i] * d[i], rec["nhi"][i] * d[i]) for i in range(3))
+        hi = sum(max(rec["nlo"][i] * d[i], rec["nhi"][i] * d[i]) for i in range(3))
+        adet = F32(max(lo, -hi))
+        adet = adet * F32(1 - 1e-5) - F32(1e-7) * (abs(lo) + abs(hi))
+        if not (adet > 0):
+            return False
+        cbm, rm = rec["cbmax"], rec["rmax"]
+        e_det = GAMMA * F32(6.1) * cbm * cbm + ALPHA
+        rdet = F32(1.0) / adet * F32(1.0001)
+        eps0 = EPS0 + F32(1.3) * (e_det + F32(4) * ALPHA) * rdet
+        rho = GAMMA * F32(2.01) * cbm * rdet
+        hl = sum(min(nu[i] * rec["lo"][i], nu[i] * rec["hi"][i]) for i in range(3))
+        hh = sum(max(nu[i] * rec["lo"][i], nu[i] * rec["hi"][i]) for i in range(3))
+        sl_h = F32(1e-6) * (abs(hl) + abs(hh)) + F32(1e-7)
+        ta, tb = (ec.hmid - (hl - sl_h)) * ec.inv_nd, (ec.hmid - (hh + sl_h)) * ec.inv_nd
+        tlo, thi = min(ta, tb), max(ta, tb)
+        atc = max(abs(tlo), abs(thi)) * ec.dn
+        kr = ec.kappa * rm
+        B = SQ3 * (kr * (F32(1) + F32(3) * eps0) + ec.lam + atc + rm)
+        den = F32(1) - F32(10.4) * kr * rho
+        if not (den > F32(0.5)):
+            return False
+        gsum = B / den * F32(1.0001)
+        eps = eps0 + F32(2) * rho * gsum
+        fine = (adet > F32(4) * e_det) and (eps <= F32(16.0)) and ((ec.smax + rec["amax"]) * max(cbm, F32(1)) <= OVF)
+        if not fine:
+            return False
+        R = (kr * (F32(1) + F32(3) * eps) + ec.lam) * F32(1.0001)
+        qxl = rec["lo"][0] + min(tlo * d[0], thi * d[0]); qxh = rec["hi"][0] + max(tlo * d[0], thi * d[0])
+        qyl = rec["lo"][1] + min(tlo * d[1], thi * d[1]); qyh = rec["hi"][1] + max(tlo * d[1], thi * d[1])
+        Rs = R * F32(1.00001) + F32(1.1e-5) * (max(abs(qxl), abs(qxh)) + max(abs(qyl), abs(qyh))) + F32(1e-5)
+        return bool((qxh + Rs < rlo[0]) or (qxl - Rs > rhi[0]) or (qyh + Rs < rlo[1]) or (qyl - Rs > rhi[1]))
+
+
 def stage2(a16, b16, c16, n16, ec, gball):
     """Shadow box of the triangle's pre-filter prism on the source plane.  gball [T] >= |s - a| for passing sources.
     -> (x0, x1, y0, y1, full)."""
@@ -279,6 +335,7 @@ def main():
         ps = prefilter_pass(s, d, a[sel], b[sel], c[sel], n[sel])          # [P, T]
         ec = EnvConsts(pos[e].numpy(), trig[e], zlo, zhi, d, s)
         sx, sy = s[:, 0].astype(F32), s[:, 1].astype(F32)
+        crecs = chunk_records(a[sel], b[sel], c[sel])          # `sel` is sorted by triangle id, like a superblock list
         # stage 1 against random 2.4 m windows of the ray set (what a superblock item is)
         rs = np.random.RandomState(e)
         for _ in range(6):
@@ -289,6 +346,11 @@ def main():
             rlo = np.array([sx[inw].min(), sy[inw].min()], dtype=F32)
             rhi = np.array([sx[inw].max(), sy[inw].max()], dtype=F32)
             rej, ill, gb = stage1(a[sel], b[sel], c[sel], ec, rlo, rhi)
+            for rec in crecs:
+                if chunk_cull(rec, ec, rlo, rhi):
+                    stats["chunk_culled"] = stats.get("chunk_culled", 0) + 1
+                    stats["chunk_viol"] = stats.get("chunk_viol", 0) + int((~rej[rec["sl"]]).sum())
+                stats["chunks"] = stats.get("chunks", 0) + 1
             bad = ps[inw][:, rej].any()
             stats["s1_viol"] = stats.get("s1_viol", 0) + int(bad)
             stats["s1_keep"] = stats.get("s1_keep", 0) + float((~rej).mean()) / 6
@@ -331,7 +393,7 @@ def main():
     print("TOTAL pass %d, box tests %d (%.2fx), triangles %d, full-range %d, violations %d" % (
         tot_pass, tot_box, tot_box / max(tot_pass, 1), tot_tri, tot_full, tot_viol))
     print({k: v / N for k, v in stats.items()})
-    return 0 if (tot_viol == 0 and stats.get("lin_viol", 0) == 0) else 1
+    return 0 if (tot_viol == 0 and stats.get("lin_viol", 0) == 0 and stats.get("chunk_viol", 0) == 0) else 1
 
 
 if __name__ == "__main__":

@@ -70,12 +70,12 @@ for ns in ("0", "444", "0", "444"):
     d, _, _ = cam.get_depths(st["pos"], eul, want_pt=False)
     print("split envs %s: median %.3f ms, min %.3f, equal to variant 3: %s" % (ns, med, mn, bool(torch.equal(d.view(torch.int16), out[3][0].view(torch.int16)))))
 _os.environ.pop("RVB_SHADOW_SPLIT")
-for sp in ("0", "3"):
+for sp in ("3", "7", "3", "7"):
     _os.environ["RVB_SHADOW_SPEC"] = sp
     cam.variant = 0
     med, mn = timed(lambda: cam.get_depths(st["pos"], eul, want_pt=False), reps=30)
     d, _, _ = cam.get_depths(st["pos"], eul, want_pt=False)
-    print("speculative slot fetch %s: median %.3f ms, min %.3f, equal to variant 3: %s" % (sp, med, mn, bool(torch.equal(d.view(torch.int16), out[3][0].view(torch.int16)))))
+    print("spec bits (1 slot prefetch, 2 record prefetch, 4 window cull) %s: median %.3f ms, min %.3f, equal to variant 3: %s" % (sp, med, mn, bool(torch.equal(d.view(torch.int16), out[3][0].view(torch.int16)))))
 _os.environ.pop("RVB_SHADOW_SPEC")
 for msh in ("1", "0", "1", "0"):
     _os.environ["RVB_SHADOW_SH"] = msh
