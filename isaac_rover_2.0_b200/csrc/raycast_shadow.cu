@@ -173,7 +173,8 @@ __device__ __forceinline__ bool stage1(const uint4& s0, const uint4& s1, const E
 // Window cull (tests/shadow_proto.py: chunk_cull): true = stage 1 would reject EVERY triangle whose record went into `c` for this
 // rectangle, so the window's 32 list entries need not be enumerated.  Stage 1's formulas on the window's worst-case inputs
 // (every quantity is monotone in them); any NaN makes a comparison false and the window is kept.
-__device__ __forceinline__ bool chunk_cull(const ChunkRec& c, const EnvC& e, float rlox, float rhix, float rloy, float rhiy) {
+__device__ __forceinline__ bool chunk_cull(const ChunkRec& c, const EnvC& e, float rlox, float rhix, float rloy, float rhiy, float& overlap) {
+    overlap = 1.0f;          // fraction of the window's (expanded) footprint that lies inside the rectangle: a cost proxy only
     const float lo = fminf(c.nxlo * e.dx, c.nxhi * e.dx) + fminf(c.nylo * e.dy, c.nyhi * e.dy) + fminf(c.nzlo * e.dz, c.nzhi * e.dz);
     const float hi = fmaxf(c.nxlo * e.dx, c.nxhi * e.dx) + fmaxf(c.nylo * e.dy, c.nyhi * e.dy) + fmaxf(c.nzlo * e.dz, c.nzhi * e.dz);
     float adet = fmaxf(lo, -hi);                                 // |n . d| >= adet for every triangle of the window
@@ -201,6 +202,9 @@ __device__ __forceinline__ bool chunk_cull(const ChunkRec& c, const EnvC& e, flo
     const float qxl = c.x0 + fminf(tlo * e.dx, thi * e.dx), qxh = c.x1 + fmaxf(tlo * e.dx, thi * e.dx);
     const float qyl = c.y0 + fminf(tlo * e.dy, thi * e.dy), qyh = c.y1 + fmaxf(tlo * e.dy, thi * e.dy);
     const float Rs = R * 1.00001f + 1.1e-5f * (fmaxf(fabsf(qxl), fabsf(qxh)) + fmaxf(fabsf(qyl), fabsf(qyh))) + 1e-5f;
+    const float ex0 = qxl - Rs, ex1 = qxh + Rs, ey0 = qyl - Rs, ey1 = qyh + Rs;
+    const float ox = fminf(ex1, rhix) - fmaxf(ex0, rlox), oy = fminf(ey1, rhiy) - fmaxf(ey0, rloy);
+    overlap = fminf(fmaxf(ox, 0.0f) * fmaxf(oy, 0.0f) * __fdividef(1.0f, (ex1 - ex0) * (ey1 - ey0)), 1.0f);
     return (qxh + Rs < rlox) || (qxl - Rs > rhix) || (qyh + Rs < rloy) || (qyl - Rs > rhiy);
 }
 
@@ -283,6 +287,8 @@ __global__ void __launch_bounds__(TT, RTC <= RT_SMALL ? 4 : 3) hm_shadow_kernel(
     __shared__ uint32_t s_warp[NW];
     __shared__ EnvC s_env;
     __shared__ int s_next, s_nitems, s_nchunks, s_bail;
+    __shared__ int s_bkt[2][8];                        // window cull: windows per cost bucket, then the next free slot of each
+    __shared__ unsigned short s_item_rays[ITEM_CAP];   // rays per item (by rank)
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     // The envs at the end of the order are cut in two (rays [0, split_at) and [split_at, P), one CTA each): the grid's last wave
@@ -570,6 +576,7 @@ __global__ void __launch_bounds__(TT, RTC <= RT_SMALL ? 4 : 3) hm_shadow_kernel(
             it.bx = (uint32_t)bxl | ((uint32_t)bxh << 16);
             it.by = (uint32_t)byl | ((uint32_t)byh << 16);
             sm.items[rank] = it;
+            s_item_rays[rank] = (unsigned short)min(mine, 65535);
         }
     }
     __syncthreads();
@@ -606,48 +613,53 @@ __global__ void __launch_bounds__(TT, RTC <= RT_SMALL ? 4 : 3) hm_shadow_kernel(
             return;
         }
         unsigned char* all_item = reinterpret_cast<unsigned char*>(sm.q1);          // [CHUNK_CAP], the queues are idle here
+        unsigned char* all_key = all_item + CHUNK_CAP;                              // [CHUNK_CAP] cost bucket, 0xFF = culled
         for (int i = tid; i < ni; i += TT)
             for (uint32_t c = sm.cum[i]; c < sm.cum[i + 1]; ++c) all_item[c] = (unsigned char)i;
-        if (tid == 0) s_next = 0;
+        if (tid < 16) s_bkt[tid >> 3][tid & 7] = 0;
         __syncthreads();
         // window cull: a window none of whose triangles stage 1 could keep for the item's ray rectangle is dropped here, 32
-        // entries at a time (one thread per window); the survivors are compacted into the chunk table the warps pull from
+        // entries at a time (one thread per window).  The survivors go into the chunk table the warps pull from, the expensive ones
+        // (many rays of the item under the window) first: the warps' last chunks are then cheap and they finish together
         const int total = s_nchunks;
         const bool cull_on = q.sb_chunk != nullptr && (q.spec_slot & 4);
-        for (int g0 = 0; g0 < total; g0 += TT) {
-            const int g = g0 + tid;
-            bool keep = false;
-            int item = 0, rel = 0;
-            if (g < total) {
-                item = all_item[g];
-                rel = g - (int)sm.cum[item];
-                keep = true;
-                if (cull_on) {
-                    const Item& it = sm.items[item];
-                    const uint4* rp = reinterpret_cast<const uint4*>(q.sb_chunk + (it.list_off >> 5) + rel);
-                    union { uint4 u[4]; ChunkRec c; } rec;
-                    rec.u[0] = __ldg(rp); rec.u[1] = __ldg(rp + 1); rec.u[2] = __ldg(rp + 2); rec.u[3] = __ldg(rp + 3);
-                    keep = !chunk_cull(rec.c, s_env, it.rlox, it.rhix, it.rloy, it.rhiy);
-                }
+        for (int g = tid; g < total; g += TT) {
+            const int item = all_item[g];
+            const Item& it = sm.items[item];
+            int key = 0;
+            if (cull_on) {
+                const uint4* rp = reinterpret_cast<const uint4*>(q.sb_chunk + (it.list_off >> 5) + (g - (int)sm.cum[item]));
+                union { uint4 u[4]; ChunkRec c; } rec;
+                rec.u[0] = __ldg(rp); rec.u[1] = __ldg(rp + 1); rec.u[2] = __ldg(rp + 2); rec.u[3] = __ldg(rp + 3);
+                float ov;
+                if (chunk_cull(rec.c, s_env, it.rlox, it.rhix, it.rloy, it.rhiy, ov)) key = 0xFF;
+                else key = 7 - min(7, (int)(sqrtf((float)s_item_rays[item] * ov) * 0.25f));      // bucket 0: >= 784 rays under the window
             }
-            const uint32_t m = __ballot_sync(0xffffffffu, keep);
-            int base = 0;
-            if (lane == 0 && m) base = atomicAdd(&s_next, __popc(m));
-            base = __shfl_sync(0xffffffffu, base, 0);
-            if (keep) {
-                const int at = base + __popc(m & ((1u << lane) - 1u));
-                sm.chunk_item[at] = (unsigned char)item;
-                sm.chunk_win[at] = (unsigned short)rel;
-            }
+            all_key[g] = (unsigned char)key;
+            if (key != 0xFF) atomicAdd(&s_bkt[0][key], 1);
         }
         __syncthreads();
         if (tid == 0) {
+            int run = 0;
+            for (int b = 0; b < 8; ++b) {
+                s_bkt[1][b] = run;
+                run += s_bkt[0][b];
+            }
             if (DBGK) {
                 atomicAdd(q.dbg + 20, (unsigned long long)total);
-                atomicAdd(q.dbg + 21, (unsigned long long)s_next);
+                atomicAdd(q.dbg + 21, (unsigned long long)run);
             }
-            s_nchunks = s_next;
-            s_next = 0;
+            s_nchunks = run;
+        }
+        __syncthreads();
+        for (int g = tid; g < total; g += TT) {
+            const int key = all_key[g];
+            if (key != 0xFF) {
+                const int item = all_item[g];
+                const int at = atomicAdd(&s_bkt[1][key], 1);
+                sm.chunk_item[at] = (unsigned char)item;
+                sm.chunk_win[at] = (unsigned short)(g - (int)sm.cum[item]);
+            }
         }
     }
     __syncthreads();
