@@ -55,6 +55,8 @@ struct TiledParams {
     int min_sh;               // bins are 2^sh x 2^sh cells, sh >= min_sh (0 = one cell; tuning hook)
     int spec_slot;            // stage 3b fetches the slot byte before the literal test (tuning hook)
     int task_rays;            // shadow kernel: rays per task of stage 3L (<= 16; tuning hook)
+    int bulk_obs;             // shadow kernel: observation row leaves through one bulk asynchronous copy (A/B switch)
+    int n_obs_cols;           // number of heightmap observation columns (sparse + dense) when obs is requested
     int64_t split_from;       // shadow kernel: order positions >= split_from are cast by two CTAs (half the rays each); -1 = none
     int split_at;             // first ray of the second half
     unsigned long long* dbg;  // optional [24] work counters / cycle counts of the shadow kernel (RVB_SHADOW_DBG=1)
@@ -178,11 +180,20 @@ static __device__ __noinline__ uint32_t literal_ray(const int32_t* row, int K, c
 // Epilogue in ray order: coalesced stores of dist / hit slot / hit triangle / pt / sources and the fused sparse+dense
 // observation columns (heightmap_distribution.py:126-133, rover.py:324-325).  res[p] = best key of local ray p; a set bit
 // in far[] marks a ray that saw a hit beyond the 11.0 miss sentinel (resolved literally here).
+// `stage` (optional, shared memory, 16-byte aligned, >= (ncols + 8) floats): the observation row is assembled there and leaves
+// the SM as ONE bulk asynchronous copy (cp.async.bulk shared -> global, the TMA unit's non-tensor mode) instead of one 4-byte
+// store per column; only when the tile is the whole pattern.  ncols = number of heightmap observation columns.
 __device__ __forceinline__ void epilogue(const TiledParams& q, int64_t n, int p0, int np, const Trig& tr, double tx, double ty,
                                          double tz, __half2 dx2, __half2 dy2, __half2 dz2, const uint32_t* res,
-                                         const uint32_t* far, int tid, int nthreads) {
+                                         const uint32_t* far, int tid, int nthreads, float* stage = nullptr, int ncols = 0) {
     const H3 dlit = {__low2half(dx2), __low2half(dy2), __low2half(dz2)};
     const bool want_geo = q.hit_tri || q.pt || q.sources;
+    // destination of column 4 (the first heightmap column) and how the row splits into an unaligned head, a 16-byte aligned body
+    // (the bulk copy) and a tail
+    const bool bulk = stage != nullptr && q.obs != nullptr && np == q.P && ncols > 8;
+    float* const grow = q.obs ? q.obs + n * q.obs_ld + 4 : nullptr;
+    const int head = bulk ? (int)(((16u - (uint32_t)((uintptr_t)grow & 15u)) & 15u) >> 2) : 0;      // floats before the body
+    float* const srow = bulk ? stage + ((4 - head) & 3) : nullptr;                                    // srow + head is 16-byte aligned
     for (int p = tid; p < np; p += nthreads) {
         uint32_t key = res[p];
         const bool far_hit = (far[p >> 5] >> (p & 31)) & 1u;
@@ -221,8 +232,13 @@ __device__ __forceinline__ void epilogue(const TiledParams& q, int64_t n, int p0
         if (q.obs) {
             const float v = __half2float(h_mul(h_from_bits(kb), __float2half_rn(0.5f)));     // fp16(dist / 2) -> f32
             const int ca = q.col_a[p0 + p], cb = q.col_b[p0 + p];
-            if (ca >= 0) q.obs[n * q.obs_ld + ca] = v;
-            if (cb >= 0) q.obs[n * q.obs_ld + cb] = v;
+            if (bulk) {
+                if (ca >= 4) srow[ca - 4] = v;
+                if (cb >= 4) srow[cb - 4] = v;
+            } else {
+                if (ca >= 0) q.obs[n * q.obs_ld + ca] = v;
+                if (cb >= 0) q.obs[n * q.obs_ld + cb] = v;
+            }
         }
         if (q.obs16) {                                                                        // the same value, kept in fp16
             const __half v = h_mul(h_from_bits(kb), __float2half_rn(0.5f));
@@ -230,6 +246,19 @@ __device__ __forceinline__ void epilogue(const TiledParams& q, int64_t n, int p0
             if (ca >= 0) q.obs16[n * q.obs16_ld + (ca - q.obs16_col0)] = v;
             if (cb >= 0) q.obs16[n * q.obs16_ld + (cb - q.obs16_col0)] = v;
         }
+    }
+    if (bulk) {
+        __syncthreads();
+        const int body = ((ncols - head) >> 2) << 2;                  // floats in the 16-byte aligned middle part
+        if (tid == 0) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            const uint32_t saddr = (uint32_t)__cvta_generic_to_shared(srow + head);
+            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(grow + head), "r"(saddr), "r"(body * 4) : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+        if (tid < head) grow[tid] = srow[tid];
+        if (tid >= 32 && tid - 32 < ncols - head - body) grow[head + body + tid - 32] = srow[head + body + tid - 32];
+        if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");      // the source must outlive the copy
     }
 }
 

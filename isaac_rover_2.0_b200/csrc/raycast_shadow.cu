@@ -62,6 +62,9 @@ constexpr int QCAP = 64;           // per-warp queues q1, q2 (each drained below
 constexpr int QCAP3 = 128;         // q4 (stage 3L pushes while it holds < 32 entries, stage 3b drains in batches of 32)
 constexpr int TASK_RAYS = 16;      // upper bound of the tuning hook q.task_rays
 constexpr int REL_BITS = 15;        // queue entries name a triangle as item << 15 | position in the item's list
+constexpr int ILL_CAP = 128;        // triangles without a bound ("ill": fp16 determinant within rounding of zero) a tile may meet before it
+                                   // is handed to the tiled kernel, whose cost does not depend on them (a 1M-triangle heightfield has ~1
+                                   // per tile; a mesh finer than the fp16 grid of its coordinates has hundreds)
 constexpr int RT_SMALL = 1664;      // ray capacity of the 4-CTAs-per-SM instantiation (the reference pattern has 1634 rays)
 
 constexpr float GAMMA = 0.00390625f;            // 2^-8
@@ -286,7 +289,7 @@ __global__ void __launch_bounds__(TT, RTC <= RT_SMALL ? 4 : 3) hm_shadow_kernel(
     __shared__ float s_red[NW][12];
     __shared__ uint32_t s_warp[NW];
     __shared__ EnvC s_env;
-    __shared__ int s_next, s_nitems, s_nchunks, s_bail;
+    __shared__ int s_next, s_nitems, s_nchunks, s_bail, s_ill;
     __shared__ int s_bkt[2][8];                        // window cull: windows per cost bucket, then the next free slot of each
     __shared__ unsigned short s_item_rays[ITEM_CAP];   // rays per item (by rank)
 
@@ -330,6 +333,7 @@ __global__ void __launch_bounds__(TT, RTC <= RT_SMALL ? 4 : 3) hm_shadow_kernel(
         s_box[2] = s_box[3] = -1;
         s_next = 0;
         s_bail = 0;
+        s_ill = 0;
     }
     const Trig tr = make_trig(q.euler, q.trig, n);
     const double tx = (double)q.pos[n * 3 + 0], ty = (double)q.pos[n * 3 + 1], tz = (double)q.pos[n * 3 + 2];
@@ -754,6 +758,16 @@ __global__ void __launch_bounds__(TT, RTC <= RT_SMALL ? 4 : 3) hm_shadow_kernel(
                 }
                 t1 += __popc(m);
                 DBG(0, 1); DBG(1, __popc(m));
+                const uint32_t mi = __ballot_sync(FULLM, keep && gball == __int_as_float(0x7f800000));
+                if (mi) {
+                    if (lane == 0) atomicAdd(&s_ill, __popc(mi));
+                    if (*reinterpret_cast<volatile int*>(&s_ill) > ILL_CAP) {       // give the tile up: every warp drops what it holds
+                        more = false; in2 = false; in3 = false;
+                        h1 = t1; h2 = t2; h4 = t4;
+                        itemA = -1;
+                        break;
+                    }
+                }
             } while (t1 - h1 < 32u);
             break;
         }
@@ -950,6 +964,10 @@ __global__ void __launch_bounds__(TT, RTC <= RT_SMALL ? 4 : 3) hm_shadow_kernel(
         }
     }
     __syncthreads();
+    if (s_ill > ILL_CAP) {          // too many triangles without a bound: the tiled kernel casts this tile (results so far are dropped)
+        if (tid == 0) q.fb_list[atomicAdd(q.fb_count, 1)] = work_id;
+        return;
+    }
 
     // ---- phase 4
     // pose and trigonometry are re-read here (volatile: no common sub-expression with phase 0) instead of living in twelve
@@ -966,7 +984,9 @@ __global__ void __launch_bounds__(TT, RTC <= RT_SMALL ? 4 : 3) hm_shadow_kernel(
             const float r_ = -ve[0], p_ = -ve[1], y_ = -ve[2];
             tr2 = {sinf(r_), cosf(r_), sinf(p_), cosf(p_), sinf(y_), cosf(y_)};
         }
-        epilogue(q, n, p0, np, tr2, ex_, ey_, ez_, dx2, dy2, dz2, sm.res, sm.far, tid, TT);
+        // the sorted rays are dead: their shared memory stages the observation row of the bulk-copy epilogue
+        epilogue(q, n, p0, np, tr2, ex_, ey_, ez_, dx2, dy2, dz2, sm.res, sm.far, tid, TT,
+                 q.bulk_obs ? reinterpret_cast<float*>(sm.rays) : nullptr, q.n_obs_cols);
     }
 }
 
@@ -1012,6 +1032,12 @@ int launch_heightmap_shadow(const rvb_terrain* t, const float* pos, const float*
     q.min_sh = 1;                                                            // 2x2-cell bins: 2 % faster than single cells (fewer tasks)
     if (const char* ms = getenv("RVB_SHADOW_SH")) q.min_sh = atoi(ms);      // tuning hook: finest bins to start from
     q.spec_slot = 7;          // bit 0: slot byte fetched ahead of the literal test, bit 1: L2 prefetch of the records, bit 2: window cull
+    // A/B switch: RVB_SHADOW_BULK = number of heightmap observation columns (1746 for the reference pattern; every
+    // one of them must be named by col_a / col_b) -> the row is staged in shared memory and stored by one cp.async.bulk
+    q.bulk_obs = 0;
+    q.n_obs_cols = 0;
+    if (const char* bo = getenv("RVB_SHADOW_BULK")) q.n_obs_cols = atoi(bo);
+    q.bulk_obs = q.n_obs_cols > 8 && (size_t)(q.n_obs_cols + 8) * 4 <= (size_t)q.tile_size * 8;
     q.task_rays = TASK_RAYS;
     if (const char* tr = getenv("RVB_SHADOW_TASK_RAYS")) q.task_rays = min(max(atoi(tr), 1), TASK_RAYS);   // tuning hook
     if (const char* sp = getenv("RVB_SHADOW_SPEC")) q.spec_slot = atoi(sp); // tuning hook

@@ -33,17 +33,21 @@ for N in (4096, 32768):
     st = {k: v.cuda() for k, v in R.synth.make_env_state(w, N, seed=100).items()}
     eul = R.tensor_quat_to_eul(st["quat"])
     cam.variant = 3
-    ref, _, _ = cam.get_depths(st["pos"], eul, want_pt=False)
+    obs_ref = torch.zeros((N, 1750), device="cuda")
+    ref, _, _ = cam.get_depths(st["pos"], eul, want_pt=False, obs=obs_ref)
     ref = ref.clone()
     cam.variant = 0
     for rnd in range(2):
         for cfg in configs:
             if cfg:
                 os.environ[cfg[0]] = cfg[1]
-            med, mn = timed(lambda: cam.get_depths(st["pos"], eul, want_pt=False), reps=30 if N == 4096 else 10)
-            d, _, _ = cam.get_depths(st["pos"], eul, want_pt=False)
-            print("N %6d %-28s median %.3f ms  min %.3f  (%.2f M envs/s)  equal to the tiled kernel: %s" % (
-                N, "=".join(cfg) if cfg else "default", med, mn, N / med / 1e3, bool(torch.equal(d.view(torch.int16), ref.view(torch.int16)))))
+            obs = torch.zeros((N, 1750), device="cuda")
+            med, mn = timed(lambda: cam.get_depths(st["pos"], eul, want_pt=False, obs=obs), reps=30 if N == 4096 else 10)
+            obs.zero_()
+            d, _, _ = cam.get_depths(st["pos"], eul, want_pt=False, obs=obs)
+            ok_obs = bool(torch.equal(obs, obs_ref)) if obs_ref is not None else None
+            print("N %6d %-28s median %.3f ms  min %.3f  (%.2f M envs/s)  equal to the tiled kernel: dist %s obs %s" % (
+                N, "=".join(cfg) if cfg else "default", med, mn, N / med / 1e3, bool(torch.equal(d.view(torch.int16), ref.view(torch.int16))), ok_obs))
             if cfg:
                 os.environ.pop(cfg[0])
     if N == 4096:
