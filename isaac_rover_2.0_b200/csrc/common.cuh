@@ -111,6 +111,7 @@ struct rvb_terrain {
     uint16_t* sb_pos;    // [n_sb_ent][RVB_SB*RVB_SB]  position of the triangle in the list of block (i % SB, j % SB); 0xFFFF = absent
     int64_t n_sb_ent;
     ChunkRec* sb_chunk;  // [ceil(n_sb_ent / 32)]
+    int64_t n_ill;       // triangles whose determinant is rounding noise even for a vertical ray (no culling bound exists for them)
 };
 #define RVB_BLK 3
 #define RVB_SB 8

@@ -165,7 +165,10 @@ extern "C" int rvb_heightmap_raycast2(const rvb_terrain* t, const float* pos, co
     const RvbObs16 o16v = {obs_h16, obs_h16_ld, obs_h16_col0};
     const RvbObs16* o16 = obs_h16 ? &o16v : nullptr;
     cudaStream_t st = as_stream(stream);
-    if (variant == 0 && t->sb_ids != nullptr) {
+    // a layer with more than 2 % of triangles the shadow kernel has no bound for (terrain.cu: n_ill): the tiled kernel is the faster one
+    bool shadow_ok = t->n_ill * 50 <= t->T;
+    if (const char* ev = getenv("RVB_SHADOW_FORCE")) shadow_ok = atoi(ev) != 0;      // tuning hook
+    if (variant == 0 && t->sb_ids != nullptr && shadow_ok) {
         float cos_steep = RVB_COS_STEEP;
         if (const char* ev = getenv("RVB_COS_STEEP")) cos_steep = (float)atof(ev);      // tuning hook; results do not depend on it
         return launch_heightmap_shadow(t, pos, euler, trig, pattern, P, N, dist, hit_slot, hit_tri, pt, sources, obs,

@@ -125,6 +125,13 @@ __global__ void build_records_kernel(const int32_t* __restrict__ tri, int64_t T,
     // cb, amax are fp16 values already (|difference of fp16| can need one more bit: round up)
     s.cb_amax = (uint32_t)__half_as_ushort(__float2half_ru(cb)) | ((uint32_t)__half_as_ushort(__float2half_ru(amax)) << 16);
     s1recs[i] = s;
+    // triangles whose fp16 determinant is rounding noise even for a vertical ray (raycast_shadow.cu stage 1: adet <= 4 e_det):
+    // the shadow kernel has no bound for them.  Counted once per layer: a mesh finer than the fp16 grid of its coordinates
+    // has many, and the heightmap ray-cast then runs the tiled kernel, whose cost does not depend on them.
+    const float e_det = 0.00390625f * 6.1f * cb * cb + 1.9073486328125e-06f;
+    const bool ill = !(fabsf(s.nz) > 4.0f * e_det);
+    const unsigned m = __ballot_sync(__activemask(), ill);
+    if (m && (threadIdx.x & 31) == (__ffs(__activemask()) - 1)) atomicAdd(bad + 1, __popc(m));
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -428,8 +435,8 @@ extern "C" int rvb_terrain_create(rvb_terrain** out, const int32_t* map_indices,
     if (e == cudaSuccess) e = cudaMalloc(&t->index, sizeof(int32_t) * G0 * G1 * t->Ks);
     if (e == cudaSuccess) e = cudaMalloc(&t->recs, sizeof(TriRec) * T);
     if (e == cudaSuccess) e = cudaMalloc(&t->s1recs, sizeof(S1Rec) * T);
-    if (e == cudaSuccess) e = cudaMalloc(&bad, sizeof(int));
-    if (e == cudaSuccess) e = cudaMemsetAsync(bad, 0, sizeof(int), st);
+    if (e == cudaSuccess) e = cudaMalloc(&bad, 2 * sizeof(int));
+    if (e == cudaSuccess) e = cudaMemsetAsync(bad, 0, 2 * sizeof(int), st);
     if (e == cudaSuccess) {
         repack_index_kernel<<<148 * 8, 256, 0, st>>>(map_indices, G0, G1, K, t->Ks, stride_g0, stride_g1, stride_k, (int32_t)T,
                                                      t->index, bad);
@@ -437,8 +444,11 @@ extern "C" int rvb_terrain_create(rvb_terrain** out, const int32_t* map_indices,
                                                                          t->recs, t->s1recs, bad);
         e = cudaGetLastError();
     }
-    if (e == cudaSuccess) e = cudaMemcpyAsync(&hbad, bad, sizeof(int), cudaMemcpyDeviceToHost, st);
+    int hb2[2] = {0, 0};
+    if (e == cudaSuccess) e = cudaMemcpyAsync(hb2, bad, 2 * sizeof(int), cudaMemcpyDeviceToHost, st);
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    hbad = hb2[0];
+    t->n_ill = hb2[1];
     if (bad) cudaFree(bad);
     if (e == cudaSuccess && !hbad) {
         const int rc = build_block_lists(t, st);
