@@ -52,7 +52,7 @@ using namespace rc;
 constexpr int TT = 256;
 constexpr int NW = TT / 32;
 constexpr int RT_MAX = 2048;       // rays per tile; must equal raycast_tiled.cu's (shared tiling of the fall-back list)
-constexpr int BIN_CAP = 6144;      // bins in the tile's bounding box (a 3.4 m x 6.6 m pattern at 45 degrees of yaw needs ~5000)
+constexpr int BIN_CAP = 2048;      // bins in the tile's bounding box (2x2-cell bins: a 3.4 m x 6.6 m pattern at 45 degrees of yaw needs ~1300)
 constexpr int SB = RVB_SB;          // blocks per superblock side
 constexpr int SBC = RVB_SB * RVB_BLK;   // cells per superblock side
 constexpr int ITEM_CAP = 64;       // superblocks per tile (7 bits travel in the stage-1 queue)
@@ -101,12 +101,15 @@ struct Smem {
     uint2* q1;           // [NW][QCAP]  stage-1 survivors: (superblock-list entry, gball bits | item)
     uint4* q2;           // [NW][QCAP]  tasks: (item << 15 | list position, ray start | count << 16, T1 | T2 << 16, T3 | sign << 15)
     uint32_t* q4;        // [NW][QCAP3]  pairs inside the prism: ray position | (item << 15 | list position) << 11
+    int32_t* q1t;        // [NW][QCAP]   triangle id of the q1 / q2 / q4 entry: travels with it, so that no stage has to go back to
+    int32_t* q2t;        // [NW][QCAP]   sb_ids (a dependent global load in front of every record fetch)
+    int32_t* q4t;        // [NW][QCAP3]
     uint32_t* far;       // [RT / 32]
 };
 
 __host__ __device__ inline size_t shadow_smem_bytes(int RT) {       // RT = ray capacity of the instantiation
     return (size_t)RT * 8 + (size_t)((RT + 3) & ~3) * 4 + (size_t)(BIN_CAP / 2 + 4) * 4 + (size_t)ITEM_CAP * 32 +
-           (size_t)(ITEM_CAP + 4) * 4 + (size_t)CHUNK_CAP * 3 + (size_t)NW * (QCAP * (8 + 16) + QCAP3 * 4) + (size_t)(((RT + 31) / 32 + 3) & ~3) * 4;
+           (size_t)(ITEM_CAP + 4) * 4 + (size_t)CHUNK_CAP * 3 + (size_t)NW * (QCAP * (8 + 16 + 4 + 4) + QCAP3 * (4 + 4)) + (size_t)(((RT + 31) / 32 + 3) & ~3) * 4;
 }
 
 __device__ __forceinline__ float rcp_up(float x) { return __fdividef(1.0f, x) * 1.000001f; }
@@ -323,7 +326,10 @@ __global__ void __launch_bounds__(TT, RTC <= RT_SMALL ? 4 : 3) hm_shadow_kernel(
     sm.q1 = reinterpret_cast<uint2*>(sm.chunk_win + CHUNK_CAP);
     sm.q2 = reinterpret_cast<uint4*>(sm.q1 + NW * QCAP);
     sm.q4 = reinterpret_cast<uint32_t*>(sm.q2 + NW * QCAP);
-    sm.far = reinterpret_cast<uint32_t*>(sm.q4 + NW * QCAP3);
+    sm.q1t = reinterpret_cast<int32_t*>(sm.q4 + NW * QCAP3);
+    sm.q2t = sm.q1t + NW * QCAP;
+    sm.q4t = sm.q2t + NW * QCAP;
+    sm.far = reinterpret_cast<uint32_t*>(sm.q4t + NW * QCAP3);
 
     // ---- phase 0
     for (int i = tid; i < BIN_CAP / 2 + 4; i += TT) sm.bins[i] = 0u;
@@ -675,6 +681,9 @@ __global__ void __launch_bounds__(TT, RTC <= RT_SMALL ? 4 : 3) hm_shadow_kernel(
     uint2* q1 = sm.q1 + warp * QCAP;
     uint4* q2 = sm.q2 + warp * QCAP;
     uint32_t* q4 = sm.q4 + warp * QCAP3;
+    int32_t* q1t = sm.q1t + warp * QCAP;
+    int32_t* q2t = sm.q2t + warp * QCAP;
+    int32_t* q4t = sm.q4t + warp * QCAP3;
     uint32_t h1 = 0, t1 = 0, h2 = 0, t2 = 0, h4 = 0, t4 = 0;          // warp-uniform
     const uint32_t lt_mask = (1u << lane) - 1u;
     const uint32_t FULLM = 0xffffffffu;
@@ -704,9 +713,11 @@ __global__ void __launch_bounds__(TT, RTC <= RT_SMALL ? 4 : 3) hm_shadow_kernel(
     bool more = true, in2 = false, in3 = false;
     // stage-2 emission state (per lane)
     uint32_t e_ent = 0, e_T12 = 0, e_T3s = 0, e_cur = 0, e_end = 0;
+    int32_t e_tri = 0;
     int e_col = 1, e_cx1 = 0, e_rlo = 0, e_rhi = 0;
     // stage-3L state (per lane): task + bit i set = ray start + i lies inside the prism
     uint32_t a_ent = 0, a_start = 0, a_mask = 0;
+    int32_t a_tri = 0;
     const int task_rays = q.task_rays;
 
     long long c_start = 0, c_dry = 0;
@@ -751,8 +762,9 @@ __global__ void __launch_bounds__(TT, RTC <= RT_SMALL ? 4 : 3) hm_shadow_kernel(
                 if (id >= 0) keep = stage1(r0, r1, e, it.rlox, it.rhix, it.rloy, it.rhiy, gball);
                 const uint32_t m = __ballot_sync(FULLM, keep);
                 if (keep) {
-                    q1[(t1 + __popc(m & lt_mask)) & (QCAP - 1)] =
-                        make_uint2(ent, ((__float_as_uint(gball) + 0x7fu) & ~0x7fu) | (uint32_t)item);
+                    const uint32_t at = (t1 + __popc(m & lt_mask)) & (QCAP - 1);
+                    q1[at] = make_uint2(ent, ((__float_as_uint(gball) + 0x7fu) & ~0x7fu) | (uint32_t)item);
+                    q1t[at] = id;
                     // stage 2 will want the triangle's record: start bringing it into L2 now
                     if (q.spec_slot & 2) asm volatile("prefetch.global.L2 [%0];" ::"l"(q.recs + id));
                 }
@@ -777,7 +789,8 @@ __global__ void __launch_bounds__(TT, RTC <= RT_SMALL ? 4 : 3) hm_shadow_kernel(
             if ((uint32_t)lane < cnt) {
                 const uint2 en = q1[(h1 + lane) & (QCAP - 1)];
                 e_ent = en.x;
-                const int32_t tri = __ldg(q.sb_ids + e_ent);
+                const int32_t tri = (q.spec_slot & 8) ? q1t[(h1 + lane) & (QCAP - 1)] : __ldg(q.sb_ids + e_ent);
+                e_tri = tri;
                 const float gball = __uint_as_float(en.y & ~0x7fu);
                 const Item& it = sm.items[en.y & 0x7fu];
                 e_ent = ((en.y & 0x7fu) << REL_BITS) | (e_ent - it.list_off);
@@ -820,7 +833,9 @@ __global__ void __launch_bounds__(TT, RTC <= RT_SMALL ? 4 : 3) hm_shadow_kernel(
                 }
                 if (have) {
                     const uint32_t c = min(e_end - e_cur, (uint32_t)task_rays);
-                    q2[(t2 + __popc(m & lt_mask)) & (QCAP - 1)] = make_uint4(e_ent, e_cur | (c << 16), e_T12, e_T3s);
+                    const uint32_t at = (t2 + __popc(m & lt_mask)) & (QCAP - 1);
+                    q2[at] = make_uint4(e_ent, e_cur | (c << 16), e_T12, e_T3s);
+                    q2t[at] = e_tri;
                     e_cur += c;
                 }
                 t2 += __popc(m);
@@ -839,8 +854,9 @@ __global__ void __launch_bounds__(TT, RTC <= RT_SMALL ? 4 : 3) hm_shadow_kernel(
                 a_ent = tk.x;
                 a_start = tk.y & 0xffffu;
                 const int c = (int)(tk.y >> 16);
-                const uint32_t ent = sm.items[a_ent >> REL_BITS].list_off + (a_ent & ((1u << REL_BITS) - 1u));
-                const int32_t tri = __ldg(q.sb_ids + ent);
+                const int32_t tri = (q.spec_slot & 8) ? q2t[(h2 + lane) & (QCAP - 1)]
+                                                      : __ldg(q.sb_ids + sm.items[a_ent >> REL_BITS].list_off + (a_ent & ((1u << REL_BITS) - 1u)));
+                a_tri = tri;
                 const uint4 r0 = __ldg(reinterpret_cast<const uint4*>(q.recs + tri));
                 const uint32_t r1 = __ldg(reinterpret_cast<const uint32_t*>(q.recs + tri) + 4);
                 const float sg = (tk.w & 0x8000u) ? -1.0f : 1.0f;
@@ -896,6 +912,7 @@ __global__ void __launch_bounds__(TT, RTC <= RT_SMALL ? 4 : 3) hm_shadow_kernel(
                     const uint32_t bit = (uint32_t)__ffs((int)a_mask) - 1u;
                     a_mask &= a_mask - 1u;
                     q4[(t4 + at) & (QCAP3 - 1)] = (a_start + bit) | code;
+                    q4t[(t4 + at) & (QCAP3 - 1)] = a_tri;
                     ++at;
                 }
                 t4 += min(total, room);
@@ -915,7 +932,7 @@ __global__ void __launch_bounds__(TT, RTC <= RT_SMALL ? 4 : 3) hm_shadow_kernel(
                     const uint32_t pc = q4[(h4 + lane) & (QCAP3 - 1)];
                     const uint2 ray = sm.rays[pc & 0x7ffu];
                     const uint32_t ent = sm.items[pc >> (11 + REL_BITS)].list_off + ((pc >> 11) & ((1u << REL_BITS) - 1u));
-                    const int32_t tri = __ldg(q.sb_ids + ent);
+                    const int32_t tri = (q.spec_slot & 8) ? q4t[(h4 + lane) & (QCAP3 - 1)] : __ldg(q.sb_ids + ent);
                     const H3 s = {h_from_bits(ray.x & 0xffff), h_from_bits(ray.x >> 16), h_from_bits(ray.y & 0xffff)};
                     const uint32_t meta = ray.y >> 16, p = meta & 0x7ffu, sub = meta >> 11;
                     // position of the triangle in the list of the ray's 3x3 block (0xFFFF: in none of its nine cell lists)
@@ -1031,7 +1048,8 @@ int launch_heightmap_shadow(const rvb_terrain* t, const float* pos, const float*
     q.presorted = 1;
     q.min_sh = 1;                                                            // 2x2-cell bins: 2 % faster than single cells (fewer tasks)
     if (const char* ms = getenv("RVB_SHADOW_SH")) q.min_sh = atoi(ms);      // tuning hook: finest bins to start from
-    q.spec_slot = 7;          // bit 0: slot byte fetched ahead of the literal test, bit 1: L2 prefetch of the records, bit 2: window cull
+    q.spec_slot = 15;         // bit 0: slot byte fetched ahead of the literal test, bit 1: L2 prefetch of the records, bit 2: window cull,
+                              // bit 3: triangle ids travel through the queues instead of being re-read from sb_ids
     // A/B switch: RVB_SHADOW_BULK = number of heightmap observation columns (1746 for the reference pattern; every
     // one of them must be named by col_a / col_b) -> the row is staged in shared memory and stored by one cp.async.bulk
     q.bulk_obs = 0;
