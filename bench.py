@@ -437,6 +437,23 @@ def run_b200(args, rank, world, local):
         h2d, d2h = pipe.h2d_bytes, pipe.d2h_bytes
         pipe.close()
         return dt_, h2d, d2h, checksum
+    # the dominant kernel by itself (no rock kernel sharing the SMs): the same launches as in the step, timed with CUDA events
+    def time_raycast_alone():
+        reps = max(3, min(args.steps, 10))
+        pos, quat = view.get_world_poses()
+        eul = R.tensor_quat_to_eul(quat)
+        for _ in range(2):
+            task.Camera.get_depths(pos, eul, obs=task.obs_buf, want_pt=False)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        a.record()
+        for i in range(reps):
+            s_ = dstates[i % n_sets]
+            task.Camera.get_depths(s_["pos"], eul, obs=task.obs_buf, want_pt=False)
+        b.record()
+        torch.cuda.synchronize()
+        return R.dist.max_over_ranks(a.elapsed_time(b) / reps * 1e-3, dev)
+    ray_alone_s = time_raycast_alone()
     dt_e2e, h2d_b, d2h_b, checksum = run_e2e(False)
     dt_e2e_p, h2d_bp, d2h_bp, checksum_p = run_e2e(True)
     clk = clocks.stop()
@@ -487,6 +504,10 @@ def run_b200(args, rank, world, local):
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": ALGO_BYTES_PER_ENV_STEP * N,
+                         "kernel_alone": {"ms": ray_alone_s * 1e3, "achieved": ALGO_BYTES_PER_ENV_STEP * N / ray_alone_s / 1e9,
+                                          "frac": ALGO_BYTES_PER_ENV_STEP * N / ray_alone_s / 1e9 / peak,
+                                          "note": "the same launch without the rock-collision kernel running beside it (in the step the "
+                                                  "two share the SMs and `achieved` is measured around the ray-cast's launches)"},
                          "kernel": "heightmap ray-cast (Camera.get_depths)",
                          "note": "contractual HBM figure on the reference-format algorithmic bytes; the kernel is bound by "
                                  "instruction issue, see issue_slots", "issue_slots": issue},
