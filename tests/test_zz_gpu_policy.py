@@ -129,20 +129,51 @@ def test_pair_launch_equals_single_launches(R):
 
 
 def test_ffma2_and_scalar_variants_are_bit_identical(R):
-    """rvb_policy_variant: the packed-FFMA2 inner loop (default) and the scalar FFMA one are both IEEE fma per element."""
+    """rvb_policy_variant: 1 (packed FFMA2 inner loop) and 0 (scalar FFMA) are both IEEE fma per element -> bit-identical;
+    2 (default: the two first encoder layers on tcgen05 with tf32 hi + lo operands, accumulators in TMEM) sums in another order and
+    stays within 1e-5 of them -- on arbitrary fp32 observations (three MMAs per k-step) and on fp16-valued ones like the step's
+    obs_buf (the A operand is exact in tf32: two MMAs per k-step)."""
     lib = R._lib.load()
     torch.manual_seed(8)
     actor, critic = _models(R)
     obs = torch.rand(1000, 1750, device="cuda")
-    assert lib.rvb_policy_variant(-1) == 1                            # default: FFMA2
+    assert lib.rvb_policy_variant(-1) == 2                            # default: tensor-core first layers for N >= 2048
     try:
+        lib.rvb_policy_variant(3)                                     # ... whatever N
+        m2, v2 = R.model.compute_pair(actor, critic, obs)
+        s2 = actor.compute(obs)[0]
+        assert lib.rvb_policy_variant(1) == 3
         m1, v1 = R.model.compute_pair(actor, critic, obs)
         assert lib.rvb_policy_variant(0) == 1
         m0, v0 = R.model.compute_pair(actor, critic, obs)
         s0 = actor.compute(obs)[0]
-    finally:
+        obs16 = obs.clone()
+        obs16[:, 4:] = (obs[:, 4:] * 5.5).half().float()              # what the ray-cast writes: fp16 values in f32 columns
         lib.rvb_policy_variant(1)
+        m1h, v1h = R.model.compute_pair(actor, critic, obs16)
+        lib.rvb_policy_variant(3)
+        m2h, v2h = R.model.compute_pair(actor, critic, obs16)
+    finally:
+        lib.rvb_policy_variant(2)
     assert torch.equal(m0, m1) and torch.equal(v0, v1) and torch.equal(s0, m1)
+    for a, b in ((m2, m1), (v2, v1), (s2, m1), (m2h, m1h), (v2h, v1h)):
+        assert (a - b).abs().max().item() <= 1e-5, (a - b).abs().max().item()
+    # ragged tile counts of the 128-env tensor-core tiles
+    for n in (1, 127, 129, 300):
+        lib.rvb_policy_variant(1)
+        ref = R.model.compute_pair(actor, critic, obs16[:n])
+        lib.rvb_policy_variant(3)
+        got = R.model.compute_pair(actor, critic, obs16[:n])
+        assert (got[0] - ref[0]).abs().max().item() <= 1e-5 and (got[1] - ref[1]).abs().max().item() <= 1e-5
+    lib.rvb_policy_variant(2)
+    big = torch.rand(2048 + 77, 1750, device="cuda")                 # default dispatch takes the tensor-core path from 2048 envs
+    big[:, 4:] = (big[:, 4:] * 5.5).half().float()
+    got = R.model.compute_pair(actor, critic, big)
+    lib.rvb_policy_variant(1)
+    ref = R.model.compute_pair(actor, critic, big)
+    lib.rvb_policy_variant(2)
+    assert (got[0] - ref[0]).abs().max().item() <= 1e-5 and (got[1] - ref[1]).abs().max().item() <= 1e-5
+    assert not torch.equal(got[0], ref[0])                             # ... and it really is another summation order
 
 
 def test_argument_validation(R):
@@ -197,7 +228,7 @@ def test_throughput_note(R):
         e1.record()
         torch.cuda.synchronize()
     finally:
-        lib.rvb_policy_variant(1)
+        lib.rvb_policy_variant(2)
     print("policy_forward_pair 65536 envs, scalar-FFMA variant: %.4f ms/launch" % (e0.elapsed_time(e1) / 5))
     print("policy_forward_pair 65536 envs: %.4f ms/launch (%.1f M envs/s, %.1f fp32 TFLOP/s)" % (
         ms, 65536 / ms / 1e3, 2 * 2 * 65536 * 243.3e3 / ms / 1e9))
