@@ -57,6 +57,7 @@ struct PolicyDev {
     const float* tc_img_s;
     const float* tc_img_d;
     int tc_cs, tc_cd;     // chunks of the sparse / dense encoder
+    const float* tc_tail; // weight stream of the remaining layers in the order policy_tail_tc_kernel consumes it (TT_* below)
 };
 
 struct rvb_policy : PolicyDev {
@@ -77,6 +78,21 @@ __device__ __forceinline__ float pl_act(float v, int kind) {
         case RVB_ACT_SIGMOID: return __fdiv_rn(1.f, __fadd_rn(1.f, expf(-v)));
         case RVB_ACT_RELU6: return fminf(fmaxf(v, 0.f), 6.f);
         default: return v;
+    }
+}
+
+// Sixteen values at once with the switch OUTSIDE the loop: inlined sixteen times, pl_act's switch (with its expm1f / tanhf / expf
+// arms) cost 270 cycles per element in the tensor-core kernels' epilogues.
+__device__ __forceinline__ void pl_act16(float* v, int kind) {
+    if (kind == RVB_ACT_LEAKYRELU) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = v[j] > 0.f ? v[j] : __fmul_rn(v[j], 0.01f);
+    } else if (kind == RVB_ACT_RELU) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
+    } else {          // statically indexed (a rolled loop would push v[] into local memory for every caller)
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = pl_act(v[j], kind);
     }
 }
 
@@ -337,7 +353,7 @@ __device__ __forceinline__ void tc_wait(uint64_t* bar, uint32_t parity) {
 template <int NETS>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 policy_l1_tc_kernel(const PolicyDev* __restrict__ p0, const PolicyDev* __restrict__ p1, const float* __restrict__ obs, int64_t obs_ld,
-                    int64_t N, float* __restrict__ h1, int dbg) {
+                    int64_t N, float* __restrict__ h1) {
     constexpr int NB = PL_E1 * NETS;                      // MMA N: 80 columns per network
     constexpr int A_FLOATS = 2 * TC_M * TC_KC;            // hi + lo, 2 x 16 KB
     constexpr int W_FLOATS = 2 * NB * TC_KC;              // hi + lo, 20 KB per network
@@ -379,9 +395,6 @@ policy_l1_tc_kernel(const PolicyDev* __restrict__ p0, const PolicyDev* __restric
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = tmem_base_s;
-    auto now = []() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; };
-    const unsigned long long t0 = now();
-    unsigned long long t1 = 0, t2 = 0;
 
     if (warp < 8) {
         // ---- loaders: warp w owns rows [16 w, 16 w + 16) of the tile, four rows per pass: lane = (row of the pass, 16-byte column
@@ -401,7 +414,7 @@ policy_l1_tc_kernel(const PolicyDev* __restrict__ p0, const PolicyDev* __restric
             for (int it = 0; it < 4; ++it) {
                 const int64_t row = rbase + 4 * it;
                 const float2* q = reinterpret_cast<const float2*>(src + row * obs_ld);
-                const bool ok = !(dbg & 2) && row < N;
+                const bool ok = row < N;
                 v[2 * it] = (ok && c16 * 4 < kmax) ? __ldg(q) : make_float2(0.f, 0.f);
                 v[2 * it + 1] = (ok && c16 * 4 + 2 < kmax) ? __ldg(q + 1) : make_float2(0.f, 0.f);
             }
@@ -430,7 +443,7 @@ policy_l1_tc_kernel(const PolicyDev* __restrict__ p0, const PolicyDev* __restric
                 *reinterpret_cast<float4*>(dst + TC_M * TC_KC) = make_float4(lo[0], lo[1], lo[2], lo[3]);
             }
             if (__any_sync(0xffffffffu, any_lo) && lane == 0) atomicOr(&s_lo[c & 63], 1u);
-            if (!(dbg & 4)) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tc_smem(&full[s])) : "memory");
         };
         float2 va[8], vb[8];
@@ -443,7 +456,6 @@ policy_l1_tc_kernel(const PolicyDev* __restrict__ p0, const PolicyDev* __restric
                 process(c + 1, vb);
             }
         }
-        t1 = now();
         // ---- epilogue: TMEM lane = row of the tile; columns [0, NB) sparse encoder (warps 0-3), [NB, 2 NB) dense encoder (warps 4-7);
         // a warp reads the TMEM quarter warp % 4
         const int q = warp & 3, enc = warp >> 2;
@@ -451,7 +463,6 @@ policy_l1_tc_kernel(const PolicyDev* __restrict__ p0, const PolicyDev* __restric
         const bool live = row < N;
         tc_wait(&dready[enc], 0);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        t2 = now();
 #pragma unroll 1
         for (int c0 = enc * NB; c0 < (enc + 1) * NB; c0 += 16) {
             uint32_t r[16];
@@ -465,7 +476,8 @@ policy_l1_tc_kernel(const PolicyDev* __restrict__ p0, const PolicyDev* __restric
                 float4 o[4];
                 float* of = reinterpret_cast<float*>(o);
 #pragma unroll
-                for (int j = 0; j < 16; ++j) of[j] = pl_act(__fadd_rn(__uint_as_float(r[j]), s_bias[c0 + j]), act_kind);
+                for (int j = 0; j < 16; ++j) of[j] = __fadd_rn(__uint_as_float(r[j]), s_bias[c0 + j]);
+                pl_act16(of, act_kind);
                 float4* dst = reinterpret_cast<float4*>(h1 + row * (2 * NB) + c0);
 #pragma unroll
                 for (int j = 0; j < 4; ++j) dst[j] = o[j];
@@ -481,10 +493,6 @@ policy_l1_tc_kernel(const PolicyDev* __restrict__ p0, const PolicyDev* __restric
                 const bool dense = c >= cs;
                 const int kc = dense ? c - cs : c;
                 constexpr uint32_t PART_BYTES = PL_E1 * TC_KC * 4;          // 10 KB: one network, one part
-                if ((dbg & 1) && c >= TC_STAGES) {          // timing experiment: no weight copies after the first round
-                    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tc_smem(&full[s])) : "memory");
-                    continue;
-                }
                 asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(tc_smem(&full[s])), "r"(2u * NETS * PART_BYTES) : "memory");
                 float* wdst = stages + s * STAGE_FLOATS + A_FLOATS;
 #pragma unroll
@@ -518,7 +526,6 @@ policy_l1_tc_kernel(const PolicyDev* __restrict__ p0, const PolicyDev* __restric
                 const bool with_lo = *reinterpret_cast<volatile uint32_t*>(&s_lo[c & 63]) != 0u;
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {                    // 8 tf32 = 32 bytes = 2 descriptor units per MMA
-                    if ((dbg & 8) && k > 0) break;               // timing experiment: one MMA pair per chunk
                     tc_mma(d_tmem, da + 2 * k, dh + 2 * k, idesc, acc);
                     tc_mma(d_tmem, da + 2 * k, dl + 2 * k, idesc, 1u);
                     if (with_lo) tc_mma(d_tmem, dal + 2 * k, dh + 2 * k, idesc, 1u);
@@ -530,14 +537,290 @@ policy_l1_tc_kernel(const PolicyDev* __restrict__ p0, const PolicyDev* __restric
             }
         }
     }
-    if ((dbg & 16) && blockIdx.x == 0 && tid == 0)
-        printf("[tc dbg] loaders done after %llu ns, accumulators ready after %llu ns, epilogue done after %llu ns\n", t1 - t0, t2 - t0, now() - t0);
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (warp == 8) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS));
 }
 
 static size_t tc_smem_bytes(int nets) { return (size_t)TC_STAGES * (2 * TC_M * TC_KC + 2 * PL_E1 * nets * TC_KC) * sizeof(float) + 1024; }
+
+
+// ------------------------------------------------------------------------------------------------------------
+// The rest of the network on tcgen05 (policy_tail_tc_kernel): Linear(80,60) x2, Linear(124,256), Linear(256,160),
+// Linear(160,128) of one network for a tile of 128 envs, chained through TMEM and shared memory, then the head.
+// Every layer: the input activations (fp32) are split into tf32 hi + lo by the four converter warps (thread = env row) and
+// written as SWIZZLE_128B operand tiles of 32 features; the weights arrive as a pre-built stream of tile images (hi + lo)
+// through two 40 KB stages filled by cp.async.bulk; one thread issues Ah.Wh + Ah.Wl + Al.Wh per 8-feature step into a TMEM
+// accumulator; the converters read it back (tcgen05.ld), add the bias, apply the activation and produce the next operand.
+// Operand space is 4 x 32 features (128 KB with hi + lo), so the 256- and 160-wide inputs are fed in two passes that
+// accumulate into the same TMEM columns.  TMEM columns: D2s [0,64) D2d [64,128) | D3 [160,416) | D4 [0,160) | D5 [160,288).
+// ------------------------------------------------------------------------------------------------------------
+#define TT_THREADS 192
+#define TT_ENTRIES 27
+#define TT_A_CHUNK (2 * TC_M * TC_KC)              // floats: hi + lo tile of one 32-feature chunk
+#define TT_W_STAGE (2 * PL_M2 * TC_KC)             // floats: the largest weight chunk (160 rows, hi + lo) = 40 KB
+#define TT_OFF_L2S 0
+#define TT_OFF_L2D (3 * 2 * 64 * TC_KC)
+#define TT_OFF_M1 (TT_OFF_L2D + 3 * 2 * 64 * TC_KC)
+#define TT_OFF_M2 (TT_OFF_M1 + 8 * 2 * 128 * TC_KC)
+#define TT_OFF_M3 (TT_OFF_M2 + 8 * 2 * PL_M2 * TC_KC)
+#define TT_FLOATS (TT_OFF_M3 + 5 * 2 * 128 * TC_KC)
+#define TT_D2S 0u
+#define TT_D2D 64u
+#define TT_D3 160u
+#define TT_D4 0u
+#define TT_D5 160u
+
+struct TailEntry {
+    int pass, achunk, rows, first, last;
+    uint32_t dcol;
+    int64_t woff;
+};
+__device__ __forceinline__ TailEntry tail_entry(int e) {
+    TailEntry t;
+    if (e < 3) t = {0, e, 64, e == 0, e == 2, TT_D2S, (int64_t)TT_OFF_L2S + (int64_t)e * 2 * 64 * TC_KC};
+    else if (e < 6) t = {1, e - 3, 64, e == 3, e == 5, TT_D2D, (int64_t)TT_OFF_L2D + (int64_t)(e - 3) * 2 * 64 * TC_KC};
+    else if (e < 14) { const int i = e - 6; t = {2, i >> 1, 128, (i >> 1) == 0, i == 7, TT_D3 + 128u * (uint32_t)(i & 1), (int64_t)TT_OFF_M1 + (int64_t)i * 2 * 128 * TC_KC}; }
+    else if (e < 22) { const int i = e - 14; t = {3 + (i >> 2), i & 3, PL_M2, i == 0, (i & 3) == 3, TT_D4, (int64_t)TT_OFF_M2 + (int64_t)i * 2 * PL_M2 * TC_KC}; }
+    else { const int i = e - 22; t = {5 + (i >> 2), i & 3, 128, i == 0, i == 3 || i == 4, TT_D5, (int64_t)TT_OFF_M3 + (int64_t)i * 2 * 128 * TC_KC}; }
+    return t;
+}
+
+// one image block of the weight stream: rows [row0, row0 + rows) x features [32 kc, 32 kc + 32) of a torch-layout weight
+__global__ void pl_tail_image_kernel(const float* __restrict__ w, int in, int out, int row0, int rows, int kc, float* __restrict__ dst) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rows * TC_KC) return;
+    const int kk = i % TC_KC, r = i / TC_KC;
+    const int k = kc * TC_KC + kk, row = row0 + r;
+    const float v = (k < in && row < out) ? w[(int64_t)row * in + k] : 0.f;
+    uint32_t hi, lo;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(v));
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lo) : "f"(__fsub_rn(v, __uint_as_float(hi))));
+    const int at = r * TC_KC + ((((kk >> 2) ^ (r & 7)) << 2) + (kk & 3));
+    dst[at] = __uint_as_float(hi);
+    dst[rows * TC_KC + at] = __uint_as_float(lo);
+}
+
+__global__ void __launch_bounds__(TT_THREADS, 1)
+policy_tail_tc_kernel(const PolicyDev* __restrict__ p0, const PolicyDev* __restrict__ p1, const float* __restrict__ obs, int64_t obs_ld,
+                      int64_t N, const float* __restrict__ h1, int h1_nets, float* __restrict__ out0, int64_t out0_ld,
+                      float* __restrict__ out1, int64_t out1_ld) {
+    const PolicyDev& P = *(blockIdx.y ? p1 : p0);
+    float* __restrict__ out = blockIdx.y ? out1 : out0;
+    const int64_t out_ld = blockIdx.y ? out1_ld : out0_ld;
+    extern __shared__ unsigned char tt_smem_raw[];
+    float* abuf = reinterpret_cast<float*>(tt_smem_raw + ((1024u - (tc_smem(tt_smem_raw) & 1023u)) & 1023u));      // 4 chunks x (hi, lo)
+    float* wbuf = abuf + 4 * TT_A_CHUNK;                                                                              // 2 stages
+    __shared__ __align__(8) uint64_t a_full, d_ready, w_full[2], w_empty[2];
+    __shared__ uint32_t tmem_base_s;
+    __shared__ float s_b[64 + 64 + PL_M1 + PL_M2 + PL_M3];          // biases: es2 | ed2 | m1 | m2 | m3
+    __shared__ float s_head[PL_MAX_HEAD * PL_M3 + PL_MAX_HEAD];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int64_t m0 = (int64_t)blockIdx.x * TC_M;
+    const int act_kind = P.act;
+    for (int i = tid; i < 64 + 64 + PL_M1 + PL_M2 + PL_M3; i += TT_THREADS) {
+        float v;
+        if (i < 64) v = i < PL_E2 ? __ldg(P.es2.bias + i) : 0.f;
+        else if (i < 128) v = i - 64 < PL_E2 ? __ldg(P.ed2.bias + i - 64) : 0.f;
+        else if (i < 128 + PL_M1) v = __ldg(P.m1.bias + i - 128);
+        else if (i < 128 + PL_M1 + PL_M2) v = __ldg(P.m2.bias + i - 128 - PL_M1);
+        else v = __ldg(P.m3.bias + i - 128 - PL_M1 - PL_M2);
+        s_b[i] = v;
+    }
+    for (int i = tid; i < P.n_head * PL_M3 + P.n_head; i += TT_THREADS)
+        s_head[i] = i < P.n_head * PL_M3 ? __ldg(P.head_w + i) : __ldg(P.head_b + i - P.n_head * PL_M3);
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(tc_smem(&a_full)), "r"(TC_M));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(tc_smem(&d_ready)));
+        for (int s = 0; s < 2; ++s) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(tc_smem(&w_full[s])));
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(tc_smem(&w_empty[s])));
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 4) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc_smem(&tmem_base_s)), "r"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = tmem_base_s;
+
+    if (warp < 4) {
+        // ---- converters: thread = env row of the tile = TMEM lane
+        const int r = tid;
+        const int64_t row = m0 + r;
+        const bool live = row < N;
+        float* arow = abuf + (r >> 3) * 256 + (r & 7) * 32;
+        // four consecutive features f .. f+3 (f % 4 == 0) of this row -> hi / lo tiles of chunk f / 32
+        auto store4 = [&](int f, float x0, float x1, float x2, float x3) {
+            const float x[4] = {x0, x1, x2, x3};
+            float hi[4], lo[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                uint32_t h, l;
+                asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(x[e]));
+                asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(l) : "f"(__fsub_rn(x[e], __uint_as_float(h))));
+                hi[e] = __uint_as_float(h); lo[e] = __uint_as_float(l);
+            }
+            float* dst = arow + (f >> 5) * TT_A_CHUNK + ((((f & 31) >> 2) ^ (r & 7)) << 2);
+            *reinterpret_cast<float4*>(dst) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+            *reinterpret_cast<float4*>(dst + TC_M * TC_KC) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+        };
+        auto publish = [&]() {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tc_smem(&a_full)) : "memory");
+        };
+        auto tmem16 = [&](uint32_t col, float* v) {          // 16 consecutive accumulator columns of this row
+            uint32_t q[16];
+            const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + col;
+            asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                         : "=r"(q[0]), "=r"(q[1]), "=r"(q[2]), "=r"(q[3]), "=r"(q[4]), "=r"(q[5]), "=r"(q[6]), "=r"(q[7]), "=r"(q[8]),
+                           "=r"(q[9]), "=r"(q[10]), "=r"(q[11]), "=r"(q[12]), "=r"(q[13]), "=r"(q[14]), "=r"(q[15])
+                         : "r"(taddr));
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(q[j]);
+        };
+        // accumulator columns [col, col + n) + bias + activation -> features [f0, f0 + n) of the operand (n % 16 == 0 here)
+        auto convert = [&](uint32_t col, const float* bias, int n, int f0, int nvalid) {
+            for (int j0 = 0; j0 < n; j0 += 16) {
+                float v[16];
+                tmem16(col + j0, v);
+#pragma unroll
+                for (int j = 0; j < 16; ++j) v[j] = __fadd_rn(v[j], bias[j0 + j]);
+                pl_act16(v, act_kind);
+#pragma unroll
+                for (int j = 0; j < 16; ++j) v[j] = (j0 + j < nvalid) ? v[j] : 0.f;
+#pragma unroll
+                for (int g = 0; g < 4; ++g)
+                    if (j0 + 4 * g < nvalid) store4(f0 + j0 + 4 * g, v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
+            }
+        };
+        int pass = 0;
+        auto wait_pass = [&]() {                     // the MMAs of pass `pass` are complete: accumulator readable, operand space free
+            tc_wait(&d_ready, (uint32_t)pass & 1u);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            ++pass;
+        };
+        // P0 / P1: the first encoder layers (policy_l1_tc_kernel's output) -> operand of the second ones
+        const float* hrow = h1 + (live ? row : 0) * (2 * PL_E1 * h1_nets) + (int)blockIdx.y * PL_E1;
+        for (int enc = 0; enc < 2; ++enc) {
+            if (enc) wait_pass();
+            const float4* src = reinterpret_cast<const float4*>(hrow + enc * PL_E1 * h1_nets);
+#pragma unroll 4
+            for (int g = 0; g < PL_E1 / 4; ++g) {
+                const float4 x = live ? __ldg(src + g) : make_float4(0.f, 0.f, 0.f, 0.f);
+                store4(4 * g, x.x, x.y, x.z, x.w);
+            }
+            for (int f = PL_E1; f < 96; f += 4) store4(f, 0.f, 0.f, 0.f, 0.f);
+            publish();
+        }
+        // P2: x = cat(proprio, x0, x1) (model.py:188-189), 4 + 60 + 60 = 124 features (+ 4 zeros)
+        wait_pass();
+        {
+            const float* orow = obs + (live ? row : 0) * obs_ld;
+            const float4 pr = live ? make_float4(__ldg(orow), __ldg(orow + 1), __ldg(orow + 2), __ldg(orow + 3)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            store4(0, pr.x, pr.y, pr.z, pr.w);          // n_proprio == 4 on this path (tc_usable)
+            convert(TT_D2S, s_b, 64, 4, PL_E2);
+            convert(TT_D2D, s_b + 64, 64, 4 + PL_E2, PL_E2);
+            store4(124, 0.f, 0.f, 0.f, 0.f);
+            publish();
+        }
+        // P3 / P4: first hidden layer (256) in two halves
+        wait_pass();
+        convert(TT_D3, s_b + 128, 128, 0, 128);
+        publish();
+        wait_pass();
+        convert(TT_D3 + 128, s_b + 128 + 128, 128, 0, 128);
+        publish();
+        // P5 / P6: second hidden layer (160): 128 + 32 features
+        wait_pass();
+        convert(TT_D4, s_b + 128 + PL_M1, 128, 0, 128);
+        publish();
+        wait_pass();
+        convert(TT_D4 + 128, s_b + 128 + PL_M1 + 128, 32, 0, 32);
+        publish();
+        // head: Linear(128, A) [+ tanh] on the third hidden layer
+        wait_pass();
+        {
+            float acc[PL_MAX_HEAD] = {0.f, 0.f, 0.f, 0.f};
+            const int n_head = P.n_head;
+            const float* b3 = s_b + 128 + PL_M1 + PL_M2;
+            for (int j0 = 0; j0 < PL_M3; j0 += 16) {
+                float v[16];
+                tmem16(TT_D5 + j0, v);
+#pragma unroll
+                for (int j = 0; j < 16; ++j) v[j] = __fadd_rn(v[j], b3[j0 + j]);
+                pl_act16(v, act_kind);
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+#pragma unroll
+                    for (int o = 0; o < PL_MAX_HEAD; ++o)
+                        if (o < n_head) acc[o] = fmaf(v[j], s_head[o * PL_M3 + j0 + j], acc[o]);
+                }
+            }
+            if (live)
+                for (int o = 0; o < P.n_head; ++o) {
+                    const float y = __fadd_rn(acc[o], s_head[P.n_head * PL_M3 + o]);
+                    out[row * out_ld + o] = P.head_tanh ? tanhf(y) : y;
+                }
+        }
+    } else if (warp == 5) {
+        // ---- weight producer
+        if (lane == 0) {
+            const float* stream = P.tc_tail;
+            for (int e = 0; e < TT_ENTRIES; ++e) {
+                const TailEntry t = tail_entry(e);
+                const int s = e & 1;
+                tc_wait(&w_empty[s], ((uint32_t)(e >> 1) & 1u) ^ 1u);
+                const uint32_t bytes = (uint32_t)(2 * t.rows * TC_KC * 4);
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(tc_smem(&w_full[s])), "r"(bytes) : "memory");
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                                 tc_smem(wbuf + s * TT_W_STAGE)),
+                             "l"(stream + t.woff), "r"(bytes), "r"(tc_smem(&w_full[s]))
+                             : "memory");
+            }
+        }
+    } else {
+        // ---- MMA issuer
+        if (lane == 0) {
+            int pass = -1;
+            for (int e = 0; e < TT_ENTRIES; ++e) {
+                const TailEntry t = tail_entry(e);
+                if (t.pass != pass) {                          // a new operand: wait for the converters
+                    pass = t.pass;
+                    tc_wait(&a_full, (uint32_t)pass & 1u);
+                }
+                const int s = e & 1;
+                tc_wait(&w_full[s], (uint32_t)(e >> 1) & 1u);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(t.rows >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
+                const float* at = abuf + t.achunk * TT_A_CHUNK;
+                const float* wt = wbuf + s * TT_W_STAGE;
+                const uint64_t ah = tc_desc(tc_smem(at)), al = tc_desc(tc_smem(at + TC_M * TC_KC)), wh = tc_desc(tc_smem(wt)),
+                               wl = tc_desc(tc_smem(wt + t.rows * TC_KC));
+                const uint32_t d = tmem_base + t.dcol;
+                uint32_t acc = t.first ? 0u : 1u;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    tc_mma(d, ah + 2 * k, wh + 2 * k, idesc, acc);
+                    tc_mma(d, ah + 2 * k, wl + 2 * k, idesc, 1u);
+                    tc_mma(d, al + 2 * k, wh + 2 * k, idesc, 1u);
+                    acc = 1u;
+                }
+                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(tc_smem(&w_empty[s])) : "memory");
+                if (t.last) asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(tc_smem(&d_ready)) : "memory");
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 4) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+}
+
+static size_t tt_smem_bytes() { return (size_t)(4 * TT_A_CHUNK + 2 * TT_W_STAGE) * sizeof(float) + 1024; }
 
 static int check_linear(const rvb_linear* L, int in, int out, const char* what) {
     if (!L || !L->weight || !L->bias) return rvb_set_error(RVB_ERR_INVALID, "rvb_policy_create: null layer", what);
@@ -589,7 +872,7 @@ extern "C" int rvb_policy_create(rvb_policy** out, int32_t n_proprio, int32_t n_
     const int64_t img_s = (int64_t)P->tc_cs * 2 * PL_E1 * TC_KC, img_d = (int64_t)P->tc_cd * 2 * PL_E1 * TC_KC;
     total = (total + 63) / 64 * 64;
     const int64_t img_at = total;
-    total += img_s + img_d;
+    total += img_s + img_d + TT_FLOATS;
     cudaError_t e = cudaMalloc((void**)&P->storage, sizeof(float) * total);
     if (e != cudaSuccess) { delete P; return rvb_set_error(RVB_ERR_NOMEM, "rvb_policy_create: cudaMalloc", cudaGetErrorString(e)); }
     P->storage_floats = total;
@@ -611,6 +894,17 @@ extern "C" int rvb_policy_create(rvb_policy** out, int32_t n_proprio, int32_t n_
         P->tc_img_s = is_; P->tc_img_d = id_;
         pl_tc_image_kernel<<<(unsigned)ceil_div((int64_t)P->tc_cs * PL_E1 * TC_KC, 256), 256, 0, st>>>(enc_sparse[0].weight, n_sparse, P->tc_cs, is_);
         pl_tc_image_kernel<<<(unsigned)ceil_div((int64_t)P->tc_cd * PL_E1 * TC_KC, 256), 256, 0, st>>>(enc_dense[0].weight, n_dense, P->tc_cd, id_);
+        // the weight stream of policy_tail_tc_kernel, block by block in consumption order (tail_entry)
+        float* tail = id_ + img_d;
+        P->tc_tail = tail;
+        auto block = [&](const rvb_linear& L, int row0, int rows, int kc, int64_t off) {
+            pl_tail_image_kernel<<<(unsigned)ceil_div((int64_t)rows * TC_KC, 256), 256, 0, st>>>(L.weight, L.in_features, L.out_features, row0, rows, kc, tail + off);
+        };
+        for (int kc = 0; kc < 3; ++kc) block(enc_sparse[1], 0, 64, kc, (int64_t)TT_OFF_L2S + (int64_t)kc * 2 * 64 * TC_KC);
+        for (int kc = 0; kc < 3; ++kc) block(enc_dense[1], 0, 64, kc, (int64_t)TT_OFF_L2D + (int64_t)kc * 2 * 64 * TC_KC);
+        for (int i = 0; i < 8; ++i) block(mlp[0], 128 * (i & 1), 128, i >> 1, (int64_t)TT_OFF_M1 + (int64_t)i * 2 * 128 * TC_KC);
+        for (int i = 0; i < 8; ++i) block(mlp[1], 0, PL_M2, i, (int64_t)TT_OFF_M2 + (int64_t)i * 2 * PL_M2 * TC_KC);
+        for (int i = 0; i < 5; ++i) block(mlp[2], 0, 128, i, (int64_t)TT_OFF_M3 + (int64_t)i * 2 * 128 * TC_KC);
     }
     e = cudaMemcpyAsync(P->head_w, head->weight, sizeof(float) * P->n_head * PL_M3, cudaMemcpyDeviceToDevice, st);
     if (e == cudaSuccess) e = cudaMemcpyAsync(P->head_b, head->bias, sizeof(float) * P->n_head, cudaMemcpyDeviceToDevice, st);
@@ -621,6 +915,7 @@ extern "C" int rvb_policy_create(rvb_policy** out, int32_t n_proprio, int32_t n_
     if (e == cudaSuccess) e = cudaFuncSetAttribute(policy_forward_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, PL_SMEM_BYTES);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(policy_l1_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem_bytes(1));
     if (e == cudaSuccess) e = cudaFuncSetAttribute(policy_l1_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem_bytes(2));
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(policy_tail_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tt_smem_bytes());
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);   // the caller may free its weight tensors on return
     if (e != cudaSuccess) {
         cudaFree(P->storage);
@@ -654,7 +949,7 @@ extern "C" int rvb_policy_variant(int v) {
 
 // the tensor-core path reads the observation rows with 8-byte loads
 static bool tc_usable(const PolicyDev* P, const float* obs, int64_t obs_ld, int64_t N) {
-    return (g_policy_variant == 3 || (g_policy_variant == 2 && N >= 2048)) && (obs_ld % 2 == 0) && (P->n_proprio % 2 == 0) && (P->n_sparse % 2 == 0) && (P->n_dense % 2 == 0) && (((uintptr_t)obs & 7u) == 0);
+    return (g_policy_variant == 3 || (g_policy_variant == 2 && N >= 2048)) && (obs_ld % 2 == 0) && (P->n_proprio == 4) && (P->n_sparse % 2 == 0) && (P->n_dense % 2 == 0) && (((uintptr_t)obs & 7u) == 0);
 }
 
 static int check_forward(const rvb_policy* P, const float* obs, int64_t obs_ld, const float* out, int64_t out_ld) {
@@ -679,10 +974,14 @@ extern "C" int rvb_policy_forward(const rvb_policy* P, const float* obs, int64_t
     float* h1 = nullptr;
     if (tc_usable(P, obs, obs_ld, N)) {
         RVB_CUDA(rvb_scratch_alloc((void**)&h1, sizeof(float) * (size_t)N * 2 * PL_E1, st));
-        policy_l1_tc_kernel<1><<<(unsigned)ceil_div(N, TC_M), TC_THREADS, tc_smem_bytes(1), st>>>(P->dev, nullptr, obs, obs_ld, N, h1, getenv("RVB_TC_DBG") ? atoi(getenv("RVB_TC_DBG")) : 0);
+        policy_l1_tc_kernel<1><<<(unsigned)ceil_div(N, TC_M), TC_THREADS, tc_smem_bytes(1), st>>>(P->dev, nullptr, obs, obs_ld, N, h1);
     }
-    kern<<<dim3((unsigned)ceil_div(N, PL_TM), 1), PL_THREADS, PL_SMEM_BYTES, st>>>(
-        P->dev, nullptr, obs, obs_ld, N, out, out_ld, nullptr, 0, h1, 1);
+    const bool tc_tail = h1 && !(getenv("RVB_TC_TAIL") && atoi(getenv("RVB_TC_TAIL")) == 0);      // A/B switch: FFMA tail after the TC first layers
+    if (tc_tail)
+        policy_tail_tc_kernel<<<dim3((unsigned)ceil_div(N, TC_M), 1), TT_THREADS, tt_smem_bytes(), st>>>(P->dev, nullptr, obs, obs_ld, N, h1, 1, out,
+                                                                                                  out_ld, nullptr, 0);
+    else
+        kern<<<dim3((unsigned)ceil_div(N, PL_TM), 1), PL_THREADS, PL_SMEM_BYTES, st>>>(P->dev, nullptr, obs, obs_ld, N, out, out_ld, nullptr, 0, h1, 1);
     const cudaError_t le = cudaGetLastError();
     if (h1) cudaFreeAsync(h1, st);
     if (le != cudaSuccess) return rvb_set_error(RVB_ERR_CUDA, "rvb_policy_forward", cudaGetErrorString(le));
@@ -706,10 +1005,15 @@ extern "C" int rvb_policy_forward_pair(const rvb_policy* A, const rvb_policy* B,
     float* h1 = nullptr;
     if (tc_usable(A, obs, obs_ld, N)) {          // both networks' first layers in one launch: they share the observation tiles
         RVB_CUDA(rvb_scratch_alloc((void**)&h1, sizeof(float) * (size_t)N * 4 * PL_E1, st));
-        policy_l1_tc_kernel<2><<<(unsigned)ceil_div(N, TC_M), TC_THREADS, tc_smem_bytes(2), st>>>(A->dev, B->dev, obs, obs_ld, N, h1, getenv("RVB_TC_DBG") ? atoi(getenv("RVB_TC_DBG")) : 0);
+        policy_l1_tc_kernel<2><<<(unsigned)ceil_div(N, TC_M), TC_THREADS, tc_smem_bytes(2), st>>>(A->dev, B->dev, obs, obs_ld, N, h1);
     }
-    kern<<<dim3((unsigned)ceil_div(N, PL_TM), 2), PL_THREADS, PL_SMEM_BYTES, st>>>(
-        A->dev, B->dev, obs, obs_ld, N, out_a, out_a_ld, out_b, out_b_ld, h1, 2);
+    const bool tc_tail = h1 && !(getenv("RVB_TC_TAIL") && atoi(getenv("RVB_TC_TAIL")) == 0);
+    if (tc_tail)
+        policy_tail_tc_kernel<<<dim3((unsigned)ceil_div(N, TC_M), 2), TT_THREADS, tt_smem_bytes(), st>>>(A->dev, B->dev, obs, obs_ld, N, h1, 2, out_a,
+                                                                                                  out_a_ld, out_b, out_b_ld);
+    else
+        kern<<<dim3((unsigned)ceil_div(N, PL_TM), 2), PL_THREADS, PL_SMEM_BYTES, st>>>(A->dev, B->dev, obs, obs_ld, N, out_a, out_a_ld, out_b, out_b_ld,
+                                                                                       h1, 2);
     const cudaError_t le = cudaGetLastError();
     if (h1) cudaFreeAsync(h1, st);
     if (le != cudaSuccess) return rvb_set_error(RVB_ERR_CUDA, "rvb_policy_forward_pair", cudaGetErrorString(le));
