@@ -317,10 +317,17 @@ def time_policy_epilogue(R, obs, steps=20, warmup=3):
     ms_eager = timed(lambda: (ea(), ec()))
     err = max((out_a - ea()).abs().max().item(), (out_c - ec()).abs().max().item())
     flops = 2 * 2 * N * (634 * 80 + 1112 * 80 + 2 * 80 * 60 + 124 * 256 + 256 * 160 + 160 * 128 + 128 * 2)
-    return {"ms": ms, "envs_per_s": N / ms * 1e3, "fp32_tflops": flops / ms / 1e9, "torch_eager_fp32_ms": ms_eager,
-            "max_abs_diff_vs_torch": err, "launches": 1, "actor_alone_ms": ms_single,
-            "what": "actor + critic (encoders [80,60] x2, mlp [256,160,128], model.py:152-241) on the step's obs_buf f32 [%d,1750]; "
-                    "one fused launch for both networks (rvb_policy_forward_pair); not included in `value`" % N}
+    lib = R._lib.load()
+    prev = lib.rvb_policy_variant(1)                 # the round-1 fp32 FFMA2 kernel, for comparison
+    try:
+        ms_ffma = timed(ours)
+    finally:
+        lib.rvb_policy_variant(prev)
+    return {"ms": ms, "envs_per_s": N / ms * 1e3, "fp32_equivalent_tflops": flops / ms / 1e9, "torch_eager_fp32_ms": ms_eager,
+            "ffma2_kernel_ms": ms_ffma, "max_abs_diff_vs_torch": err, "launches": 2, "actor_alone_ms": ms_single,
+            "what": "actor + critic (encoders [80,60] x2, mlp [256,160,128], model.py:152-241) on the step's obs_buf f32 [%d,1750] through "
+                    "rvb_policy_forward_pair: two launches, tcgen05 kind::tf32 MMAs with hi + lo split operands (fp32-grade), accumulators "
+                    "in TMEM (policy_l1_tc_kernel + policy_tail_tc_kernel); not included in `value`" % N}
 
 
 # ------------------------------------------------------------------------------------------------ B200 arm
@@ -331,6 +338,7 @@ def run_b200(args, rank, world, local):
         raise RuntimeError("bench.py: no CUDA device -- this arm has no CPU path")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa_cpus = None if args.no_numa else R.dist.bind_to_gpu_numa(local)      # before any pinned buffer exists
     N = args.envs
     if not N:
         free_b, _ = torch.cuda.mem_get_info(dev)
@@ -493,7 +501,7 @@ def run_b200(args, rank, world, local):
             "setup": {"raycast_variant": args.variant, "fused_step": not args.unfused, "index_build_s": round(t_index, 3),
                       "rock_triangles": int(w.rock_triangles.shape[0]), "stones": int(w.stone_info.shape[0]),
                       "stats_reduction": "compute stream" if args.sync_reduce else "asynchronous, NCCL stream",
-                      "device_reset_in_step": device_reset,
+                      "device_reset_in_step": device_reset, "cpus_after_numa_binding": numa_cpus,
                       "resets_per_step": reset_counts[0] / max(args.steps, 1), "goals_drawn_per_step": reset_counts[1] / max(args.steps, 1),
                       "reset_rate": reset_counts[0] / max(args.steps, 1) / N},
             "rays_per_s": value * P_RAYS,
@@ -564,6 +572,7 @@ def main():
     ap.add_argument("--ref-device", default="cpu", help="reference arm: cpu (the baseline) or cuda:0 (its own eager deployment)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-reset", action="store_true", help="leave the device-side reset path out of the step")
+    ap.add_argument("--no-numa", action="store_true", help="do not bind the process to the CPUs local to its GPU")
     ap.add_argument("--unfused", action="store_true", help="one library call per reference call instead of rvb_env_step")
     ap.add_argument("--sync-reduce", action="store_true", help="all-reduce the statistics on the compute stream every step")
     args = ap.parse_args()

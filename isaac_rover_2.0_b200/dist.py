@@ -31,6 +31,25 @@ def init_from_env(backend=None):
     return rank, world, local
 
 
+def bind_to_gpu_numa(local_rank):
+    """Pin this process to the CPUs NVML lists as local to its GPU (nvmlDeviceSetCpuAffinity), BEFORE any pinned host buffer
+    is allocated: the pages of a pinned buffer live on the NUMA node of the thread that allocates them, and a GPU that writes
+    its 0.9 GB observation block per step into the other socket's memory shares the inter-socket link with every other rank
+    doing the same.  Returns the number of CPUs in the new affinity mask, or None if NVML is not available."""
+    try:
+        import pynvml as nv
+        nv.nvmlInit()
+        try:
+            uuid = torch.cuda.get_device_properties(local_rank).uuid
+            h = nv.nvmlDeviceGetHandleByUUID(("GPU-" + str(uuid)).encode())
+        except Exception:
+            h = nv.nvmlDeviceGetHandleByIndex(local_rank)
+        nv.nvmlDeviceSetCpuAffinity(h)
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return None
+
+
 def reduce_stats(stats, async_op=False):
     """In-place all-reduce(sum) of a per-rank statistics vector (f64 [16]) on the current stream (NCCL) --
     the only exchange of the step.  No-op in a single process."""
