@@ -358,24 +358,27 @@ policy_l1_tc_kernel(const PolicyDev* __restrict__ p0, const PolicyDev* __restric
     constexpr int A_FLOATS = 2 * TC_M * TC_KC;            // hi + lo, 2 x 16 KB
     constexpr int W_FLOATS = 2 * NB * TC_KC;              // hi + lo, 20 KB per network
     constexpr int STAGE_FLOATS = A_FLOATS + W_FLOATS;
-    constexpr uint32_t TMEM_COLS = NETS == 2 ? 512u : 256u;      // 2 x 80 x NETS accumulator columns, a power of two
+    constexpr uint32_t TMEM_COLS = NETS == 2 ? 256u : 128u;      // 80 x NETS accumulator columns, a power of two
     constexpr int LOADERS = 8 * 32;                       // warps 0-7; warp 8 issues the MMAs, warp 9 streams the weights
     extern __shared__ unsigned char tc_smem_raw[];
     // SWIZZLE_128B operands want 1024-byte aligned tiles: align by hand (the launch reserves 1 KB of slack)
     float* stages = reinterpret_cast<float*>(tc_smem_raw + ((1024u - (tc_smem(tc_smem_raw) & 1023u)) & 1023u));
-    __shared__ __align__(8) uint64_t full[TC_STAGES], empty[TC_STAGES], dready[2];
+    __shared__ __align__(8) uint64_t full[TC_STAGES], empty[TC_STAGES], dready;
     __shared__ uint32_t tmem_base_s;
     __shared__ uint32_t s_lo[64];                         // chunk c of this tile has a non-zero lo part of A
-    __shared__ float s_bias[2 * PL_E1 * 2];               // [encoder][network][80]
+    __shared__ float s_bias[PL_E1 * 2];                   // [network][80] of this CTA's encoder
     const PolicyDev& P0 = *p0;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int cs = P0.tc_cs, cd = P0.tc_cd, nchunks = cs + cd;
+    // blockIdx.y = encoder (0 sparse, 1 dense): the two first layers of a tile run as two CTAs, 20 and 35 chunks long -- the
+    // latency of a tile (what a small batch sees) is the longer one, not their sum
+    const bool dense = blockIdx.y != 0;
+    const int nchunks = dense ? P0.tc_cd : P0.tc_cs;
     const int act_kind = P0.act;                          // rvb_policy_forward_pair requires the same activation of both networks
     if (tid < 64) s_lo[tid] = 0u;
-    for (int i = tid; i < 2 * NB; i += TC_THREADS) {
-        const int enc = i / NB, net = (i % NB) / PL_E1, col = i % PL_E1;
+    for (int i = tid; i < NB; i += TC_THREADS) {
+        const int net = i / PL_E1, col = i % PL_E1;
         const PolicyDev& P = (NETS == 2 && net) ? *p1 : P0;
-        s_bias[i] = __ldg((enc ? P.ed1.bias : P.es1.bias) + col);
+        s_bias[i] = __ldg((dense ? P.ed1.bias : P.es1.bias) + col);
     }
     const int64_t m0 = (int64_t)blockIdx.x * TC_M;
     if (tid == 0) {
@@ -383,8 +386,7 @@ policy_l1_tc_kernel(const PolicyDev* __restrict__ p0, const PolicyDev* __restric
             asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(tc_smem(&full[s])), "r"(LOADERS + 1));
             asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(tc_smem(&empty[s])));
         }
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(tc_smem(&dready[0])));
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(tc_smem(&dready[1])));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(tc_smem(&dready)));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 8) {
@@ -404,12 +406,12 @@ policy_l1_tc_kernel(const PolicyDev* __restrict__ p0, const PolicyDev* __restric
         // while chunk c is split and stored (two register buffers in ping-pong: a copy would wait for the loads it should hide).
         const int ri = lane >> 3, c16 = lane & 7;
         const int64_t rbase = m0 + warp * 16 + ri;
-        const float* obase = obs + P0.n_proprio + c16 * 4;
+        const float* obase = obs + P0.n_proprio + (dense ? P0.n_sparse : 0) + c16 * 4;
+        const int kall = dense ? P0.n_dense : P0.n_sparse;
         auto fetch = [&](int c, float2* v) {
-            const bool dense = c >= cs;
-            const int k0 = (dense ? c - cs : c) * TC_KC;
-            const int kmax = (dense ? P0.n_dense : P0.n_sparse) - k0;              // valid columns of this chunk (even)
-            const float* src = obase + (dense ? P0.n_sparse : 0) + k0;
+            const int k0 = c * TC_KC;
+            const int kmax = kall - k0;                                             // valid columns of this chunk (even)
+            const float* src = obase + k0;
 #pragma unroll
             for (int it = 0; it < 4; ++it) {
                 const int64_t row = rbase + 4 * it;
@@ -456,15 +458,16 @@ policy_l1_tc_kernel(const PolicyDev* __restrict__ p0, const PolicyDev* __restric
                 process(c + 1, vb);
             }
         }
-        // ---- epilogue: TMEM lane = row of the tile; columns [0, NB) sparse encoder (warps 0-3), [NB, 2 NB) dense encoder (warps 4-7);
-        // a warp reads the TMEM quarter warp % 4
-        const int q = warp & 3, enc = warp >> 2;
+        // ---- epilogue: TMEM lane = row of the tile, columns [0, NB) = (network, 80); a warp reads the TMEM quarter warp % 4, warps
+        // 0-3 the first half of the columns, warps 4-7 the second
+        const int q = warp & 3, half = warp >> 2;
         const int64_t row = m0 + q * 32 + lane;
         const bool live = row < N;
-        tc_wait(&dready[enc], 0);
+        tc_wait(&dready, 0);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll 1
-        for (int c0 = enc * NB; c0 < (enc + 1) * NB; c0 += 16) {
+        constexpr int G = NB / 16;                          // groups of 16 columns: 5 (one network) or 10
+        for (int c0 = (half ? (G + 1) / 2 : 0) * 16; c0 < (half ? G : (G + 1) / 2) * 16; c0 += 16) {
             uint32_t r[16];
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
             asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
@@ -478,7 +481,7 @@ policy_l1_tc_kernel(const PolicyDev* __restrict__ p0, const PolicyDev* __restric
 #pragma unroll
                 for (int j = 0; j < 16; ++j) of[j] = __fadd_rn(__uint_as_float(r[j]), s_bias[c0 + j]);
                 pl_act16(of, act_kind);
-                float4* dst = reinterpret_cast<float4*>(h1 + row * (2 * NB) + c0);
+                float4* dst = reinterpret_cast<float4*>(h1 + row * (2 * NB) + (dense ? NB : 0) + c0);
 #pragma unroll
                 for (int j = 0; j < 4; ++j) dst[j] = o[j];
             }
@@ -490,8 +493,7 @@ policy_l1_tc_kernel(const PolicyDev* __restrict__ p0, const PolicyDev* __restric
                 const int s = c % TC_STAGES;
                 const uint32_t ph = (uint32_t)(c / TC_STAGES) & 1u;
                 tc_wait(&empty[s], ph ^ 1u);
-                const bool dense = c >= cs;
-                const int kc = dense ? c - cs : c;
+                const int kc = c;
                 constexpr uint32_t PART_BYTES = PL_E1 * TC_KC * 4;          // 10 KB: one network, one part
                 asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(tc_smem(&full[s])), "r"(2u * NETS * PART_BYTES) : "memory");
                 float* wdst = stages + s * STAGE_FLOATS + A_FLOATS;
@@ -517,12 +519,11 @@ policy_l1_tc_kernel(const PolicyDev* __restrict__ p0, const PolicyDev* __restric
                 const uint32_t ph = (uint32_t)(c / TC_STAGES) & 1u;
                 tc_wait(&full[s], ph);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const bool dense = c >= cs;
-                const uint32_t d_tmem = tmem_base + (dense ? NB : 0);
+                const uint32_t d_tmem = tmem_base;
                 const float* st = stages + s * STAGE_FLOATS;
                 const uint64_t da = tc_desc(tc_smem(st)), dal = tc_desc(tc_smem(st + TC_M * TC_KC)), dh = tc_desc(tc_smem(st + A_FLOATS)),
                                dl = tc_desc(tc_smem(st + A_FLOATS + NB * TC_KC));
-                uint32_t acc = (c == 0 || c == cs) ? 0u : 1u;
+                uint32_t acc = c == 0 ? 0u : 1u;
                 const bool with_lo = *reinterpret_cast<volatile uint32_t*>(&s_lo[c & 63]) != 0u;
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {                    // 8 tf32 = 32 bytes = 2 descriptor units per MMA
@@ -532,8 +533,7 @@ policy_l1_tc_kernel(const PolicyDev* __restrict__ p0, const PolicyDev* __restric
                     acc = 1u;
                 }
                 asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(tc_smem(&empty[s])) : "memory");
-                if (c == cs - 1) asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(tc_smem(&dready[0])) : "memory");
-                if (c == nchunks - 1) asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(tc_smem(&dready[1])) : "memory");
+                if (c == nchunks - 1) asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(tc_smem(&dready)) : "memory");
             }
         }
     }
@@ -935,11 +935,10 @@ extern "C" int rvb_policy_destroy(rvb_policy* P) {
 
 extern "C" int64_t rvb_policy_bytes(const rvb_policy* P) { return P ? P->storage_floats * (int64_t)sizeof(float) : 0; }
 
-// 2 (default) = the two first encoder layers on tcgen05 (policy_l1_tc_kernel) when the batch is large enough to fill the GPU with
-// 128-env tiles (N >= 2048; a tile's 55 chunks are a serial pipeline of 45 us, so small batches are no faster than on the FFMA path), the rest packed
-// FFMA2; 3 = tcgen05 first layers whatever N (tests); 1 = packed FFMA2 throughout; 0 = scalar FFMA throughout.  1 and 0 are
-// bit-identical; 2 / 3 differ from them in the summation order of the first layers (all within 2e-5 of the fp64 oracle, the gate
-// of the tests).
+// 2 (default) = the whole network on tcgen05 (policy_l1_tc_kernel + policy_tail_tc_kernel: faster than the FFMA path from a single
+// 128-env tile upwards); 3 = the same (kept for the tests that force the path); 1 = packed FFMA2 throughout (round 1's kernel);
+// 0 = scalar FFMA throughout.  1 and 0 are bit-identical; 2 / 3 differ from them in the summation order (all within 2e-5 of the
+// fp64 oracle, the gate of the tests).  RVB_TC_TAIL=0 keeps the FFMA kernel for the layers after the first (A/B switch).
 static int g_policy_variant = 2;
 extern "C" int rvb_policy_variant(int v) {
     const int prev = g_policy_variant;
@@ -948,8 +947,8 @@ extern "C" int rvb_policy_variant(int v) {
 }
 
 // the tensor-core path reads the observation rows with 8-byte loads
-static bool tc_usable(const PolicyDev* P, const float* obs, int64_t obs_ld, int64_t N) {
-    return (g_policy_variant == 3 || (g_policy_variant == 2 && N >= 2048)) && (obs_ld % 2 == 0) && (P->n_proprio == 4) && (P->n_sparse % 2 == 0) && (P->n_dense % 2 == 0) && (((uintptr_t)obs & 7u) == 0);
+static bool tc_usable(const PolicyDev* P, const float* obs, int64_t obs_ld, int64_t /*N*/) {
+    return (g_policy_variant == 3 || g_policy_variant == 2) && (obs_ld % 2 == 0) && (P->n_proprio == 4) && (P->n_sparse % 2 == 0) && (P->n_dense % 2 == 0) && (((uintptr_t)obs & 7u) == 0);
 }
 
 static int check_forward(const rvb_policy* P, const float* obs, int64_t obs_ld, const float* out, int64_t out_ld) {
@@ -974,7 +973,7 @@ extern "C" int rvb_policy_forward(const rvb_policy* P, const float* obs, int64_t
     float* h1 = nullptr;
     if (tc_usable(P, obs, obs_ld, N)) {
         RVB_CUDA(rvb_scratch_alloc((void**)&h1, sizeof(float) * (size_t)N * 2 * PL_E1, st));
-        policy_l1_tc_kernel<1><<<(unsigned)ceil_div(N, TC_M), TC_THREADS, tc_smem_bytes(1), st>>>(P->dev, nullptr, obs, obs_ld, N, h1);
+        policy_l1_tc_kernel<1><<<dim3((unsigned)ceil_div(N, TC_M), 2), TC_THREADS, tc_smem_bytes(1), st>>>(P->dev, nullptr, obs, obs_ld, N, h1);
     }
     const bool tc_tail = h1 && !(getenv("RVB_TC_TAIL") && atoi(getenv("RVB_TC_TAIL")) == 0);      // A/B switch: FFMA tail after the TC first layers
     if (tc_tail)
@@ -1005,7 +1004,7 @@ extern "C" int rvb_policy_forward_pair(const rvb_policy* A, const rvb_policy* B,
     float* h1 = nullptr;
     if (tc_usable(A, obs, obs_ld, N)) {          // both networks' first layers in one launch: they share the observation tiles
         RVB_CUDA(rvb_scratch_alloc((void**)&h1, sizeof(float) * (size_t)N * 4 * PL_E1, st));
-        policy_l1_tc_kernel<2><<<(unsigned)ceil_div(N, TC_M), TC_THREADS, tc_smem_bytes(2), st>>>(A->dev, B->dev, obs, obs_ld, N, h1);
+        policy_l1_tc_kernel<2><<<dim3((unsigned)ceil_div(N, TC_M), 2), TC_THREADS, tc_smem_bytes(2), st>>>(A->dev, B->dev, obs, obs_ld, N, h1);
     }
     const bool tc_tail = h1 && !(getenv("RVB_TC_TAIL") && atoi(getenv("RVB_TC_TAIL")) == 0);
     if (tc_tail)

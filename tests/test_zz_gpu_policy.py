@@ -130,14 +130,14 @@ def test_pair_launch_equals_single_launches(R):
 
 def test_ffma2_and_scalar_variants_are_bit_identical(R):
     """rvb_policy_variant: 1 (packed FFMA2 inner loop) and 0 (scalar FFMA) are both IEEE fma per element -> bit-identical;
-    2 (default: the two first encoder layers on tcgen05 with tf32 hi + lo operands, accumulators in TMEM) sums in another order and
+    2 (default: the network on tcgen05 with tf32 hi + lo operands, accumulators in TMEM) sums in another order and
     stays within 1e-5 of them -- on arbitrary fp32 observations (three MMAs per k-step) and on fp16-valued ones like the step's
     obs_buf (the A operand is exact in tf32: two MMAs per k-step)."""
     lib = R._lib.load()
     torch.manual_seed(8)
     actor, critic = _models(R)
     obs = torch.rand(1000, 1750, device="cuda")
-    assert lib.rvb_policy_variant(-1) == 2                            # default: tensor-core first layers for N >= 2048
+    assert lib.rvb_policy_variant(-1) == 2                            # default: the whole network on tcgen05
     try:
         lib.rvb_policy_variant(3)                                     # ... whatever N
         m2, v2 = R.model.compute_pair(actor, critic, obs)
@@ -166,7 +166,7 @@ def test_ffma2_and_scalar_variants_are_bit_identical(R):
         got = R.model.compute_pair(actor, critic, obs16[:n])
         assert (got[0] - ref[0]).abs().max().item() <= 1e-5 and (got[1] - ref[1]).abs().max().item() <= 1e-5
     lib.rvb_policy_variant(2)
-    big = torch.rand(2048 + 77, 1750, device="cuda")                 # default dispatch takes the tensor-core path from 2048 envs
+    big = torch.rand(2048 + 77, 1750, device="cuda")                 # the default dispatch is the tensor-core path
     big[:, 4:] = (big[:, 4:] * 5.5).half().float()
     got = R.model.compute_pair(actor, critic, big)
     lib.rvb_policy_variant(1)
