@@ -465,8 +465,8 @@ policy_l1_tc_kernel(const PolicyDev* __restrict__ p0, const PolicyDev* __restric
         const bool live = row < N;
         tc_wait(&dready, 0);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-#pragma unroll 1
         constexpr int G = NB / 16;                          // groups of 16 columns: 5 (one network) or 10
+#pragma unroll 1
         for (int c0 = (half ? (G + 1) / 2 : 0) * 16; c0 < (half ? G : (G + 1) / 2) * 16; c0 += 16) {
             uint32_t r[16];
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
@@ -555,7 +555,7 @@ static size_t tc_smem_bytes(int nets) { return (size_t)TC_STAGES * (2 * TC_M * T
 // Operand space is 4 x 32 features (128 KB with hi + lo), so the 256- and 160-wide inputs are fed in two passes that
 // accumulate into the same TMEM columns.  TMEM columns: D2s [0,64) D2d [64,128) | D3 [160,416) | D4 [0,160) | D5 [160,288).
 // ------------------------------------------------------------------------------------------------------------
-#define TT_THREADS 192
+#define TT_THREADS 320
 #define TT_ENTRIES 27
 #define TT_A_CHUNK (2 * TC_M * TC_KC)              // floats: hi + lo tile of one 32-feature chunk
 #define TT_W_STAGE (2 * PL_M2 * TC_KC)             // floats: the largest weight chunk (160 rows, hi + lo) = 40 KB
@@ -630,7 +630,7 @@ policy_tail_tc_kernel(const PolicyDev* __restrict__ p0, const PolicyDev* __restr
     for (int i = tid; i < P.n_head * PL_M3 + P.n_head; i += TT_THREADS)
         s_head[i] = i < P.n_head * PL_M3 ? __ldg(P.head_w + i) : __ldg(P.head_b + i - P.n_head * PL_M3);
     if (tid == 0) {
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(tc_smem(&a_full)), "r"(TC_M));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(tc_smem(&a_full)), "r"(2 * TC_M));
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(tc_smem(&d_ready)));
         for (int s = 0; s < 2; ++s) {
             asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(tc_smem(&w_full[s])));
@@ -638,7 +638,7 @@ policy_tail_tc_kernel(const PolicyDev* __restrict__ p0, const PolicyDev* __restr
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 4) {
+    if (warp == 8) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc_smem(&tmem_base_s)), "r"(512));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
     }
@@ -647,9 +647,10 @@ policy_tail_tc_kernel(const PolicyDev* __restrict__ p0, const PolicyDev* __restr
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = tmem_base_s;
 
-    if (warp < 4) {
-        // ---- converters: thread = env row of the tile = TMEM lane
-        const int r = tid;
+    if (warp < 8) {
+        // ---- converters: two threads per env row of the tile (= TMEM lane; a warp reaches the TMEM quarter warp % 4): warps 0-3 take
+        // the even groups of 16 features, warps 4-7 the odd ones
+        const int r = (warp & 3) * 32 + lane, half = warp >> 2;
         const int64_t row = m0 + r;
         const bool live = row < N;
         float* arow = abuf + (r >> 3) * 256 + (r & 7) * 32;
@@ -674,7 +675,7 @@ policy_tail_tc_kernel(const PolicyDev* __restrict__ p0, const PolicyDev* __restr
         };
         auto tmem16 = [&](uint32_t col, float* v) {          // 16 consecutive accumulator columns of this row
             uint32_t q[16];
-            const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + col;
+            const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + col;
             asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
                          : "=r"(q[0]), "=r"(q[1]), "=r"(q[2]), "=r"(q[3]), "=r"(q[4]), "=r"(q[5]), "=r"(q[6]), "=r"(q[7]), "=r"(q[8]),
                            "=r"(q[9]), "=r"(q[10]), "=r"(q[11]), "=r"(q[12]), "=r"(q[13]), "=r"(q[14]), "=r"(q[15])
@@ -685,7 +686,7 @@ policy_tail_tc_kernel(const PolicyDev* __restrict__ p0, const PolicyDev* __restr
         };
         // accumulator columns [col, col + n) + bias + activation -> features [f0, f0 + n) of the operand (n % 16 == 0 here)
         auto convert = [&](uint32_t col, const float* bias, int n, int f0, int nvalid) {
-            for (int j0 = 0; j0 < n; j0 += 16) {
+            for (int j0 = 16 * half; j0 < n; j0 += 32) {
                 float v[16];
                 tmem16(col + j0, v);
 #pragma unroll
@@ -709,23 +710,26 @@ policy_tail_tc_kernel(const PolicyDev* __restrict__ p0, const PolicyDev* __restr
         for (int enc = 0; enc < 2; ++enc) {
             if (enc) wait_pass();
             const float4* src = reinterpret_cast<const float4*>(hrow + enc * PL_E1 * h1_nets);
-#pragma unroll 4
-            for (int g = 0; g < PL_E1 / 4; ++g) {
+#pragma unroll 5
+            for (int g = half; g < PL_E1 / 4; g += 2) {
                 const float4 x = live ? __ldg(src + g) : make_float4(0.f, 0.f, 0.f, 0.f);
                 store4(4 * g, x.x, x.y, x.z, x.w);
             }
-            for (int f = PL_E1; f < 96; f += 4) store4(f, 0.f, 0.f, 0.f, 0.f);
+            for (int f = PL_E1 + 4 * half; f < 96; f += 8) store4(f, 0.f, 0.f, 0.f, 0.f);
             publish();
         }
         // P2: x = cat(proprio, x0, x1) (model.py:188-189), 4 + 60 + 60 = 124 features (+ 4 zeros)
         wait_pass();
         {
             const float* orow = obs + (live ? row : 0) * obs_ld;
-            const float4 pr = live ? make_float4(__ldg(orow), __ldg(orow + 1), __ldg(orow + 2), __ldg(orow + 3)) : make_float4(0.f, 0.f, 0.f, 0.f);
-            store4(0, pr.x, pr.y, pr.z, pr.w);          // n_proprio == 4 on this path (tc_usable)
+            if (half == 0) {
+                const float4 pr = live ? make_float4(__ldg(orow), __ldg(orow + 1), __ldg(orow + 2), __ldg(orow + 3)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                store4(0, pr.x, pr.y, pr.z, pr.w);          // n_proprio == 4 on this path (tc_usable)
+            } else {
+                store4(124, 0.f, 0.f, 0.f, 0.f);
+            }
             convert(TT_D2S, s_b, 64, 4, PL_E2);
             convert(TT_D2D, s_b + 64, 64, 4 + PL_E2, PL_E2);
-            store4(124, 0.f, 0.f, 0.f, 0.f);
             publish();
         }
         // P3 / P4: first hidden layer (256) in two halves
@@ -744,7 +748,7 @@ policy_tail_tc_kernel(const PolicyDev* __restrict__ p0, const PolicyDev* __restr
         publish();
         // head: Linear(128, A) [+ tanh] on the third hidden layer
         wait_pass();
-        {
+        if (half == 0) {
             float acc[PL_MAX_HEAD] = {0.f, 0.f, 0.f, 0.f};
             const int n_head = P.n_head;
             const float* b3 = s_b + 128 + PL_M1 + PL_M2;
@@ -767,7 +771,7 @@ policy_tail_tc_kernel(const PolicyDev* __restrict__ p0, const PolicyDev* __restr
                     out[row * out_ld + o] = P.head_tanh ? tanhf(y) : y;
                 }
         }
-    } else if (warp == 5) {
+    } else if (warp == 9) {
         // ---- weight producer
         if (lane == 0) {
             const float* stream = P.tc_tail;
@@ -817,7 +821,7 @@ policy_tail_tc_kernel(const PolicyDev* __restrict__ p0, const PolicyDev* __restr
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    if (warp == 4) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+    if (warp == 8) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
 }
 
 static size_t tt_smem_bytes() { return (size_t)(4 * TT_A_CHUNK + 2 * TT_W_STAGE) * sizeof(float) + 1024; }

@@ -767,3 +767,49 @@ def test_drop_in_constructors_load_reference_asset_files(R, world20, tmp_path, m
     s7 = R.read_stone_info(str(tmp_path / "stone_info.npy"))
     assert s7.shape == (w.stone_info.shape[0], 7) and s7.is_cuda
     assert torch.equal(s7[:, 6].cpu(), (torch.maximum(w.stone_info[:, 3], w.stone_info[:, 4]) / 4).float())
+
+
+def test_reference_constructor_and_post_physics_contract(R, world20, tmp_path, monkeypatch):
+    """RoverTask.from_reference(name, sim_config, env, offset) -- the reference's constructor signature (tasks/rover.py:81-87):
+    numEnvs / reward scales come from sim_config.task_config, the assets from the reference's relative paths, and
+    post_physics_step follows rl_task.py:239-259: progress_buf always advances, the observation / metrics / reset work only while
+    env._world.is_playing(); get_states / get_extras exist."""
+    import types
+    w = world20
+    for sub, idx, tri, ver in (("knn_terrain", w.map_indices, w.triangles, w.vertices),
+                               ("knn_rocks", w.rock_indices, w.rock_triangles, w.rock_vertices)):
+        d = tmp_path / "tasks" / "utils" / "terrain" / sub
+        d.mkdir(parents=True)
+        torch.save(idx, d / "map_indices.pt"); torch.save(tri, d / "triangles.pt"); torch.save(ver, d / "vertices.pt")
+    monkeypatch.chdir(tmp_path)
+    N = 48
+    st = R.synth.make_env_state(w, N, seed=12)
+    playing = {"on": True}
+    env = types.SimpleNamespace(_world=types.SimpleNamespace(is_playing=lambda: playing["on"]))
+    rewards = dict(R.rover.DEFAULT_REWARDS)
+    rewards["pos_reward"] = 2.0
+    sim_config = types.SimpleNamespace(config={"seed": 42}, task_config={"env": {"numEnvs": N}, "rewards": rewards})
+    view = R.synth.SyntheticRoverView(st["pos"].cuda(), st["quat"].cuda(), st["joints"].cuda())
+    from isaac_rover_b200.terrain_utils import stone_info_from_array
+    task = R.RoverTask.from_reference("Rover", sim_config, env, None, rover_view=view,
+                                      stone_info=stone_info_from_array(w.stone_info.numpy(), device="cuda:0"), heightmap=w.heightmap)
+    assert task.num_envs == N and task._name == "Rover" and task.rew_scales["pos_reward"] == 2.0 and task._task_cfg is sim_config.task_config
+    ref = R.synth.make_task(w, st, device="cuda:0", level=1)
+    ref.rew_scales["pos_reward"] = 2.0
+    task.linear_velocity.input_state(st["prev_actions"][:, 0].cuda())          # the history make_task starts from
+    task.angular_velocity.input_state(st["prev_actions"][:, 1].cuda())
+    for t in (task, ref):
+        t.curriculum_level = 1
+        t.target_positions = st["target"].cuda().clone()
+        t.progress_buf = st["progress"].cuda().clone()
+        t.apply_actions(st["actions"].cuda())
+        t.rover_rot = R.tensor_quat_to_eul(st["quat"].cuda())
+    a, b = task.post_physics_step(), ref.post_physics_step()
+    assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1]) and torch.equal(a[2], b[2])      # files + config == in-memory construction
+    assert task.get_states().shape == (N, 0) and task.get_extras() is task.extras
+    # paused simulation: only the step counter moves (rl_task.py:248-250)
+    playing["on"] = False
+    obs0, rew0, prog0 = task.obs_buf.clone(), task.rew_buf.clone(), task.progress_buf.clone()
+    view.pos = view.pos + 1.0
+    task.post_physics_step()
+    assert torch.equal(task.progress_buf, prog0 + 1) and torch.equal(task.obs_buf, obs0) and torch.equal(task.rew_buf, rew0)
