@@ -194,6 +194,46 @@ __device__ __forceinline__ void epilogue(const TiledParams& q, int64_t n, int p0
     float* const grow = q.obs ? q.obs + n * q.obs_ld + 4 : nullptr;
     const int head = bulk ? (int)(((16u - (uint32_t)((uintptr_t)grow & 15u)) & 15u) >> 2) : 0;      // floats before the body
     float* const srow = bulk ? stage + ((4 - head) & 3) : nullptr;                                    // srow + head is 16-byte aligned
+    // Fast path (the production call: distances + observation columns only, no ray of the tile saw a hit beyond the miss sentinel):
+    // every load of the thread's <= 8 rays is issued before the first store -- in the general loop below a ray's column indices,
+    // its stores and the next ray's loads form one dependent chain, and the CTA sits in this tail at memory latency (the obs
+    // output cost 4.6 % of the kernel)
+    {
+        bool any_far = false;
+        for (int i = tid; i < (np + 31) / 32; i += nthreads) any_far |= far[i] != 0u;
+        any_far = __syncthreads_or(any_far ? 1 : 0) != 0;
+        if (!any_far && !want_geo && !q.hit_slot && np <= 8 * nthreads && !bulk && (q.spec_slot & 16)) {
+            uint32_t key[8];
+            int ca[8], cb[8];
+            const bool want_cols = q.obs != nullptr || q.obs16 != nullptr;
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int p = tid + u * nthreads;
+                key[u] = p < np ? res[p] : 0u;
+                ca[u] = (want_cols && p < np) ? __ldg(q.col_a + p0 + p) : -1;
+                cb[u] = (want_cols && p < np) ? __ldg(q.col_b + p0 + p) : -1;
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int p = tid + u * nthreads;
+                if (p < np) {
+                    const __half d = h_from_bits(key_bits(key[u]));
+                    q.dist[n * q.P + p0 + p] = d;
+                    const __half hv = h_mul(d, __float2half_rn(0.5f));                       // fp16(dist / 2)
+                    if (q.obs) {
+                        const float v = __half2float(hv);
+                        if (ca[u] >= 0) q.obs[n * q.obs_ld + ca[u]] = v;
+                        if (cb[u] >= 0) q.obs[n * q.obs_ld + cb[u]] = v;
+                    }
+                    if (q.obs16) {
+                        if (ca[u] >= 0) q.obs16[n * q.obs16_ld + (ca[u] - q.obs16_col0)] = hv;
+                        if (cb[u] >= 0) q.obs16[n * q.obs16_ld + (cb[u] - q.obs16_col0)] = hv;
+                    }
+                }
+            }
+            return;
+        }
+    }
     for (int p = tid; p < np; p += nthreads) {
         uint32_t key = res[p];
         const bool far_hit = (far[p >> 5] >> (p & 31)) & 1u;

@@ -1048,8 +1048,9 @@ int launch_heightmap_shadow(const rvb_terrain* t, const float* pos, const float*
     q.presorted = 1;
     q.min_sh = 1;                                                            // 2x2-cell bins: 2 % faster than single cells (fewer tasks)
     if (const char* ms = getenv("RVB_SHADOW_SH")) q.min_sh = atoi(ms);      // tuning hook: finest bins to start from
-    q.spec_slot = 15;         // bit 0: slot byte fetched ahead of the literal test, bit 1: L2 prefetch of the records, bit 2: window cull,
-                              // bit 3: triangle ids travel through the queues instead of being re-read from sb_ids
+    q.spec_slot = 31;         // bit 0: slot byte fetched ahead of the literal test, bit 1: L2 prefetch of the records, bit 2: window cull,
+                              // bit 3: triangle ids travel through the queues instead of being re-read from sb_ids, bit 4: the epilogue
+                              // issues all of a thread's loads before its first store (raycast_common.cuh)
     // A/B switch: RVB_SHADOW_BULK = number of heightmap observation columns (1746 for the reference pattern; every
     // one of them must be named by col_a / col_b) -> the row is staged in shared memory and stored by one cp.async.bulk
     q.bulk_obs = 0;
