@@ -351,7 +351,9 @@ def run_b200(args, rank, world, local):
     t_index = time.perf_counter() - t0
     n_sets = 3
     states = [synth.make_env_state(w, N, seed=100 + s, env_offset=rank * N) for s in range(n_sets)]
-    task = synth.make_task(w, states[0], device=str(dev), level=2, num_envs_total=N * world)
+    # compact_terrain: the heightmap layer keeps no K-contiguous copy of the index (rvb_terrain_release_index) -- the production
+    # kernels never read it; `setup.heightmap_layer_gb` is what the layer then holds, `index_gb` the reference's own tensor
+    task = synth.make_task(w, states[0], device=str(dev), level=2, num_envs_total=N * world, compact_terrain=not args.full_layer and args.variant in (0, 3))
     task.env_offset = rank * N
     w.map_indices = w.rock_indices = None          # the layers own K-contiguous copies
     torch.cuda.empty_cache()
@@ -502,6 +504,8 @@ def run_b200(args, rank, world, local):
                       "rock_triangles": int(w.rock_triangles.shape[0]), "stones": int(w.stone_info.shape[0]),
                       "stats_reduction": "compute stream" if args.sync_reduce else "asynchronous, NCCL stream",
                       "device_reset_in_step": device_reset, "cpus_after_numa_binding": numa_cpus,
+                      "heightmap_layer_gb": round(task.Camera.layer.bytes() / 1e9, 3), "heightmap_layer_keeps_index_copy": task.Camera.layer.has_index,
+                      "index_gb": round(w.map_indices.numel() * 4 / 1e9, 3),
                       "resets_per_step": reset_counts[0] / max(args.steps, 1), "goals_drawn_per_step": reset_counts[1] / max(args.steps, 1),
                       "reset_rate": reset_counts[0] / max(args.steps, 1) / N},
             "rays_per_s": value * P_RAYS,
@@ -578,6 +582,7 @@ def main():
     ap.add_argument("--ref-device", default="cpu", help="reference arm: cpu (the baseline) or cuda:0 (its own eager deployment)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-reset", action="store_true", help="leave the device-side reset path out of the step")
+    ap.add_argument("--full-layer", action="store_true", help="the heightmap layer keeps its K-contiguous index copy (+3.2 GB; what the cross-check variants 1 / 2 read)")
     ap.add_argument("--no-numa", action="store_true", help="do not bind the process to the CPUs local to its GPU")
     ap.add_argument("--unfused", action="store_true", help="one library call per reference call instead of rvb_env_step")
     ap.add_argument("--sync-reduce", action="store_true", help="all-reduce the statistics on the compute stream every step")

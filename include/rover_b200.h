@@ -67,6 +67,12 @@ int rvb_terrain_create(rvb_terrain** out,
 int rvb_terrain_destroy(rvb_terrain* t);
 /* bytes of device memory owned by the handle */
 int64_t rvb_terrain_bytes(const rvb_terrain* t);
+/* Gives back the handle's K-contiguous copy of map_indices (G0*G1*K int32 -- the same size as the reference's tensor,
+ * camera.py:154-157; more than half of a layer).  The production heightmap ray-cast (variants 0 and 3 of rvb_heightmap_raycast,
+ * rvb_env_step) never reads it; afterwards variants 1 / 2, rvb_cast_rays and rvb_rock_collision on THIS handle return
+ * RVB_ERR_INVALID.  Needs the block lists (K <= 255).  Synchronises the device.  rvb_terrain_has_index: 1 / 0. */
+int rvb_terrain_release_index(rvb_terrain* t);
+int rvb_terrain_has_index(const rvb_terrain* t);
 
 /* ------------------------------------------------------------------------------------------------
  * Camera.get_depths (utils/camera/camera.py:60-145) = _depth_transform (:165-212) + _height_lookup

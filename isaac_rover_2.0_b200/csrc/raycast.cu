@@ -162,6 +162,7 @@ extern "C" int rvb_heightmap_raycast2(const rvb_terrain* t, const float* pos, co
     RVB_REQUIRE(!obs_h16 || (col_a && col_b && obs_h16_ld > 0 && obs_h16_col0 >= 0), "rvb_heightmap_raycast2: obs_h16 needs col_a, col_b, obs_h16_ld");
     RVB_REQUIRE(variant >= 0 && variant <= 3, "rvb_heightmap_raycast: variant must be 0, 1, 2 or 3");
     RVB_REQUIRE(!obs_h16 || variant != 1, "rvb_heightmap_raycast2: the per-pair cross-check kernel (variant 1) has no packed output");
+    RVB_REQUIRE(variant != 2 || t->index != nullptr, "rvb_heightmap_raycast: variant 2 reads the index the layer released (rvb_terrain_release_index)");
     const RvbObs16 o16v = {obs_h16, obs_h16_ld, obs_h16_col0};
     const RvbObs16* o16 = obs_h16 ? &o16v : nullptr;
     cudaStream_t st = as_stream(stream);
@@ -177,6 +178,7 @@ extern "C" int rvb_heightmap_raycast2(const rvb_terrain* t, const float* pos, co
     if (variant != 1)
         return launch_heightmap_tiled(t, pos, euler, trig, pattern, P, N, dist, hit_slot, hit_tri, pt, sources, obs,
                                       obs_ld, col_a, col_b, variant == 2, o16, st);
+    RVB_REQUIRE(t->index != nullptr, "rvb_heightmap_raycast: variant 1 reads the index the layer released (rvb_terrain_release_index)");
     RVB_REQUIRE(N <= 65535, "rvb_heightmap_raycast: variant 1 handles at most 65535 envs per call");
     __half* src16 = (__half*)sources;
     __half* scratch = nullptr;
@@ -200,6 +202,7 @@ extern "C" int rvb_cast_rays(const rvb_terrain* t, const uint16_t* sources, cons
     RVB_REQUIRE(R >= 0, "rvb_cast_rays: R < 0");
     if (R == 0) return RVB_OK;
     RVB_REQUIRE(t && sources && directions && dist, "rvb_cast_rays: null pointer");
+    RVB_REQUIRE(t->index != nullptr, "rvb_cast_rays: the layer released its index (rvb_terrain_release_index)");
     (void)variant;
     if (R == 0) return RVB_OK;
     cudaStream_t st = as_stream(stream);

@@ -176,6 +176,27 @@ static __device__ __noinline__ uint32_t literal_ray(const int32_t* row, int K, c
     return best;
 }
 
+// The same two look-ups for a layer whose K-contiguous index was released (rvb_terrain_release_index): the K-list of cell
+// (cx, cy) is the set of entries of its 3x3 block's union list whose slot byte for the sub-cell is not 0xFF, and that byte IS the
+// slot.  min() over keys that carry the slot does not depend on the order the candidates are visited in.
+static __device__ __noinline__ uint32_t literal_ray_blk(const int32_t* ids, const uint4* slots, int n, int sub, const TriRec* recs,
+                                                        H3 s, H3 d) {
+    uint32_t best = 0xffffffffu;
+    for (int e = 0; e < n; ++e) {
+        const uint32_t slot = __ldg(reinterpret_cast<const unsigned char*>(slots + e) + sub);
+        if (slot == 0xffu) continue;
+        H3 a, b, c, nn;
+        unpack_rec(recs + __ldg(ids + e), a, b, c, nn);
+        best = min(best, make_key(h_bits(pair_test(s, d, a, b, c, nn)), slot));
+    }
+    return best;
+}
+
+static __device__ __noinline__ int32_t tri_of_slot_blk(const int32_t* ids, const uint4* slots, int n, int sub, int slot) {
+    for (int e = 0; e < n; ++e)
+        if ((int)__ldg(reinterpret_cast<const unsigned char*>(slots + e) + sub) == slot) return __ldg(ids + e);
+    return 0;
+}
 
 // Epilogue in ray order: coalesced stores of dist / hit slot / hit triangle / pt / sources and the fused sparse+dense
 // observation columns (heightmap_distribution.py:126-133, rover.py:324-325).  res[p] = best key of local ray p; a set bit
@@ -244,7 +265,13 @@ __device__ __forceinline__ void epilogue(const TiledParams& q, int64_t n, int p0
             const H3 s = {h_from_double(xo), h_from_double(yo), h_from_double(zo)};
             const int cx = cell_coord(s.x, q.shift_x, q.res, q.inv_res, q.G0 - 1, q.sem);
             const int cy = min(cell_coord(s.y, q.shift_y, q.res, q.inv_res, q.G0 - 1, q.sem), q.G1 - 1);
-            key = literal_ray(q.index + ((int64_t)cx * q.G1 + cy) * q.Ks, q.K, q.recs, s, dlit);
+            if (q.index) {
+                key = literal_ray(q.index + ((int64_t)cx * q.G1 + cy) * q.Ks, q.K, q.recs, s, dlit);
+            } else {
+                const uint32_t bi = (uint32_t)(cx / RVB_BLK) * (uint32_t)q.nBy + (uint32_t)(cy / RVB_BLK);
+                const uint32_t o0 = __ldg(q.blk_off + bi), o1 = __ldg(q.blk_off + bi + 1);
+                key = literal_ray_blk(q.blk_ids + o0, q.blk_slots + o0, (int)(o1 - o0), (cx % RVB_BLK) * RVB_BLK + cy % RVB_BLK, q.recs, s, dlit);
+            }
         }
         const unsigned short kb = key_bits(key);
         const int slot = (int)((key >> 1) & 0x7fffu);
@@ -260,7 +287,13 @@ __device__ __forceinline__ void epilogue(const TiledParams& q, int64_t n, int p0
             if (q.hit_tri) {
                 const int cx = cell_coord(hx, q.shift_x, q.res, q.inv_res, q.G0 - 1, q.sem);
                 const int cy = min(cell_coord(hy, q.shift_y, q.res, q.inv_res, q.G0 - 1, q.sem), q.G1 - 1);
-                q.hit_tri[o] = __ldg(q.index + ((int64_t)cx * q.G1 + cy) * q.Ks + slot);
+                if (q.index) {
+                    q.hit_tri[o] = __ldg(q.index + ((int64_t)cx * q.G1 + cy) * q.Ks + slot);
+                } else {
+                    const uint32_t bi = (uint32_t)(cx / RVB_BLK) * (uint32_t)q.nBy + (uint32_t)(cy / RVB_BLK);
+                    const uint32_t o0 = __ldg(q.blk_off + bi), o1 = __ldg(q.blk_off + bi + 1);
+                    q.hit_tri[o] = tri_of_slot_blk(q.blk_ids + o0, q.blk_slots + o0, (int)(o1 - o0), (cx % RVB_BLK) * RVB_BLK + cy % RVB_BLK, slot);
+                }
             }
             if (q.pt) {
                 const __half k = h_from_bits(kb);

@@ -498,9 +498,31 @@ extern "C" int rvb_terrain_destroy(rvb_terrain* t) {
     return RVB_OK;
 }
 
+// The K-contiguous copy of the index (G0*G1*Ks int32, 3.2 GB on the benchmark world) is what the per-pair cross-check kernel, the
+// rock kernel and rvb_cast_rays read.  The production heightmap ray-cast does not: the shadow and tiled kernels enumerate the block
+// / superblock lists, and the two rare look-ups that went through the index (a ray with a hit beyond 11 m, the optional hit-triangle
+// output) can be answered from the block lists (raycast_common.cuh).  A heightmap layer can therefore give the copy back.
+extern "C" int rvb_terrain_release_index(rvb_terrain* t) {
+    RVB_REQUIRE(t != nullptr, "rvb_terrain_release_index: null handle");
+    if (!t->index) return RVB_OK;
+    RVB_REQUIRE(t->blk_ids != nullptr && t->blk_slots != nullptr,
+                "rvb_terrain_release_index: the layer has no block lists (K > 255), its kernels read the index");
+    int prev = 0;
+    RVB_CUDA(cudaGetDevice(&prev));
+    RVB_CUDA(cudaSetDevice(t->device));
+    cudaError_t e = cudaDeviceSynchronize();          // launches that still read the copy
+    if (e == cudaSuccess) e = cudaFree(t->index);
+    cudaSetDevice(prev);
+    RVB_CUDA(e);
+    t->index = nullptr;
+    return RVB_OK;
+}
+
+extern "C" int rvb_terrain_has_index(const rvb_terrain* t) { return t && t->index ? 1 : 0; }
+
 extern "C" int64_t rvb_terrain_bytes(const rvb_terrain* t) {
     if (!t) return 0;
-    return (int64_t)sizeof(int32_t) * t->G0 * t->G1 * t->Ks + (int64_t)(sizeof(TriRec) + sizeof(S1Rec)) * t->T +
+    return (t->index ? (int64_t)sizeof(int32_t) * t->G0 * t->G1 * t->Ks : 0) + (int64_t)(sizeof(TriRec) + sizeof(S1Rec)) * t->T +
            (t->blk_ids ? (int64_t)(sizeof(uint4) + sizeof(int32_t)) * t->n_ent + (int64_t)sizeof(uint32_t) * ((int64_t)t->nBx * t->nBy + 1) : 0) +
            (t->sb_ids ? (int64_t)(sizeof(int32_t) + sizeof(uint16_t) * RVB_SB * RVB_SB) * t->n_sb_ent + (int64_t)sizeof(uint32_t) * ((int64_t)t->nSBx * t->nSBy + 1) +
                          (int64_t)sizeof(ChunkRec) * ceil_div(t->n_sb_ent > 0 ? t->n_sb_ent : 1, 32) : 0);

@@ -64,10 +64,11 @@ class Memory():
 class RoverTask():
     def __init__(self, rover_view, num_envs, terrain_assets, rock_assets, stone_info, heightmap,
                  device='cuda:0', shift=None, rewards=None, horizontal_scale=0.025, vertical_scale=1,
-                 sem=_lib.SEM_TORCH_CUDA, num_envs_total=None, rover_name="rover_view"):
+                 sem=_lib.SEM_TORCH_CUDA, num_envs_total=None, rover_name="rover_view", compact_terrain=False):
         """terrain_assets / rock_assets: (map_indices [K,G,G], triangles, vertices) of knn_terrain / knn_rocks
         (None -> loaded from the reference's relative paths); stone_info f32 [S,7] (read_stone_info);
-        heightmap f32 [H,H] (heightmap_tensor.pt, rover.py:210)."""
+        heightmap f32 [H,H] (heightmap_tensor.pt, rover.py:210).
+        compact_terrain: the heightmap layer gives back its copy of the index (Camera(compact=True)): same step, 3.2 GB less."""
         self._lib = _lib.load()
         self._device = device
         self._rover = rover_view
@@ -76,7 +77,7 @@ class RoverTask():
         self.num_envs_total = num_envs if num_envs_total is None else num_envs_total
         self.sem = sem
         self.shift = torch.tensor([0, 0, 0.0], device=device) if shift is None else shift.to(device)
-        self.Camera = Camera(device, self.shift, debug=False, assets=terrain_assets, sem=sem)
+        self.Camera = Camera(device, self.shift, debug=False, assets=terrain_assets, sem=sem, compact=compact_terrain)
         self.num_exteroceptive = self.Camera.get_num_exteroceptive()
         self.Rock_detector = Rock_Detection(device, self.shift, debug=False, assets=rock_assets, sem=sem)
         self.global_step = 0

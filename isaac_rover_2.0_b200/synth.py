@@ -271,7 +271,7 @@ class SyntheticRoverView:
         self.velocity_targets = velocities
 
 
-def make_task(world, st, device="cuda:0", level=2, sem=0, num_envs_total=None):
+def make_task(world, st, device="cuda:0", level=2, sem=0, num_envs_total=None, compact_terrain=False):
     """RoverTask mirror wired to a SyntheticRoverView holding the env state `st` (make_env_state)."""
     from .rover import RoverTask
     from .terrain_utils import stone_info_from_array
@@ -281,7 +281,7 @@ def make_task(world, st, device="cuda:0", level=2, sem=0, num_envs_total=None):
     task = RoverTask(view, N, (world.map_indices, world.triangles, world.vertices),
                      (world.rock_indices, world.rock_triangles, world.rock_vertices),
                      stone_info_from_array(world.stone_info.numpy(), device=dev), world.heightmap, device=device,
-                     horizontal_scale=world.hm_res, sem=sem, num_envs_total=num_envs_total)
+                     horizontal_scale=world.hm_res, sem=sem, num_envs_total=num_envs_total, compact_terrain=compact_terrain)
     task.curriculum_level = level
     task.target_positions = st["target"].to(dev).clone()
     task.progress_buf = st["progress"].to(dev).clone()

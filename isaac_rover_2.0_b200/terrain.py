@@ -47,6 +47,15 @@ class TerrainLayer:
     def bytes(self):
         return int(self._lib.rvb_terrain_bytes(self.handle))
 
+    def release_index(self):
+        """Frees the handle's K-contiguous index copy (more than half of the layer).  The production heightmap ray-cast does not
+        read it; the per-pair cross-check variants, `cast_rays` and the rock kernel do and raise on this layer afterwards."""
+        _lib.check(self._lib.rvb_terrain_release_index(self.handle))
+
+    @property
+    def has_index(self):
+        return bool(self._lib.rvb_terrain_has_index(self.handle))
+
     def close(self):
         if getattr(self, "_h", None) is not None:
             self._lib.rvb_terrain_destroy(self._h)

@@ -392,6 +392,50 @@ def test_edge_cases(R, O, world20):
         R.Ackermann(torch.zeros(4), torch.zeros(4))
 
 
+def test_compact_layer_matches_full_layer(R, O, world20):
+    """rvb_terrain_release_index: a heightmap layer without its K-contiguous index copy returns the same distances, hit slots,
+    hit triangles and points -- including the two look-ups that went through the index (a ray whose only hit lies beyond the
+    11 m miss sentinel, the hit-triangle output) -- and refuses the entry points that need the copy."""
+    w = world20
+    assets = (w.map_indices, w.triangles, w.vertices)
+    full = R.Camera("cuda:0", torch.tensor([0, 0, 0.0]), assets=assets)
+    lean = R.Camera("cuda:0", torch.tensor([0, 0, 0.0]), assets=assets, compact=True)
+    G, K = w.map_indices.shape[1], w.map_indices.shape[0]
+    assert full.layer.has_index and not lean.layer.has_index
+    assert full.layer.bytes() - lean.layer.bytes() == 4 * G * G * ((K + 1) // 2 * 2)
+    st = {k: v.cuda() for k, v in R.synth.make_env_state(w, 509, seed=31).items()}
+    pos, eul = st["pos"].clone(), R.tensor_quat_to_eul(st["quat"]).clone()
+    # envs 11 .. 45 m above the mesh (hits beyond the sentinel; camera.py:121-127 keeps the first slot <= 11.0), outside the map
+    # and upside down
+    pos[:40, 2] += torch.linspace(10.5, 45.0, 40, device="cuda")
+    eul[:40, :2] = 0                      # level: the rays point straight down and hit inside their own cell's list
+    pos[40:44] = torch.tensor([[-5.0, -5.0, 1.0], [30.0, 3.0, 1.0], [10.0, 10.0, 0.8], [0.0, 19.99, 0.5]], device="cuda")
+    eul[41:44] = torch.tensor([[0.1, -0.1, 2.0], [3.1, 0.0, 0.0], [1.2, -1.2, -3.0]], device="cuda")
+    for variant in (0, 3):
+        full.variant = lean.variant = variant
+        d0, pt0, s0 = full.get_depths(pos, eul, want_hits=True)
+        slot0, tri0 = full.last_hit_slot.clone(), full.last_hit_tri.clone()
+        d1, pt1, s1 = lean.get_depths(pos, eul, want_hits=True)
+        assert torch.equal(bits(d0), bits(d1)) and torch.equal(bits(pt0), bits(pt1)) and torch.equal(bits(s0), bits(s1))
+        assert torch.equal(slot0, lean.last_hit_slot) and torch.equal(tri0, lean.last_hit_tri)
+    far = (pos[:, 2] > 20).nonzero().flatten()
+    assert (d0[far] == 11).all() and (slot0[far] > 0).any()          # the far-hit walk ran and did not just return slot 0
+    for variant in (1, 2):
+        lean.variant = variant
+        with pytest.raises(RuntimeError, match="released"):
+            lean.get_depths(pos, eul)
+    with pytest.raises(RuntimeError, match="released"):
+        R.cast_rays(lean.layer, s0.reshape(-1, 3)[:64], s0.reshape(-1, 3)[:64])
+    lean.layer.release_index()                                          # idempotent
+    # the whole fused step on a compact heightmap layer
+    st = R.synth.make_env_state(w, 256, seed=8, margin=3.0)
+    a = R.synth.make_task(w, st, level=2)
+    b = R.synth.make_task(w, st, level=2, compact_terrain=True)
+    ra, rb = a.hot_step(st["actions"].cuda()), b.hot_step(st["actions"].cuda())
+    assert torch.equal(ra[0], rb[0]) and torch.equal(ra[1], rb[1]) and torch.equal(ra[2], rb[2])
+    assert not b.Camera.layer.has_index and b.Rock_detector.layer.has_index
+
+
 def test_full_size_properties(R, world20):
     """4096 envs: variant 0 == variant 1 bit for bit, determinism, translation of the same env set."""
     w = world20
