@@ -42,7 +42,7 @@ def raycast_hash():
     that kernel) is tied to -- bench.py quotes the capture only for the build it was taken from."""
     import hashlib
     h = hashlib.sha256(" ".join(NVCC_FLAGS).encode())
-    for f in ("common.cuh", "raycast_common.cuh", "raycast_shadow.cu", "raycast_tiled.cu"):
+    for f in ("common.cuh", "raycast_common.cuh", "shadow_bounds.cuh", "raycast_shadow.cu", "raycast_tiled.cu"):
         h.update(f.encode())
         with open(os.path.join(CSRC, f), "rb") as fh:
             h.update(fh.read())

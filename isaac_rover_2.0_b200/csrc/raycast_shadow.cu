@@ -38,6 +38,7 @@
 #include <string.h>
 
 #include "raycast_common.cuh"
+#include "shadow_bounds.cuh"
 
 int fill_tiled_params(const rvb_terrain* t, const float* pos, const float* euler, const float* trig, const double* pattern,
                       int64_t P, int64_t N, uint16_t* dist, int32_t* hit_slot, int32_t* hit_tri, uint16_t* pt,
@@ -67,14 +68,6 @@ constexpr int ILL_CAP = 128;        // triangles without a bound ("ill": fp16 de
                                    // per tile; a mesh finer than the fp16 grid of its coordinates has hundreds)
 constexpr int RT_SMALL = 1664;      // ray capacity of the 4-CTAs-per-SM instantiation (the reference pattern has 1634 rays)
 
-constexpr float GAMMA = 0.00390625f;            // 2^-8
-constexpr float ALPHA = 1.9073486328125e-06f;   // 2^-19
-constexpr float EPS0 = 0.1057f;
-constexpr float L_CAP = 64.0f;
-constexpr float OVF = 16000.0f;
-constexpr float SQ3 = 1.7320509f;
-constexpr float LIN_SLACK = 1.0005f;            // stage 3L: fp32 evaluation of N*, M* (error <= 2^-13 of E_N, E_M) + threshold sums
-
 struct Item {
     uint32_t list_off, list_len;
     float rlox, rhix, rloy, rhiy;   // rectangle holding the sources of the superblock's rays
@@ -82,13 +75,6 @@ struct Item {
     uint32_t by;
 };
 static_assert(sizeof(Item) == 32, "Item");
-
-struct EnvC {
-    float dx, dy, dz;               // d = -normalize(dir) as the reference rounds it (fp16 values)
-    float nux, nuy, nuz;            // normal of the source plane
-    float inv_nd, hmid, hlo, hhi;   // nu . s in [hlo, hhi] for every source of the tile
-    float kappa, lam, dn, smax;
-};
 
 struct Smem {
     uint2* rays;         // [RT]  sorted by block: (sx | sy << 16, sz | (p | sub << 11) << 16)
@@ -112,8 +98,6 @@ __host__ __device__ inline size_t shadow_smem_bytes(int RT) {       // RT = ray 
            (size_t)(ITEM_CAP + 4) * 4 + (size_t)CHUNK_CAP * 3 + (size_t)NW * (QCAP * (8 + 16 + 4 + 4) + QCAP3 * (4 + 4)) + (size_t)(((RT + 31) / 32 + 3) & ~3) * 4;
 }
 
-__device__ __forceinline__ float rcp_up(float x) { return __fdividef(1.0f, x) * 1.000001f; }
-__device__ __forceinline__ float hf(uint32_t bits16) { return __half2float(__ushort_as_half((unsigned short)bits16)); }
 // bins are u16 pairs packed into the u32 words the histogram's atomicAdd works on (little endian: even bin = low half)
 __device__ __forceinline__ uint32_t off16(const uint32_t* bins, int bin) { return reinterpret_cast<const unsigned short*>(bins)[bin]; }
 
@@ -142,76 +126,6 @@ __device__ __forceinline__ void ffma2(float& d0, float& d1, float a0, float a1, 
         "fma.rn.f32x2 rc, ra, rb, rc;\n\tmov.b64 {%0, %1}, rc;\n\t}"
         : "+f"(d0), "+f"(d1)
         : "f"(a0), "f"(a1), "f"(b));
-}
-
-// Stage 1 (tests/shadow_proto.py: stage1).  Returns false if no source inside the rectangle can pass; gball >= |s - a|
-// for every passing source (+inf: no bound, the caller must test every ray of the item).
-__device__ __forceinline__ bool stage1(const uint4& s0, const uint4& s1, const EnvC& e, float rlox, float rhix, float rloy, float rhiy, float& gball) {
-    // S1Rec (common.cuh): centroid, radius, b x c, magnitudes -- computed once per layer by build_records_kernel (terrain.cu)
-    const float qx0 = __uint_as_float(s0.x), qy0 = __uint_as_float(s0.y), qz0 = __uint_as_float(s0.z), r = __uint_as_float(s0.w);
-    const float nx = __uint_as_float(s1.x), ny = __uint_as_float(s1.y), nz = __uint_as_float(s1.z);
-    const float cb = hf(s1.w & 0xffffu), amax = hf(s1.w >> 16);
-    const float adet = fabsf(fmaf(nx, e.dx, fmaf(ny, e.dy, nz * e.dz)));
-    const float e_det = GAMMA * 6.1f * cb * cb + ALPHA;
-    const float rdet = rcp_up(adet);
-    const float eps0 = EPS0 + 1.3f * (e_det + 4.0f * ALPHA) * rdet;
-    const float rho = GAMMA * 2.01f * cb * rdet;
-    const float tc = (e.hmid - fmaf(qx0, e.nux, fmaf(qy0, e.nuy, qz0 * e.nuz))) * e.inv_nd;
-    const float atc = fabsf(tc) * e.dn;
-    const float kr = e.kappa * r;
-    const float Bn = SQ3 * (kr * (1.0f + 3.0f * eps0) + e.lam + atc + r);
-    const float den = 1.0f - 10.4f * kr * rho;
-    const float gsum = Bn * rcp_up(den);
-    const float eps = eps0 + 2.0f * rho * gsum;
-    const float R = kr * (1.0f + 3.0f * eps) + e.lam;
-    const bool fine = (den > 0.5f) && (adet > 4.0f * e_det) && (eps <= 16.0f) && ((e.smax + amax) * fmaxf(cb, 1.0f) <= OVF);
-    if (!fine) {                     // also every NaN case
-        gball = __int_as_float(0x7f800000);
-        return true;
-    }
-    gball = R + atc + r;
-    const float qx = fmaf(tc, e.dx, qx0), qy = fmaf(tc, e.dy, qy0);
-    const float Rs = R * 1.00001f + 1e-5f * (fabsf(qx) + fabsf(qy));
-    const bool out = (qx + Rs < rlox) || (qx - Rs > rhix) || (qy + Rs < rloy) || (qy - Rs > rhiy);
-    return !out;
-}
-
-// Window cull (tests/shadow_proto.py: chunk_cull): true = stage 1 would reject EVERY triangle whose record went into `c` for this
-// rectangle, so the window's 32 list entries need not be enumerated.  Stage 1's formulas on the window's worst-case inputs
-// (every quantity is monotone in them); any NaN makes a comparison false and the window is kept.
-__device__ __forceinline__ bool chunk_cull(const ChunkRec& c, const EnvC& e, float rlox, float rhix, float rloy, float rhiy, float& overlap) {
-    overlap = 1.0f;          // fraction of the window's (expanded) footprint that lies inside the rectangle: a cost proxy only
-    const float lo = fminf(c.nxlo * e.dx, c.nxhi * e.dx) + fminf(c.nylo * e.dy, c.nyhi * e.dy) + fminf(c.nzlo * e.dz, c.nzhi * e.dz);
-    const float hi = fmaxf(c.nxlo * e.dx, c.nxhi * e.dx) + fmaxf(c.nylo * e.dy, c.nyhi * e.dy) + fmaxf(c.nzlo * e.dz, c.nzhi * e.dz);
-    float adet = fmaxf(lo, -hi);                                 // |n . d| >= adet for every triangle of the window
-    adet = adet * 0.99999f - 1e-7f * (fabsf(lo) + fabsf(hi));
-    if (!(adet > 0.0f) || !(c.x0 == c.x0)) return false;
-    const float e_det = GAMMA * 6.1f * c.cbmax * c.cbmax + ALPHA;
-    const float rdet = rcp_up(adet) * 1.0001f;
-    const float eps0 = EPS0 + 1.3f * (e_det + 4.0f * ALPHA) * rdet;
-    const float rho = GAMMA * 2.01f * c.cbmax * rdet;
-    const float hl = fminf(e.nux * c.x0, e.nux * c.x1) + fminf(e.nuy * c.y0, e.nuy * c.y1) + fminf(e.nuz * c.z0, e.nuz * c.z1);
-    const float hh = fmaxf(e.nux * c.x0, e.nux * c.x1) + fmaxf(e.nuy * c.y0, e.nuy * c.y1) + fmaxf(e.nuz * c.z0, e.nuz * c.z1);
-    const float slh = 1e-6f * (fabsf(hl) + fabsf(hh)) + 1e-7f;
-    const float ta = (e.hmid - (hl - slh)) * e.inv_nd, tb = (e.hmid - (hh + slh)) * e.inv_nd;
-    const float tlo = fminf(ta, tb), thi = fmaxf(ta, tb);
-    const float atc = fmaxf(fabsf(tlo), fabsf(thi)) * e.dn;
-    const float kr = e.kappa * c.rmax;
-    const float Bn = SQ3 * (kr * (1.0f + 3.0f * eps0) + e.lam + atc + c.rmax);
-    const float den = 1.0f - 10.4f * kr * rho;
-    if (!(den > 0.5f)) return false;
-    const float gsum = Bn * rcp_up(den) * 1.0001f;
-    const float eps = eps0 + 2.0f * rho * gsum;
-    const bool fine = (adet > 4.0f * e_det) && (eps <= 16.0f) && ((e.smax + c.amax) * fmaxf(c.cbmax, 1.0f) <= OVF);
-    if (!fine) return false;
-    const float R = (kr * (1.0f + 3.0f * eps) + e.lam) * 1.0001f;
-    const float qxl = c.x0 + fminf(tlo * e.dx, thi * e.dx), qxh = c.x1 + fmaxf(tlo * e.dx, thi * e.dx);
-    const float qyl = c.y0 + fminf(tlo * e.dy, thi * e.dy), qyh = c.y1 + fmaxf(tlo * e.dy, thi * e.dy);
-    const float Rs = R * 1.00001f + 1.1e-5f * (fmaxf(fabsf(qxl), fabsf(qxh)) + fmaxf(fabsf(qyl), fabsf(qyh))) + 1e-5f;
-    const float ex0 = qxl - Rs, ex1 = qxh + Rs, ey0 = qyl - Rs, ey1 = qyh + Rs;
-    const float ox = fminf(ex1, rhix) - fmaxf(ex0, rlox), oy = fminf(ey1, rhiy) - fmaxf(ey0, rloy);
-    overlap = fminf(fmaxf(ox, 0.0f) * fmaxf(oy, 0.0f) * __fdividef(1.0f, (ex1 - ex0) * (ey1 - ey0)), 1.0f);
-    return (qxh + Rs < rlox) || (qxl - Rs > rhix) || (qyh + Rs < rloy) || (qyl - Rs > rhiy);
 }
 
 // positive fp32 (or +inf) -> its upper 16 bits, rounded up

@@ -22,7 +22,7 @@ def test_shadow_bounds_are_conservative(args):
 
 
 def test_constants_match_kernel():
-    src = open(os.path.join(ROOT, "isaac_rover_2.0_b200", "csrc", "raycast_shadow.cu")).read()
+    src = "".join(open(os.path.join(ROOT, "isaac_rover_2.0_b200", "csrc", f)).read() for f in ("shadow_bounds.cuh", "raycast_shadow.cu"))
     for needle in ("GAMMA = 0.00390625f", "ALPHA = 1.9073486328125e-06f", "EPS0 = 0.1057f", "L_CAP = 64.0f", "OVF = 16000.0f",
                    "0x2E68u", "0x3C6Bu"):
         assert needle in src, needle
