@@ -397,6 +397,9 @@ policy_l1_tc_kernel(const PolicyDev* __restrict__ p0, const PolicyDev* __restric
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = tmem_base_s;
+    // programmatic dependent launch: the tail kernel's CTAs may be scheduled from here on (they allocate TMEM, initialise their
+    // barriers and start streaming their weight images, then wait for THIS grid to complete before they read h1)
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
     if (warp < 8) {
         // ---- loaders: warp w owns rows [16 w, 16 w + 16) of the tile, four rows per pass: lane = (row of the pass, 16-byte column
@@ -705,7 +708,9 @@ policy_tail_tc_kernel(const PolicyDev* __restrict__ p0, const PolicyDev* __restr
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             ++pass;
         };
-        // P0 / P1: the first encoder layers (policy_l1_tc_kernel's output) -> operand of the second ones
+        // P0 / P1: the first encoder layers (policy_l1_tc_kernel's output) -> operand of the second ones.  Launched as a programmatic
+        // dependent of that kernel: everything above ran beside its last CTAs; its results are visible after this wait.
+        asm volatile("griddepcontrol.wait;" ::: "memory");
         const float* hrow = h1 + (live ? row : 0) * (2 * PL_E1 * h1_nets) + (int)blockIdx.y * PL_E1;
         for (int enc = 0; enc < 2; ++enc) {
             if (enc) wait_pass();
@@ -965,6 +970,23 @@ static int check_forward(const rvb_policy* P, const float* obs, int64_t obs_ld, 
     return RVB_OK;
 }
 
+// The tail kernel as a programmatic dependent of the first-layer kernel in front of it on `st` (RVB_POLICY_PDL=0: plain launch).
+static cudaError_t launch_tail_tc(dim3 grid, cudaStream_t st, const PolicyDev* a, const PolicyDev* b, const float* obs, int64_t obs_ld,
+                                  int64_t N, const float* h1, int nets, float* out0, int64_t out0_ld, float* out1, int64_t out1_ld) {
+    static const bool pdl = !(getenv("RVB_POLICY_PDL") && atoi(getenv("RVB_POLICY_PDL")) == 0);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3(TT_THREADS);
+    cfg.dynamicSmemBytes = tt_smem_bytes();
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, policy_tail_tc_kernel, a, b, obs, obs_ld, N, h1, nets, out0, out0_ld, out1, out1_ld);
+}
+
 extern "C" int rvb_policy_forward(const rvb_policy* P, const float* obs, int64_t obs_ld, int64_t N, float* out, int64_t out_ld,
                                   void* stream) {
     RVB_REQUIRE(P, "rvb_policy_forward: null handle");
@@ -981,8 +1003,7 @@ extern "C" int rvb_policy_forward(const rvb_policy* P, const float* obs, int64_t
     }
     const bool tc_tail = h1 && !(getenv("RVB_TC_TAIL") && atoi(getenv("RVB_TC_TAIL")) == 0);      // A/B switch: FFMA tail after the TC first layers
     if (tc_tail)
-        policy_tail_tc_kernel<<<dim3((unsigned)ceil_div(N, TC_M), 1), TT_THREADS, tt_smem_bytes(), st>>>(P->dev, nullptr, obs, obs_ld, N, h1, 1, out,
-                                                                                                  out_ld, nullptr, 0);
+        launch_tail_tc(dim3((unsigned)ceil_div(N, TC_M), 1), st, P->dev, nullptr, obs, obs_ld, N, h1, 1, out, out_ld, nullptr, 0);
     else
         kern<<<dim3((unsigned)ceil_div(N, PL_TM), 1), PL_THREADS, PL_SMEM_BYTES, st>>>(P->dev, nullptr, obs, obs_ld, N, out, out_ld, nullptr, 0, h1, 1);
     const cudaError_t le = cudaGetLastError();
@@ -1012,8 +1033,7 @@ extern "C" int rvb_policy_forward_pair(const rvb_policy* A, const rvb_policy* B,
     }
     const bool tc_tail = h1 && !(getenv("RVB_TC_TAIL") && atoi(getenv("RVB_TC_TAIL")) == 0);
     if (tc_tail)
-        policy_tail_tc_kernel<<<dim3((unsigned)ceil_div(N, TC_M), 2), TT_THREADS, tt_smem_bytes(), st>>>(A->dev, B->dev, obs, obs_ld, N, h1, 2, out_a,
-                                                                                                  out_a_ld, out_b, out_b_ld);
+        launch_tail_tc(dim3((unsigned)ceil_div(N, TC_M), 2), st, A->dev, B->dev, obs, obs_ld, N, h1, 2, out_a, out_a_ld, out_b, out_b_ld);
     else
         kern<<<dim3((unsigned)ceil_div(N, PL_TM), 2), PL_THREADS, PL_SMEM_BYTES, st>>>(A->dev, B->dev, obs, obs_ld, N, out_a, out_a_ld, out_b, out_b_ld,
                                                                                        h1, 2);
