@@ -384,14 +384,21 @@ static int build_block_lists(rvb_terrain* t, cudaStream_t st) {
     t->nBy = (int32_t)ceil_div(t->G1, RVB_BLK);
     const int64_t nb = (int64_t)t->nBx * t->nBy;
     if (t->K > 255 || nb >= ((int64_t)1 << 31)) return RVB_OK;      // per-cell path only
-    uint32_t* counts = nullptr;
+    // temporaries of this function: freed on every exit, the early error returns included (the handle's own arrays are freed by
+    // rvb_terrain_create when this function fails)
+    struct Tmp {
+        uint32_t* counts = nullptr;
+        void* scan = nullptr;
+        ~Tmp() { cudaFree(scan); cudaFree(counts); }
+    } tm;
+    uint32_t*& counts = tm.counts;
+    void*& tmp = tm.scan;
     RVB_CUDA(cudaMalloc(&t->blk_off, sizeof(uint32_t) * (nb + 1)));
     RVB_CUDA(cudaMalloc(&counts, sizeof(uint32_t) * (nb + 1)));
     RVB_CUDA(cudaMemsetAsync(counts, 0, sizeof(uint32_t) * (nb + 1), st));
     build_blocks_kernel<<<(unsigned)nb, BLK_THREADS, 0, st>>>(t->index, (int)t->G0, (int)t->G1, (int)t->K, (int)t->Ks, t->nBy, nullptr,
                                                              counts, nullptr, nullptr);
     RVB_LAUNCH_CHECK();
-    void* tmp = nullptr;
     size_t tmp_bytes = 0;
     cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, counts, t->blk_off, (int)(nb + 1), st);
     RVB_CUDA(cudaMalloc(&tmp, tmp_bytes));
@@ -399,8 +406,6 @@ static int build_block_lists(rvb_terrain* t, cudaStream_t st) {
     uint32_t total = 0;
     RVB_CUDA(cudaMemcpyAsync(&total, t->blk_off + nb, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
     RVB_CUDA(cudaStreamSynchronize(st));
-    cudaFree(tmp);
-    cudaFree(counts);
     t->n_ent = total;
     RVB_CUDA(cudaMalloc(&t->blk_ids, sizeof(int32_t) * (size_t)(total > 0 ? total : 1)));
     RVB_CUDA(cudaMalloc(&t->blk_slots, sizeof(uint4) * (size_t)(total > 0 ? total : 1)));
