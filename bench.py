@@ -505,7 +505,7 @@ def run_b200(args, rank, world, local):
                       "stats_reduction": "compute stream" if args.sync_reduce else "asynchronous, NCCL stream",
                       "device_reset_in_step": device_reset, "cpus_after_numa_binding": numa_cpus,
                       "heightmap_layer_gb": round(task.Camera.layer.bytes() / 1e9, 3), "heightmap_layer_keeps_index_copy": task.Camera.layer.has_index,
-                      "index_gb": round(w.K * w.G * w.G * 4 / 1e9, 3),
+                      "index_gb": round(w.K * w.G * w.G * 4 / 1e9, 3), "rock_layer_gb": round(task.Rock_detector.layer.bytes() / 1e9, 3),
                       "resets_per_step": reset_counts[0] / max(args.steps, 1), "goals_drawn_per_step": reset_counts[1] / max(args.steps, 1),
                       "reset_rate": reset_counts[0] / max(args.steps, 1) / N},
             "rays_per_s": value * P_RAYS,

@@ -64,6 +64,19 @@ int rvb_terrain_create(rvb_terrain** out,
                        const uint16_t* vertices, int64_t V,
                        float res, float shift_x, float shift_y,
                        int sem, void* stream);
+/* flags (rvb_terrain_create2; rvb_terrain_create = flags 0):
+ *   RVB_LAYER_INDEX_ONLY  build the K-contiguous index and the triangle records only, not the block / superblock lists of the
+ *                         heightmap ray-cast's production kernels: the layer of a Rock_Detection (rock_detect.py:151-158), whose
+ *                         kernel scans the K-lists themselves -- 3.2 GB instead of 6 GB for the reference's rock index.
+ *                         rvb_heightmap_raycast on such a layer runs the per-cell kernels (variants 1 / 2 and what 0 / 3 fall back to). */
+#define RVB_LAYER_INDEX_ONLY 1
+int rvb_terrain_create2(rvb_terrain** out,
+                        const int32_t* map_indices, int64_t G0, int64_t G1, int64_t K,
+                        int64_t stride_g0, int64_t stride_g1, int64_t stride_k,
+                        const int32_t* triangles, int64_t T,
+                        const uint16_t* vertices, int64_t V,
+                        float res, float shift_x, float shift_y,
+                        int sem, int flags, void* stream);
 int rvb_terrain_destroy(rvb_terrain* t);
 /* bytes of device memory owned by the handle */
 int64_t rvb_terrain_bytes(const rvb_terrain* t);

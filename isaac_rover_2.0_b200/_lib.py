@@ -13,6 +13,7 @@ _lib = None
 
 SEM_TORCH_CUDA = 0
 SEM_TORCH_CPU = 1
+LAYER_INDEX_ONLY = 1          # rvb_terrain_create2 flag
 N_STATS = 16
 
 p = C.c_void_p
@@ -50,6 +51,7 @@ _SIGNATURES = {
     "rvb_last_error": (C.c_char_p, []),
     "rvb_terrain_create": (C.c_int, [C.POINTER(p), p, i64, i64, i64, i64, i64, i64, p, i64, p, i64, f32, f32, f32, C.c_int, p]),
     "rvb_terrain_destroy": (C.c_int, [p]),
+    "rvb_terrain_create2": (C.c_int, [C.POINTER(p), p, i64, i64, i64, i64, i64, i64, p, i64, p, i64, f32, f32, f32, C.c_int, C.c_int, p]),
     "rvb_terrain_bytes": (i64, [p]),
     "rvb_terrain_release_index": (C.c_int, [p]),
     "rvb_terrain_has_index": (C.c_int, [p]),
@@ -95,7 +97,7 @@ def lib_path():
 
 
 # kernels launched per entry point (for bench.py's `gpu_launches` claim)
-KERNELS_PER_CALL = {"rvb_terrain_create": 2, "rvb_heightmap_raycast": 4, "rvb_heightmap_raycast2": 4, "rvb_cast_rays": 2, "rvb_ray_distance": 1,
+KERNELS_PER_CALL = {"rvb_terrain_create": 2, "rvb_terrain_create2": 2, "rvb_heightmap_raycast": 4, "rvb_heightmap_raycast2": 4, "rvb_cast_rays": 2, "rvb_ray_distance": 1,
                     "rvb_rock_collision": 1, "rvb_rock_collision2": 1, "rvb_check_collision": 1, "rvb_quat_to_euler": 1, "rvb_ackermann": 1,
                     "rvb_history_push": 1, "rvb_obs_proprio": 1, "rvb_obs_gather": 1, "rvb_reward_reset": 2, "rvb_env_step": 8,
     "rvb_stone_validate": 1, "rvb_spawn_validate": 1, "rvb_height_lookup": 1, "rvb_build_knn_index": 6, "rvb_reset_targets": 1,

@@ -18,7 +18,8 @@ class Rock_Detection():
         if assets is None:
             assets = tuple(torch.load(ASSET_DIR + f) for f in ("map_indices.pt", "triangles.pt", "vertices.pt"))
         mi, tri, ver = assets
-        self.layer = TerrainLayer(mi, tri, ver, shift, res=self.horizontal, device=device, sem=sem)
+        # the rock kernel scans the K-lists themselves: no block / superblock lists for this layer
+        self.layer = TerrainLayer(mi, tri, ver, shift, res=self.horizontal, device=device, sem=sem, index_only=True)
         self.rock_indices = mi.to(device).swapaxes(0, 1).swapaxes(1, 2)
         self.triangles = tri.to(device)
         self.vertices = ver.to(device)

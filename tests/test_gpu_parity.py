@@ -434,6 +434,9 @@ def test_compact_layer_matches_full_layer(R, O, world20):
     ra, rb = a.hot_step(st["actions"].cuda()), b.hot_step(st["actions"].cuda())
     assert torch.equal(ra[0], rb[0]) and torch.equal(ra[1], rb[1]) and torch.equal(ra[2], rb[2])
     assert not b.Camera.layer.has_index and b.Rock_detector.layer.has_index
+    # the rock layer is built without the lists of the heightmap kernels (RVB_LAYER_INDEX_ONLY): index + two 32-byte records per triangle
+    rl = b.Rock_detector.layer
+    assert rl.bytes() == 4 * rl.G0 * rl.G1 * ((rl.K + 1) // 2 * 2) + 64 * rl.T
 
 
 def test_full_size_properties(R, world20):
