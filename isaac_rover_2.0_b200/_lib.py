@@ -138,7 +138,8 @@ def load():
                 raise RuntimeError("librover_b200.so is stale and its sources do not compile: %s" % e)
             import warnings                         # no compiler on this box: a present library is still usable, but say so
             warnings.warn("librover_b200.so is older than its sources and could not be rebuilt (%s); using it as is" % e)
-    raw = C.CDLL(_build.LIB)
+    # ROVER_B200_LIB: another build of the same ABI (same-box A/B of two builds; tools/shadow_quick.py)
+    raw = C.CDLL(os.environ.get("ROVER_B200_LIB") or _build.LIB)
     lib = _Lib()
     for name, (res, args) in _SIGNATURES.items():
         fn = getattr(raw, name)                     # AttributeError here = ABI mismatch, fail loudly
