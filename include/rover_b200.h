@@ -86,6 +86,10 @@ int64_t rvb_terrain_bytes(const rvb_terrain* t);
  * RVB_ERR_INVALID.  Needs the block lists (K <= 255).  Synchronises the device.  rvb_terrain_has_index: 1 / 0. */
 int rvb_terrain_release_index(rvb_terrain* t);
 int rvb_terrain_has_index(const rvb_terrain* t);
+/* Triangles of the layer whose fp16 determinant is within rounding of zero even for a vertical ray (zero area, edge-on): the shadow
+ * kernel has no culling bound for them.  More than 2 % of T => variant 0 of rvb_heightmap_raycast runs the tiled kernel for the
+ * whole layer; fewer => a tile that meets more than 128 of them is handed to the tiled kernel.  Results never depend on it. */
+int64_t rvb_terrain_unbounded_triangles(const rvb_terrain* t);
 
 /* ------------------------------------------------------------------------------------------------
  * Camera.get_depths (utils/camera/camera.py:60-145) = _depth_transform (:165-212) + _height_lookup

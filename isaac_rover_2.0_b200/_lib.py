@@ -55,6 +55,7 @@ _SIGNATURES = {
     "rvb_terrain_bytes": (i64, [p]),
     "rvb_terrain_release_index": (C.c_int, [p]),
     "rvb_terrain_has_index": (C.c_int, [p]),
+    "rvb_terrain_unbounded_triangles": (i64, [p]),
     "rvb_heightmap_raycast": (C.c_int, [p, p, p, p, p, i64, i64, p, p, p, p, p, p, i64, p, p, C.c_int, p]),
     "rvb_heightmap_raycast2": (C.c_int, [p, p, p, p, p, i64, i64, p, p, p, p, p, p, i64, p, i64, C.c_int, p, p, C.c_int, p]),
     "rvb_cast_rays": (C.c_int, [p, p, p, i64, p, p, p, p, C.c_int, p]),

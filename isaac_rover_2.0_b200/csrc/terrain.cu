@@ -534,6 +534,8 @@ extern "C" int rvb_terrain_release_index(rvb_terrain* t) {
 
 extern "C" int rvb_terrain_has_index(const rvb_terrain* t) { return t && t->index ? 1 : 0; }
 
+extern "C" int64_t rvb_terrain_unbounded_triangles(const rvb_terrain* t) { return t ? (int64_t)t->n_ill : 0; }
+
 extern "C" int64_t rvb_terrain_bytes(const rvb_terrain* t) {
     if (!t) return 0;
     return (t->index ? (int64_t)sizeof(int32_t) * t->G0 * t->G1 * t->Ks : 0) + (int64_t)(sizeof(TriRec) + sizeof(S1Rec)) * t->T +

@@ -60,6 +60,11 @@ class TerrainLayer:
     def has_index(self):
         return bool(self._lib.rvb_terrain_has_index(self.handle))
 
+    @property
+    def unbounded_triangles(self):
+        """Triangles the shadow kernel has no culling bound for (rvb_terrain_unbounded_triangles)."""
+        return int(self._lib.rvb_terrain_unbounded_triangles(self.handle))
+
     def close(self):
         if getattr(self, "_h", None) is not None:
             self._lib.rvb_terrain_destroy(self._h)

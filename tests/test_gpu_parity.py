@@ -439,6 +439,42 @@ def test_compact_layer_matches_full_layer(R, O, world20):
     assert rl.bytes() == 4 * rl.G0 * rl.G1 * ((rl.K + 1) // 2 * 2) + 64 * rl.T
 
 
+@pytest.mark.parametrize("patch,route", [(2.0, "tiles"), (4.6, "layer")])
+def test_degenerate_triangles_take_the_exact_paths(R, patch, route, monkeypatch):
+    """A mesh with edge-on triangles (all vertices of a patch moved onto one vertical plane: fp16 determinant 0 for a vertical ray,
+    the reference's result for them is rounding noise that has to be reproduced).  The shadow kernel has no culling bound for
+    them: tiles that meet more than 128 are handed to the tiled kernel (1 % of the mesh: `tiles`), a layer with more than 2 %
+    goes to the tiled kernel altogether (`layer`; RVB_SHADOW_FORCE=1 keeps it on the shadow kernel, every tile over the patch
+    handed back).  Always: bit-identical to the per-pair kernel."""
+    w = R.synth.make_world(length=20.0, nv=200, K=64, n_stones=8, seed=5, build_index=None)
+    v = w.vertices.clone()
+    lo, hi = 9.0 - patch / 2, 9.0 + patch / 2
+    inside = (v[:, 0].float() > lo) & (v[:, 0].float() < hi) & (v[:, 1].float() > lo) & (v[:, 1].float() < hi)
+    v[inside, 0] = 9.0
+    w.vertices = v
+    w.map_indices = R.build_knn_index(w.triangles, w.vertices, w.G, w.res, w.K, device="cuda:0")
+    cam = R.Camera("cuda:0", torch.tensor([0, 0, 0.0]), assets=(w.map_indices, w.triangles, w.vertices))
+    T, ill = w.triangles.shape[0], cam.layer.unbounded_triangles
+    assert (ill * 50 > T) == (route == "layer") and ill > 500, (ill, T)
+    st = R.synth.make_env_state(w, 384, seed=12, margin=3.0)
+    g = torch.Generator().manual_seed(3)
+    st["pos"][:256, :2] = 9.0 + (torch.rand(256, 2, generator=g) - 0.5) * (patch + 4.0)          # over and around the patch
+    st = {k: v_.cuda() for k, v_ in st.items()}
+    eul = R.tensor_quat_to_eul(st["quat"])
+    cam.variant = 1
+    d1, pt1, _ = cam.get_depths(st["pos"], eul, want_hits=True)
+    s1, t1 = cam.last_hit_slot.clone(), cam.last_hit_tri.clone()
+    for force in (None, "1"):
+        if force:
+            monkeypatch.setenv("RVB_SHADOW_FORCE", force)
+        cam.variant = 0
+        d0, pt0, _ = cam.get_depths(st["pos"], eul, want_hits=True)
+        assert torch.equal(bits(d0), bits(d1)) and torch.equal(bits(pt0), bits(pt1))
+        assert torch.equal(cam.last_hit_slot, s1) and torch.equal(cam.last_hit_tri, t1)
+    monkeypatch.delenv("RVB_SHADOW_FORCE", raising=False)
+    assert (d1 != 11).float().mean() > 0.5
+
+
 def test_full_size_properties(R, world20):
     """4096 envs: variant 0 == variant 1 bit for bit, determinism, translation of the same env set."""
     w = world20
