@@ -63,6 +63,14 @@ struct __align__(16) TriRec {
 };
 static_assert(sizeof(TriRec) == 32, "TriRec must be one 32-byte sector");
 
+// One 32-byte record (TriRec, S1Rec: 32-byte aligned) through the read-only path in ONE instruction: sm_100's 256-bit load
+// (LDG.E.256) instead of a 128-bit + a 64/128-bit one -- half the LSU instructions and L1 wavefronts of the record gathers.
+__device__ __forceinline__ void ldg_rec32(const void* p, uint4& lo, uint4& hi) {
+    asm("ld.global.nc.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+        : "=r"(lo.x), "=r"(lo.y), "=r"(lo.z), "=r"(lo.w), "=r"(hi.x), "=r"(hi.y), "=r"(hi.z), "=r"(hi.w)
+        : "l"(p));
+}
+
 // Per-triangle inputs of the shadow kernel's stage 1 (raycast_shadow.cu), pre-computed once per layer with the very fp32
 // operations the kernel used to run per (env, triangle): centroid, bounding radius, b x c, and the two magnitudes the
 // error bounds scale with (rounded UP to fp16: a larger value only widens the bounds).

@@ -554,7 +554,10 @@ __global__ void __launch_bounds__(TT, RTC <= RT_SMALL ? 4 : 3) hm_shadow_kernel(
             if (cull_on) {
                 const uint4* rp = reinterpret_cast<const uint4*>(q.sb_chunk + (it.list_off >> 5) + (g - (int)sm.cum[item]));
                 union { uint4 u[4]; ChunkRec c; } rec;
-                rec.u[0] = __ldg(rp); rec.u[1] = __ldg(rp + 1); rec.u[2] = __ldg(rp + 2); rec.u[3] = __ldg(rp + 3);
+                uint4 c0, c1, c2, c3;
+                ldg_rec32(rp, c0, c1);
+                ldg_rec32(rp + 2, c2, c3);
+                rec.u[0] = c0; rec.u[1] = c1; rec.u[2] = c2; rec.u[3] = c3;
                 float ov;
                 if (chunk_cull(rec.c, s_env, it.rlox, it.rhix, it.rloy, it.rhiy, ov)) key = 0xFF;
                 else key = 7 - min(7, (int)(sqrtf((float)s_item_rays[item] * ov) * 0.25f));      // bucket 0: >= 784 rays under the window
@@ -665,8 +668,7 @@ __global__ void __launch_bounds__(TT, RTC <= RT_SMALL ? 4 : 3) hm_shadow_kernel(
                 const int item = itemA;
                 uint4 r0 = make_uint4(0, 0, 0, 0), r1 = r0;
                 if (id >= 0) {
-                    r0 = __ldg(reinterpret_cast<const uint4*>(q.s1 + id));
-                    r1 = __ldg(reinterpret_cast<const uint4*>(q.s1 + id) + 1);
+                    ldg_rec32(q.s1 + id, r0, r1);
                 }
                 idA = idB; itemA = itemB; entA = entB;
                 pull(idB, entB, itemB);

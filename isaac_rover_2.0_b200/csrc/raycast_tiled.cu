@@ -304,10 +304,10 @@ __device__ __forceinline__ void hm_tiled_body(const TiledParams& q, const int wo
         for (int c0 = 0; c0 < U; c0 += 64) {
             const int j0 = c0 + 2 * lane;
             const int2 ids_next = (j0 + 64 < U) ? __ldg(rowl + (c0 >> 1) + 32) : make_int2(0, 0);   // in flight during the ray loop
-            const uint4* r0 = reinterpret_cast<const uint4*>(q.recs + ids.x);
-            const uint4* r1 = reinterpret_cast<const uint4*>(q.recs + ids.y);
-            const uint4 a0 = __ldg(r0), b0 = __ldg(r1);
-            const uint2 a1 = __ldg(reinterpret_cast<const uint2*>(r0 + 1)), b1 = __ldg(reinterpret_cast<const uint2*>(r1 + 1));
+            uint4 a0, a1w, b0, b1w;
+            ldg_rec32(q.recs + ids.x, a0, a1w);
+            ldg_rec32(q.recs + ids.y, b0, b1w);
+            const uint2 a1 = make_uint2(a1w.x, a1w.y), b1 = make_uint2(b1w.x, b1w.y);
             const Tri2 t = pack_tri2(a0, a1, b0, b1);
             const Cand2 cd = make_cand2(t, dx2, dy2, dz2, j0 < U, j0 + 1 < U);
             uint32_t ra = ray0;
