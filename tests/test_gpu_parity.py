@@ -140,6 +140,29 @@ def test_golden_rock_cast_given_reference_rays(R, golden, grock):
     assert torch.equal(task_col.cpu(), golden["ref_rock_collision"])
 
 
+@pytest.mark.parametrize("K", [1, 2, 7, 37, 64, 65, 100, 129, 200])
+def test_rock_kernel_candidate_counts(R, K):
+    """The rock kernel (K / 64 full warp iterations per ray + the rays' tails scanned together, several rays per warp iteration)
+    against the per-pair kernel behind cast_rays on the rays it generated itself: distances and hit triangles bit for bit for
+    every split of K into full iterations and tail."""
+    w = R.synth.make_world(length=12.0, nv=44, K=200, n_stones=8, seed=3, build_index=None)
+    kr = min(K, w.rock_triangles.shape[0])
+    idx = R.build_knn_index(w.rock_triangles, w.rock_vertices, w.G, w.res, kr, device="cuda:0")
+    rock = R.Rock_Detection("cuda:0", torch.tensor([0, 0, 0.0]), assets=(idx, w.rock_triangles, w.rock_vertices))
+    st = {k: v.cuda() for k, v in R.synth.make_env_state(w, 300, seed=21 + K, margin=2.0).items()}
+    g = torch.Generator().manual_seed(K)
+    stones = w.stone_info[:, :2].float()
+    st["pos"][:200, :2] = (stones[torch.randint(0, stones.shape[0], (200,), generator=g)] + torch.rand(200, 2, generator=g) - 0.5).cuda()
+    eul = R.tensor_quat_to_eul(st["quat"])
+    wheel, body = rock.get_collisions(st["pos"], eul, st["joints"], want_hits=True, want_rays=True)
+    rays = rock.last_rays.reshape(-1, 6)
+    dist, pt, slot, tri = R.cast_rays(rock.layer, rays[:, 0:3], rays[:, 3:6], want_hits=True)
+    mine = torch.cat((wheel, body), 1).reshape(-1)
+    assert torch.equal(bits(mine), bits(dist))
+    assert torch.equal(rock.last_hit_tri.reshape(-1), tri)
+    assert (mine != 11).float().mean() > 0.02 or K < 7
+
+
 def test_golden_ray_distance(R, golden):
     k, pt = R.ray_distance(golden["in_rd_src"].cuda(), golden["in_rd_dir"].cuda(), golden["in_rd_tri"].cuda())
     assert_bits_equal(k, golden["ref_rd_k"], "known-answer k")
