@@ -15,7 +15,7 @@ class Camera():
         """assets: optional (map_indices [K,G,G] int32, triangles [T,3] int32, vertices [V,3] fp16); when None
         the three .pt files are loaded from ASSET_DIR exactly as the reference does.
         compact: the layer gives back its K-contiguous copy of the index once its lists are built (TerrainLayer.release_index):
-        2.8 GB instead of 6.0 GB on the benchmark world, same results; only the production variants (0, 3) run on such a layer."""
+        5.0 GB instead of 8.2 GB on the benchmark world, same results; only the production variants (0, 3) run on such a layer."""
         self.debug = debug
         self.device = device
         self.partition = True

@@ -38,7 +38,7 @@ struct TiledParams {
     // shadow kernel (raycast_shadow.cu): superblock candidate lists + the list of (env, tile) work items it hands back
     const uint32_t* sb_off;
     const int32_t* sb_ids;
-    const uint16_t* sb_pos;
+    const unsigned char* sb_slot9;
     const ChunkRec* sb_chunk;   // bounds per window of 32 list entries (chunk culling); NULL = none
     int nSBy;
     float cos_steep;          // envs whose ray direction is flatter than this go to the fall-back list

@@ -17,8 +17,8 @@
 //              exact linear forms N* = (s - a) . (c x d), M* = (s - a) . (d x b) in fp32 (three packed FFMA2 per ray) against
 //              the thresholds stage 2 derived for the triangle -- the same three half-planes whose corners make the box;
 //   stage 3b   the (ray, triangle) pairs left (about 1.2 per hit): LITERAL evaluation of ray_casting.py:34-59 with its
-//              three IEEE divisions, membership + slot of the triangle in the ray's own cell list (one look-up in the
-//              superblock entry -> block-list position table), atomicMin on (order-preserving fp16 bits, slot) = torch.min.
+//              three IEEE divisions, membership + slot of the triangle in the ray's own cell list (one byte of the superblock
+//              entry's per-cell slot table, sb_slot9), atomicMin on (order-preserving fp16 bits, slot) = torch.min.
 // Two instantiations: <= 1664 rays per tile (64 registers, 55 KB shared memory, 4 CTAs per SM) and <= 2048 (3 CTAs per SM).
 //
 // Bit-exactness rests on stage 3b alone; stages 1-3L only have to be CONSERVATIVE (never drop a pair the literal test
@@ -851,30 +851,23 @@ __global__ void __launch_bounds__(TT, RTC <= RT_SMALL ? 4 : 3) hm_shadow_kernel(
                     const int32_t tri = (q.spec_slot & 8) ? q4t[(h4 + lane) & (QCAP3 - 1)] : __ldg(q.sb_ids + ent);
                     const H3 s = {h_from_bits(ray.x & 0xffff), h_from_bits(ray.x >> 16), h_from_bits(ray.y & 0xffff)};
                     const uint32_t meta = ray.y >> 16, p = meta & 0x7ffu, sub = meta >> 11;
-                    // position of the triangle in the list of the ray's 3x3 block (0xFFFF: in none of its nine cell lists)
+                    // slot of the triangle in the K-list of the ray's own cell (0xFF: not in it): ONE look-up in the superblock entry's
+                    // table, issued before the literal test runs so that its latency hides behind the arithmetic
                     const int cx = cell_coord(s.x, q.shift_x, q.res, q.inv_res, q.G0 - 1, q.sem);
                     const int cy = min(cell_coord(s.y, q.shift_y, q.res, q.inv_res, q.G0 - 1, q.sem), q.G1 - 1);
                     const int bx = cx / RVB_BLK, by = cy / RVB_BLK;
-                    const uint32_t pos16 = __ldg(q.sb_pos + (size_t)ent * (SB * SB) + (uint32_t)((bx % SB) * SB + (by % SB)));
-                    const uint32_t o0 = __ldg(q.blk_off + (uint32_t)bx * (uint32_t)q.nBy + (uint32_t)by);
-                    // the slot is fetched before the literal test runs (four in five pairs need it): its latency hides behind the
-                    // arithmetic instead of following it
-                    uint32_t slot = 0xffu;
-                    if (q.spec_slot && pos16 != 0xffffu) slot = __ldg(reinterpret_cast<const unsigned char*>(q.blk_slots + o0 + pos16) + sub);
+                    const uint32_t slot = __ldg(q.sb_slot9 + ((size_t)ent * (SB * SB) + (uint32_t)((bx % SB) * SB + (by % SB))) * 9 + sub);
                     H3 a, b, c, nn;
                     unpack_rec(q.recs + tri, a, b, c, nn);
                     const __half k = pair_test(s, d16, a, b, c, nn);
                     const uint32_t key0 = make_key(h_bits(k), 0u), ord = key0 >> 16;
                     // a hit at exactly 11.0 equals the all-miss result (slot 0); a hit farther than a confirmed one cannot win
                     if (DBGK && h_bits(k) != RVB_H_MISS) atomicAdd(q.dbg + 8, 1ull);
-                    if (h_bits(k) != RVB_H_MISS && pos16 != 0xffffu && (ord > ORD_MISS || ord <= (sm.res[p] >> 16))) {
+                    if (h_bits(k) != RVB_H_MISS && slot != 0xffu && (ord > ORD_MISS || ord <= (sm.res[p] >> 16))) {
                         if (DBGK) atomicAdd(q.dbg + 9, 1ull);
-                        if (!q.spec_slot) slot = __ldg(reinterpret_cast<const unsigned char*>(q.blk_slots + o0 + pos16) + sub);
-                        if (slot != 0xffu) {                // the triangle is in the ray's own cell list
-                            const uint32_t key = key0 | (slot << 1);
-                            if (ord > ORD_MISS) atomicOr(&sm.far[p >> 5], 1u << (p & 31));      // k > 11: see epilogue
-                            else atomicMin(&sm.res[p], key);
-                        }
+                        const uint32_t key = key0 | (slot << 1);          // the triangle is in the ray's own cell list
+                        if (ord > ORD_MISS) atomicOr(&sm.far[p >> 5], 1u << (p & 31));      // k > 11: see epilogue
+                        else atomicMin(&sm.res[p], key);
                     }
                 }
                 h4 += cnt;
@@ -929,7 +922,7 @@ int launch_heightmap_shadow(const rvb_terrain* t, const float* pos, const float*
                             const double* pattern, int64_t P, int64_t N, uint16_t* dist, int32_t* hit_slot,
                             int32_t* hit_tri, uint16_t* pt, uint16_t* sources, float* obs, int64_t obs_ld,
                             const int32_t* col_a, const int32_t* col_b, float cos_steep, const RvbObs16* o16, cudaStream_t st) {
-    RVB_REQUIRE(t->sb_ids != nullptr && t->sb_pos != nullptr && t->blk_ids != nullptr && t->s1recs != nullptr, "heightmap ray-cast (shadow): layer has no block lists");
+    RVB_REQUIRE(t->sb_ids != nullptr && t->sb_slot9 != nullptr && t->blk_ids != nullptr && t->s1recs != nullptr, "heightmap ray-cast (shadow): layer has no block lists");
     rc::TiledParams q;
     int rc_ = fill_tiled_params(t, pos, euler, trig, pattern, P, N, dist, hit_slot, hit_tri, pt, sources, obs, obs_ld, col_a,
                                 col_b, o16, q);
@@ -964,7 +957,7 @@ int launch_heightmap_shadow(const rvb_terrain* t, const float* pos, const float*
     q.presorted = 1;
     q.min_sh = 1;                                                            // 2x2-cell bins: 2 % faster than single cells (fewer tasks)
     if (const char* ms = getenv("RVB_SHADOW_SH")) q.min_sh = atoi(ms);      // tuning hook: finest bins to start from
-    q.spec_slot = 31;         // bit 0: slot byte fetched ahead of the literal test, bit 1: L2 prefetch of the records, bit 2: window cull,
+    q.spec_slot = 31;         // bit 0: (unused since the slot table) bit 1: L2 prefetch of the records, bit 2: window cull,
                               // bit 3: triangle ids travel through the queues instead of being re-read from sb_ids, bit 4: the epilogue
                               // issues all of a thread's loads before its first store (raycast_common.cuh)
     // A/B switch: RVB_SHADOW_BULK = number of heightmap observation columns (1746 for the reference pattern; every

@@ -385,7 +385,7 @@ int fill_tiled_params(const rvb_terrain* t, const float* pos, const float* euler
     memset(&q, 0, sizeof(q));
     q.index = t->index; q.recs = t->recs; q.s1 = t->s1recs;
     q.blk_off = t->blk_off; q.blk_ids = t->blk_ids; q.blk_slots = t->blk_slots; q.nBy = t->nBy;
-    q.sb_off = t->sb_off; q.sb_ids = t->sb_ids; q.sb_pos = t->sb_pos; q.sb_chunk = t->sb_chunk; q.nSBy = t->nSBy;
+    q.sb_off = t->sb_off; q.sb_ids = t->sb_ids; q.sb_slot9 = t->sb_slot9; q.sb_chunk = t->sb_chunk; q.nSBy = t->nSBy;
     q.G0 = (int)t->G0; q.G1 = (int)t->G1; q.K = (int)t->K; q.Ks = (int)t->Ks;
     q.res = t->res; q.inv_res = 1.0f / t->res; q.shift_x = t->shift_x; q.shift_y = t->shift_y; q.sem = t->sem;
     q.pos = pos; q.euler = euler; q.trig = trig; q.pattern = pattern;
