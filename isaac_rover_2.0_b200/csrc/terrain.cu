@@ -129,7 +129,10 @@ __global__ void build_records_kernel(const int32_t* __restrict__ tri, int64_t T,
     // the shadow kernel has no bound for them.  Counted once per layer: a mesh finer than the fp16 grid of its coordinates
     // has many, and the heightmap ray-cast then runs the tiled kernel, whose cost does not depend on them.
     const float e_det = 0.00390625f * 6.1f * cb * cb + 1.9073486328125e-06f;
-    const bool ill = !(fabsf(s.nz) > 4.0f * e_det);
+    // (a triangle whose fp16 normal is exactly zero is not counted: it can never be hit -- det = n . d = 0 makes the reference's
+    // quotients inf / NaN, which fail its test -- and is left out of the superblock lists altogether, see sb_keys_kernel)
+    const bool dead = ((h_bits(n.x) | h_bits(n.y) | h_bits(n.z)) & 0x7fffu) == 0u;
+    const bool ill = !dead && !(fabsf(s.nz) > 4.0f * e_det);
     const unsigned m = __ballot_sync(__activemask(), ill);
     if (m && (threadIdx.x & 31) == (__ffs(__activemask()) - 1)) atomicAdd(bad + 1, __popc(m));
 }
@@ -228,12 +231,21 @@ build_blocks_kernel(const int32_t* __restrict__ index, int G0, int G1, int K, in
 // ------------------------------------------------------------------------------------------------
 // Superblock lists: keys (superblock << 32 | id) of every block-list entry, radix-sorted and made unique.
 // ------------------------------------------------------------------------------------------------
-__global__ void sb_keys_kernel(const uint32_t* __restrict__ blk_off, const int32_t* __restrict__ blk_ids, int nBy, int nSBy,
-                               unsigned long long* __restrict__ keys) {
+// Triangles whose fp16 normal n = b x c is exactly zero (collapsed vertices: a mesh finer than the fp16 grid of its coordinates has
+// millions) get the all-ones key: they sort behind every superblock and are cut off.  No ray can hit them (det = n . d = 0 ->
+// the reference's n, m are inf / NaN and fail ray_casting.py:59), so the kernel that ENUMERATES triangles need not see them; the
+// block lists and the index keep them (their slots exist, and the far-hit walk evaluates every slot literally).
+__global__ void sb_keys_kernel(const uint32_t* __restrict__ blk_off, const int32_t* __restrict__ blk_ids, const TriRec* __restrict__ recs,
+                               int nBy, int nSBy, unsigned long long* __restrict__ keys) {
     const int I = blockIdx.x / nBy, J = blockIdx.x % nBy;
     const unsigned long long sb = (unsigned long long)((I / RVB_SB) * nSBy + (J / RVB_SB)) << 32;
     const uint32_t o0 = blk_off[blockIdx.x], o1 = blk_off[blockIdx.x + 1];
-    for (uint32_t e = o0 + threadIdx.x; e < o1; e += blockDim.x) keys[e] = sb | (uint32_t)blk_ids[e];
+    for (uint32_t e = o0 + threadIdx.x; e < o1; e += blockDim.x) {
+        const int32_t id = blk_ids[e];
+        const TriRec& r = recs[id];
+        const bool dead = ((h_bits(r.n[0]) | h_bits(r.n[1]) | h_bits(r.n[2])) & 0x7fffu) == 0u;
+        keys[e] = dead ? ~0ull : (sb | (uint32_t)id);
+    }
 }
 
 __global__ void sb_offsets_kernel(const unsigned long long* __restrict__ keys, int64_t n, int64_t nsb, uint32_t* __restrict__ off) {
@@ -355,9 +367,8 @@ static int build_superblock_lists(rvb_terrain* t, cudaStream_t st) {
     if (e == cudaSuccess) e = cudaMalloc(&d_num, sizeof(int64_t));
     int64_t n_u = 0;
     if (e == cudaSuccess) {
-        sb_keys_kernel<<<(unsigned)nb, 128, 0, st>>>(t->blk_off, t->blk_ids, t->nBy, t->nSBy, k0);
-        int sb_bits = 1;
-        while (((int64_t)1 << sb_bits) < nsb) ++sb_bits;
+        sb_keys_kernel<<<(unsigned)nb, 128, 0, st>>>(t->blk_off, t->blk_ids, t->recs, t->nBy, t->nSBy, k0);
+        const int sb_bits = 32;          // all 64 key bits: the all-ones key of the dropped triangles has to sort last
         size_t b0 = 0, b1 = 0;
         cub::DeviceRadixSort::SortKeys(nullptr, b0, k0, k1, (int)n, 0, 32 + sb_bits, st);
         cub::DeviceSelect::Unique(nullptr, b1, k1, k0, d_num, (int)n, st);
@@ -369,6 +380,9 @@ static int build_superblock_lists(rvb_terrain* t, cudaStream_t st) {
             cub::DeviceSelect::Unique(tmp, b, k1, k0, d_num, (int)n, st);
             e = cudaMemcpyAsync(&n_u, d_num, sizeof(int64_t), cudaMemcpyDeviceToHost, st);
             if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+            unsigned long long last = 0;
+            if (e == cudaSuccess && n_u > 0) e = cudaMemcpy(&last, k0 + n_u - 1, sizeof(last), cudaMemcpyDeviceToHost);
+            if (e == cudaSuccess && n_u > 0 && last == ~0ull) --n_u;          // the dropped triangles' one surviving key
         }
     }
     if (e == cudaSuccess) {
