@@ -17,7 +17,7 @@ int launch_heightmap_shadow(const rvb_terrain* t, const float* pos, const float*
                            int32_t* hit_tri, uint16_t* pt, uint16_t* sources, float* obs, int64_t obs_ld,
                            const int32_t* col_a, const int32_t* col_b, float cos_steep, const RvbObs16* o16, cudaStream_t st);
 // envs whose ray direction has |d_z| below this are ray-cast by the tiled kernel (their prisms are long slivers)
-#define RVB_COS_STEEP 0.8f
+#define RVB_COS_STEEP 0.7f
 
 
 // ------------------------------------------------------------------------------------------------
