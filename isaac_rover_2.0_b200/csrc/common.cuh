@@ -116,7 +116,7 @@ struct rvb_terrain {
     int32_t nSBx, nSBy;
     uint32_t* sb_off;    // [nSBx*nSBy + 1]
     int32_t* sb_ids;     // [n_sb_ent]
-    unsigned char* sb_slot9;   // [n_sb_ent][RVB_SB*RVB_SB][9]  slot of the triangle in the K-list of cell s of block (i % SB, j % SB); 0xFF = absent
+    unsigned char* sb_slot9;   // [n_sb_ent][24][24]  slot of the triangle in the K-list of cell (cx % 24, cy % 24) of the superblock; 0xFF = absent
     int64_t n_sb_ent;
     ChunkRec* sb_chunk;  // [ceil(n_sb_ent / 32)]
     int64_t n_ill;       // triangles whose determinant is rounding noise even for a vertical ray (no culling bound exists for them)

@@ -13,7 +13,7 @@
 //              prism's cross-section on the source plane against the rectangle of the superblock's rays, from the
 //              triangle's pre-computed 32-byte stage-1 record (centroid, radius, b x c; terrain.cu);
 //   stage 2    survivors: exact corners of the cross-section -> xy box -> bin columns -> ray ranges (tasks);
-//   stage 3L   rays of a task (one triangle, <= 16 consecutive sorted rays; one task per lane) against the prism ITSELF: the
+//   stage 3L   rays of a task (one triangle, <= 20 consecutive sorted rays; one task per lane) against the prism ITSELF: the
 //              exact linear forms N* = (s - a) . (c x d), M* = (s - a) . (d x b) in fp32 (three packed FFMA2 per ray) against
 //              the thresholds stage 2 derived for the triangle -- the same three half-planes whose corners make the box;
 //   stage 3b   the (ray, triangle) pairs left (about 1.2 per hit): LITERAL evaluation of ray_casting.py:34-59 with its
@@ -61,7 +61,7 @@ constexpr int CHUNK = 32;          // list entries per pulled work chunk (one st
 constexpr int CHUNK_CAP = 1024;    // chunks per tile (u8 chunk -> item table)
 constexpr int QCAP = 64;           // per-warp queues q1, q2 (each drained below 32 after every push of <= 32)
 constexpr int QCAP3 = 128;         // q4 (stage 3L pushes while it holds < 32 entries, stage 3b drains in batches of 32)
-constexpr int TASK_RAYS = 16;      // upper bound of the tuning hook q.task_rays
+constexpr int TASK_RAYS = 20;      // rays per task (<= 32: one mask bit each); sweep with the shipped kernel: 8 +5 %, 12 +1 %, 16 +0.45 %, 20 best, 24 +0.2 %, 32 +1 %
 constexpr int REL_BITS = 15;        // queue entries name a triangle as item << 15 | position in the item's list
 constexpr int ILL_CAP = 128;        // triangles without a bound ("ill": fp16 determinant within rounding of zero) a tile may meet before it
                                    // is handed to the tiled kernel, whose cost does not depend on them (a 1M-triangle heightfield has ~1
@@ -77,7 +77,7 @@ struct Item {
 static_assert(sizeof(Item) == 32, "Item");
 
 struct Smem {
-    uint2* rays;         // [RT]  sorted by block: (sx | sy << 16, sz | (p | sub << 11) << 16)
+    uint2* rays;         // [RT]  sorted by block: (sx | sy << 16, sz | (p | (cy % 24) << 11) << 16)
     uint32_t* res;       // [RT]  best key per local ray id
     uint32_t* bins;      // [BIN_CAP / 2 + 2]  u16 counters, then exclusive offsets (column-major bins)
     Item* items;         // [ITEM_CAP]
@@ -290,9 +290,8 @@ __global__ void __launch_bounds__(TT, RTC <= RT_SMALL ? 4 : 3) hm_shadow_kernel(
             r_sxy[i] = (uint32_t)h_bits(hx) | ((uint32_t)h_bits(hy) << 16);
             int cx = cell_coord(hx, q.shift_x, q.res, q.inv_res, q.G0 - 1, q.sem);
             int cy = min(cell_coord(hy, q.shift_y, q.res, q.inv_res, q.G0 - 1, q.sem), q.G1 - 1);   // camera.py:243
-            const int bx = cx / RVB_BLK, by = cy / RVB_BLK;
-            const uint32_t sub = (uint32_t)((cx - bx * RVB_BLK) * RVB_BLK + (cy - by * RVB_BLK));
-            r_sz[i] = (uint32_t)h_bits(hz) | (((uint32_t)p | (sub << 11)) << 16);
+            // (the 5 spare bits next to p: the cell's y within its superblock, half of the slot-table index of stage 3b)
+            r_sz[i] = (uint32_t)h_bits(hz) | (((uint32_t)p | ((uint32_t)(cy % SBC) << 11)) << 16);
             r_cell[i] = (cx << 16) | cy;
             mnx = min(mnx, cx); mxx = max(mxx, cx); mny = min(mny, cy); mxy = max(mxy, cy);
             const float fx = __half2float(hx), fy = __half2float(hy), fz = __half2float(hz);
@@ -850,13 +849,11 @@ __global__ void __launch_bounds__(TT, RTC <= RT_SMALL ? 4 : 3) hm_shadow_kernel(
                     const uint32_t ent = sm.items[pc >> (11 + REL_BITS)].list_off + ((pc >> 11) & ((1u << REL_BITS) - 1u));
                     const int32_t tri = (q.spec_slot & 8) ? q4t[(h4 + lane) & (QCAP3 - 1)] : __ldg(q.sb_ids + ent);
                     const H3 s = {h_from_bits(ray.x & 0xffff), h_from_bits(ray.x >> 16), h_from_bits(ray.y & 0xffff)};
-                    const uint32_t meta = ray.y >> 16, p = meta & 0x7ffu, sub = meta >> 11;
+                    const uint32_t meta = ray.y >> 16, p = meta & 0x7ffu, cym = meta >> 11;
                     // slot of the triangle in the K-list of the ray's own cell (0xFF: not in it): ONE look-up in the superblock entry's
-                    // table, issued before the literal test runs so that its latency hides behind the arithmetic
+                    // per-cell table, issued before the literal test runs so that its latency hides behind the arithmetic
                     const int cx = cell_coord(s.x, q.shift_x, q.res, q.inv_res, q.G0 - 1, q.sem);
-                    const int cy = min(cell_coord(s.y, q.shift_y, q.res, q.inv_res, q.G0 - 1, q.sem), q.G1 - 1);
-                    const int bx = cx / RVB_BLK, by = cy / RVB_BLK;
-                    const uint32_t slot = __ldg(q.sb_slot9 + ((size_t)ent * (SB * SB) + (uint32_t)((bx % SB) * SB + (by % SB))) * 9 + sub);
+                    const uint32_t slot = __ldg(q.sb_slot9 + (size_t)ent * (SBC * SBC) + (uint32_t)((cx % SBC) * SBC) + cym);
                     H3 a, b, c, nn;
                     unpack_rec(q.recs + tri, a, b, c, nn);
                     const __half k = pair_test(s, d16, a, b, c, nn);
@@ -967,7 +964,7 @@ int launch_heightmap_shadow(const rvb_terrain* t, const float* pos, const float*
     if (const char* bo = getenv("RVB_SHADOW_BULK")) q.n_obs_cols = atoi(bo);
     q.bulk_obs = q.n_obs_cols > 8 && (size_t)(q.n_obs_cols + 8) * 4 <= (size_t)q.tile_size * 8;
     q.task_rays = TASK_RAYS;
-    if (const char* tr = getenv("RVB_SHADOW_TASK_RAYS")) q.task_rays = min(max(atoi(tr), 1), TASK_RAYS);   // tuning hook
+    if (const char* tr = getenv("RVB_SHADOW_TASK_RAYS")) q.task_rays = min(max(atoi(tr), 1), 32);   // tuning hook
     if (const char* sp = getenv("RVB_SHADOW_SPEC")) q.spec_slot = atoi(sp); // tuning hook
     RvbSide* side_p = nullptr;
     RVB_CUDA(rvb_side_stream(1, &side_p));

@@ -304,9 +304,12 @@ __global__ void sb_slot9_kernel(const uint32_t* __restrict__ sb_off, const uint1
         const uint16_t p16 = pos[(size_t)ent * (RVB_SB * RVB_SB) + b];
         uint4 sl = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
         if (p16 != 0xffffu && I < nBx && J < nBy) sl = blk_slots[blk_off[(uint32_t)I * nBy + J] + p16];
+        // laid out by CELL of the superblock (24 x 24): the kernel indexes it with (cx % 24) * 24 + cy % 24
         const unsigned char* sb = reinterpret_cast<const unsigned char*>(&sl);
-        unsigned char* o = out + ((size_t)ent * (RVB_SB * RVB_SB) + b) * 9;
-        for (int i = 0; i < 9; ++i) o[i] = sb[i];
+        constexpr int SBC = RVB_SB * RVB_BLK;
+        unsigned char* o = out + (size_t)ent * (SBC * SBC);
+        const int ci0 = (int)(b / RVB_SB) * RVB_BLK, cj0 = (int)(b % RVB_SB) * RVB_BLK;
+        for (int i = 0; i < 9; ++i) o[(ci0 + i / RVB_BLK) * SBC + cj0 + i % RVB_BLK] = sb[i];
     }
 }
 
