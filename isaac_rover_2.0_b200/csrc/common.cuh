@@ -111,8 +111,8 @@ struct rvb_terrain {
     uint4* blk_slots;    // [n_ent]  byte s = slot in sub-cell s (s = (cx % BLK) * BLK + cy % BLK), other bytes 0xFF
     int64_t n_ent;
     // Superblock lists (built with the block lists): the union of the K-lists of RVB_SB x RVB_SB blocks, sorted by id.
-    // The shadow ray-cast kernel enumerates these (a superset of every member cell's candidates) and looks the slot up
-    // in the block lists only for the few candidates a ray can actually hit.
+    // The shadow ray-cast kernel enumerates these (a superset of every member cell's candidates) and, for the few candidates a
+    // ray can actually hit, reads membership + slot in the ray's own K-list from the entry's per-cell table (sb_slot9).
     int32_t nSBx, nSBy;
     uint32_t* sb_off;    // [nSBx*nSBy + 1]
     int32_t* sb_ids;     // [n_sb_ent]
