@@ -4,7 +4,7 @@
 cd "$GRAFT_REPO_ROOT" 2>/dev/null || true
 mkdir -p gpurun_out
 TAG=${1:-r2}
-SEL='golden_get_depths or golden_rock_detection or golden_task_step or fused_step or reset_targets_matches or compact_layer or edge_cases or pre_physics_step_device or hooks_agree'
+SEL='rock_kernel_candidate_counts or degenerate or golden_get_depths or golden_rock_detection or golden_task_step or fused_step or reset_targets_matches or compact_layer or edge_cases or pre_physics_step_device or hooks_agree'
 timeout 1200 compute-sanitizer --tool memcheck --error-exitcode 7 --print-limit 20 python -m pytest tests -m gpu -q -x -k "$SEL" > gpurun_out/sanitize_memcheck_$TAG.txt 2>&1
 echo "memcheck rc=$?"; tail -8 gpurun_out/sanitize_memcheck_$TAG.txt
 timeout 900 compute-sanitizer --tool memcheck --error-exitcode 7 --print-limit 20 python -m pytest tests/test_zz_gpu_policy.py -m gpu -q -x -k "golden_reference_outputs or pair_launch or strided_rows" > gpurun_out/sanitize_memcheck_policy_$TAG.txt 2>&1
